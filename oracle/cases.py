@@ -1,0 +1,312 @@
+"""Reference test cases restated for the oracle (test infrastructure, NOT product code).
+
+Each builder returns a ``RefCase`` with the reference's .usr callbacks (usrdat2, uservp,
+userini, userinc, usersrc, usersol) restated in numpy, plus the tolerances the reference's
+``userchk`` enforces.  File:line citations point at /root/reference/tests/<case>/.
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import numpy as np
+
+from . import oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+
+def _load_mesh(name):
+    d = np.load(os.path.join(GOLDEN, name))
+    return O.mesh_from_arrays(int(d["ndim"]), d["xc"], d["yc"], d["zc"],
+                              [[str(c) for c in row] for row in d["cbc"]], d["vertex"]), d["part"]
+
+
+def _rescale(case, lo, hi):
+    """usrdat2 pattern: affine map of the mesh bounding box onto [lo,hi]^d."""
+    for arr, l, h in zip((case.xm1, case.ym1, case.zm1)[:case.ldim], lo, hi):
+        mn, mx = arr.min(), arr.max()
+        s = (h - l) / (mx - mn)
+        arr[:] = s * (arr - mn) + l
+
+
+# ------------------------------------------------------------------------------------
+# tests/3dboxper : periodic box, standing mode omega = sqrt(3)
+# ------------------------------------------------------------------------------------
+def usersol_3dboxper(case, tt):
+    """tests/3dboxper/3dboxper.usr:45-86"""
+    omega = math.sqrt(3.0)
+    tmph = math.sin(omega * tt) / omega
+    tmpe = math.cos(omega * tt)
+    xx, yy, zz = case.xm1, case.ym1, case.zm1
+    n = case.npts
+    shn = np.zeros(3 * n); sen = np.zeros(3 * n)
+    shn[0:n] = 2 * np.cos(xx) * np.sin(yy) * np.cos(zz) * tmph
+    shn[n:2 * n] = -np.sin(xx) * np.cos(yy) * np.cos(zz) * tmph
+    shn[2 * n:] = np.sin(xx) * np.sin(yy) * np.sin(zz) * tmph
+    sen[0:n] = 0.0
+    sen[n:2 * n] = np.cos(xx) * np.sin(yy) * np.sin(zz) * tmpe
+    sen[2 * n:] = np.cos(xx) * np.cos(yy) * np.cos(zz) * tmpe
+    return shn, sen
+
+
+def usrdat2_3dboxper(case):
+    """tests/3dboxper/3dboxper.usr:138-167: sx*(x-xmin) with sx = 2*pi/(xmax-xmin)."""
+    pi = 4.0 * math.atan(1.0)
+    for arr in (case.xm1, case.ym1, case.zm1):
+        mn, mx = arr.min(), arr.max()
+        s = 2 * pi / (mx - mn)
+        arr[:] = s * (arr - mn)
+
+
+def case_3dboxper(nx1=9, mesh=None):
+    """tests/3dboxper (128 hex from .re2/.map, all periodic; N=8; dt=2e-4, 50 steps, upwind).
+    Tolerances: L2 5e-10, Linf 5e-9 (3dboxper.usr:181-193)."""
+    if mesh is None:
+        mesh, _ = _load_mesh("3dboxper_mesh.npz")
+    c = O.RefCase(mesh, nx1, upwind=True, usrdat2=usrdat2_3dboxper)
+    c.set_dt(-0.0002)
+    c.usersol = usersol_3dboxper
+    shn, sen = usersol_3dboxper(c, 0.0)
+    c.hn[:] = shn; c.en[:] = sen
+    c.tol = dict(l2=[5e-10] * 6, linf=[5e-9] * 6)
+    c.nsteps = 50
+    return c
+
+
+def case_boxper(nel=(2, 2, 2), nx1=6, dt=-0.0002):
+    """Synthetic periodic .box variant of 3dboxper on [0,2pi]^3."""
+    pi2 = 2 * 4.0 * math.atan(1.0)
+    mesh = O.box_mesh(nel, ((0.0, pi2),) * 3, ("P  ",) * 6)
+    c = O.RefCase(mesh, nx1, upwind=True)
+    c.set_dt(dt)
+    c.usersol = usersol_3dboxper
+    shn, sen = usersol_3dboxper(c, 0.0)
+    c.hn[:] = shn; c.en[:] = sen
+    return c
+
+
+# ------------------------------------------------------------------------------------
+# tests/3dboxpec : PEC cavity
+# ------------------------------------------------------------------------------------
+def usersol_3dboxpec(case, tt):
+    """tests/3dboxpec/3dboxpec.usr:64-115"""
+    pi = 4.0 * math.atan(1.0)
+    ww = pi
+    sqrt2, sqrt3, sqrt6 = math.sqrt(2.0), math.sqrt(3.0), math.sqrt(6.0)
+    tmph = math.cos(ww * sqrt3 * tt) / sqrt6
+    tmpe = math.sin(ww * sqrt3 * tt) / sqrt2
+    xx, yy, zz = case.xm1, case.ym1, case.zm1
+    n = case.npts
+    shn = np.zeros(3 * n); sen = np.zeros(3 * n)
+    shn[0:n] = -np.sin(ww * xx) * np.cos(ww * yy) * np.cos(ww * zz) * tmph
+    shn[n:2 * n] = -np.cos(ww * xx) * np.sin(ww * yy) * np.cos(ww * zz) * tmph
+    shn[2 * n:] = 2 * np.cos(ww * xx) * np.cos(ww * yy) * np.sin(ww * zz) * tmph
+    sen[0:n] = -np.cos(ww * xx) * np.sin(ww * yy) * np.sin(ww * zz) * tmpe
+    sen[n:2 * n] = np.sin(ww * xx) * np.cos(ww * yy) * np.sin(ww * zz) * tmpe
+    sen[2 * n:] = 0
+    return shn, sen
+
+
+def usrdat2_3dboxpec(case):
+    """tests/3dboxpec/3dboxpec.usr:151-183: sx*(x-xmin)-1 with sx = 2/(xmax-xmin)."""
+    for arr in (case.xm1, case.ym1, case.zm1):
+        mn, mx = arr.min(), arr.max()
+        s = 2.0 / (mx - mn)
+        arr[:] = s * (arr - mn) - 1
+
+
+def case_3dboxpec(nx1=9, mesh=None):
+    """tests/3dboxpec (27 hex from .rea/.map, PEC walls; N=8; dt=5e-3, 1000 steps).
+    Tolerances: L2 5e-8, Linf 5e-7 (3dboxpec.usr:198-210)."""
+    if mesh is None:
+        mesh, _ = _load_mesh("3dboxpec_mesh.npz")
+    c = O.RefCase(mesh, nx1, upwind=True, usrdat2=usrdat2_3dboxpec)
+    c.set_dt(-0.005)
+    c.usersol = usersol_3dboxpec
+    shn, sen = usersol_3dboxpec(c, 0.0)
+    c.hn[:] = shn; c.en[:] = sen
+    c.tol = dict(l2=[5e-8] * 6, linf=[5e-7] * 6)
+    c.nsteps = 1000
+    return c
+
+
+def case_boxpec(nel=(2, 2, 2), nx1=6, dt=-0.005):
+    """Synthetic PEC .box cavity on [-1,1]^3 with the 3dboxpec solution."""
+    mesh = O.box_mesh(nel, ((-1.0, 1.0),) * 3, ("PEC",) * 6)
+    c = O.RefCase(mesh, nx1, upwind=True)
+    c.set_dt(dt)
+    c.usersol = usersol_3dboxpec
+    shn, sen = usersol_3dboxpec(c, 0.0)
+    c.hn[:] = shn; c.en[:] = sen
+    return c
+
+
+# ------------------------------------------------------------------------------------
+# tests/3ddielectric : plane wave through a dielectric interface, PML in +-y
+# ------------------------------------------------------------------------------------
+class _Dielectric:
+    """tests/3ddielectric/3ddielectric.usr (uservp :170-262, usrdat2 :271-303,
+    userinc :6-50, userini :52-81, usersol :83-151)."""
+
+    def __init__(self, twomat: bool):
+        self.twomat = twomat
+        self.omega = 2.0
+        self.eps1 = 1.0
+        self.eps2 = 2.0 if twomat else 1.0
+        self.mu1 = self.mu2 = 1.0
+        z1 = math.sqrt(self.mu1 / self.eps1)
+        z2 = math.sqrt(self.mu2 / self.eps2)
+        self.reflte = (z1 - z2) / (z1 + z2)
+        self.trante = 2 * z1 / (z1 + z2)
+        self.refltm = (z2 - z1) / (z1 + z2)
+        self.trantm = 2 * z2 / (z1 + z2)
+
+    def usrdat2(self, case):
+        for arr, s in zip((case.xm1, case.ym1, case.zm1), (5.0, 10.0, 5.0)):
+            mn, mx = arr.min(), arr.max()
+            arr[:] = s * (arr - mn) / (mx - mn) - (s / 2.0)
+
+    def _mid(self, case):
+        # ym1(nx1/2,nx1/2,nx1/2,e), 1-based integer division
+        h = case.nx1 // 2 - 1
+        n = case.nx1
+        return h + n * h + n * n * h
+
+    def uservp(self, case):
+        ym = case.ym1.reshape(case.nelt, case.nxyz)
+        upper = ym[:, self._mid(case)] > 0
+        eps = np.where(upper, self.eps1, self.eps2)
+        mu = np.where(upper, self.mu1, self.mu2)
+        case.permittivity[:] = np.repeat(eps, case.nxyz)
+        case.permeability[:] = np.repeat(mu, case.nxyz)
+        self.upper = upper
+        inc = []
+        for e in range(case.nelt):
+            if upper[e]:
+                # NB: the reference never resets `markinc` to .true. per face
+                # (3ddielectric.usr:233-252): once a face fails, later faces of that
+                # element are skipped.  Only the -y face (slot 1, checked first) can
+                # qualify on this mesh, so the quirk is harmless but restated.
+                markinc = True
+                for f in range(case.nfaces):
+                    base = e * case.nxzf * case.nfaces + case.nxzf * f
+                    js = np.arange(base, base + case.nxzf)
+                    ks = case.cemface[js]
+                    if np.any(np.abs(case.ym1[ks]) > 1e-8):
+                        markinc = False
+                    if markinc:
+                        inc.extend(js.tolist())
+        self.incindex = np.array(inc, dtype=np.int64)
+
+    def userinc(self, case):
+        j = self.incindex
+        k = case.cemface[j]
+        eps = case.permittivity[k]; mu = case.permeability[k]
+        eta = np.sqrt(mu / eps)
+        ky = self.omega * np.sqrt(mu * eps)
+        yy = case.ym1[k]
+
+        def cb(tt, fhx, fhy, fhz, fex, fey, fez):
+            uinc = np.cos(-ky * yy - self.omega * tt)
+            fhz[j] = fhz[j] + uinc
+            fex[j] = fex[j] + eta * uinc
+            fez[j] = fez[j] + uinc
+            fhx[j] = fhx[j] - uinc / eta
+
+        return cb
+
+    def usersol(self, case, tt):
+        n = case.npts
+        eps = case.permittivity; mu = case.permeability
+        eta = np.sqrt(mu / eps)
+        ky = self.omega * np.sqrt(eps * mu)
+        yy = case.ym1
+        upper = np.repeat(self.upper, case.nxyz)
+        inpml = np.repeat(case.pmltag != 0, case.nxyz)
+        order, referr = case.pmlorder, case.pmlreferr
+        pmlfac = np.zeros(n)
+        # upper region (+y PML: sym face 4)
+        d = case.pmlouter[3] - case.pmlinner[3]
+        smax = -(order + 1) * math.log(referr) / (2 * eta * d)
+        with np.errstate(invalid="ignore"):
+            fu = (smax * d / (order + 1)) * ((yy - case.pmlinner[3]) / d) ** (order + 1)
+        d2 = case.pmlinner[2] - case.pmlouter[2]
+        smax2 = -(order + 1) * math.log(referr) / (2 * eta * d2)
+        with np.errstate(invalid="ignore"):
+            fl = (smax2 * d2 / (order + 1)) * ((case.pmlinner[2] - yy) / d2) ** (order + 1)
+        pmlfac = np.where(inpml, np.where(upper, fu, fl), 0.0)
+        uu_u = np.exp(-eta * pmlfac) * np.cos(ky * yy - self.omega * tt)
+        uu_l = np.exp(-eta * pmlfac) * np.cos(-ky * yy - self.omega * tt)
+        shn = np.zeros(3 * n); sen = np.zeros(3 * n)
+        shn[2 * n:] = np.where(upper, self.reflte * uu_u, self.trante * uu_l)          # hz
+        sen[0:n] = np.where(upper, -eta * self.reflte * uu_u, eta * self.trante * uu_l)  # ex
+        sen[2 * n:] = np.where(upper, self.refltm * uu_u, self.trantm * uu_l)          # ez
+        shn[0:n] = np.where(upper, self.refltm * uu_u / eta, -self.trantm * uu_l / eta)  # hx
+        return shn, sen
+
+
+def case_3ddielectric(twomat=False, nx1=9, nel=(4, 8, 4)):
+    """tests/3ddielectric (.box 4x8x4, BC P,P,PML,PML,P,P; N=8; dt=5e-3; 1000 steps;
+    param(70)=1 -> two materials; PML thick 2, order 3, referr 1e-10).
+    Tolerances 5e-4 / 5e-3 on hx,hz,ex,ez (3ddielectric.usr userchk)."""
+    mesh = O.box_mesh(nel, ((-1.0, 1.0),) * 3, ("P  ", "P  ", "PML", "PML", "P  ", "P  "))
+    u = _Dielectric(twomat)
+    c = O.RefCase(mesh, nx1, upwind=True, usrdat2=u.usrdat2, uservp=u.uservp,
+                  param={77: 2, 78: 3.0, 79: 1e-10, 70: 1 if twomat else 0})
+    c.user = u
+    c.set_dt(-0.005)
+    c.usersol = lambda case, tt: u.usersol(case, tt)
+    shn, sen = u.usersol(c, 0.0)
+    c.hn[:] = shn; c.en[:] = sen
+    n = c.npts
+    for k in range(3):  # userini :67-78
+        c.pmlbn[k * n:(k + 1) * n] = c.permeability * shn[k * n:(k + 1) * n]
+        c.pmldn[k * n:(k + 1) * n] = c.permittivity * sen[k * n:(k + 1) * n]
+    c.set_callback("userinc", u.userinc(c))
+    c.tol = dict(l2=[5e-4] * 6, linf=[5e-3] * 6)
+    c.nsteps = 1000
+    return c
+
+
+# ------------------------------------------------------------------------------------
+# tests/3dboxpml : Gaussian-pulsed dipole in an all-PML box (stability check only)
+# ------------------------------------------------------------------------------------
+def usersrc_3dboxpml(case):
+    """tests/3dboxpml/3dboxpml.usr:30-88: Gaussian approximation of a Hertzian dipole,
+    srcez -= i0*norm*exp(-r^2/(2 w^2)) * sin(-omega t) * bm1."""
+    omega, width = 2.0, 0.1
+    norm = 1.0 / (math.sqrt(8 * math.atan(1.0)) * width) ** 3
+    i0 = 1.0 / norm
+    xfac = -0.5 * ((case.xm1 - 0.0) / width) ** 2
+    yfac = -0.5 * ((case.ym1 - 0.0) / width) ** 2
+    zfac = -0.5 * ((case.zm1 - 0.0) / width) ** 2
+    g = i0 * norm * np.exp(xfac + yfac + zfac)
+
+    def cb(tt, shx, shy, shz, sex, sey, sez):
+        tfac = math.sin(-omega * tt)
+        sez[:] = sez - g * (tfac * case.bmn)
+
+    cb.profile = g  # spatial profile (per node), time factor sin(-omega t) * bm1
+    cb.omega = omega
+    return cb
+
+
+def case_3dboxpml(nx1=9, nel=(6, 6, 6)):
+    """tests/3dboxpml (.box 6^3, all PML, thick 1, order 3, referr 1e-8, CFL 0.1; zero
+    initial fields; usrdat2 maps onto [-1,1]^3).  userchk only bounds |fields| <= 1."""
+    mesh = O.box_mesh(nel, ((-1.0, 1.0),) * 3, ("PML",) * 6)
+
+    def usrdat2(case):
+        for arr in (case.xm1, case.ym1, case.zm1):
+            mn, mx = arr.min(), arr.max()
+            arr[:] = 2.0 * (arr - mn) / (mx - mn) - 2.0 / 2.0
+
+    c = O.RefCase(mesh, nx1, upwind=True, usrdat2=usrdat2, param={77: 1, 78: 3.0, 79: 1e-8})
+    c.set_dt(0.1)
+    c.usersrc_fn = usersrc_3dboxpml(c)
+    c.set_callback("usersrc", c.usersrc_fn)
+    c.usersol = lambda case, tt: (np.zeros(3 * case.npts), np.zeros(3 * case.npts))
+    c.tol = dict(l2=[1.0] * 6, linf=[1.0] * 6)
+    c.nsteps = 2000
+    return c
