@@ -1,0 +1,159 @@
+/*
+ * nekcem_b200.h -- C ABI of libnekcem_b200.so
+ *
+ * A B200-native (sm_100a) implementation of NekCEM's time-domain Maxwell SEDG
+ * right-hand side fused with its 5-stage low-storage RK update.  This header is
+ * the drop-in boundary: every entry point names the reference interface it
+ * replaces (paths relative to the NekCEM tree).  Plain pointers and sizes only;
+ * no C++/torch types.  Host language on the reference side is Fortran; the
+ * `ISO_C_BINDING` module that binds these symbols is in fortran/nekcem_b200_mod.F90
+ * and INTEGRATION.md shows the call sites.
+ *
+ * Conventions (identical to the reference's COMMON blocks):
+ *   - real == double; integer == 32-bit; gs ids are 64-bit (INTEGER*8).
+ *   - arrays are column-major, element-major: node (i,j,k,e) at
+ *     i + nx1*(j + nx1*(k + nx1*e)); vector fields are (npts,3).
+ *   - face arrays are (nx1*nz1, 2*ldim, nelt) with the face slot in PREPROCESSOR
+ *     order 1..6 = (-y,+x,+y,-x,-z,+z), exactly like `area/unx` (src/nek5_coef.F:1187-1235)
+ *     and `cemface` (src/cem_common.F:214-283).
+ *   - index arrays (cempec, pmlptr, dindex) hold 1-BASED indices as in Fortran.
+ *   - every function returns 0 on success; on failure it returns nonzero and
+ *     nekcem_b200_last_error() describes it.  The trailing-underscore Fortran twins
+ *     (src: nekcem_b200/csrc/fortran_abi.cu) print the message and exit(1), which is the
+ *     reference's own error behaviour (`exitt`, src/nek5_comm_mpi.F:650-692; jl `fail`,
+ *     src/jl/fail.c:11-17).
+ *   - one host thread per context (the reference runs one thread per MPI rank).
+ *   - There is NO CPU fallback: a context created with a device needs a B200; compute
+ *     entry points fail loudly otherwise.
+ */
+#ifndef NEKCEM_B200_H
+#define NEKCEM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NEKCEM_B200_ABI_VERSION 1
+
+/* ---- array ids for nekcem_b200_set_array / get_array ------------------------------
+ * Each id names the reference COMMON array it mirrors; this is the list that
+ * `acc_copy_all_in` uploads (src/cem_drive.F:397-480). */
+enum nekcem_b200_array {
+    NKB_DXM1 = 0,      /* dxm1(nx1,nx1)        src/DXYZ:4-7                           */
+    NKB_W3MN,          /* w3mn(nxyz)           src/GEOM (flat w3m1), cem_maxwell.F:153 */
+    NKB_RXMN, NKB_RYMN, NKB_RZMN, /* rxmn..  (npts) unnormalised cofactors, src/GEOM:30-45 */
+    NKB_SXMN, NKB_SYMN, NKB_SZMN,
+    NKB_TXMN, NKB_TYMN, NKB_TZMN,
+    NKB_BMN,           /* bmn(npts) = jac*w3   src/GEOM:33                            */
+    NKB_HBM1, NKB_EBM1,/* 1/(mu*bm), 1/(eps*bm) src/EMWAVE:20-21, cem_maxwell.F:183-186 */
+    NKB_UNXM, NKB_UNYM, NKB_UNZM, NKB_AREAM, /* (nxzfl) src/GEOM:52-56                   */
+    NKB_Y_0, NKB_Y_1, NKB_Z_0, NKB_Z_1,      /* (nxzfl) src/EMWAVE:40-47                 */
+    NKB_HN, NKB_EN,    /* (npts,3)             src/EMWAVE:5-6                          */
+    NKB_KHN, NKB_KEN,  /* (npts,3) RK registers src/EMWAVE:9-10                        */
+    NKB_PERMITTIVITY, NKB_PERMEABILITY,      /* (npts) src/EMWAVE:31-32 (PML only)      */
+    NKB_PMLSIGMA,      /* (npts,3)             src/PML:11                              */
+    NKB_PMLBN, NKB_PMLDN, NKB_KPMLBN, NKB_KPMLDN, /* (npts,3) src/PML:14-28              */
+    NKB_ARRAY_COUNT
+};
+
+/* ---- problem description (the scalars the hot path reads from COMMON) -------------- */
+typedef struct nekcem_b200_desc {
+    int32_t abi_version; /* NEKCEM_B200_ABI_VERSION */
+    int32_t ldim;        /* 3 (2D TE/TM path: see DESIGN.md "next")                  */
+    int32_t nx1;         /* points per direction, N+1 (SIZE: lx1)                    */
+    int32_t nelt;        /* local element count (SIZE/DIMN)                          */
+    int32_t imode;       /* 3 = 3D, 2 = TM, 1 = TE (src/INPUT:18-47, cem_param.F)    */
+    int32_t ifupwind;    /* param(19)=0 -> 1 (C0=1); central flux -> 0 (C0=0)        */
+    int32_t ifpec;       /* any 'PEC' face (setlog, src/nek5_bdry.F:68-92)           */
+    int32_t ifpml;       /* any 'PML' face                                           */
+    int32_t device;      /* CUDA device ordinal; -1 = host-only planning context     */
+    int32_t strict;      /* 1: no-FMA kernels, bit-faithful to the CPU arithmetic    */
+    int32_t rank;        /* MPI rank (nid) and size (np): one rank <-> one GPU       */
+    int32_t nranks;
+} nekcem_b200_desc;
+
+const char *nekcem_b200_last_error(void);
+
+/* Lifetime.  Replaces the device-residency hooks `acc_copy_all_in` /
+ * `acc_copy_all_out` (src/cem_drive.F:161-165, 397-566). */
+int nekcem_b200_create(const nekcem_b200_desc *desc, int *handle);
+int nekcem_b200_destroy(int handle);
+
+/* Upload one COMMON array (count = number of elements of that array). */
+int nekcem_b200_set_array(int handle, int which, const double *host, int64_t count);
+/* Download (the `!$ACC UPDATE HOST(hn,en,...)` points: tests/3dboxper/3dboxper.usr:199,
+ * src/io.F:193-195). */
+int nekcem_b200_get_array(int handle, int which, double *host, int64_t count);
+
+/* Face connectivity.  glo_num are the face-point global ids the reference hands to
+ * `gs_setup(gsh_face,glo_num,ntot,nekcomm,np)` (src/nek5_connect11.F:2217-2223,
+ * src/jl/gs.c:1898-1907): two face points are paired iff they carry the same non-zero id.
+ * cempec/ncempec is the 1-based face-point list of `cem_maxwell_pec_init`
+ * (src/cem_maxwell.F:1338-1366; 'PEC' and 'PML' faces). */
+int nekcem_b200_set_faces(int handle, const int64_t *glo_num, int64_t nxzfl,
+                          const int32_t *cempec, int32_t ncempec);
+
+/* PML element list `pmlptr(1:maxpml)` (1-based), src/cem_maxwell_pml.F:461-468. */
+int nekcem_b200_set_pml(int handle, const int32_t *pmlptr, int32_t maxpml);
+
+/* Multi-rank face exchange (replaces gs_op_fields on gsh_face between ranks,
+ * src/cem_maxwell.F:962, src/jl/gs.c:471-512, with grouped ncclSend/ncclRecv).
+ * Rank 0 obtains an id, the host code broadcasts its 128 bytes (MPI_Bcast in the
+ * Fortran shim), every rank calls comm_init. */
+int nekcem_b200_comm_unique_id(char id[128]);
+int nekcem_b200_comm_init(int handle, const char id[128]);
+
+/* Host-side planning of the inter-rank exchange; exposed so that the host logic can be
+ * driven (and tested) with any transport.  face_singletons: ids that are unpaired on this
+ * rank.  face_remote: given every rank's singleton ids (concatenated, counts[r] each),
+ * builds per-peer send/recv lists.  nekcem_b200_setup() calls these itself over NCCL when
+ * nranks > 1 and a communicator exists. */
+int nekcem_b200_face_singletons(int handle, int64_t *ids, int64_t capacity, int64_t *count);
+int nekcem_b200_face_remote(int handle, const int64_t *counts, const int64_t *all_ids);
+/* Plan queries (for tests / diagnostics). */
+int nekcem_b200_plan_npeers(int handle, int32_t *npeers, int64_t *nhalo);
+int nekcem_b200_plan_peer(int handle, int32_t ipeer, int32_t *peer_rank, int64_t *count,
+                          int64_t *send_facepts /* capacity count, 0-based face points */);
+int nekcem_b200_plan_vmap(int handle, int32_t *vmapP, int64_t nxzfl);
+int nekcem_b200_plan_elements(int handle, int32_t *n_interior, int32_t *n_boundary);
+
+/* Finish setup: builds vmapP / element lists, uploads them.  Replaces the setup half of
+ * cem_maxwell_init that depends on connectivity (src/cem_maxwell.F:165-186). */
+int nekcem_b200_setup(int handle);
+
+/* Volume source hook (8f rank 1; covers tests/3dboxpml/3dboxpml.usr:30-88):
+ * res(comp) -= profile(i) * (amp*sin(omega*rktime+phase) * bmn(i)) inside every stage,
+ * at the reference's `usersrc` position (src/cem_maxwell.F:503).  comp: 0..2 = H, 3..5 = E. */
+int nekcem_b200_set_volume_source(int handle, int comp, const double *profile, double amp,
+                                  double omega, double phase);
+
+/* The hot path.  Replaces `cem_maxwell_op_rk` (src/cem_maxwell.F:327-345): nsteps time
+ * steps of 5 x {rk_c; cem_maxwell_op; rk_maxwell_ab}; advances the context's time by
+ * nsteps*dt like time_advancing_pde (src/cem_drive.F:618-654). */
+int nekcem_b200_set_time(int handle, double time, double dt);
+int nekcem_b200_get_time(int handle, double *time);
+int nekcem_b200_step(int handle, int nsteps);
+/* One RK stage (rkstep = 1..5) for stage-level parity tests. */
+int nekcem_b200_stage(int handle, int rkstep);
+int nekcem_b200_synchronize(int handle);
+
+/* cem_error (src/cem_common.F:1335-1355) on device: l2[c] = sqrt(sum(err*bm*err)/vol),
+ * linf[c] = max|err| for the six components against exact (npts,3)+(npts,3) host arrays.
+ * Sums are LOCAL to the rank (the caller reduces like glsc3/glamax). */
+int nekcem_b200_error_sums(int handle, const double *exact_hn, const double *exact_en,
+                           double sumsq[6], double linf[6]);
+
+/* Device-time of the last nekcem_b200_step call in milliseconds (CUDA events on the
+ * compute stream) and the number of kernels it launched. */
+int nekcem_b200_last_step_ms(int handle, float *ms, int64_t *launches);
+
+/* Algorithmic HBM bytes per stage for this context: 280 B/node +
+ * 116 B/face point (+ PML add-on for PML elements). */
+int nekcem_b200_algorithmic_bytes(int handle, double *bytes_per_stage);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEKCEM_B200_H */

@@ -1,0 +1,304 @@
+"""Host-side mirror of the reference's Maxwell operator interface over libnekcem_b200.so.
+
+The reference's "operator API" for this path is a set of Fortran subroutine names plus
+COMMON blocks.  This module is the Python stand-in for that Fortran host
+side, used by the tests, ``bench.py`` and ``__graft_entry__``: same names, same argument
+meaning, same error behaviour (an error in the library raises ``NekcemB200Error`` where
+the reference would ``call exitt(1)``).
+
+    cem_maxwell_init   -> MaxwellB200.cem_maxwell_init(arrays)   (src/cem_maxwell.F:65-191)
+    acc_copy_all_in    -> done by cem_maxwell_init / set_array   (src/cem_drive.F:397-480)
+    cem_maxwell_op_rk  -> MaxwellB200.cem_maxwell_op_rk(nsteps)  (src/cem_maxwell.F:327-345)
+    !$ACC UPDATE HOST  -> MaxwellB200.hn / .en / get_array       (tests/3dboxper/3dboxper.usr:199)
+    cem_error          -> MaxwellB200.cem_error                  (src/cem_common.F:1335-1355)
+
+There is no CPU fallback: the CUDA library must be present and, for compute, a B200.
+Index arrays are 0-based on the Python side and converted to the ABI's 1-based form here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIBPATH = os.path.join(_HERE, "lib", "libnekcem_b200.so")
+ABI_VERSION = 1
+
+ARRAY_IDS = {name: i for i, name in enumerate([
+    "dxm1", "w3mn", "rxmn", "rymn", "rzmn", "sxmn", "symn", "szmn", "txmn", "tymn", "tzmn",
+    "bmn", "hbm1", "ebm1", "unxm", "unym", "unzm", "aream", "Y_0", "Y_1", "Z_0", "Z_1",
+    "hn", "en", "khn", "ken", "permittivity", "permeability", "pmlsigma", "pmlbn", "pmldn",
+    "kpmlbn", "kpmldn"])}
+
+GEOMETRY_ARRAYS = ["dxm1", "w3mn", "rxmn", "rymn", "rzmn", "sxmn", "symn", "szmn", "txmn",
+                   "tymn", "tzmn", "bmn", "hbm1", "ebm1", "unxm", "unym", "unzm", "aream",
+                   "Y_0", "Y_1", "Z_0", "Z_1"]
+PML_ARRAYS = ["permittivity", "permeability", "pmlsigma", "pmlbn", "pmldn"]
+
+
+class NekcemB200Error(RuntimeError):
+    pass
+
+
+class Desc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "abi_version", "ldim", "nx1", "nelt", "imode", "ifupwind", "ifpec", "ifpml", "device",
+        "strict", "rank", "nranks")]
+
+
+_lib = None
+c_dp = C.POINTER(C.c_double)
+c_i64p = C.POINTER(C.c_int64)
+c_i32p = C.POINTER(C.c_int32)
+
+
+def lib():
+    """Load libnekcem_b200.so (fails loudly if the CUDA extension has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIBPATH):
+            raise NekcemB200Error(
+                f"{LIBPATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                "g.build()'` (nvcc, sm_100a).  There is no CPU fallback.")
+        L = C.CDLL(LIBPATH)
+        L.nekcem_b200_last_error.restype = C.c_char_p
+        L.nekcem_b200_create.argtypes = [C.POINTER(Desc), C.POINTER(C.c_int)]
+        L.nekcem_b200_destroy.argtypes = [C.c_int]
+        L.nekcem_b200_set_array.argtypes = [C.c_int, C.c_int, c_dp, C.c_int64]
+        L.nekcem_b200_get_array.argtypes = [C.c_int, C.c_int, c_dp, C.c_int64]
+        L.nekcem_b200_set_faces.argtypes = [C.c_int, c_i64p, C.c_int64, c_i32p, C.c_int32]
+        L.nekcem_b200_set_pml.argtypes = [C.c_int, c_i32p, C.c_int32]
+        L.nekcem_b200_comm_unique_id.argtypes = [C.c_char_p]
+        L.nekcem_b200_comm_init.argtypes = [C.c_int, C.c_char_p]
+        L.nekcem_b200_face_singletons.argtypes = [C.c_int, c_i64p, C.c_int64, c_i64p]
+        L.nekcem_b200_face_remote.argtypes = [C.c_int, c_i64p, c_i64p]
+        L.nekcem_b200_plan_npeers.argtypes = [C.c_int, c_i32p, c_i64p]
+        L.nekcem_b200_plan_peer.argtypes = [C.c_int, C.c_int32, c_i32p, c_i64p, c_i64p]
+        L.nekcem_b200_plan_vmap.argtypes = [C.c_int, c_i32p, C.c_int64]
+        L.nekcem_b200_plan_elements.argtypes = [C.c_int, c_i32p, c_i32p]
+        L.nekcem_b200_setup.argtypes = [C.c_int]
+        L.nekcem_b200_set_volume_source.argtypes = [C.c_int, C.c_int, c_dp, C.c_double,
+                                                    C.c_double, C.c_double]
+        L.nekcem_b200_set_time.argtypes = [C.c_int, C.c_double, C.c_double]
+        L.nekcem_b200_get_time.argtypes = [C.c_int, c_dp]
+        L.nekcem_b200_step.argtypes = [C.c_int, C.c_int]
+        L.nekcem_b200_stage.argtypes = [C.c_int, C.c_int]
+        L.nekcem_b200_synchronize.argtypes = [C.c_int]
+        L.nekcem_b200_error_sums.argtypes = [C.c_int, c_dp, c_dp, c_dp, c_dp]
+        L.nekcem_b200_last_step_ms.argtypes = [C.c_int, C.POINTER(C.c_float), c_i64p]
+        L.nekcem_b200_algorithmic_bytes.argtypes = [C.c_int, c_dp]
+        _lib = L
+    return _lib
+
+
+def _chk(rc):
+    if rc != 0:
+        raise NekcemB200Error(lib().nekcem_b200_last_error().decode())
+
+
+def _dp(a):
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"], "need contiguous float64"
+    return a.ctypes.data_as(c_dp)
+
+
+def comm_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    _chk(lib().nekcem_b200_comm_unique_id(buf))
+    return buf.raw
+
+
+class MaxwellB200:
+    """One context = one rank's share of the mesh on one GPU."""
+
+    def __init__(self, ldim: int, nx1: int, nelt: int, imode: int = 3, upwind: bool = True,
+                 ifpec: bool = False, ifpml: bool = False, device: int = 0, rank: int = 0,
+                 nranks: int = 1):
+        self.L = lib()
+        d = Desc(ABI_VERSION, ldim, nx1, nelt, imode, int(upwind), int(ifpec), int(ifpml),
+                 device, 0, rank, nranks)
+        h = C.c_int(-1)
+        _chk(self.L.nekcem_b200_create(C.byref(d), C.byref(h)))
+        self.h = h.value
+        self.ldim, self.nx1, self.nelt = ldim, nx1, nelt
+        self.nxyz = nx1 ** 3 if ldim == 3 else nx1 ** 2
+        self.nxzf = nx1 ** 2 if ldim == 3 else nx1
+        self.nfaces = 2 * ldim
+        self.npts = self.nxyz * nelt
+        self.nxzfl = self.nxzf * self.nfaces * nelt
+        self.rank, self.nranks = rank, nranks
+        self.volvm1 = None
+
+    # -- lifetime ----------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h >= 0:
+            self.L.nekcem_b200_destroy(self.h)
+            self.h = -1
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- acc_copy_all_in / UPDATE HOST ---------------------------------------------------
+    def set_array(self, name: str, arr: np.ndarray):
+        a = np.ascontiguousarray(arr, dtype=np.float64).reshape(-1)
+        _chk(self.L.nekcem_b200_set_array(self.h, ARRAY_IDS[name], _dp(a), a.size))
+
+    def get_array(self, name: str) -> np.ndarray:
+        which = ARRAY_IDS[name]
+        if name in ("dxm1",):
+            n = self.nx1 * self.nx1
+        elif name == "w3mn":
+            n = self.nxyz
+        elif name in ("unxm", "unym", "unzm", "aream", "Y_0", "Y_1", "Z_0", "Z_1"):
+            n = self.nxzfl
+        elif name in ("hn", "en", "khn", "ken", "pmlsigma", "pmlbn", "pmldn", "kpmlbn",
+                      "kpmldn"):
+            n = 3 * self.npts
+        else:
+            n = self.npts
+        out = np.zeros(n)
+        _chk(self.L.nekcem_b200_get_array(self.h, which, _dp(out), n))
+        return out
+
+    @property
+    def hn(self):
+        return self.get_array("hn")
+
+    @property
+    def en(self):
+        return self.get_array("en")
+
+    def set_faces(self, glo_num: np.ndarray, cempec0: np.ndarray):
+        """glo_num: face-point global ids (int64, nxzfl); cempec0: 0-based PEC/PML face points."""
+        g = np.ascontiguousarray(glo_num, dtype=np.int64)
+        p = np.ascontiguousarray(np.asarray(cempec0, dtype=np.int64) + 1, dtype=np.int32)
+        _chk(self.L.nekcem_b200_set_faces(self.h, g.ctypes.data_as(c_i64p), g.size,
+                                          p.ctypes.data_as(c_i32p), p.size))
+
+    def set_pml(self, pmlptr0: np.ndarray):
+        p = np.ascontiguousarray(np.asarray(pmlptr0, dtype=np.int64) + 1, dtype=np.int32)
+        _chk(self.L.nekcem_b200_set_pml(self.h, p.ctypes.data_as(c_i32p), p.size))
+
+    # -- multi-rank plumbing ---------------------------------------------------------------
+    def comm_init(self, uid: bytes):
+        _chk(self.L.nekcem_b200_comm_init(self.h, uid))
+
+    def face_singletons(self) -> np.ndarray:
+        cnt = C.c_int64(0)
+        _chk(self.L.nekcem_b200_face_singletons(self.h, None, 0, C.byref(cnt)))
+        ids = np.zeros(max(cnt.value, 1), dtype=np.int64)
+        _chk(self.L.nekcem_b200_face_singletons(self.h, ids.ctypes.data_as(c_i64p), ids.size,
+                                                C.byref(cnt)))
+        return ids[:cnt.value]
+
+    def face_remote(self, counts, all_ids):
+        c = np.ascontiguousarray(counts, dtype=np.int64)
+        a = np.ascontiguousarray(all_ids, dtype=np.int64)
+        if a.size == 0:
+            a = np.zeros(1, dtype=np.int64)
+        _chk(self.L.nekcem_b200_face_remote(self.h, c.ctypes.data_as(c_i64p),
+                                            a.ctypes.data_as(c_i64p)))
+
+    def plan(self):
+        """Exchange plan: (vmapP, [(peer_rank, send_facepts)], nhalo, n_interior, n_boundary)."""
+        npeers = C.c_int32(0); nhalo = C.c_int64(0)
+        _chk(self.L.nekcem_b200_plan_npeers(self.h, C.byref(npeers), C.byref(nhalo)))
+        peers = []
+        for ipeer in range(npeers.value):
+            r = C.c_int32(0); cnt = C.c_int64(0)
+            _chk(self.L.nekcem_b200_plan_peer(self.h, ipeer, C.byref(r), C.byref(cnt), None))
+            fp = np.zeros(cnt.value, dtype=np.int64)
+            _chk(self.L.nekcem_b200_plan_peer(self.h, ipeer, C.byref(r), C.byref(cnt),
+                                              fp.ctypes.data_as(c_i64p)))
+            peers.append((r.value, fp))
+        vm = np.zeros(self.nxzfl, dtype=np.int32)
+        _chk(self.L.nekcem_b200_plan_vmap(self.h, vm.ctypes.data_as(c_i32p), vm.size))
+        ni = C.c_int32(0); nb = C.c_int32(0)
+        _chk(self.L.nekcem_b200_plan_elements(self.h, C.byref(ni), C.byref(nb)))
+        return vm, peers, nhalo.value, ni.value, nb.value
+
+    # -- cem_maxwell_init ----------------------------------------------------------------
+    def cem_maxwell_init(self, arrays: dict, free_after_upload: bool = False):
+        """Upload the COMMON arrays the hot path reads (what acc_copy_all_in lists,
+        src/cem_drive.F:430-458) and the face connectivity.  ``arrays`` maps the reference's
+        array names to numpy arrays; 'glo_num' (int64) and 'cempec' (0-based) describe the
+        faces; 'pmlptr' (0-based) the PML elements."""
+        for name in GEOMETRY_ARRAYS:
+            self.set_array(name, arrays[name])
+            if free_after_upload:
+                arrays[name] = None
+        if len(arrays.get("pmlptr", ())) > 0:
+            for name in PML_ARRAYS:
+                if arrays.get(name) is not None:
+                    self.set_array(name, arrays[name])
+            self.set_pml(arrays["pmlptr"])
+        for name in ("hn", "en", "khn", "ken"):
+            if arrays.get(name) is not None:
+                self.set_array(name, arrays[name])
+        self.set_faces(arrays["glo_num"], arrays.get("cempec", np.zeros(0, dtype=np.int64)))
+        if "volvm1" in arrays:
+            self.volvm1 = float(arrays["volvm1"])
+
+    def setup(self):
+        _chk(self.L.nekcem_b200_setup(self.h))
+
+    def set_volume_source(self, comp, profile, amp, omega, phase):
+        p = None if profile is None else _dp(np.ascontiguousarray(profile, dtype=np.float64))
+        _chk(self.L.nekcem_b200_set_volume_source(self.h, comp, p, amp, omega, phase))
+
+    # -- time stepping -------------------------------------------------------------------
+    def set_time(self, time: float, dt: float):
+        _chk(self.L.nekcem_b200_set_time(self.h, time, dt))
+
+    @property
+    def time(self) -> float:
+        t = C.c_double(0)
+        _chk(self.L.nekcem_b200_get_time(self.h, C.byref(t)))
+        return t.value
+
+    def cem_maxwell_op_rk(self, nsteps: int = 1, sync: bool = True):
+        """nsteps time steps of the 5-stage LSRK (src/cem_maxwell.F:327-345)."""
+        _chk(self.L.nekcem_b200_step(self.h, nsteps))
+        if sync:
+            self.synchronize()
+
+    step = cem_maxwell_op_rk
+
+    def stage(self, rkstep: int):
+        _chk(self.L.nekcem_b200_stage(self.h, rkstep))
+
+    def synchronize(self):
+        _chk(self.L.nekcem_b200_synchronize(self.h))
+
+    def last_step_ms(self):
+        ms = C.c_float(0); n = C.c_int64(0)
+        _chk(self.L.nekcem_b200_last_step_ms(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def algorithmic_bytes_per_stage(self) -> float:
+        b = C.c_double(0)
+        _chk(self.L.nekcem_b200_algorithmic_bytes(self.h, C.byref(b)))
+        return b.value
+
+    # -- cem_error -----------------------------------------------------------------------
+    def error_sums(self, exact_hn, exact_en):
+        s = np.zeros(6); m = np.zeros(6)
+        _chk(self.L.nekcem_b200_error_sums(
+            self.h, _dp(np.ascontiguousarray(exact_hn, dtype=np.float64)),
+            _dp(np.ascontiguousarray(exact_en, dtype=np.float64)), _dp(s), _dp(m)))
+        return s, m
+
+    def cem_error(self, exact_hn, exact_en, volvm1=None, reduce=None):
+        """(l2[6], linf[6]) as cem_error; ``reduce(sums, maxes)`` performs the glsc3/glamax
+        all-reduce when running on several ranks."""
+        s, m = self.error_sums(exact_hn, exact_en)
+        if reduce is not None:
+            s, m = reduce(s, m)
+        vol = self.volvm1 if volvm1 is None else volvm1
+        l2 = s / vol
+        l2 = np.where(l2 > 0, np.sqrt(np.maximum(l2, 0)), l2)
+        return l2, m

@@ -1,0 +1,102 @@
+// Fortran-callable twins of the C ABI: lowercase + trailing underscore (-DUNDERSCORE /
+// gfortran default, src/jl/name.h:35-37), every argument by reference, no return value.
+// On failure they print the message and exit(1) -- the reference's own error behaviour
+// (exitt, src/nek5_comm_mpi.F:650-692; jl fail(), src/jl/fail.c:11-17).
+// The ISO_C_BINDING module fortran/nekcem_b200_mod.F90 binds the C names directly; these
+// twins serve fixed-form F77 call sites that cannot use BIND(C).
+#include <cstdio>
+#include <cstdlib>
+
+#include "../../include/nekcem_b200.h"
+
+#define NKB_EXPORT extern "C" __attribute__((visibility("default")))
+
+static void check(int rc, const char *what)
+{
+    if (rc != 0) {
+        fprintf(stderr, "nekcem_b200: %s failed: %s\n", what, nekcem_b200_last_error());
+        exit(1);
+    }
+}
+
+NKB_EXPORT void nekcem_b200_create_(const int *ldim, const int *nx1, const int *nelt,
+                                    const int *imode, const int *ifupwind, const int *ifpec,
+                                    const int *ifpml, const int *device, const int *rank,
+                                    const int *nranks, int *handle)
+{
+    nekcem_b200_desc d{};
+    d.abi_version = NEKCEM_B200_ABI_VERSION;
+    d.ldim = *ldim; d.nx1 = *nx1; d.nelt = *nelt; d.imode = *imode;
+    d.ifupwind = *ifupwind; d.ifpec = *ifpec; d.ifpml = *ifpml;
+    d.device = *device; d.strict = 0; d.rank = *rank; d.nranks = *nranks;
+    check(nekcem_b200_create(&d, handle), "nekcem_b200_create");
+}
+
+NKB_EXPORT void nekcem_b200_destroy_(const int *h) { check(nekcem_b200_destroy(*h), "destroy"); }
+
+NKB_EXPORT void nekcem_b200_set_array_(const int *h, const int *which, const double *host,
+                                       const long long *count)
+{
+    check(nekcem_b200_set_array(*h, *which, host, *count), "nekcem_b200_set_array");
+}
+
+NKB_EXPORT void nekcem_b200_get_array_(const int *h, const int *which, double *host,
+                                       const long long *count)
+{
+    check(nekcem_b200_get_array(*h, *which, host, *count), "nekcem_b200_get_array");
+}
+
+NKB_EXPORT void nekcem_b200_set_faces_(const int *h, const long long *glo_num,
+                                       const long long *nxzfl, const int *cempec,
+                                       const int *ncempec)
+{
+    check(nekcem_b200_set_faces(*h, (const int64_t *)glo_num, *nxzfl, cempec, *ncempec),
+          "nekcem_b200_set_faces");
+}
+
+NKB_EXPORT void nekcem_b200_set_pml_(const int *h, const int *pmlptr, const int *maxpml)
+{
+    check(nekcem_b200_set_pml(*h, pmlptr, *maxpml), "nekcem_b200_set_pml");
+}
+
+NKB_EXPORT void nekcem_b200_comm_unique_id_(char *id)
+{
+    check(nekcem_b200_comm_unique_id(id), "nekcem_b200_comm_unique_id");
+}
+
+NKB_EXPORT void nekcem_b200_comm_init_(const int *h, const char *id)
+{
+    check(nekcem_b200_comm_init(*h, id), "nekcem_b200_comm_init");
+}
+
+NKB_EXPORT void nekcem_b200_setup_(const int *h) { check(nekcem_b200_setup(*h), "nekcem_b200_setup"); }
+
+NKB_EXPORT void nekcem_b200_set_time_(const int *h, const double *time, const double *dt)
+{
+    check(nekcem_b200_set_time(*h, *time, *dt), "nekcem_b200_set_time");
+}
+
+// replaces `call cem_maxwell_op_rk` (src/cem_drive.F:628)
+NKB_EXPORT void nekcem_b200_step_(const int *h, const int *nsteps)
+{
+    check(nekcem_b200_step(*h, *nsteps), "nekcem_b200_step");
+}
+
+NKB_EXPORT void nekcem_b200_synchronize_(const int *h)
+{
+    check(nekcem_b200_synchronize(*h), "nekcem_b200_synchronize");
+}
+
+NKB_EXPORT void nekcem_b200_set_volume_source_(const int *h, const int *comp,
+                                               const double *profile, const double *amp,
+                                               const double *omega, const double *phase)
+{
+    check(nekcem_b200_set_volume_source(*h, *comp, profile, *amp, *omega, *phase),
+          "nekcem_b200_set_volume_source");
+}
+
+NKB_EXPORT void nekcem_b200_error_sums_(const int *h, const double *exact_hn,
+                                        const double *exact_en, double *sumsq, double *linf)
+{
+    check(nekcem_b200_error_sums(*h, exact_hn, exact_en, sumsq, linf), "nekcem_b200_error_sums");
+}

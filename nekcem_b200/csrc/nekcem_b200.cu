@@ -1,0 +1,913 @@
+// libnekcem_b200: context, host-side planning (face pairing, element lists, inter-rank
+// exchange plan) and the C ABI declared in include/nekcem_b200.h.
+//
+// Host logic restated from the reference (no code copied):
+//   face pairing      = semantics of gs_setup/gs_op on gsh_face (src/jl/gs.c:1898-1907,
+//                       src/nek5_connect11.F:2179-2233): equal non-zero ids are one point
+//   face -> volume    = cem_set_fc_ptr (src/cem_common.F:214-283)
+//   boundary handling = cem_maxwell_pec_init / flux_pec (src/cem_maxwell.F:1338-1426)
+//   step driver       = cem_maxwell_op_rk + rk_c + rk_storage (src/cem_maxwell.F:327-345,
+//                       src/cem_common.F:2-16, 78-114)
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/nekcem_b200.h"
+#include "stage_args.h"
+
+namespace nkb {
+int launch_stage(const StageArgs &a, int nx1, bool pml, void *stream);
+}
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+
+#define CUDA_OK(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail("CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__,          \
+                        __LINE__, cudaGetErrorString(e_));                                     \
+    } while (0)
+#define NCCL_OK(call)                                                                          \
+    do {                                                                                       \
+        ncclResult_t r_ = (call);                                                              \
+        if (r_ != ncclSuccess)                                                                 \
+            return fail("NCCL error at %s:%d: %s", __FILE__, __LINE__, ncclGetErrorString(r_)); \
+    } while (0)
+
+struct Peer {
+    int rank = -1;
+    std::vector<int64_t> send_fp; // local face points, sorted by shared id
+    int64_t off = 0;              // offset (in face points) into sendbuf / halo
+};
+
+struct Ctx {
+    nekcem_b200_desc d{};
+    int n = 0, nxyz = 0, nxzf = 0, nfaces = 0;
+    int64_t npts = 0, nxzfl = 0, ld = 0;
+    bool host_only = false;
+    bool setup_done = false;
+    // device arrays mirroring COMMON blocks (nullptr when not set)
+    double *dev[NKB_ARRAY_COUNT] = {};
+    bool have[NKB_ARRAY_COUNT] = {};
+    double *u[2] = {nullptr, nullptr}; // ping-pong (6,ld): H then E
+    int cur = 0;
+    double *kf = nullptr; // (6,ld)
+    double *hY = nullptr, *hZ = nullptr;
+    int *vmapP_d = nullptr;
+    int *elist_d = nullptr; // concatenated lists
+    int list_off[4] = {}, list_n[4] = {}; // [interior plain, interior pml, boundary plain, boundary pml]
+    // host planning data
+    std::vector<int64_t> glo;
+    std::vector<int32_t> cempec;
+    std::vector<int32_t> vmapP;
+    std::vector<int32_t> pml_el; // 0-based
+    std::vector<std::pair<int64_t, int64_t>> singles; // (id, face point)
+    bool local_matched = false, remote_planned = false;
+    std::vector<Peer> peers;
+    int64_t nhalo = 0;
+    int n_interior = 0, n_boundary = 0;
+    // comm
+    ncclComm_t comm = nullptr;
+    bool has_comm = false;
+    cudaStream_t s_compute = nullptr, s_comm = nullptr;
+    cudaEvent_t ev_stage = nullptr, ev_halo = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    double *sendbuf = nullptr, *halo = nullptr;
+    int *send_node = nullptr;
+    // time stepping
+    double time = 0.0, dt = 0.0;
+    double rk4a[5], rk4b[5], rk4c[6];
+    // volume source
+    double *src_prof = nullptr;
+    int src_comp = 0;
+    double src_amp = 0, src_omega = 0, src_phase = 0;
+    // diagnostics
+    float last_ms = 0.f;
+    int64_t last_launches = 0;
+    double *red_d = nullptr; // reduction scratch
+    int red_blocks = 0;
+};
+
+std::vector<std::unique_ptr<Ctx>> g_ctx;
+
+Ctx *get(int h)
+{
+    if (h < 0 || h >= (int)g_ctx.size() || !g_ctx[h]) {
+        fail("invalid nekcem_b200 handle %d", h);
+        return nullptr;
+    }
+    return g_ctx[h].get();
+}
+
+int64_t array_count(const Ctx *c, int which)
+{
+    switch (which) {
+    case NKB_DXM1: return (int64_t)c->n * c->n;
+    case NKB_W3MN: return c->nxyz;
+    case NKB_RXMN: case NKB_RYMN: case NKB_RZMN: case NKB_SXMN: case NKB_SYMN: case NKB_SZMN:
+    case NKB_TXMN: case NKB_TYMN: case NKB_TZMN: case NKB_BMN: case NKB_HBM1: case NKB_EBM1:
+    case NKB_PERMITTIVITY: case NKB_PERMEABILITY:
+        return c->npts;
+    case NKB_UNXM: case NKB_UNYM: case NKB_UNZM: case NKB_AREAM:
+    case NKB_Y_0: case NKB_Y_1: case NKB_Z_0: case NKB_Z_1:
+        return c->nxzfl;
+    case NKB_HN: case NKB_EN: case NKB_KHN: case NKB_KEN:
+    case NKB_PMLSIGMA: case NKB_PMLBN: case NKB_PMLDN: case NKB_KPMLBN: case NKB_KPMLDN:
+        return 3 * c->npts;
+    default: return -1;
+    }
+}
+
+// face point (slot s, point p) -> node inside the element, = cemface (cem_common.F:234-260)
+inline int face_node(int n, int s, int p)
+{
+    const int n2 = n * n, pa = p % n, pb = p / n;
+    switch (s) {
+    case 0: return pa + n2 * pb;
+    case 1: return (n - 1) + n * pa + n2 * pb;
+    case 2: return pa + n * (n - 1) + n2 * pb;
+    case 3: return n * pa + n2 * pb;
+    case 4: return pa + n * pb;
+    default: return pa + n * pb + n2 * (n - 1);
+    }
+}
+
+// rk_storage, ifrk45 branch (src/cem_common.F:86-104)
+void rk_storage(Ctx *c)
+{
+    c->rk4a[0] = 0.0;
+    c->rk4a[1] = -567301805773.0 / 1357537059087.0;
+    c->rk4a[2] = -2404267990393.0 / 2016746695238.0;
+    c->rk4a[3] = -3550918686646.0 / 2091501179385.0;
+    c->rk4a[4] = -1275806237668.0 / 842570457699.0;
+    c->rk4b[0] = 1432997174477.0 / 9575080441755.0;
+    c->rk4b[1] = 5161836677717.0 / 13612068292357.0;
+    c->rk4b[2] = 1720146321549.0 / 2090206949498.0;
+    c->rk4b[3] = 3134564353537.0 / 4481467310338.0;
+    c->rk4b[4] = 2277821191437.0 / 14882151754819.0;
+    c->rk4c[0] = 0.0;
+    c->rk4c[1] = 1432997174477.0 / 9575080441755.0;
+    c->rk4c[2] = 2526269341429.0 / 6820363962896.0;
+    c->rk4c[3] = 2006345519317.0 / 3224310063776.0;
+    c->rk4c[4] = 2802321613138.0 / 2924317926251.0;
+    c->rk4c[5] = 1.0;
+}
+
+// ---------------------------------------------------------------------------------------
+// small device kernels
+// ---------------------------------------------------------------------------------------
+__global__ void half_inverse_kernel(const double *x, double *y, long long n)
+{
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) y[i] = 0.5 / x[i];
+}
+
+// pack the traces of the send face points: sendbuf[q][c] = u[c][send_node[q]]
+__global__ void pack_kernel(const double *u, long long ld, const int *send_node, double *sendbuf,
+                            long long nsend)
+{
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= nsend * 6) return;
+    long long q = t / 6;
+    int c = (int)(t - q * 6);
+    sendbuf[t] = u[c * ld + send_node[q]];
+}
+
+// cem_error partial sums (src/cem_common.F:1335-1355): per block, per component
+__global__ void error_kernel(const double *u, long long ld, const double *exact, long long npts,
+                             const double *bm, double *part /* [blocks][12] */)
+{
+    __shared__ double ssum[256], smax[256];
+    for (int c = 0; c < 6; c++) {
+        double sum = 0.0, mx = 0.0;
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npts;
+             i += (long long)gridDim.x * blockDim.x) {
+            double err = exact[c * npts + i] - u[c * ld + i];
+            sum += err * bm[i] * err;
+            mx = fmax(mx, fabs(err));
+        }
+        ssum[threadIdx.x] = sum;
+        smax[threadIdx.x] = mx;
+        __syncthreads();
+        for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+            if (threadIdx.x < s) {
+                ssum[threadIdx.x] += ssum[threadIdx.x + s];
+                smax[threadIdx.x] = fmax(smax[threadIdx.x], smax[threadIdx.x + s]);
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            part[blockIdx.x * 12 + c] = ssum[0];
+            part[blockIdx.x * 12 + 6 + c] = smax[0];
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// host planning
+// ---------------------------------------------------------------------------------------
+int match_local(Ctx *c)
+{
+    if (c->glo.empty()) return fail("nekcem_b200_set_faces has not been called");
+    const int64_t nf = c->nxzfl;
+    const int n = c->n, nfp = c->nxzf * c->nfaces;
+    c->vmapP.assign(nf, -2);
+    std::vector<std::pair<int64_t, int64_t>> v;
+    v.reserve(nf);
+    for (int64_t j = 0; j < nf; j++)
+        if (c->glo[j] != 0) v.emplace_back(c->glo[j], j);
+    std::sort(v.begin(), v.end());
+    c->singles.clear();
+    for (size_t a = 0; a < v.size();) {
+        size_t b = a;
+        while (b < v.size() && v[b].first == v[a].first) b++;
+        if (b - a == 2) {
+            const int64_t j0 = v[a].second, j1 = v[a + 1].second;
+            const int64_t e0 = j0 / nfp, e1 = j1 / nfp;
+            const int f0 = (int)(j0 - e0 * nfp), f1 = (int)(j1 - e1 * nfp);
+            const int64_t n0 = e0 * c->nxyz + face_node(n, f0 / c->nxzf, f0 % c->nxzf);
+            const int64_t n1 = e1 * c->nxyz + face_node(n, f1 / c->nxzf, f1 % c->nxzf);
+            c->vmapP[j0] = (int32_t)n1;
+            c->vmapP[j1] = (int32_t)n0;
+        } else if (b - a == 1) {
+            c->singles.emplace_back(v[a].first, v[a].second);
+        } else {
+            return fail("face id %lld is shared by %zu local face points (expected <= 2)",
+                        (long long)v[a].first, b - a);
+        }
+        a = b;
+    }
+    // physical boundaries: PEC-like faces get the mirror code (-1); refined later for ids
+    // that turn out to be shared with another rank
+    for (int32_t q : c->cempec) {
+        if (q < 1 || q > nf) return fail("cempec entry %d out of range 1..%lld", q, (long long)nf);
+        if (c->vmapP[q - 1] == -2) c->vmapP[q - 1] = -1;
+    }
+    c->local_matched = true;
+    return 0;
+}
+
+int plan_remote(Ctx *c, const int64_t *counts, const int64_t *all_ids)
+{
+    if (!c->local_matched) return fail("face_remote called before local matching");
+    const int R = c->d.nranks, me = c->d.rank;
+    std::map<int64_t, int64_t> mine; // id -> face point
+    for (auto &s : c->singles) mine[s.first] = s.second;
+    c->peers.clear();
+    int64_t off = 0, pos = 0;
+    for (int r = 0; r < R; r++) {
+        const int64_t cnt = counts[r];
+        if (r != me) {
+            std::vector<std::pair<int64_t, int64_t>> shared;
+            for (int64_t q = 0; q < cnt; q++) {
+                auto it = mine.find(all_ids[pos + q]);
+                if (it != mine.end()) shared.emplace_back(it->first, it->second);
+            }
+            if (!shared.empty()) {
+                std::sort(shared.begin(), shared.end());
+                Peer p;
+                p.rank = r;
+                p.off = off;
+                for (auto &s : shared) p.send_fp.push_back(s.second);
+                off += (int64_t)shared.size();
+                c->peers.push_back(std::move(p));
+            }
+        }
+        pos += cnt;
+    }
+    c->nhalo = off;
+    for (auto &p : c->peers)
+        for (size_t q = 0; q < p.send_fp.size(); q++) {
+            const int64_t slot = p.off + (int64_t)q;
+            if (slot + 3 > 2147483647LL) return fail("halo too large");
+            c->vmapP[p.send_fp[q]] = (int32_t)(-(slot + 3));
+        }
+    c->remote_planned = true;
+    return 0;
+}
+
+int build_lists(Ctx *c, std::vector<int32_t> &lists)
+{
+    const int nfp = c->nxzf * c->nfaces;
+    std::vector<char> is_b(c->d.nelt, 0), is_pml(c->d.nelt, 0);
+    for (auto &p : c->peers)
+        for (int64_t fp : p.send_fp) is_b[fp / nfp] = 1;
+    for (int32_t e : c->pml_el) is_pml[e] = 1;
+    std::vector<int32_t> L[4];
+    for (int e = 0; e < c->d.nelt; e++) L[(is_b[e] ? 2 : 0) + (is_pml[e] ? 1 : 0)].push_back(e);
+    lists.clear();
+    for (int q = 0; q < 4; q++) {
+        c->list_off[q] = (int)lists.size();
+        c->list_n[q] = (int)L[q].size();
+        lists.insert(lists.end(), L[q].begin(), L[q].end());
+    }
+    c->n_interior = c->list_n[0] + c->list_n[1];
+    c->n_boundary = c->list_n[2] + c->list_n[3];
+    return 0;
+}
+
+int exchange_singletons_nccl(Ctx *c)
+{
+    const int R = c->d.nranks;
+    // counts
+    int64_t mycnt = (int64_t)c->singles.size();
+    int64_t *d_cnt = nullptr;
+    CUDA_OK(cudaMalloc(&d_cnt, sizeof(int64_t) * (R + 1)));
+    CUDA_OK(cudaMemcpy(d_cnt + R, &mycnt, sizeof(int64_t), cudaMemcpyHostToDevice));
+    NCCL_OK(ncclAllGather(d_cnt + R, d_cnt, 1, ncclInt64, c->comm, c->s_comm));
+    CUDA_OK(cudaStreamSynchronize(c->s_comm));
+    std::vector<int64_t> counts(R);
+    CUDA_OK(cudaMemcpy(counts.data(), d_cnt, sizeof(int64_t) * R, cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaFree(d_cnt));
+    int64_t mx = 0, tot = 0;
+    for (auto v : counts) {
+        mx = std::max(mx, v);
+        tot += v;
+    }
+    if (mx == 0) {
+        std::vector<int64_t> none;
+        return plan_remote(c, counts.data(), none.data());
+    }
+    int64_t *d_ids = nullptr;
+    CUDA_OK(cudaMalloc(&d_ids, sizeof(int64_t) * mx * (R + 1)));
+    std::vector<int64_t> ids(mx, 0);
+    for (size_t q = 0; q < c->singles.size(); q++) ids[q] = c->singles[q].first;
+    CUDA_OK(cudaMemcpy(d_ids + mx * R, ids.data(), sizeof(int64_t) * mx, cudaMemcpyHostToDevice));
+    NCCL_OK(ncclAllGather(d_ids + mx * R, d_ids, mx, ncclInt64, c->comm, c->s_comm));
+    CUDA_OK(cudaStreamSynchronize(c->s_comm));
+    std::vector<int64_t> padded(mx * R), all;
+    CUDA_OK(cudaMemcpy(padded.data(), d_ids, sizeof(int64_t) * mx * R, cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaFree(d_ids));
+    all.reserve(tot);
+    for (int r = 0; r < R; r++)
+        all.insert(all.end(), padded.begin() + r * mx, padded.begin() + r * mx + counts[r]);
+    return plan_remote(c, counts.data(), all.data());
+}
+
+int require(Ctx *c, std::initializer_list<int> ids)
+{
+    static const char *names[NKB_ARRAY_COUNT] = {
+        "dxm1", "w3mn", "rxmn", "rymn", "rzmn", "sxmn", "symn", "szmn", "txmn", "tymn", "tzmn",
+        "bmn", "hbm1", "ebm1", "unxm", "unym", "unzm", "aream", "Y_0", "Y_1", "Z_0", "Z_1", "hn",
+        "en", "khn", "ken", "permittivity", "permeability", "pmlsigma", "pmlbn", "pmldn",
+        "kpmlbn", "kpmldn"};
+    for (int id : ids)
+        if (!c->have[id]) return fail("array '%s' has not been uploaded", names[id]);
+    return 0;
+}
+
+int ensure_dev(Ctx *c, int which)
+{
+    if (c->dev[which]) return 0;
+    const int64_t cnt = array_count(c, which);
+    CUDA_OK(cudaMalloc(&c->dev[which], sizeof(double) * cnt));
+    CUDA_OK(cudaMemset(c->dev[which], 0, sizeof(double) * cnt));
+    return 0;
+}
+
+int run_stage(Ctx *c, int rkstep /*1..5*/)
+{
+    nkb::StageArgs a{};
+    a.u_in = c->u[c->cur];
+    a.u_out = c->u[c->cur ^ 1];
+    a.kf = c->kf;
+    a.ld = c->ld;
+    a.rx = c->dev[NKB_RXMN]; a.ry = c->dev[NKB_RYMN]; a.rz = c->dev[NKB_RZMN];
+    a.sx = c->dev[NKB_SXMN]; a.sy = c->dev[NKB_SYMN]; a.sz = c->dev[NKB_SZMN];
+    a.tx = c->dev[NKB_TXMN]; a.ty = c->dev[NKB_TYMN]; a.tz = c->dev[NKB_TZMN];
+    a.hbm1 = c->dev[NKB_HBM1]; a.ebm1 = c->dev[NKB_EBM1]; a.bmn = c->dev[NKB_BMN];
+    a.D = c->dev[NKB_DXM1];
+    a.w3 = c->dev[NKB_W3MN];
+    a.unx = c->dev[NKB_UNXM]; a.uny = c->dev[NKB_UNYM]; a.unz = c->dev[NKB_UNZM];
+    a.area = c->dev[NKB_AREAM];
+    a.hY = c->hY; a.Y1 = c->dev[NKB_Y_1]; a.hZ = c->hZ; a.Z1 = c->dev[NKB_Z_1];
+    a.vmapP = c->vmapP_d;
+    a.halo = c->halo;
+    a.ca = c->rk4a[rkstep - 1];
+    a.cb = c->rk4b[rkstep - 1];
+    a.dt = c->dt;
+    a.C0 = c->d.ifupwind ? 1.0 : 0.0;
+    a.sig = c->dev[NKB_PMLSIGMA]; a.eps = c->dev[NKB_PERMITTIVITY]; a.mu = c->dev[NKB_PERMEABILITY];
+    a.pB = c->dev[NKB_PMLBN]; a.pD = c->dev[NKB_PMLDN];
+    a.kB = c->dev[NKB_KPMLBN]; a.kD = c->dev[NKB_KPMLDN];
+    a.npts = c->npts;
+    a.src_prof = c->src_prof;
+    a.src_comp = c->src_comp;
+    // rk_c (src/cem_common.F:12): rktime = time + dt*rk4c(i)
+    const double rktime = c->time + c->dt * c->rk4c[rkstep - 1];
+    a.src_tfac = c->src_prof ? c->src_amp * sin(c->src_omega * rktime + c->src_phase) : 0.0;
+
+    auto launch_list = [&](int q) -> int {
+        if (c->list_n[q] == 0) return 0;
+        nkb::StageArgs b = a;
+        b.elist = c->elist_d + c->list_off[q];
+        b.nel = c->list_n[q];
+        int rc = nkb::launch_stage(b, c->n, (q & 1) != 0, c->s_compute);
+        if (rc < 0) return fail("nx1=%d is not supported by the stage kernels (2..14)", c->n);
+        if (rc > 0) return fail("stage kernel launch failed: %s",
+                                cudaGetErrorString(cudaGetLastError()));
+        c->last_launches++;
+        return 0;
+    };
+
+    const bool exchange = !c->peers.empty();
+    if (exchange) {
+        // side stream: pack stage-start traces, grouped send/recv (replaces gs_op_fields
+        // between ranks, src/cem_maxwell.F:962); overlaps the interior-element launches
+        CUDA_OK(cudaStreamWaitEvent(c->s_comm, c->ev_stage, 0));
+        const long long tot = c->nhalo * 6;
+        pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c->s_comm>>>(
+            a.u_in, c->ld, c->send_node, c->sendbuf, c->nhalo);
+        c->last_launches++;
+        NCCL_OK(ncclGroupStart());
+        for (auto &p : c->peers) {
+            const size_t cnt = p.send_fp.size() * 6;
+            NCCL_OK(ncclSend(c->sendbuf + 6 * p.off, cnt, ncclDouble, p.rank, c->comm, c->s_comm));
+            NCCL_OK(ncclRecv(c->halo + 6 * p.off, cnt, ncclDouble, p.rank, c->comm, c->s_comm));
+        }
+        NCCL_OK(ncclGroupEnd());
+        CUDA_OK(cudaEventRecord(c->ev_halo, c->s_comm));
+    }
+    if (launch_list(0)) return 1;
+    if (launch_list(1)) return 1;
+    if (exchange) CUDA_OK(cudaStreamWaitEvent(c->s_compute, c->ev_halo, 0));
+    if (launch_list(2)) return 1;
+    if (launch_list(3)) return 1;
+    CUDA_OK(cudaEventRecord(c->ev_stage, c->s_compute));
+    c->cur ^= 1;
+    return 0;
+}
+
+} // namespace
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+#pragma GCC visibility push(default)
+
+const char *nekcem_b200_last_error(void) { return g_err.c_str(); }
+
+int nekcem_b200_create(const nekcem_b200_desc *desc, int *handle)
+{
+    if (!desc || !handle) return fail("null argument");
+    if (desc->abi_version != NEKCEM_B200_ABI_VERSION)
+        return fail("ABI version mismatch: caller %d, library %d", desc->abi_version,
+                    NEKCEM_B200_ABI_VERSION);
+    if (desc->ldim != 3 || desc->imode != 3)
+        return fail("only the 3D path (ldim=3, imode=3) is implemented; got ldim=%d imode=%d",
+                    desc->ldim, desc->imode);
+    if (desc->nx1 < 2 || desc->nx1 > 14)
+        return fail("nx1=%d outside the supported range 2..14", desc->nx1);
+    if (desc->nelt < 1) return fail("nelt must be >= 1");
+    if (desc->strict != 0) return fail("strict (no-FMA) kernels are not built in this version");
+    if (desc->nranks < 1 || desc->rank < 0 || desc->rank >= desc->nranks)
+        return fail("bad rank/nranks %d/%d", desc->rank, desc->nranks);
+    auto c = std::make_unique<Ctx>();
+    c->d = *desc;
+    c->n = desc->nx1;
+    c->nxyz = c->n * c->n * c->n;
+    c->nxzf = c->n * c->n;
+    c->nfaces = 6;
+    c->npts = (int64_t)c->nxyz * desc->nelt;
+    c->nxzfl = (int64_t)c->nxzf * c->nfaces * desc->nelt;
+    if (c->npts > 2147483647LL - 64) return fail("npts exceeds 32-bit node indexing");
+    c->ld = ((c->npts + 31) / 32) * 32;
+    c->host_only = desc->device < 0;
+    rk_storage(c.get());
+    if (!c->host_only) {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev == 0)
+            return fail("no CUDA device available (%s); libnekcem_b200 has no CPU fallback",
+                        cudaGetErrorString(e));
+        if (desc->device >= ndev) return fail("device %d out of range (%d devices)", desc->device, ndev);
+        CUDA_OK(cudaSetDevice(desc->device));
+        cudaDeviceProp prop;
+        CUDA_OK(cudaGetDeviceProperties(&prop, desc->device));
+        if (prop.major != 10)
+            return fail("device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                        desc->device, prop.major, prop.minor);
+        CUDA_OK(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
+        CUDA_OK(cudaStreamCreateWithFlags(&c->s_comm, cudaStreamNonBlocking));
+        CUDA_OK(cudaEventCreateWithFlags(&c->ev_stage, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreate(&c->ev_t0));
+        CUDA_OK(cudaEventCreate(&c->ev_t1));
+        for (int q = 0; q < 2; q++) {
+            CUDA_OK(cudaMalloc(&c->u[q], sizeof(double) * 6 * c->ld));
+            CUDA_OK(cudaMemset(c->u[q], 0, sizeof(double) * 6 * c->ld));
+        }
+        CUDA_OK(cudaMalloc(&c->kf, sizeof(double) * 6 * c->ld));
+        CUDA_OK(cudaMemset(c->kf, 0, sizeof(double) * 6 * c->ld));
+        CUDA_OK(cudaEventRecord(c->ev_stage, c->s_compute));
+    }
+    g_ctx.push_back(std::move(c));
+    *handle = (int)g_ctx.size() - 1;
+    return 0;
+}
+
+int nekcem_b200_destroy(int handle)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (!c->host_only) {
+        cudaSetDevice(c->d.device);
+        cudaDeviceSynchronize();
+        if (c->has_comm) ncclCommDestroy(c->comm);
+        for (auto &p : c->dev) cudaFree(p);
+        cudaFree(c->u[0]); cudaFree(c->u[1]); cudaFree(c->kf);
+        cudaFree(c->hY); cudaFree(c->hZ); cudaFree(c->vmapP_d); cudaFree(c->elist_d);
+        cudaFree(c->sendbuf); cudaFree(c->halo); cudaFree(c->send_node);
+        cudaFree(c->src_prof); cudaFree(c->red_d);
+        cudaEventDestroy(c->ev_stage); cudaEventDestroy(c->ev_halo);
+        cudaEventDestroy(c->ev_t0); cudaEventDestroy(c->ev_t1);
+        cudaStreamDestroy(c->s_compute); cudaStreamDestroy(c->s_comm);
+    }
+    g_ctx[handle].reset();
+    return 0;
+}
+
+int nekcem_b200_set_array(int handle, int which, const double *host, int64_t count)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (which < 0 || which >= NKB_ARRAY_COUNT) return fail("bad array id %d", which);
+    if (!host) return fail("null host pointer");
+    const int64_t want = array_count(c, which);
+    if (count != want)
+        return fail("array id %d: count %lld, expected %lld", which, (long long)count, (long long)want);
+    if (c->host_only) return fail("host-only planning context: no device arrays");
+    CUDA_OK(cudaSetDevice(c->d.device));
+    CUDA_OK(cudaStreamSynchronize(c->s_compute));
+    if (which == NKB_HN || which == NKB_EN || which == NKB_KHN || which == NKB_KEN) {
+        double *base = (which == NKB_HN || which == NKB_EN) ? c->u[c->cur] : c->kf;
+        const int c0 = (which == NKB_HN || which == NKB_KHN) ? 0 : 3;
+        CUDA_OK(cudaMemcpy2D(base + c0 * c->ld, sizeof(double) * c->ld, host,
+                             sizeof(double) * c->npts, sizeof(double) * c->npts, 3,
+                             cudaMemcpyHostToDevice));
+    } else {
+        if (ensure_dev(c, which)) return 1;
+        CUDA_OK(cudaMemcpy(c->dev[which], host, sizeof(double) * count, cudaMemcpyHostToDevice));
+        if (which == NKB_Y_0 || which == NKB_Z_0) {
+            double *&h = (which == NKB_Y_0) ? c->hY : c->hZ;
+            if (!h) CUDA_OK(cudaMalloc(&h, sizeof(double) * count));
+            half_inverse_kernel<<<(unsigned)((count + 255) / 256), 256, 0, c->s_compute>>>(
+                c->dev[which], h, count);
+            CUDA_OK(cudaStreamSynchronize(c->s_compute));
+        }
+    }
+    c->have[which] = true;
+    return 0;
+}
+
+int nekcem_b200_get_array(int handle, int which, double *host, int64_t count)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (which < 0 || which >= NKB_ARRAY_COUNT) return fail("bad array id %d", which);
+    if (!host) return fail("null host pointer");
+    const int64_t want = array_count(c, which);
+    if (count != want)
+        return fail("array id %d: count %lld, expected %lld", which, (long long)count, (long long)want);
+    if (c->host_only) return fail("host-only planning context: no device arrays");
+    CUDA_OK(cudaSetDevice(c->d.device));
+    CUDA_OK(cudaStreamSynchronize(c->s_compute));
+    if (which == NKB_HN || which == NKB_EN || which == NKB_KHN || which == NKB_KEN) {
+        const double *base = (which == NKB_HN || which == NKB_EN) ? c->u[c->cur] : c->kf;
+        const int c0 = (which == NKB_HN || which == NKB_KHN) ? 0 : 3;
+        CUDA_OK(cudaMemcpy2D(host, sizeof(double) * c->npts, base + c0 * c->ld,
+                             sizeof(double) * c->ld, sizeof(double) * c->npts, 3,
+                             cudaMemcpyDeviceToHost));
+    } else {
+        if (!c->dev[which]) return fail("array id %d was never set", which);
+        CUDA_OK(cudaMemcpy(host, c->dev[which], sizeof(double) * count, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+int nekcem_b200_set_faces(int handle, const int64_t *glo_num, int64_t nxzfl, const int32_t *cempec,
+                          int32_t ncempec)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (nxzfl != c->nxzfl) return fail("nxzfl %lld, expected %lld", (long long)nxzfl, (long long)c->nxzfl);
+    if (!glo_num) return fail("null glo_num");
+    if (ncempec < 0 || (ncempec > 0 && !cempec)) return fail("bad cempec");
+    c->glo.assign(glo_num, glo_num + nxzfl);
+    c->cempec.assign(cempec, cempec + ncempec);
+    c->local_matched = c->remote_planned = c->setup_done = false;
+    return match_local(c);
+}
+
+int nekcem_b200_set_pml(int handle, const int32_t *pmlptr, int32_t maxpml)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (maxpml < 0 || (maxpml > 0 && !pmlptr)) return fail("bad pmlptr");
+    c->pml_el.clear();
+    for (int q = 0; q < maxpml; q++) {
+        if (pmlptr[q] < 1 || pmlptr[q] > c->d.nelt) return fail("pmlptr(%d)=%d out of range", q + 1, pmlptr[q]);
+        c->pml_el.push_back(pmlptr[q] - 1);
+    }
+    c->setup_done = false;
+    return 0;
+}
+
+int nekcem_b200_comm_unique_id(char id[128])
+{
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    ncclUniqueId u;
+    NCCL_OK(ncclGetUniqueId(&u));
+    memcpy(id, &u, 128);
+    return 0;
+}
+
+int nekcem_b200_comm_init(int handle, const char id[128])
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (c->host_only) return fail("host-only planning context: no communicator");
+    if (c->d.nranks == 1) return 0;
+    CUDA_OK(cudaSetDevice(c->d.device));
+    ncclUniqueId u;
+    memcpy(&u, id, 128);
+    NCCL_OK(ncclCommInitRank(&c->comm, c->d.nranks, u, c->d.rank));
+    c->has_comm = true;
+    return 0;
+}
+
+int nekcem_b200_face_singletons(int handle, int64_t *ids, int64_t capacity, int64_t *count)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (!c->local_matched) return fail("set_faces first");
+    *count = (int64_t)c->singles.size();
+    if (ids) {
+        if (capacity < *count) return fail("capacity %lld < %lld", (long long)capacity, (long long)*count);
+        for (size_t q = 0; q < c->singles.size(); q++) ids[q] = c->singles[q].first;
+    }
+    return 0;
+}
+
+int nekcem_b200_face_remote(int handle, const int64_t *counts, const int64_t *all_ids)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (!counts) return fail("null counts");
+    return plan_remote(c, counts, all_ids);
+}
+
+int nekcem_b200_plan_npeers(int handle, int32_t *npeers, int64_t *nhalo)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    *npeers = (int32_t)c->peers.size();
+    *nhalo = c->nhalo;
+    return 0;
+}
+
+int nekcem_b200_plan_peer(int handle, int32_t ipeer, int32_t *peer_rank, int64_t *count,
+                          int64_t *send_facepts)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (ipeer < 0 || ipeer >= (int)c->peers.size()) return fail("bad peer index");
+    const Peer &p = c->peers[ipeer];
+    *peer_rank = p.rank;
+    *count = (int64_t)p.send_fp.size();
+    if (send_facepts) std::copy(p.send_fp.begin(), p.send_fp.end(), send_facepts);
+    return 0;
+}
+
+int nekcem_b200_plan_vmap(int handle, int32_t *vmapP, int64_t nxzfl)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (nxzfl != c->nxzfl || !c->local_matched) return fail("plan_vmap: not ready");
+    std::copy(c->vmapP.begin(), c->vmapP.end(), vmapP);
+    return 0;
+}
+
+int nekcem_b200_plan_elements(int handle, int32_t *n_interior, int32_t *n_boundary)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    std::vector<int32_t> lists;
+    build_lists(c, lists);
+    *n_interior = c->n_interior;
+    *n_boundary = c->n_boundary;
+    return 0;
+}
+
+int nekcem_b200_setup(int handle)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (!c->local_matched) return fail("nekcem_b200_set_faces has not been called");
+    if (c->host_only) return fail("host-only planning context cannot be set up for compute");
+    CUDA_OK(cudaSetDevice(c->d.device));
+    if (require(c, {NKB_DXM1, NKB_W3MN, NKB_RXMN, NKB_RYMN, NKB_RZMN, NKB_SXMN, NKB_SYMN,
+                    NKB_SZMN, NKB_TXMN, NKB_TYMN, NKB_TZMN, NKB_BMN, NKB_HBM1, NKB_EBM1,
+                    NKB_UNXM, NKB_UNYM, NKB_UNZM, NKB_AREAM, NKB_Y_0, NKB_Y_1, NKB_Z_0,
+                    NKB_Z_1}))
+        return 1;
+    if (!c->pml_el.empty()) {
+        if (require(c, {NKB_PERMITTIVITY, NKB_PERMEABILITY, NKB_PMLSIGMA})) return 1;
+        for (int id : {NKB_PMLBN, NKB_PMLDN, NKB_KPMLBN, NKB_KPMLDN})
+            if (ensure_dev(c, id)) return 1;
+    }
+    if (c->d.nranks > 1 && !c->remote_planned) {
+        if (!c->has_comm) return fail("nranks>1: call nekcem_b200_comm_init (or face_remote) before setup");
+        if (exchange_singletons_nccl(c)) return 1;
+    }
+    std::vector<int32_t> lists;
+    build_lists(c, lists);
+    cudaFree(c->vmapP_d); cudaFree(c->elist_d); cudaFree(c->sendbuf); cudaFree(c->halo);
+    cudaFree(c->send_node);
+    c->vmapP_d = nullptr; c->elist_d = nullptr; c->sendbuf = c->halo = nullptr; c->send_node = nullptr;
+    CUDA_OK(cudaMalloc(&c->vmapP_d, sizeof(int) * c->nxzfl));
+    CUDA_OK(cudaMemcpy(c->vmapP_d, c->vmapP.data(), sizeof(int) * c->nxzfl, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMalloc(&c->elist_d, sizeof(int) * std::max<size_t>(lists.size(), 1)));
+    CUDA_OK(cudaMemcpy(c->elist_d, lists.data(), sizeof(int) * lists.size(), cudaMemcpyHostToDevice));
+    if (c->nhalo > 0) {
+        if (!c->has_comm) return fail("inter-rank faces exist but no communicator was initialised");
+        const int nfp = c->nxzf * c->nfaces;
+        std::vector<int> send_node(c->nhalo);
+        for (auto &p : c->peers)
+            for (size_t q = 0; q < p.send_fp.size(); q++) {
+                const int64_t fp = p.send_fp[q], e = fp / nfp;
+                const int f = (int)(fp - e * nfp);
+                send_node[p.off + q] = (int)(e * c->nxyz + face_node(c->n, f / c->nxzf, f % c->nxzf));
+            }
+        CUDA_OK(cudaMalloc(&c->send_node, sizeof(int) * c->nhalo));
+        CUDA_OK(cudaMemcpy(c->send_node, send_node.data(), sizeof(int) * c->nhalo, cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMalloc(&c->sendbuf, sizeof(double) * 6 * c->nhalo));
+        CUDA_OK(cudaMalloc(&c->halo, sizeof(double) * 6 * c->nhalo));
+        CUDA_OK(cudaMemset(c->halo, 0, sizeof(double) * 6 * c->nhalo));
+    }
+    if (!c->red_d) {
+        c->red_blocks = 1024;
+        CUDA_OK(cudaMalloc(&c->red_d, sizeof(double) * 12 * c->red_blocks));
+    }
+    CUDA_OK(cudaDeviceSynchronize());
+    c->setup_done = true;
+    return 0;
+}
+
+int nekcem_b200_set_volume_source(int handle, int comp, const double *profile, double amp,
+                                  double omega, double phase)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (c->host_only) return fail("host-only planning context");
+    if (comp < 0 || comp > 5) return fail("source component %d out of range 0..5", comp);
+    CUDA_OK(cudaSetDevice(c->d.device));
+    CUDA_OK(cudaStreamSynchronize(c->s_compute));
+    if (!profile) {
+        cudaFree(c->src_prof);
+        c->src_prof = nullptr;
+        return 0;
+    }
+    if (!c->src_prof) CUDA_OK(cudaMalloc(&c->src_prof, sizeof(double) * c->npts));
+    CUDA_OK(cudaMemcpy(c->src_prof, profile, sizeof(double) * c->npts, cudaMemcpyHostToDevice));
+    c->src_comp = comp;
+    c->src_amp = amp;
+    c->src_omega = omega;
+    c->src_phase = phase;
+    return 0;
+}
+
+int nekcem_b200_set_time(int handle, double time, double dt)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    c->time = time;
+    c->dt = dt;
+    return 0;
+}
+
+int nekcem_b200_get_time(int handle, double *time)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    *time = c->time;
+    return 0;
+}
+
+int nekcem_b200_stage(int handle, int rkstep)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (!c->setup_done) return fail("nekcem_b200_setup has not completed");
+    if (rkstep < 1 || rkstep > 5) return fail("rkstep %d out of range 1..5", rkstep);
+    CUDA_OK(cudaSetDevice(c->d.device));
+    return run_stage(c, rkstep);
+}
+
+int nekcem_b200_step(int handle, int nsteps)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (!c->setup_done) return fail("nekcem_b200_setup has not completed");
+    if (c->dt == 0.0) return fail("dt is zero: call nekcem_b200_set_time");
+    CUDA_OK(cudaSetDevice(c->d.device));
+    c->last_launches = 0;
+    CUDA_OK(cudaEventRecord(c->ev_t0, c->s_compute));
+    for (int s = 0; s < nsteps; s++) {
+        for (int rk = 1; rk <= 5; rk++)
+            if (run_stage(c, rk)) return 1;
+        c->time = c->time + c->dt;
+    }
+    CUDA_OK(cudaEventRecord(c->ev_t1, c->s_compute));
+    return 0;
+}
+
+int nekcem_b200_synchronize(int handle)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (c->host_only) return 0;
+    CUDA_OK(cudaSetDevice(c->d.device));
+    CUDA_OK(cudaStreamSynchronize(c->s_comm));
+    CUDA_OK(cudaStreamSynchronize(c->s_compute));
+    return 0;
+}
+
+int nekcem_b200_last_step_ms(int handle, float *ms, int64_t *launches)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    CUDA_OK(cudaSetDevice(c->d.device));
+    CUDA_OK(cudaEventSynchronize(c->ev_t1));
+    CUDA_OK(cudaEventElapsedTime(&c->last_ms, c->ev_t0, c->ev_t1));
+    if (ms) *ms = c->last_ms;
+    if (launches) *launches = c->last_launches;
+    return 0;
+}
+
+int nekcem_b200_error_sums(int handle, const double *exact_hn, const double *exact_en,
+                           double sumsq[6], double linf[6])
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (!c->setup_done) return fail("nekcem_b200_setup has not completed");
+    CUDA_OK(cudaSetDevice(c->d.device));
+    double *ex = nullptr;
+    CUDA_OK(cudaMalloc(&ex, sizeof(double) * 6 * c->npts));
+    CUDA_OK(cudaMemcpy(ex, exact_hn, sizeof(double) * 3 * c->npts, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(ex + 3 * c->npts, exact_en, sizeof(double) * 3 * c->npts, cudaMemcpyHostToDevice));
+    const int nb = (int)std::min<int64_t>(c->red_blocks, (c->npts + 255) / 256);
+    error_kernel<<<nb, 256, 0, c->s_compute>>>(c->u[c->cur], c->ld, ex, c->npts, c->dev[NKB_BMN], c->red_d);
+    std::vector<double> part(12 * nb);
+    CUDA_OK(cudaStreamSynchronize(c->s_compute));
+    CUDA_OK(cudaMemcpy(part.data(), c->red_d, sizeof(double) * 12 * nb, cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaFree(ex));
+    for (int q = 0; q < 6; q++) {
+        double s = 0.0, m = 0.0;
+        for (int b = 0; b < nb; b++) {
+            s += part[b * 12 + q];
+            m = std::max(m, part[b * 12 + 6 + q]);
+        }
+        sumsq[q] = s;
+        linf[q] = m;
+    }
+    return 0;
+}
+
+int nekcem_b200_algorithmic_bytes(int handle, double *bytes_per_stage)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    // volume 280 B/node, 116 B/face point; PML element node +240 B
+    double b = 280.0 * (double)c->npts + 116.0 * (double)c->nxzfl;
+    b += 240.0 * (double)c->pml_el.size() * (double)c->nxyz;
+    *bytes_per_stage = b;
+    return 0;
+}
+
+#pragma GCC visibility pop
+} // extern "C"

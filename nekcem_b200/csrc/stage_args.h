@@ -1,0 +1,39 @@
+// Arguments of one fused RK-stage launch (internal; not part of the C ABI).
+#pragma once
+#include <cstdint>
+
+namespace nkb {
+
+struct StageArgs {
+    // fields: ping-pong H,E (6 components, leading dimension ld) and the RK register k
+    const double *u_in;
+    double *u_out;
+    double *kf;
+    long long ld;
+    // volume geometry (npts each) -- src/GEOM:30-45
+    const double *rx, *ry, *rz, *sx, *sy, *sz, *tx, *ty, *tz;
+    const double *hbm1, *ebm1, *bmn;
+    const double *D;  // dxm1, column-major n x n
+    const double *w3; // w3mn(nxyz)
+    // face geometry/material (nxzfl each).  hY = 0.5/Y_0, hZ = 0.5/Z_0 (computed once at setup:
+    // the reference evaluates 0.5/Y0 first in every product, src/cem_maxwell.F:976-979)
+    const double *unx, *uny, *unz, *area, *hY, *Y1, *hZ, *Z1;
+    const int *vmapP;   // >=0: local volume node of the neighbour trace; -1: PEC mirror;
+                        // -2: unpaired non-PEC face; <=-3: halo slot -(v+3)
+    const double *halo; // [nhalo][6] traces received from peer ranks
+    const int *elist;   // element ids handled by this launch
+    int nel;
+    double ca, cb, dt, C0;
+    // PML auxiliary fields (PML launches only) -- src/PML
+    const double *sig, *eps, *mu;
+    double *pB, *pD, *kB, *kD;
+    long long npts;
+    // separable volume source (usersrc hook)
+    const double *src_prof;
+    int src_comp;
+    double src_tfac;
+};
+
+typedef void (*stage_launch_fn)(const StageArgs &a, int nx1, bool pml, void *stream);
+
+} // namespace nkb

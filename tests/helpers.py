@@ -1,0 +1,59 @@
+"""Shared test helpers: feed an oracle RefCase (the stand-in for the Fortran COMMON blocks)
+through the C ABI and compare fields."""
+import numpy as np
+
+from nekcem_b200 import MaxwellB200
+from nekcem_b200.api import GEOMETRY_ARRAYS
+
+
+def arrays_from_refcase(c, elems=None):
+    """COMMON-block arrays of a RefCase as the dict MaxwellB200.cem_maxwell_init expects.
+    ``elems`` (sorted global element ids) restricts to one rank's partition."""
+    d = {}
+    if elems is None:
+        elems = np.arange(c.nelt)
+    elems = np.asarray(elems)
+    vol = (elems[:, None] * c.nxyz + np.arange(c.nxyz)[None, :]).reshape(-1)
+    nfp = c.nxzf * c.nfaces
+    fac = (elems[:, None] * nfp + np.arange(nfp)[None, :]).reshape(-1)
+    for name in GEOMETRY_ARRAYS:
+        a = getattr(c, name)
+        if name in ("dxm1", "w3mn"):
+            d[name] = a.copy()
+        elif a.size == c.npts:
+            d[name] = a[vol].copy()
+        else:
+            d[name] = a[fac].copy()
+    for name in ("permittivity", "permeability"):
+        d[name] = getattr(c, name)[vol].copy()
+    for name in ("hn", "en", "khn", "ken", "pmlsigma", "pmlbn", "pmldn"):
+        a = getattr(c, name).reshape(3, c.npts)
+        d[name] = a[:, vol].copy().reshape(-1)
+    d["glo_num"] = c.glo_num[fac].copy()
+    # cempec / pmlptr renumbered to the local element order
+    loc = -np.ones(c.nelt, dtype=np.int64)
+    loc[elems] = np.arange(elems.size)
+    pec = c.cempec[:c.ncempec].astype(np.int64)
+    pe = pec // nfp
+    keep = loc[pe] >= 0
+    d["cempec"] = loc[pe[keep]] * nfp + pec[keep] % nfp
+    pml = c.pmlptr[:c.maxpml].astype(np.int64)
+    d["pmlptr"] = loc[pml][loc[pml] >= 0]
+    d["volvm1"] = c.volvm1
+    return d
+
+
+def solver_from_refcase(c, device=0):
+    s = MaxwellB200(c.ldim, c.nx1, c.nelt, imode=c.imode, upwind=bool(c.s.ifupwind),
+                    ifpec=c.ifpec, ifpml=c.ifpml, device=device)
+    s.cem_maxwell_init(arrays_from_refcase(c))
+    s.setup()
+    s.set_time(c.s.time, c.s.dt)
+    return s
+
+
+def rel_l2(a, b):
+    """relative L2 difference of two field vectors (all components together)."""
+    a = np.asarray(a); b = np.asarray(b)
+    den = np.sqrt(np.sum(b * b))
+    return float(np.sqrt(np.sum((a - b) ** 2)) / (den if den > 0 else 1.0))
