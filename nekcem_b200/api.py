@@ -237,8 +237,13 @@ class MaxwellB200:
                     self.set_array(name, arrays[name])
             self.set_pml(arrays["pmlptr"])
         for name in ("hn", "en", "khn", "ken"):
-            if arrays.get(name) is not None:
-                self.set_array(name, arrays[name])
+            a = arrays.get(name)
+            if a is not None:
+                self.set_array(name, a)
+        if free_after_upload:
+            for name in ("hn", "en"):
+                if name in arrays:
+                    arrays[name] = None
         self.set_faces(arrays["glo_num"], arrays.get("cempec", np.zeros(0, dtype=np.int64)))
         if "volvm1" in arrays:
             self.volvm1 = float(arrays["volvm1"])

@@ -1,0 +1,100 @@
+"""C-ABI library: loads without a GPU, exports every symbol include/nekcem_b200.h declares,
+host-side planning works in a host-only context, compute entry points fail loudly."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from nekcem_b200 import MaxwellB200, NekcemB200Error, lib
+from nekcem_b200.api import ARRAY_IDS, LIBPATH
+from nekcem_b200.boxcase import BoxCase
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "nekcem_b200.h")).read()
+    names = set(re.findall(r"\b(nekcem_b200_[a-z0-9_]+)\s*\(", hdr))
+    assert len(names) >= 25
+    L = C.CDLL(LIBPATH)
+    for n in sorted(names):
+        assert hasattr(L, n), f"{n} declared in the header but not exported"
+    for n in ("nekcem_b200_create_", "nekcem_b200_step_", "nekcem_b200_set_array_"):
+        assert hasattr(L, n), f"Fortran twin {n} missing"
+
+
+def test_array_enum_matches_header():
+    hdr = open(os.path.join(ROOT, "include", "nekcem_b200.h")).read()
+    body = hdr[hdr.index("enum nekcem_b200_array"):]
+    body = body[body.index("{") + 1:body.index("NKB_ARRAY_COUNT")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    ids = re.findall(r"NKB_([A-Z0-9_]+)", body)
+    assert [i.lower() for i in ids] == [k.lower() for k in ARRAY_IDS]
+
+
+def test_bad_arguments_fail_loudly():
+    with pytest.raises(NekcemB200Error, match="nx1"):
+        MaxwellB200(3, 40, 8, device=-1)
+    with pytest.raises(NekcemB200Error, match="3D path"):
+        MaxwellB200(2, 8, 8, imode=1, device=-1)
+    s = MaxwellB200(3, 4, 27, device=-1)
+    with pytest.raises(NekcemB200Error, match="host-only"):
+        s.set_array("rxmn", np.zeros(s.npts))
+    with pytest.raises(NekcemB200Error, match="set_faces has not been called"):
+        s.setup()
+    with pytest.raises(NekcemB200Error, match="nxzfl"):
+        s.set_faces(np.zeros(5, dtype=np.int64), np.zeros(0))
+    s.close()
+    L = lib()
+    assert L.nekcem_b200_step(12345, 1) != 0
+    assert b"invalid" in L.nekcem_b200_last_error()
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(NekcemB200Error, match="no CUDA device|CPU fallback"):
+        MaxwellB200(3, 4, 27, device=0)
+
+
+def test_host_plan_periodic_box():
+    b = BoxCase((3, 4, 5), 4)
+    s = MaxwellB200(3, 4, b.nelt, device=-1)
+    s.set_faces(b.array("glo_num"), b.array("cempec"))
+    vm, peers, nhalo, ni, nb = s.plan()
+    assert not peers and nhalo == 0 and ni == b.nelt and nb == 0
+    assert vm.min() >= 0  # every face point has a local partner
+    # the partner's partner is the own node: build own node index per face point
+    n, nfp = 4, 6 * 16
+    own = np.zeros(s.nxzfl, dtype=np.int64)
+    for e in range(b.nelt):
+        for f in range(6):
+            for p in range(16):
+                a, bb = p % n, p // n
+                node = [a + 16 * bb, 3 + 4 * a + 16 * bb, a + 12 + 16 * bb, 4 * a + 16 * bb,
+                        a + 4 * bb, a + 4 * bb + 48][f]
+                own[e * nfp + f * 16 + p] = e * 64 + node
+    inv = {int(o): j for j, o in enumerate(own)}  # face nodes are shared by up to 3 faces ...
+    x, y, z = b.coords()
+    L = b.length
+    for arr in (x, y, z):
+        d = np.abs(arr[own] - arr[vm])
+        d = np.minimum(d, np.abs(d - L))
+        assert d.max() < 1e-12
+    s.close()
+
+
+def test_host_plan_pec_box_codes():
+    b = BoxCase((2, 2, 2), 3, bc="PEC")
+    s = MaxwellB200(3, 3, b.nelt, device=-1)
+    g = b.array("glo_num")
+    s.set_faces(g, b.array("cempec"))
+    vm = s.plan()[0]
+    assert np.all(vm[g == 0] == -1) and np.all(vm[g != 0] >= 0)
+    s.set_faces(g, np.zeros(0))  # unpaired and not PEC -> code -2
+    vm = s.plan()[0]
+    assert np.all(vm[g == 0] == -2)
+    s.close()

@@ -1,0 +1,183 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on
+the same inputs, plus the reference's analytic known-answer tolerances evaluated on the GPU
+result.  Tolerance: north_star asks for <= 1e-12 relative L2 in FP64."""
+import numpy as np
+import pytest
+
+from helpers import arrays_from_refcase, rel_l2, solver_from_refcase
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+def _fields(obj):
+    return np.concatenate([obj.hn, obj.en])
+
+
+@pytest.mark.parametrize("nx1", [2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14])
+def test_periodic_box_every_order(nx1):
+    from oracle import cases
+    c = cases.case_boxper((3, 3, 4), nx1, dt=-1e-3)
+    s = solver_from_refcase(c)
+    c.step(3); s.step(3)
+    assert rel_l2(_fields(s), _fields(c)) <= TOL
+    assert abs(s.time - c.time) < 1e-15
+    s.close()
+
+
+def test_stage_by_stage_parity():
+    """every RK stage separately: fields and the RK register k"""
+    from oracle import cases
+    c = cases.case_3dboxper()
+    s = solver_from_refcase(c)
+    for rk in range(1, 6):
+        c.stage(rk); s.stage(rk)
+        s.synchronize()
+        assert rel_l2(_fields(s), _fields(c)) <= TOL, rk
+        kg = np.concatenate([s.get_array("khn"), s.get_array("ken")])
+        ko = np.concatenate([c.khn, c.ken])
+        assert rel_l2(kg, ko) <= TOL, rk
+    s.close()
+
+
+def test_kat_3dboxper_on_gpu():
+    """the reference's 3dboxper test end to end on the GPU: 50 steps, error norms by the
+    device-side cem_error against usersol with the .usr tolerances (5e-10 / 5e-9)."""
+    from oracle import cases
+    c = cases.case_3dboxper()
+    s = solver_from_refcase(c)
+    for target in list(range(1, 11)) + [50]:
+        n = target - round(s.time / c.dt)
+        s.step(n); c.step(n)
+        shn, sen = c.usersol(c, s.time)
+        l2, linf = s.cem_error(shn, sen)
+        assert np.all(l2 <= 5e-10) and np.all(linf <= 5e-9), (target, l2, linf)
+        l2o, linfo = c.errors(c.usersol)          # identical norms as the CPU path reports
+        assert np.allclose(l2, l2o, rtol=1e-6, atol=1e-16)
+        assert np.allclose(linf, linfo, rtol=1e-6, atol=1e-16)
+    assert rel_l2(_fields(s), _fields(c)) <= TOL
+    s.close()
+
+
+def test_kat_3dboxpec_on_gpu():
+    """tests/3dboxpec (PEC boundary-flux path): 200 steps, tolerances 5e-8 / 5e-7."""
+    from oracle import cases
+    c = cases.case_3dboxpec()
+    s = solver_from_refcase(c)
+    for _ in range(2):
+        s.step(100); c.step(100)
+        shn, sen = c.usersol(c, s.time)
+        l2, linf = s.cem_error(shn, sen)
+        assert np.all(l2 <= 5e-8) and np.all(linf <= 5e-7)
+        assert rel_l2(_fields(s), _fields(c)) <= TOL
+    s.close()
+
+
+@pytest.mark.parametrize("twomat", [False, True])
+def test_dielectric_pml_parity(twomat):
+    """heterogeneous eps/mu (Y/Z face impedances) + PML auxiliary fields fused in the stage
+    kernel.  The userinc injection is a host callback (8f rank 1) and is switched off on both
+    sides; everything else is the tests/3ddielectric configuration."""
+    from oracle import cases
+    c = cases.case_3ddielectric(twomat)
+    c.s.userinc = type(c.s.userinc)()  # NULL callback
+    s = solver_from_refcase(c)
+    s.step(20); c.step(20)
+    assert rel_l2(_fields(s), _fields(c)) <= TOL
+    assert rel_l2(s.get_array("pmlbn"), c.pmlbn) <= TOL
+    assert rel_l2(s.get_array("pmldn"), c.pmldn) <= TOL
+    assert rel_l2(s.get_array("kpmlbn"), c.kpmlbn) <= TOL
+    s.close()
+
+
+def test_3dboxpml_with_dipole_source():
+    """tests/3dboxpml: all-PML box driven by the Gaussian dipole through the volume-source
+    hook (usersrc position of the reference)."""
+    from oracle import cases
+    c = cases.case_3dboxpml(nx1=7)
+    s = solver_from_refcase(c)
+    fn = c.usersrc_fn
+    # srcez -= g * (sin(-omega t) * bm)  ->  comp 5 (Ez), amp 1, omega -2, phase 0
+    s.set_volume_source(5, fn.profile, 1.0, -fn.omega, 0.0)
+    s.step(40); c.step(40)
+    assert np.max(np.abs(c.en)) > 1e-8
+    assert rel_l2(_fields(s), _fields(c)) <= TOL
+    assert rel_l2(s.get_array("pmldn"), c.pmldn) <= TOL
+    s.close()
+
+
+def test_central_flux():
+    from oracle import cases, oracle as O
+    mesh = O.box_mesh((3, 3, 3), ((0.0, 2 * np.pi),) * 3, ("P  ",) * 6)
+    c = O.RefCase(mesh, 6, upwind=False)
+    c.set_dt(-1e-3)
+    c.hn[:], c.en[:] = cases.usersol_3dboxper(c, 0.0)
+    s = solver_from_refcase(c)
+    s.step(4); c.step(4)
+    assert rel_l2(_fields(s), _fields(c)) <= TOL
+    s.close()
+
+
+def test_deformed_mesh_general_metrics():
+    """non-affine (trilinear, sheared) elements exercise all nine metric terms and
+    non-axis-aligned face normals"""
+    from oracle import cases, oracle as O
+    mesh = O.box_mesh((3, 3, 3), ((-1.0, 1.0),) * 3, ("PEC",) * 6)
+
+    def warp(case):
+        x, y, z = case.xm1.copy(), case.ym1.copy(), case.zm1.copy()
+        case.xm1[:] = x + 0.08 * np.sin(np.pi * y) * np.sin(np.pi * z)
+        case.ym1[:] = y + 0.06 * np.sin(np.pi * x) * np.sin(np.pi * z)
+        case.zm1[:] = z + 0.05 * np.sin(np.pi * x) * np.sin(np.pi * y)
+
+    c = O.RefCase(mesh, 7, upwind=True, usrdat2=warp)
+    c.set_dt(-2e-3)
+    c.hn[:], c.en[:] = cases.usersol_3dboxpec(c, 0.0)
+    assert np.abs(c.rymn).max() > 1e-3  # genuinely curved metrics
+    s = solver_from_refcase(c)
+    s.step(5); c.step(5)
+    assert rel_l2(_fields(s), _fields(c)) <= TOL
+    s.close()
+
+
+def test_step_composition_and_host_roundtrip():
+    """step(2) == step(1);step(1); fields survive a D2H/H2D round trip bit-exactly"""
+    from oracle import cases
+    c = cases.case_boxper((3, 3, 3), 8, dt=-1e-3)
+    a = solver_from_refcase(c)
+    b = solver_from_refcase(c)
+    a.step(2)
+    b.step(1)
+    hn, en = b.hn, b.en
+    b.set_array("hn", hn); b.set_array("en", en)
+    b.step(1)
+    assert np.array_equal(a.hn, b.hn) and np.array_equal(a.en, b.en)
+    a.close(); b.close()
+
+
+def test_full_size_properties():
+    """BASELINE-size properties that need no oracle: on a 32^3-element N=7 periodic box the
+    upwind scheme must not create energy, and the result must match the analytic solution to
+    the accuracy the reference's userchk demands of 3dboxper."""
+    from nekcem_b200 import MaxwellB200
+    from nekcem_b200.boxcase import BoxCase
+    case = BoxCase((32, 32, 32), 8)
+    s = MaxwellB200(3, 8, case.nelt, device=0)
+    s.cem_maxwell_init(case.lazy(), free_after_upload=True)
+    s.setup()
+    s.set_time(0.0, 2e-4)
+    bm = case.array("bmn")
+
+    def energy():
+        return float(np.sum(bm * (s.hn.reshape(3, -1) ** 2).sum(0))
+                     + np.sum(bm * (s.en.reshape(3, -1) ** 2).sum(0)))
+
+    e0 = energy()
+    s.step(10)
+    e1 = energy()
+    assert e1 <= e0 * (1 + 1e-13)
+    shn, sen = case.fields(s.time)
+    l2, linf = s.cem_error(shn, sen)
+    assert np.all(l2 <= 5e-10) and np.all(linf <= 5e-9)
+    s.close()

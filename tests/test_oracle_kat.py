@@ -1,0 +1,65 @@
+"""Pins the CPU oracle with the reference's own known-answer tests: the analytic solutions
+and the L2/Linf tolerances compiled into tests/<case>/<case>.usr.  The
+meshes of 3dboxper / 3dboxpec come from the reference's .re2/.rea/.map files via the
+committed fixtures in tests/golden/ (generator: tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+
+from oracle import cases
+
+
+def _check(c, steps_to_check, nsteps):
+    done = 0
+    for target in steps_to_check:
+        c.step(target - done)
+        done = target
+        l2, linf = c.errors(c.usersol)
+        for k in range(6):
+            assert l2[k] <= c.tol["l2"][k], (target, k, l2[k])
+            assert linf[k] <= c.tol["linf"][k], (target, k, linf[k])
+    assert done == nsteps
+    return l2, linf
+
+
+def test_kat_3dboxper_full():
+    """tests/3dboxper: 128 elements, N=8, 50 steps of dt=2e-4; userchk at steps 1..10 and 50
+    with L2 <= 5e-10, Linf <= 5e-9 (3dboxper.usr:181-212)."""
+    c = cases.case_3dboxper()
+    assert c.nelt == 128 and c.nx1 == 9 and c.npts == 93312
+    l2, linf = _check(c, list(range(1, 11)) + [50], 50)
+    assert max(l2) > 1e-12  # the scheme's truncation error is visible: not a trivial pass
+
+
+def test_kat_3dboxpec_full():
+    """tests/3dboxpec: 27 elements, PEC walls, 1000 steps of dt=5e-3; L2 <= 5e-8, Linf <= 5e-7
+    (3dboxpec.usr:198-228), checked every iocomm=10... here every 100 steps."""
+    c = cases.case_3dboxpec()
+    assert c.ifpec and not c.ifpml and c.ncempec == 9 * 6 * 81
+    _check(c, list(range(100, 1001, 100)), 1000)
+
+
+@pytest.mark.parametrize("twomat", [False, True])
+def test_kat_3ddielectric(twomat):
+    """tests/3ddielectric (1 and 2 materials): PML in +-y, plane-wave injection through
+    userinc; tolerances 5e-4 / 5e-3 on hx,hz,ex,ez and ~1e-14 / 1e-12 on the zero components
+    hy, ey (3ddielectric.usr userchk).  300 of the 1000 steps (the error is periodic)."""
+    c = cases.case_3ddielectric(twomat)
+    assert c.ifpml and c.maxpml == 64 and c.user.incindex.size == 16 * 81
+    for target in (100, 200, 300):
+        c.step(100)
+        l2, linf = c.errors(c.usersol)
+        for k in (0, 2, 3, 5):
+            assert l2[k] <= 5e-4 and linf[k] <= 5e-3, (target, k, l2[k], linf[k])
+        for k in (1, 4):
+            assert l2[k] <= 5e-14 and linf[k] <= 5e-12, (target, k, l2[k], linf[k])
+
+
+def test_kat_3dboxpml_stability():
+    """tests/3dboxpml: all-PML box with a Gaussian dipole; userchk only requires the fields to
+    stay below 1.0.  200 of the 2000 steps at CFL 0.1."""
+    c = cases.case_3dboxpml(nx1=7, nel=(6, 6, 6))
+    assert c.maxpml == 6 ** 3 - 4 ** 3
+    c.step(200)
+    assert np.all(np.isfinite(c.hn)) and np.all(np.isfinite(c.en))
+    assert np.max(np.abs(c.en)) < 1.0 and np.max(np.abs(c.hn)) < 1.0
+    assert np.max(np.abs(c.en)) > 1e-6  # the source did radiate

@@ -1,0 +1,98 @@
+"""Unit checks of the oracle's building blocks and of the product-side box generator against
+the oracle's literal restatement of the reference setup."""
+import numpy as np
+import pytest
+
+from helpers import arrays_from_refcase
+from nekcem_b200.boxcase import BoxCase, dgll, gll, gllnid_box
+from oracle import cases, oracle as O
+
+
+@pytest.mark.parametrize("n", [2, 3, 5, 8, 9, 12, 16])
+def test_gll_quadrature(n):
+    z, w = O.zwgll(n)
+    assert z[0] == -1.0 and z[-1] == 1.0 and np.all(np.diff(z) > 0)
+    assert abs(w.sum() - 2.0) < 1e-13
+    for p in range(0, 2 * n - 2):  # exact for degree <= 2n-3
+        exact = 0.0 if p % 2 else 2.0 / (p + 1)
+        assert abs(np.dot(w, z ** p) - exact) < 1e-12
+    z2, w2 = gll(n)
+    assert np.max(np.abs(z - z2)) < 1e-14 and np.max(np.abs(w - w2)) < 1e-14
+
+
+@pytest.mark.parametrize("n", [3, 8, 9, 16])
+def test_dgll(n):
+    z, _ = O.zwgll(n)
+    d, dt = O.dgll(z)
+    D = d.reshape(n, n).T  # column-major -> D[i, j]
+    assert np.allclose(dt.reshape(n, n), D, atol=0)  # dt(j,i) = d(i,j)
+    for p in range(n):
+        exact = p * z ** (p - 1) if p > 0 else 0 * z
+        assert np.max(np.abs(D @ z ** p - exact)) < 1e-10
+    assert np.max(np.abs(D - dgll(z))) < 1e-12
+
+
+def test_mxm_left_to_right():
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((5, 7)); b = rng.standard_normal((7, 4))
+    c = np.zeros(20)
+    O.lib().ora_mxm(O.dp(np.asfortranarray(a).reshape(-1, order="F").copy()), 5,
+                    O.dp(np.asfortranarray(b).reshape(-1, order="F").copy()), 7, O.dp(c), 4)
+    ref = np.zeros((5, 4))
+    for i in range(5):
+        for j in range(4):
+            s = a[i, 0] * b[0, j]
+            for k in range(1, 7):
+                s = s + a[i, k] * b[k, j]
+            ref[i, j] = s
+    assert np.array_equal(c.reshape(4, 5).T, ref)  # bit-exact summation order
+
+
+def test_gs_pairwise_sum():
+    ids = np.array([5, 0, 7, 5, 9, 7, 0], dtype=np.int64)
+    L = O.lib()
+    import ctypes as C
+    g = L.ora_gs_setup(ids.ctypes.data_as(C.POINTER(C.c_longlong)), ids.size)
+    u = np.arange(14, dtype=np.float64)  # two fields, stride 7
+    L.ora_gs_op_fields(g, O.dp(u), 7, 2, 1)
+    assert list(u[:7]) == [3, 1, 7, 3, 4, 7, 6]
+    assert list(u[7:]) == [17, 8, 21, 17, 11, 21, 13]
+    L.ora_gs_free(g)
+
+
+def test_cemface_and_face_ids_pair_coincident_points():
+    c = cases.case_3dboxper()
+    # paired face points are geometrically identical modulo the 2*pi period
+    order = np.argsort(c.glo_num, kind="stable")
+    g = c.glo_num[order]
+    assert np.all(g[0::2] == g[1::2]) and np.all(g[0:-2:2] != g[2::2])
+    a, b = c.cemface[order[0::2]], c.cemface[order[1::2]]
+    for x in (c.xm1, c.ym1, c.zm1):
+        d = np.abs(x[a] - x[b])
+        d = np.minimum(d, np.abs(d - 2 * np.pi))
+        assert d.max() < 1e-12
+    # unit outward normals of a pair are opposite, areas equal
+    ja, jb = order[0::2], order[1::2]
+    assert np.max(np.abs(c.unxm[ja] + c.unxm[jb])) < 1e-12
+    assert np.max(np.abs(c.aream[ja] - c.aream[jb])) < 1e-13
+
+
+def test_boxcase_matches_oracle_setup():
+    c = cases.case_boxper((3, 4, 5), 6)
+    b = BoxCase((3, 4, 5), 6)
+    A, B = arrays_from_refcase(c), b.arrays()
+    for k, a in A.items():
+        if k in ("glo_num", "cempec", "pmlptr", "volvm1") or k not in B:
+            continue
+        a = np.asarray(a); bb = np.asarray(B[k])
+        assert a.shape == bb.shape, k
+        assert np.max(np.abs(a - bb)) <= 1e-12 * max(1.0, np.max(np.abs(a))), k
+    assert abs(A["volvm1"] - B["volvm1"]) < 1e-10
+
+
+def test_pencil_map():
+    g = gllnid_box(4, 4, 8, 2)
+    assert np.array_equal(np.bincount(g), [64, 64])
+    assert np.all(g[: 4 * 4 * 4] == 0) and np.all(g[4 * 4 * 4:] == 1)  # z-slabs
+    g = gllnid_box(2, 3, 5, 4)  # uneven: 15 pencils over 4 ranks, boustrophedon order
+    assert sorted(np.bincount(g) // 2) == [3, 4, 4, 4]
