@@ -25,7 +25,7 @@
 #include "stage_args.h"
 
 namespace nkb {
-int launch_stage(const StageArgs &a, int nx1, bool pml, void *stream);
+int launch_stage(const StageArgs &a, const double *Dhost, int nx1, bool pml, void *stream);
 }
 
 namespace {
@@ -76,6 +76,7 @@ struct Ctx {
     int cur = 0;
     double *kf = nullptr; // (6,ld)
     double *hY = nullptr, *hZ = nullptr;
+    std::vector<double> D_host; // dxm1: passed to the stage kernel by value (constant bank)
     int *vmapP_d = nullptr;
     int *elist_d = nullptr; // concatenated lists
     int list_off[4] = {}, list_n[4] = {}; // [interior plain, interior pml, boundary plain, boundary pml]
@@ -425,8 +426,8 @@ int run_stage(Ctx *c, int rkstep /*1..5*/)
         nkb::StageArgs b = a;
         b.elist = c->elist_d + c->list_off[q];
         b.nel = c->list_n[q];
-        int rc = nkb::launch_stage(b, c->n, (q & 1) != 0, c->s_compute);
-        if (rc < 0) return fail("nx1=%d is not supported by the stage kernels (2..14)", c->n);
+        int rc = nkb::launch_stage(b, c->D_host.data(), c->n, (q & 1) != 0, c->s_compute);
+        if (rc < 0) return fail("nx1=%d is not supported by the stage kernels (2..16)", c->n);
         if (rc > 0) return fail("stage kernel launch failed: %s",
                                 cudaGetErrorString(cudaGetLastError()));
         c->last_launches++;
@@ -480,8 +481,8 @@ int nekcem_b200_create(const nekcem_b200_desc *desc, int *handle)
     if (desc->ldim != 3 || desc->imode != 3)
         return fail("only the 3D path (ldim=3, imode=3) is implemented; got ldim=%d imode=%d",
                     desc->ldim, desc->imode);
-    if (desc->nx1 < 2 || desc->nx1 > 14)
-        return fail("nx1=%d outside the supported range 2..14", desc->nx1);
+    if (desc->nx1 < 2 || desc->nx1 > 16)
+        return fail("nx1=%d outside the supported range 2..16", desc->nx1);
     if (desc->nelt < 1) return fail("nelt must be >= 1");
     if (desc->strict != 0) return fail("strict (no-FMA) kernels are not built in this version");
     if (desc->nranks < 1 || desc->rank < 0 || desc->rank >= desc->nranks)
@@ -572,6 +573,7 @@ int nekcem_b200_set_array(int handle, int which, const double *host, int64_t cou
     } else {
         if (ensure_dev(c, which)) return 1;
         CUDA_OK(cudaMemcpy(c->dev[which], host, sizeof(double) * count, cudaMemcpyHostToDevice));
+        if (which == NKB_DXM1) c->D_host.assign(host, host + count);
         if (which == NKB_Y_0 || which == NKB_Z_0) {
             double *&h = (which == NKB_Y_0) ? c->hY : c->hZ;
             if (!h) CUDA_OK(cudaMalloc(&h, sizeof(double) * count));

@@ -15,7 +15,7 @@ def _fields(obj):
     return np.concatenate([obj.hn, obj.en])
 
 
-@pytest.mark.parametrize("nx1", [2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14])
+@pytest.mark.parametrize("nx1", [2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16])
 def test_periodic_box_every_order(nx1):
     from oracle import cases
     c = cases.case_boxper((3, 3, 4), nx1, dt=-1e-3)
