@@ -149,6 +149,10 @@ int nekcem_b200_error_sums(int handle, const double *exact_hn, const double *exa
  * compute stream) and the number of kernels it launched. */
 int nekcem_b200_last_step_ms(int handle, float *ms, int64_t *launches);
 
+/* Performance tunables (no effect on results).  "pf_dist": how many half-task CTAs ahead the
+ * stage kernel prefetches the staged field components into L2 (0 = off). */
+int nekcem_b200_set_option(int handle, const char *name, int value);
+
 /* Algorithmic HBM bytes per stage for this context: 280 B/node +
  * 116 B/face point (+ PML add-on for PML elements). */
 int nekcem_b200_algorithmic_bytes(int handle, double *bytes_per_stage);

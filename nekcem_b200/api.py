@@ -81,6 +81,7 @@ def lib():
         L.nekcem_b200_setup.argtypes = [C.c_int]
         L.nekcem_b200_set_volume_source.argtypes = [C.c_int, C.c_int, c_dp, C.c_double,
                                                     C.c_double, C.c_double]
+        L.nekcem_b200_set_option.argtypes = [C.c_int, C.c_char_p, C.c_int]
         L.nekcem_b200_set_time.argtypes = [C.c_int, C.c_double, C.c_double]
         L.nekcem_b200_get_time.argtypes = [C.c_int, c_dp]
         L.nekcem_b200_step.argtypes = [C.c_int, C.c_int]
@@ -254,6 +255,9 @@ class MaxwellB200:
     def set_volume_source(self, comp, profile, amp, omega, phase):
         p = None if profile is None else _dp(np.ascontiguousarray(profile, dtype=np.float64))
         _chk(self.L.nekcem_b200_set_volume_source(self.h, comp, p, amp, omega, phase))
+
+    def set_option(self, name: str, value: int):
+        _chk(self.L.nekcem_b200_set_option(self.h, name.encode(), int(value)))
 
     # -- time stepping -------------------------------------------------------------------
     def set_time(self, time: float, dt: float):

@@ -107,6 +107,7 @@ struct Ctx {
     // diagnostics
     float last_ms = 0.f;
     int64_t last_launches = 0;
+    int pf_dist = 0;
     double *red_d = nullptr; // reduction scratch
     int red_blocks = 0;
 };
@@ -396,9 +397,8 @@ int run_stage(Ctx *c, int rkstep /*1..5*/)
     a.u_out = c->u[c->cur ^ 1];
     a.kf = c->kf;
     a.ld = c->ld;
-    a.rx = c->dev[NKB_RXMN]; a.ry = c->dev[NKB_RYMN]; a.rz = c->dev[NKB_RZMN];
-    a.sx = c->dev[NKB_SXMN]; a.sy = c->dev[NKB_SYMN]; a.sz = c->dev[NKB_SZMN];
-    a.tx = c->dev[NKB_TXMN]; a.ty = c->dev[NKB_TYMN]; a.tz = c->dev[NKB_TZMN];
+    for (int q = 0; q < 9; q++) a.met[q] = c->dev[NKB_RXMN + q];
+    a.pf_dist = c->pf_dist;
     a.hbm1 = c->dev[NKB_HBM1]; a.ebm1 = c->dev[NKB_EBM1]; a.bmn = c->dev[NKB_BMN];
     a.D = c->dev[NKB_DXM1];
     a.w3 = c->dev[NKB_W3MN];
@@ -801,6 +801,19 @@ int nekcem_b200_set_volume_source(int handle, int comp, const double *profile, d
     c->src_omega = omega;
     c->src_phase = phase;
     return 0;
+}
+
+int nekcem_b200_set_option(int handle, const char *name, int value)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (!name) return fail("null option name");
+    if (strcmp(name, "pf_dist") == 0) {
+        if (value < 0) return fail("pf_dist must be >= 0");
+        c->pf_dist = value;
+        return 0;
+    }
+    return fail("unknown option '%s'", name);
 }
 
 int nekcem_b200_set_time(int handle, double time, double dt)

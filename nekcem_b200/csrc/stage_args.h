@@ -11,7 +11,7 @@ struct StageArgs {
     double *kf;
     long long ld;
     // volume geometry (npts each) -- src/GEOM:30-45
-    const double *rx, *ry, *rz, *sx, *sy, *sz, *tx, *ty, *tz;
+    const double *met[9]; // rxmn,rymn,rzmn,sxmn,symn,szmn,txmn,tymn,tzmn
     const double *hbm1, *ebm1, *bmn;
     const double *D;  // dxm1, column-major n x n
     const double *w3; // w3mn(nxyz)
@@ -23,6 +23,7 @@ struct StageArgs {
     const double *halo; // [nhalo][6] traces received from peer ranks
     const int *elist;   // element ids handled by this launch
     int nel;
+    int pf_dist;        // L2 prefetch distance (in half-tasks) for the staged source components
     double ca, cb, dt, C0;
     // PML auxiliary fields (PML launches only) -- src/PML
     const double *sig, *eps, *mu;
@@ -33,7 +34,5 @@ struct StageArgs {
     int src_comp;
     double src_tfac;
 };
-
-typedef void (*stage_launch_fn)(const StageArgs &a, int nx1, bool pml, void *stream);
 
 } // namespace nkb

@@ -18,12 +18,17 @@
 //       times face area, lifted into the smem residual
 //       [restrict_to_face :604-652, flux3d :922-1002, flux_pec :1368-1426, add_flux_to_res
 //        :725-735]
-//   P4  t-pencils: thread (i,j), adds the t-part and finishes every node of its line:
-//       PML ADEs [pml_step, src/cem_maxwell_pml.F:508-592], volume source [usersrc hook :503],
-//       inverse mass [invqmass :1878-1886] and the low-storage RK update [rk4_upd,
-//       src/cem_common.F:18-76], written to the ping-pong field buffer.
+//   P4  t-pencils: thread (i,j), adds the weighted t-part to the smem residual
+//   P5  streaming epilogue, one node per thread and pass, coalesced, every load of a pass
+//       issued before the first use: PML ADEs [pml_step, src/cem_maxwell_pml.F:508-592],
+//       volume source [usersrc hook :503], inverse mass [invqmass :1878-1886] and the
+//       low-storage RK update [rk4_upd, src/cem_common.F:18-76], written to the ping-pong
+//       field buffer.
 //
-// Shared-memory traffic is ~33 accesses per node per half-task (vs 21n for a naive
+// Memory-level parallelism is explicit: the prologue prefetches every array of the half-task
+// into L2 (one warp per array), each pencil phase loads the cofactors of all its outputs before
+// the first FMA, and the epilogue loads EPI_UNROLL nodes ahead.
+// Shared-memory traffic is ~40 accesses per node per half-task (vs 21n for a naive
 // per-node dot product), which is what keeps n = 16 off the shared-memory roofline.
 // Arithmetic: same products as the reference; the 6-term curl sum is associated by
 // direction ((r-part + s-part)*w + lift) + w*t-part, and nvcc contracts a*b+c into FMA --
@@ -39,6 +44,19 @@ namespace nkb {
 __device__ __forceinline__ double ldg(const double *p) { return __ldg(p); }
 __device__ __forceinline__ int ldg(const int *p) { return __ldg(p); }
 
+// pull a 128-byte line into L2 without occupying a register or shared memory
+__device__ __forceinline__ void prefetch_l2(const void *p)
+{
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+// one warp prefetches `bytes` starting at base (any alignment)
+__device__ __forceinline__ void prefetch_chunk(const void *base, int bytes, int lane)
+{
+    const char *b = (const char *)base;
+    for (int off = lane * 128; off < bytes; off += 32 * 128) prefetch_l2(b + off);
+    if (lane == 0) prefetch_l2(b + bytes - 8);
+}
+
 // ---- compile-time geometry of one half-task --------------------------------------------
 __host__ __device__ constexpr int pad_j(int n)
 {
@@ -50,10 +68,18 @@ __host__ __device__ constexpr int pad_k(int n)
 {
     return (n == 3 || n == 4 || n == 7) ? 3 : (n == 10 ? 7 : 0);
 }
-__host__ __device__ constexpr int split_for(int n) { return n <= 5 ? 4 : 2; }
+// threads per pencil: each computes ceil(n/split) of the pencil's n outputs
+__host__ __device__ constexpr int split_for(int n) { return n <= 5 ? 4 : (n <= 13 ? 2 : 1); }
 __host__ __device__ constexpr int threads_for(int n)
 {
     return ((n * n * split_for(n) + 31) / 32) * 32;
+}
+__host__ __device__ constexpr int regs_for(int n)
+{
+    // pencil of 3 components (6n) + cofactors and weight of the thread's outputs + working set
+    int hn = (n + split_for(n) - 1) / split_for(n);
+    int r = 6 * n + 8 * hn + 36;
+    return r > 255 ? 255 : r;
 }
 __host__ __device__ constexpr int min_blocks_for(int n)
 {
@@ -62,11 +88,13 @@ __host__ __device__ constexpr int min_blocks_for(int n)
     int by_smem = (227 * 1024) / (6 * sc * 8 + 1024);
     int by_thr = 2048 / threads_for(n);
     int b = by_smem < by_thr ? by_smem : by_thr;
-    int by_reg = 65536 / (threads_for(n) * (6 * n + 40)); // 3n doubles of pencil + working set
+    int by_reg = 65536 / (threads_for(n) * regs_for(n));
     if (b > by_reg) b = by_reg;
     if (b > 16) b = 16;
     return b < 1 ? 1 : b;
 }
+
+constexpr int EPI_UNROLL = 4; // nodes per thread whose loads are in flight together
 
 template <int N>
 struct StageParams {
@@ -74,134 +102,92 @@ struct StageParams {
     double D[N * N]; // dxm1, column-major: D(i,m) at i + N*m  (constant bank operand)
 };
 
-// d[c] = sum_m D(OUT,m) * u[c][m], left to right (mxfK order)
-template <int N, int OUT>
-__device__ __forceinline__ void deriv3(const double (&D)[N * N], const double (&u)[3][N],
-                                       double (&d)[3])
+// One pencil phase.  DIR 0/1/2 = r/s/t.  The thread owns the line of N points starting at smem
+// offset `so` (stride SST) / element node `no` (stride GST) and produces outputs O0..O1-1:
+//   d_c   = sum_m D(o,m) u_c(m)                      (mxfK order, left to right)
+//   part  = (d3*my - d2*mz, d1*mz - d3*mx, d2*mx - d1*my)   with this direction's cofactors
+//   DIR 0: R  = part          DIR 1: R = (R + part) * (sg*w3)        DIR 2: R = R + (sg*w3)*part
+template <int N, int DIR, int O0, int O1, int SST, int GST>
+__device__ __forceinline__ void pencil_phase(const double (&D)[N * N], const StageArgs &a,
+                                             const double *U, double *R, int SC, int so, int no,
+                                             long long ebase, double sg)
 {
+    constexpr int NO = O1 - O0;
+    if constexpr (NO > 0) {
+        // cofactors (and weight) of every output first: NO*3(+1) independent loads in flight
+        double mx[NO], my[NO], mz[NO], wv[NO];
+        const long long g0 = ebase + no + (long long)GST * O0;
+        if constexpr (DIR == 0 && N % 2 == 0 && O0 % 2 == 0 && NO % 2 == 0) {
+            // outputs are contiguous in memory: 16-byte loads
 #pragma unroll
-    for (int c = 0; c < 3; c++) d[c] = D[OUT] * u[c][0];
+            for (int o = 0; o < NO; o += 2) {
+                const double2 vx = __ldg(reinterpret_cast<const double2 *>(a.met[0] + g0 + o));
+                const double2 vy = __ldg(reinterpret_cast<const double2 *>(a.met[1] + g0 + o));
+                const double2 vz = __ldg(reinterpret_cast<const double2 *>(a.met[2] + g0 + o));
+                mx[o] = vx.x; mx[o + 1] = vx.y;
+                my[o] = vy.x; my[o + 1] = vy.y;
+                mz[o] = vz.x; mz[o + 1] = vz.y;
+            }
+        } else {
 #pragma unroll
-    for (int m = 1; m < N; m++) {
+            for (int o = 0; o < NO; o++) {
+                mx[o] = ldg(a.met[3 * DIR] + g0 + GST * o);
+                my[o] = ldg(a.met[3 * DIR + 1] + g0 + GST * o);
+                mz[o] = ldg(a.met[3 * DIR + 2] + g0 + GST * o);
+            }
+        }
+        if constexpr (DIR != 0) {
 #pragma unroll
-        for (int c = 0; c < 3; c++) d[c] = d[c] + D[OUT + N * m] * u[c][m];
-    }
-}
-
-// curl contribution of one direction: (u1d,u2d,u3d) derivatives with cofactors (mx,my,mz)
-__device__ __forceinline__ void curl_part(const double (&d)[3], double mx, double my, double mz,
-                                          double (&c)[3])
-{
-    c[0] = d[2] * my - d[1] * mz;
-    c[1] = d[0] * mz - d[2] * mx;
-    c[2] = d[1] * mx - d[0] * my;
-}
-
-// ---- P1: r-pencil outputs i in [I0, I1) ----------------------------------------------------
-template <int N, int I0, int I1>
-__device__ __forceinline__ void r_outputs(const double (&D)[N * N], const double (&u)[3][N],
-                                          const StageArgs &a, long long grow, double *Rrow,
-                                          int SC)
-{
-    if constexpr (I0 < I1) {
-        double d[3], c[3];
-        deriv3<N, I0>(D, u, d);
-        curl_part(d, ldg(a.rx + grow + I0), ldg(a.ry + grow + I0), ldg(a.rz + grow + I0), c);
-        Rrow[I0] = c[0];
-        Rrow[SC + I0] = c[1];
-        Rrow[2 * SC + I0] = c[2];
-        r_outputs<N, I0 + 1, I1>(D, u, a, grow, Rrow, SC);
-    }
-}
-
-// ---- P2: s-pencil outputs j in [J0, J1) ------------------------------------------------------
-template <int N, int J0, int J1, int SJ>
-__device__ __forceinline__ void s_outputs(const double (&D)[N * N], const double (&u)[3][N],
-                                          const StageArgs &a, long long gcol, int ncol, double sg,
-                                          double *Rcol, int SC)
-{
-    if constexpr (J0 < J1) {
-        double d[3], c[3];
-        deriv3<N, J0>(D, u, d);
-        curl_part(d, ldg(a.sx + gcol + N * J0), ldg(a.sy + gcol + N * J0), ldg(a.sz + gcol + N * J0), c);
-        const double wv = sg * ldg(a.w3 + ncol + N * J0);
-        Rcol[SJ * J0] = (Rcol[SJ * J0] + c[0]) * wv;
-        Rcol[SC + SJ * J0] = (Rcol[SC + SJ * J0] + c[1]) * wv;
-        Rcol[2 * SC + SJ * J0] = (Rcol[2 * SC + SJ * J0] + c[2]) * wv;
-        s_outputs<N, J0 + 1, J1, SJ>(D, u, a, gcol, ncol, sg, Rcol, SC);
-    }
-}
-
-// ---- P4: t-pencil outputs k in [K0, K1): finishes the node ------------------------------------
-template <int N, int K0, int K1, int SK, bool PML>
-__device__ __forceinline__ void t_outputs(const double (&D)[N * N], const double (&u)[3][N],
-                                          const StageArgs &a, long long gnode, int node, int g,
-                                          double sg, const double *Rt, int SC)
-{
-    if constexpr (K0 < K1) {
-        constexpr int N2 = N * N;
-        const long long gi = gnode + (long long)N2 * K0;
-        double d[3], c[3], r[3];
-        deriv3<N, K0>(D, u, d);
-        curl_part(d, ldg(a.tx + gi), ldg(a.ty + gi), ldg(a.tz + gi), c);
-        const double wv = sg * ldg(a.w3 + node + N2 * K0);
-        r[0] = Rt[SK * K0] + wv * c[0];
-        r[1] = Rt[SC + SK * K0] + wv * c[1];
-        r[2] = Rt[2 * SC + SK * K0] + wv * c[2];
-        const long long cold = (g == 0 ? 3 : 0) * a.ld; // components being updated
-        const double o0 = ldg(a.u_in + cold + gi), o1 = ldg(a.u_in + cold + a.ld + gi),
-                     o2 = ldg(a.u_in + cold + 2 * a.ld + gi);
-        if (PML) { // pml_step, src/cem_maxwell_pml.F:540-585, then the PML half of rk_maxwell_ab
-            const double bm1 = ldg(a.bmn + gi);
-            const double bm1inv = 1.0 / bm1;
-            const double sigx = a.sig[gi], sigy = a.sig[a.npts + gi], sigz = a.sig[2 * a.npts + gi];
-            const double permitt = a.eps[gi];
-            const double sxp = sigx / permitt, syp = sigy / permitt, szp = sigz / permitt;
-            double *pF = g == 0 ? a.pD : a.pB;
-            double *kF = g == 0 ? a.kD : a.kB;
-            const double b0 = pF[gi], b1 = pF[a.npts + gi], b2 = pF[2 * a.npts + gi];
-            const double rb0 = r[0] * bm1inv - syp * b0;
-            const double rb1 = r[1] * bm1inv - szp * b1;
-            const double rb2 = r[2] * bm1inv - sxp * b2;
-            double p0, p1, p2;
-            if (g == 0) {
-                p0 = -syp * b0 + sxp * b0 - sigz * o0;
-                p1 = -szp * b1 + syp * b1 - sigx * o1;
-                p2 = -sxp * b2 + szp * b2 - sigy * o2;
+            for (int o = 0; o < NO; o++) wv[o] = ldg(a.w3 + no + GST * (O0 + o));
+        }
+        double u[3][N];
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int m = 0; m < N; m++) u[c][m] = U[c * SC + so + SST * m];
+#pragma unroll
+        for (int o = 0; o < NO; o++) {
+            double d[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) d[c] = D[O0 + o] * u[c][0];
+#pragma unroll
+            for (int m = 1; m < N; m++) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) d[c] = d[c] + D[(O0 + o) + N * m] * u[c][m];
+            }
+            const double c0 = d[2] * my[o] - d[1] * mz[o];
+            const double c1 = d[0] * mz[o] - d[2] * mx[o];
+            const double c2 = d[1] * mx[o] - d[0] * my[o];
+            double *Ro = R + so + SST * (O0 + o);
+            if constexpr (DIR == 0) {
+                Ro[0] = c0; Ro[SC] = c1; Ro[2 * SC] = c2;
+            } else if constexpr (DIR == 1) {
+                const double w = sg * wv[o];
+                Ro[0] = (Ro[0] + c0) * w;
+                Ro[SC] = (Ro[SC] + c1) * w;
+                Ro[2 * SC] = (Ro[2 * SC] + c2) * w;
             } else {
-                const double permeab = a.mu[gi];
-                p0 = -syp * b0 + sxp * b0 - szp * permeab * o0;
-                p1 = -szp * b1 + syp * b1 - sxp * permeab * o1;
-                p2 = -sxp * b2 + szp * b2 - syp * permeab * o2;
-            }
-            r[0] = r[0] + p0 * bm1; r[1] = r[1] + p1 * bm1; r[2] = r[2] + p2 * bm1;
-            double kk;
-            kk = a.ca * kF[gi] + a.dt * rb0; kF[gi] = kk; pF[gi] = b0 + a.cb * kk;
-            kk = a.ca * kF[a.npts + gi] + a.dt * rb1; kF[a.npts + gi] = kk;
-            pF[a.npts + gi] = b1 + a.cb * kk;
-            kk = a.ca * kF[2 * a.npts + gi] + a.dt * rb2; kF[2 * a.npts + gi] = kk;
-            pF[2 * a.npts + gi] = b2 + a.cb * kk;
-        }
-        if (a.src_prof != nullptr) { // usersrc hook: res(comp) -= profile*(tfac*bm)
-            const int cs = a.src_comp - (g == 0 ? 3 : 0);
-            if (cs >= 0 && cs < 3) {
-                const double sv = ldg(a.src_prof + gi) * (a.src_tfac * ldg(a.bmn + gi));
-                if (cs == 0) r[0] -= sv;
-                else if (cs == 1) r[1] -= sv;
-                else r[2] -= sv;
+                const double w = sg * wv[o];
+                Ro[0] = Ro[0] + w * c0;
+                Ro[SC] = Ro[SC] + w * c1;
+                Ro[2 * SC] = Ro[2 * SC] + w * c2;
             }
         }
-        const double mb = ldg((g == 0 ? a.ebm1 : a.hbm1) + gi);
-        r[0] *= mb; r[1] *= mb; r[2] *= mb;
-        double kk;
-        kk = a.ca * a.kf[cold + gi] + a.dt * r[0]; a.kf[cold + gi] = kk;
-        a.u_out[cold + gi] = o0 + a.cb * kk;
-        kk = a.ca * a.kf[cold + a.ld + gi] + a.dt * r[1]; a.kf[cold + a.ld + gi] = kk;
-        a.u_out[cold + a.ld + gi] = o1 + a.cb * kk;
-        kk = a.ca * a.kf[cold + 2 * a.ld + gi] + a.dt * r[2]; a.kf[cold + 2 * a.ld + gi] = kk;
-        a.u_out[cold + 2 * a.ld + gi] = o2 + a.cb * kk;
-        t_outputs<N, K0 + 1, K1, SK, PML>(D, u, a, gnode, node, g, sg, Rt, SC);
     }
+}
+
+// dispatch on the thread's output range (h = which 1/SPLIT of the outputs)
+template <int N, int DIR, int SPLIT, int SST, int GST>
+__device__ __forceinline__ void pencil_split(const double (&D)[N * N], const StageArgs &a,
+                                             const double *U, double *R, int SC, int so, int no,
+                                             long long ebase, double sg, int h)
+{
+    constexpr int HN = (N + SPLIT - 1) / SPLIT;
+    constexpr int E1 = HN < N ? HN : N, E2 = 2 * HN < N ? 2 * HN : N, E3 = 3 * HN < N ? 3 * HN : N;
+    if (h == 0) pencil_phase<N, DIR, 0, E1, SST, GST>(D, a, U, R, SC, so, no, ebase, sg);
+    if (SPLIT > 1 && h == 1) pencil_phase<N, DIR, E1, E2, SST, GST>(D, a, U, R, SC, so, no, ebase, sg);
+    if (SPLIT > 2 && h == 2) pencil_phase<N, DIR, E2, E3, SST, GST>(D, a, U, R, SC, so, no, ebase, sg);
+    if (SPLIT > 3 && h == 3) pencil_phase<N, DIR, E3, N, SST, GST>(D, a, U, R, SC, so, no, ebase, sg);
 }
 
 template <int N, bool PML>
@@ -211,7 +197,7 @@ __global__ void __launch_bounds__(threads_for(N), min_blocks_for(N))
     constexpr int N2 = N * N, N3 = N2 * N, NF = 6 * N2;
     constexpr int SPLIT = split_for(N), NT = threads_for(N);
     constexpr int SJ = N + pad_j(N), SK = SJ * N + pad_k(N), SC = SK * N;
-    constexpr int HN = (N + SPLIT - 1) / SPLIT; // outputs per thread of a pencil
+    constexpr int FPT = (2 * N2 + NT - 1) / NT; // face points per thread and flux round
     const StageArgs &a = prm.a;
     extern __shared__ double smem[];
     double *U = smem;          // [3][SC] source components at stage start
@@ -221,173 +207,289 @@ __global__ void __launch_bounds__(threads_for(N), min_blocks_for(N))
     const int e = a.elist[blockIdx.x >> 1];
     const int g = blockIdx.x & 1; // 0: E <- curl H ; 1: H <- -curl E
     const long long ebase = (long long)e * N3;
+    const long long cold = (g == 0 ? 3 : 0) * a.ld; // components being updated
     const double *__restrict__ src = a.u_in + (g == 0 ? 0 : 3) * a.ld;
-    const double *__restrict__ oth = a.u_in + (g == 0 ? 3 : 0) * a.ld;
+    const double *__restrict__ oth = a.u_in + cold;
     const double sg = g == 0 ? 1.0 : -1.0;
 
-    // ---- P0: stage the source components ---------------------------------------------------
-#pragma unroll 8
-    for (int q = tid; q < 3 * N3; q += NT) {
-        const int c = q / N3, r = q - c * N3;
-        const int i = r % N, j = (r / N) % N, k = r / N2;
-        U[c * SC + i + SJ * j + SK * k] = ldg(src + c * a.ld + ebase + r);
+    // ---- prologue: put every HBM request of this half-task in flight now ------------------
+    // (a) L2 prefetch of the element's metric, mass, RK-register, old-field and face arrays:
+    //     one warp per array, no registers or shared memory held while the data travels
+    {
+        const int warp = tid >> 5, lane = tid & 31;
+        constexpr int NW = NT / 32;
+        for (int arr = warp; arr < 23; arr += NW) {
+            const void *base;
+            int bytes = N3 * 8;
+            if (arr < 9) base = a.met[arr] + ebase;
+            else if (arr < 12) base = a.kf + cold + (arr - 9) * a.ld + ebase;
+            else if (arr < 15) base = a.u_in + cold + (arr - 12) * a.ld + ebase;
+            else if (arr == 15) base = (g == 0 ? a.ebm1 : a.hbm1) + ebase;
+            else {
+                const long long fbase = (long long)e * NF;
+                bytes = NF * 8;
+                if (arr == 16) base = a.unx + fbase;
+                else if (arr == 17) base = a.uny + fbase;
+                else if (arr == 18) base = a.unz + fbase;
+                else if (arr == 19) base = a.area + fbase;
+                else if (arr == 20) base = (g == 0 ? a.hZ : a.hY) + fbase;
+                else if (arr == 21) base = (g == 0 ? a.Z1 : a.Y1) + fbase;
+                else { base = a.vmapP + fbase; bytes = NF * 4; }
+            }
+            prefetch_chunk(base, bytes, lane);
+        }
+        // (b) the source components of the half-task that will start pf_dist CTAs from now
+        if (a.pf_dist > 0) {
+            const int b2 = blockIdx.x + a.pf_dist;
+            if (b2 < 2 * a.nel && warp < 3) {
+                const int e2 = a.elist[b2 >> 1];
+                prefetch_chunk(a.u_in + ((b2 & 1) ? 3 : 0) * a.ld + warp * a.ld + (long long)e2 * N3,
+                               N3 * 8, lane);
+            }
+        }
     }
+    // (c) neighbour ids of this thread's face points in each of the three flux rounds
+    int vpn[3][FPT];
+#pragma unroll
+    for (int f = 0; f < FPT; f++) {
+        const int q = tid + f * NT;
+        vpn[0][f] = vpn[1][f] = vpn[2][f] = -2;
+        if (q < 2 * N2) {
+            const int hi = q / N2, fp0 = q - hi * N2;
+            const long long fb = (long long)e * NF + fp0;
+            vpn[0][f] = ldg(a.vmapP + fb + (hi ? 1 : 3) * N2);
+            vpn[1][f] = ldg(a.vmapP + fb + (hi ? 2 : 0) * N2);
+            vpn[2][f] = ldg(a.vmapP + fb + (hi ? 5 : 4) * N2);
+        }
+    }
+
+    // ---- P0: stage the source components ---------------------------------------------------
+    {
+        constexpr int PER = (3 * N3 + NT - 1) / NT;
+        constexpr int UNR = PER < 12 ? PER : 12;
+#pragma unroll 1
+        for (int q0 = 0; q0 < PER; q0 += UNR) {
+            double v[UNR];
+#pragma unroll
+            for (int x = 0; x < UNR; x++) {
+                const int q = tid + (q0 + x) * NT;
+                const int c = q / N3, r = q - c * N3;
+                v[x] = q < 3 * N3 ? ldg(src + c * a.ld + ebase + r) : 0.0;
+            }
+#pragma unroll
+            for (int x = 0; x < UNR; x++) {
+                const int q = tid + (q0 + x) * NT;
+                const int c = q / N3, r = q - c * N3;
+                const int i = r % N, j = (r / N) % N, k = r / N2;
+                if (q < 3 * N3) U[c * SC + i + SJ * j + SK * k] = v[x];
+            }
+        }
+    }
+    // (d) neighbour traces of those face points -> L2
+#pragma unroll
+    for (int rd = 0; rd < 3; rd++)
+#pragma unroll
+        for (int f = 0; f < FPT; f++)
+            if (vpn[rd][f] >= 0) {
+#pragma unroll
+                for (int c = 0; c < 6; c++) prefetch_l2(a.u_in + c * a.ld + vpn[rd][f]);
+            }
     __syncthreads();
 
     const int p = tid % N2, h = tid / N2;
     const int pa = p % N, pb = p / N;
 
     // ---- P1: r-pencils, thread (j,k) = (pa,pb) ------------------------------------------------
-    if (h < SPLIT) {
-        double u[3][N];
-        const double *Urow = U + SJ * pa + SK * pb;
-#pragma unroll
-        for (int c = 0; c < 3; c++)
-#pragma unroll
-            for (int m = 0; m < N; m++) u[c][m] = Urow[c * SC + m];
-        const long long grow = ebase + N * pa + N2 * pb;
-        double *Rrow = R + SJ * pa + SK * pb;
-        if (h == 0) r_outputs<N, 0, (HN < N ? HN : N)>(prm.D, u, a, grow, Rrow, SC);
-        if (SPLIT > 1 && h == 1)
-            r_outputs<N, HN, (2 * HN < N ? 2 * HN : N)>(prm.D, u, a, grow, Rrow, SC);
-        if (SPLIT > 2 && h == 2)
-            r_outputs<N, 2 * HN, (3 * HN < N ? 3 * HN : N)>(prm.D, u, a, grow, Rrow, SC);
-        if (SPLIT > 3 && h == 3) r_outputs<N, 3 * HN, N>(prm.D, u, a, grow, Rrow, SC);
-    }
+    if (h < SPLIT)
+        pencil_split<N, 0, SPLIT, 1, 1>(prm.D, a, U, R, SC, SJ * pa + SK * pb, N * pa + N2 * pb,
+                                        ebase, sg, h);
     __syncthreads();
-
     // ---- P2: s-pencils, thread (i,k) = (pa,pb) ------------------------------------------------
-    if (h < SPLIT) {
-        double u[3][N];
-        const double *Ucol = U + pa + SK * pb;
-#pragma unroll
-        for (int c = 0; c < 3; c++)
-#pragma unroll
-            for (int m = 0; m < N; m++) u[c][m] = Ucol[c * SC + SJ * m];
-        const long long gcol = ebase + pa + N2 * pb;
-        const int ncol = pa + N2 * pb;
-        double *Rcol = R + pa + SK * pb;
-        if (h == 0) s_outputs<N, 0, (HN < N ? HN : N), SJ>(prm.D, u, a, gcol, ncol, sg, Rcol, SC);
-        if (SPLIT > 1 && h == 1)
-            s_outputs<N, HN, (2 * HN < N ? 2 * HN : N), SJ>(prm.D, u, a, gcol, ncol, sg, Rcol, SC);
-        if (SPLIT > 2 && h == 2)
-            s_outputs<N, 2 * HN, (3 * HN < N ? 3 * HN : N), SJ>(prm.D, u, a, gcol, ncol, sg, Rcol,
-                                                              SC);
-        if (SPLIT > 3 && h == 3) s_outputs<N, 3 * HN, N, SJ>(prm.D, u, a, gcol, ncol, sg, Rcol, SC);
-    }
+    if (h < SPLIT)
+        pencil_split<N, 1, SPLIT, SJ, N>(prm.D, a, U, R, SC, pa + SK * pb, pa + N2 * pb, ebase, sg,
+                                         h);
     __syncthreads();
 
     // ---- P3: surface flux, three rounds of two opposite faces ---------------------------------
     // slot order of the reference (cemface, cem_common.F:234-260): -y,+x,+y,-x,-z,+z
-#pragma unroll 1
+#pragma unroll
     for (int rd = 0; rd < 3; rd++) {
-        for (int q = tid; q < 2 * N2; q += NT) {
-            const int hi = q / N2, fp0 = q - hi * N2;
-            const int fa = fp0 % N, fb = fp0 / N;
-            int s, node, sn;
-            if (rd == 0) { // +-x
-                s = hi ? 1 : 3;
-                node = (hi ? N - 1 : 0) + N * fa + N2 * fb;
-                sn = (hi ? N - 1 : 0) + SJ * fa + SK * fb;
-            } else if (rd == 1) { // +-y
-                s = hi ? 2 : 0;
-                node = fa + N * (hi ? N - 1 : 0) + N2 * fb;
-                sn = fa + SJ * (hi ? N - 1 : 0) + SK * fb;
-            } else { // +-z
-                s = hi ? 5 : 4;
-                node = fa + N * fb + N2 * (hi ? N - 1 : 0);
-                sn = fa + SJ * fb + SK * (hi ? N - 1 : 0);
-            }
-            const long long jf = (long long)e * NF + s * N2 + fp0;
-            const double unx = ldg(a.unx + jf), uny = ldg(a.uny + jf), unz = ldg(a.unz + jf);
-            const int vp = ldg(a.vmapP + jf);
-            const double S0 = U[sn], S1 = U[SC + sn], S2 = U[2 * SC + sn];
-            const long long gn = ebase + node;
-            const double O0 = ldg(oth + gn), O1 = ldg(oth + a.ld + gn), O2 = ldg(oth + 2 * a.ld + gn);
-            // own (H,E)
-            const double Hx = g == 0 ? S0 : O0, Hy = g == 0 ? S1 : O1, Hz = g == 0 ? S2 : O2;
-            const double Ex = g == 0 ? O0 : S0, Ey = g == 0 ? O1 : S1, Ez = g == 0 ? O2 : S2;
-            // -n x E, -n x H of the own side (flux3d :946-955)
-            double s0 = -uny * Ez + unz * Ey;
-            double s1 = -unz * Ex + unx * Ez;
-            double s2 = -unx * Ey + uny * Ex;
-            double s3 = -uny * Hz + unz * Hy;
-            double s4 = -unz * Hx + unx * Hz;
-            double s5 = -unx * Hy + uny * Hx;
-            if (vp >= 0 || vp <= -3) {
-                double pHx, pHy, pHz, pEx, pEy, pEz;
-                if (vp >= 0) {
-                    pHx = ldg(a.u_in + vp);
-                    pHy = ldg(a.u_in + a.ld + vp);
-                    pHz = ldg(a.u_in + 2 * a.ld + vp);
-                    pEx = ldg(a.u_in + 3 * a.ld + vp);
-                    pEy = ldg(a.u_in + 4 * a.ld + vp);
-                    pEz = ldg(a.u_in + 5 * a.ld + vp);
-                } else {
-                    const double *hp = a.halo + 6ll * (long long)(-(vp + 3));
-                    pHx = hp[0]; pHy = hp[1]; pHz = hp[2];
-                    pEx = hp[3]; pEy = hp[4]; pEz = hp[5];
+#pragma unroll
+        for (int f = 0; f < FPT; f++) {
+            const int q = tid + f * NT;
+            if (q < 2 * N2) {
+                const int hi = q / N2, fp0 = q - hi * N2;
+                const int fa = fp0 % N, fb = fp0 / N;
+                int s, node, sn;
+                if (rd == 0) { // +-x
+                    s = hi ? 1 : 3;
+                    node = (hi ? N - 1 : 0) + N * fa + N2 * fb;
+                    sn = (hi ? N - 1 : 0) + SJ * fa + SK * fb;
+                } else if (rd == 1) { // +-y
+                    s = hi ? 2 : 0;
+                    node = fa + N * (hi ? N - 1 : 0) + N2 * fb;
+                    sn = fa + SJ * (hi ? N - 1 : 0) + SK * fb;
+                } else { // +-z
+                    s = hi ? 5 : 4;
+                    node = fa + N * fb + N2 * (hi ? N - 1 : 0);
+                    sn = fa + SJ * fb + SK * (hi ? N - 1 : 0);
                 }
-                // neighbour's (-n+ x E+) with n+ = -n-  (the gs_op_fields sum of :962)
-                s0 = s0 - (-uny * pEz + unz * pEy);
-                s1 = s1 - (-unz * pEx + unx * pEz);
-                s2 = s2 - (-unx * pEy + uny * pEx);
-                s3 = s3 - (-uny * pHz + unz * pHy);
-                s4 = s4 - (-unz * pHx + unx * pHz);
-                s5 = s5 - (-unx * pHy + uny * pHx);
-            } else if (vp == -1) { // 'PEC' / 'PML' outer face: cem_maxwell_flux_pec :1397-1405
-                s0 = 2.0 * s0; s1 = 2.0 * s1; s2 = 2.0 * s2;
-                s3 = 0.0; s4 = 0.0; s5 = 0.0;
+                const long long jf = (long long)e * NF + s * N2 + fp0;
+                const double unx = ldg(a.unx + jf), uny = ldg(a.uny + jf), unz = ldg(a.unz + jf);
+                const int vp = vpn[rd][f];
+                const double S0 = U[sn], S1 = U[SC + sn], S2 = U[2 * SC + sn];
+                const long long gn = ebase + node;
+                const double O0 = ldg(oth + gn), O1 = ldg(oth + a.ld + gn),
+                             O2 = ldg(oth + 2 * a.ld + gn);
+                // own (H,E)
+                const double Hx = g == 0 ? S0 : O0, Hy = g == 0 ? S1 : O1, Hz = g == 0 ? S2 : O2;
+                const double Ex = g == 0 ? O0 : S0, Ey = g == 0 ? O1 : S1, Ez = g == 0 ? O2 : S2;
+                // -n x E, -n x H of the own side (flux3d :946-955)
+                double s0 = -uny * Ez + unz * Ey;
+                double s1 = -unz * Ex + unx * Ez;
+                double s2 = -unx * Ey + uny * Ex;
+                double s3 = -uny * Hz + unz * Hy;
+                double s4 = -unz * Hx + unx * Hz;
+                double s5 = -unx * Hy + uny * Hx;
+                if (vp >= 0 || vp <= -3) {
+                    double pHx, pHy, pHz, pEx, pEy, pEz;
+                    if (vp >= 0) {
+                        pHx = ldg(a.u_in + vp);
+                        pHy = ldg(a.u_in + a.ld + vp);
+                        pHz = ldg(a.u_in + 2 * a.ld + vp);
+                        pEx = ldg(a.u_in + 3 * a.ld + vp);
+                        pEy = ldg(a.u_in + 4 * a.ld + vp);
+                        pEz = ldg(a.u_in + 5 * a.ld + vp);
+                    } else {
+                        const double *hp = a.halo + 6ll * (long long)(-(vp + 3));
+                        pHx = hp[0]; pHy = hp[1]; pHz = hp[2];
+                        pEx = hp[3]; pEy = hp[4]; pEz = hp[5];
+                    }
+                    // neighbour's (-n+ x E+) with n+ = -n-  (the gs_op_fields sum of :962)
+                    s0 = s0 - (-uny * pEz + unz * pEy);
+                    s1 = s1 - (-unz * pEx + unx * pEz);
+                    s2 = s2 - (-unx * pEy + uny * pEx);
+                    s3 = s3 - (-uny * pHz + unz * pHy);
+                    s4 = s4 - (-unz * pHx + unx * pHz);
+                    s5 = s5 - (-unx * pHy + uny * pHx);
+                } else if (vp == -1) { // 'PEC' / 'PML' outer face: cem_maxwell_flux_pec :1397-1405
+                    s0 = 2.0 * s0; s1 = 2.0 * s1; s2 = 2.0 * s2;
+                    s3 = 0.0; s4 = 0.0; s5 = 0.0;
+                }
+                const double ar = ldg(a.area + jf);
+                double f0, f1, f2;
+                if (g == 1) { // flux into resH (:976-986)
+                    const double hY = ldg(a.hY + jf), Y1 = ldg(a.Y1 + jf);
+                    const double Y02 = -(hY * Y1), C02Y = hY * a.C0;
+                    const double fu1 = uny * s5 - unz * s4;
+                    const double fu2 = unz * s3 - unx * s5;
+                    const double fu3 = unx * s4 - uny * s3;
+                    f0 = ar * (Y02 * s0 - C02Y * fu1);
+                    f1 = ar * (Y02 * s1 - C02Y * fu2);
+                    f2 = ar * (Y02 * s2 - C02Y * fu3);
+                } else { // flux into resE (:987-997)
+                    const double hZ = ldg(a.hZ + jf), Z1 = ldg(a.Z1 + jf);
+                    const double Z02 = hZ * Z1, C02Z = hZ * a.C0;
+                    const double fw1 = uny * s2 - unz * s1;
+                    const double fw2 = unz * s0 - unx * s2;
+                    const double fw3 = unx * s1 - uny * s0;
+                    f0 = ar * (Z02 * s3 - C02Z * fw1);
+                    f1 = ar * (Z02 * s4 - C02Z * fw2);
+                    f2 = ar * (Z02 * s5 - C02Z * fw3);
+                }
+                R[sn] += f0;
+                R[SC + sn] += f1;
+                R[2 * SC + sn] += f2;
             }
-            const double ar = ldg(a.area + jf);
-            double f0, f1, f2;
-            if (g == 1) { // flux into resH (:976-986)
-                const double hY = ldg(a.hY + jf), Y1 = ldg(a.Y1 + jf);
-                const double Y02 = -(hY * Y1), C02Y = hY * a.C0;
-                const double fu1 = uny * s5 - unz * s4;
-                const double fu2 = unz * s3 - unx * s5;
-                const double fu3 = unx * s4 - uny * s3;
-                f0 = ar * (Y02 * s0 - C02Y * fu1);
-                f1 = ar * (Y02 * s1 - C02Y * fu2);
-                f2 = ar * (Y02 * s2 - C02Y * fu3);
-            } else { // flux into resE (:987-997)
-                const double hZ = ldg(a.hZ + jf), Z1 = ldg(a.Z1 + jf);
-                const double Z02 = hZ * Z1, C02Z = hZ * a.C0;
-                const double fw1 = uny * s2 - unz * s1;
-                const double fw2 = unz * s0 - unx * s2;
-                const double fw3 = unx * s1 - uny * s0;
-                f0 = ar * (Z02 * s3 - C02Z * fw1);
-                f1 = ar * (Z02 * s4 - C02Z * fw2);
-                f2 = ar * (Z02 * s5 - C02Z * fw3);
-            }
-            R[sn] += f0;
-            R[SC + sn] += f1;
-            R[2 * SC + sn] += f2;
         }
         __syncthreads();
     }
 
-    // ---- P4: t-pencils, thread (i,j) = (pa,pb): finish the nodes ------------------------------
-    if (h < SPLIT) {
-        double u[3][N];
-        const double *Ut = U + pa + SJ * pb;
+    // ---- P4: t-pencils, thread (i,j) = (pa,pb) ------------------------------------------------
+    if (h < SPLIT)
+        pencil_split<N, 2, SPLIT, SK, N2>(prm.D, a, U, R, SC, pa + SJ * pb, pa + N * pb, ebase, sg,
+                                          h);
+    __syncthreads();
+
+    // ---- P5: streaming epilogue ------------------------------------------------------------------
+    {
+        constexpr int PER = (N3 + NT - 1) / NT;
+        constexpr int UNR = PER < EPI_UNROLL ? PER : EPI_UNROLL;
+        double *__restrict__ kfp = a.kf + cold + ebase;
+        double *__restrict__ uop = a.u_out + cold + ebase;
+        const double *__restrict__ mbp = (g == 0 ? a.ebm1 : a.hbm1) + ebase;
+#pragma unroll 1
+        for (int q0 = 0; q0 < PER; q0 += UNR) {
+            double o[UNR][3], kk[UNR][3], mb[UNR];
 #pragma unroll
-        for (int c = 0; c < 3; c++)
+            for (int x = 0; x < UNR; x++) {
+                const int node = tid + (q0 + x) * NT;
+                const int nd = node < N3 ? node : N3 - 1;
 #pragma unroll
-            for (int m = 0; m < N; m++) u[c][m] = Ut[c * SC + SK * m];
-        const int node = pa + N * pb;
-        const long long gnode = ebase + node;
-        const double *Rt = R + pa + SJ * pb;
-        if (h == 0)
-            t_outputs<N, 0, (HN < N ? HN : N), SK, PML>(prm.D, u, a, gnode, node, g, sg, Rt, SC);
-        if (SPLIT > 1 && h == 1)
-            t_outputs<N, HN, (2 * HN < N ? 2 * HN : N), SK, PML>(prm.D, u, a, gnode, node, g, sg,
-                                                               Rt, SC);
-        if (SPLIT > 2 && h == 2)
-            t_outputs<N, 2 * HN, (3 * HN < N ? 3 * HN : N), SK, PML>(prm.D, u, a, gnode, node, g,
-                                                                   sg, Rt, SC);
-        if (SPLIT > 3 && h == 3)
-            t_outputs<N, 3 * HN, N, SK, PML>(prm.D, u, a, gnode, node, g, sg, Rt, SC);
+                for (int c = 0; c < 3; c++) {
+                    o[x][c] = ldg(oth + c * a.ld + ebase + nd);
+                    kk[x][c] = kfp[c * a.ld + nd];
+                }
+                mb[x] = ldg(mbp + nd);
+            }
+#pragma unroll
+            for (int x = 0; x < UNR; x++) {
+                const int node = tid + (q0 + x) * NT;
+                if (node < N3) {
+                    const int i = node % N, j = (node / N) % N, k = node / N2;
+                    const int sn = i + SJ * j + SK * k;
+                    const long long gi = ebase + node;
+                    double r[3] = {R[sn], R[SC + sn], R[2 * SC + sn]};
+                    if (PML) { // pml_step (src/cem_maxwell_pml.F:540-585) + PML half of rk_maxwell_ab
+                        const double bm1 = ldg(a.bmn + gi);
+                        const double bm1inv = 1.0 / bm1;
+                        const double sigx = a.sig[gi], sigy = a.sig[a.npts + gi],
+                                     sigz = a.sig[2 * a.npts + gi];
+                        const double permitt = a.eps[gi];
+                        const double sxp = sigx / permitt, syp = sigy / permitt, szp = sigz / permitt;
+                        double *pF = g == 0 ? a.pD : a.pB;
+                        double *kF = g == 0 ? a.kD : a.kB;
+                        const double b0 = pF[gi], b1 = pF[a.npts + gi], b2 = pF[2 * a.npts + gi];
+                        const double rb0 = r[0] * bm1inv - syp * b0;
+                        const double rb1 = r[1] * bm1inv - szp * b1;
+                        const double rb2 = r[2] * bm1inv - sxp * b2;
+                        double p0, p1, p2;
+                        if (g == 0) {
+                            p0 = -syp * b0 + sxp * b0 - sigz * o[x][0];
+                            p1 = -szp * b1 + syp * b1 - sigx * o[x][1];
+                            p2 = -sxp * b2 + szp * b2 - sigy * o[x][2];
+                        } else {
+                            const double permeab = a.mu[gi];
+                            p0 = -syp * b0 + sxp * b0 - szp * permeab * o[x][0];
+                            p1 = -szp * b1 + syp * b1 - sxp * permeab * o[x][1];
+                            p2 = -sxp * b2 + szp * b2 - syp * permeab * o[x][2];
+                        }
+                        r[0] = r[0] + p0 * bm1; r[1] = r[1] + p1 * bm1; r[2] = r[2] + p2 * bm1;
+                        double t;
+                        t = a.ca * kF[gi] + a.dt * rb0; kF[gi] = t; pF[gi] = b0 + a.cb * t;
+                        t = a.ca * kF[a.npts + gi] + a.dt * rb1; kF[a.npts + gi] = t;
+                        pF[a.npts + gi] = b1 + a.cb * t;
+                        t = a.ca * kF[2 * a.npts + gi] + a.dt * rb2; kF[2 * a.npts + gi] = t;
+                        pF[2 * a.npts + gi] = b2 + a.cb * t;
+                    }
+                    if (a.src_prof != nullptr) { // usersrc hook: res(comp) -= profile*(tfac*bm)
+                        const int cs = a.src_comp - (g == 0 ? 3 : 0);
+                        if (cs >= 0 && cs < 3) {
+                            const double sv = ldg(a.src_prof + gi) * (a.src_tfac * ldg(a.bmn + gi));
+                            if (cs == 0) r[0] -= sv;
+                            else if (cs == 1) r[1] -= sv;
+                            else r[2] -= sv;
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const double t = a.ca * kk[x][c] + a.dt * (r[c] * mb[x]);
+                        kfp[c * a.ld + node] = t;
+                        uop[c * a.ld + node] = o[x][c] + a.cb * t;
+                    }
+                }
+            }
+        }
     }
 }
 
