@@ -8,10 +8,12 @@
 //
 //   P0  stage the 3 source components of the element (n^3 nodes each) in shared memory
 //   P1  r-pencils: thread (j,k) holds the n-point line of each source component in registers,
-//       applies D (kernel-parameter constant bank, no loads) and stores the r-part of the curl
-//       [maxwell_wght_curl, src/cem_maxwell.F:1428-1497; local_grad3, src/nek5_grad.F:2-19;
-//        mxfK left-to-right sums, src/nek5_mxm_std.F:173-190]
-//   P2  s-pencils: thread (i,k), adds the s-part, multiplies by the quadrature weight w3mn
+//       applies D (kernel parameter -> uniform registers, no memory loads) and stores the raw
+//       r-derivatives [local_grad3, src/nek5_grad.F:2-19; mxfK left-to-right sums,
+//       src/nek5_mxm_std.F:173-190]
+//   P2  s-pencils: thread (i,k): s-derivatives, then the r- and s-parts of the weighted curl with
+//       the cofactors rx..sz (coalesced along i) and the quadrature weight w3mn
+//       [maxwell_wght_curl, src/cem_maxwell.F:1428-1497]
 //   P3  surface flux in three rounds (+-x, +-y, +-z faces; no node is touched twice in a
 //       round): own trace from smem/global, neighbour trace through vmapP (the gs_op_fields
 //       pair-sum of src/cem_maxwell.F:962) or the NCCL halo, PEC mirror, upwind/central flux,
@@ -58,33 +60,56 @@ __device__ __forceinline__ void prefetch_chunk(const void *base, int bytes, int 
 }
 
 // ---- compile-time geometry of one half-task --------------------------------------------
-__host__ __device__ constexpr int pad_j(int n)
-{
-    // row padding that makes the r- and s-pencil accesses bank-conflict free (64-bit banks):
-    // found by exhaustive search (scripts/smem_banks.py)
-    return (n == 6 || n == 14) ? 3 : ((n == 8 || n == 12 || n == 16) ? 1 : 0);
-}
+__host__ __device__ constexpr int pad_j(int n) { return (n == 6 || n == 14) ? 3 : (n == 12 ? 1 : 0); }
 __host__ __device__ constexpr int pad_k(int n)
 {
     return (n == 3 || n == 4 || n == 7) ? 3 : (n == 10 ? 7 : 0);
 }
+// Shared-memory layout of one component of an element.  n = 8 and n = 16 use an XOR swizzle
+// (no padding) that makes the r-, s-, t-pencil and the linear access patterns all free of
+// 64-bit bank conflicts; other orders use the padding found by scripts/smem_banks.py.
+template <int N>
+struct Lay {
+    static constexpr bool SWZ = (N == 8 || N == 16);
+    static constexpr int SJ = SWZ ? N : N + pad_j(N);
+    static constexpr int SK = SWZ ? N * N : SJ * N + pad_k(N);
+    static constexpr int SC = SK * N;
+    __device__ __forceinline__ static int at(int i, int j, int k)
+    {
+        if constexpr (N == 8) return (i ^ ((j >> 1) + 4 * (k & 1))) + 8 * (j ^ (k & 1)) + 64 * k;
+        else if constexpr (N == 16) return (i ^ j) + 16 * j + 256 * k;
+        else return i + SJ * j + SK * k;
+    }
+};
 // threads per pencil: each computes ceil(n/split) of the pencil's n outputs
 __host__ __device__ constexpr int split_for(int n) { return n <= 5 ? 4 : (n <= 13 ? 2 : 1); }
 __host__ __device__ constexpr int threads_for(int n)
 {
     return ((n * n * split_for(n) + 31) / 32) * 32;
 }
+__host__ __device__ constexpr int outputs_for(int n) { return (n + split_for(n) - 1) / split_for(n); }
+// outputs whose cofactors are loaded together (s-phase needs 7 doubles per output, t-phase 4)
+__host__ __device__ constexpr int batch_s(int n)
+{
+    int no = outputs_for(n);
+    return no <= 2 ? no : (no + 1) / 2;
+}
+__host__ __device__ constexpr int batch_t(int n)
+{
+    int no = outputs_for(n);
+    return no <= 8 ? no : (no + 1) / 2;
+}
 __host__ __device__ constexpr int regs_for(int n)
 {
-    // pencil of 3 components (6n) + cofactors and weight of the thread's outputs + working set
-    int hn = (n + split_for(n) - 1) / split_for(n);
-    int r = 6 * n + 8 * hn + 36;
+    // pencil of 3 components (6n) + cofactor batch + working set
+    int r = 6 * n + 14 * batch_s(n) + 40;
     return r > 255 ? 255 : r;
 }
 __host__ __device__ constexpr int min_blocks_for(int n)
 {
     // occupancy target used for the register cap: limited by smem (227 KB) and 2048 threads
-    int sj = n + pad_j(n), sc = (sj * n + pad_k(n)) * n;
+    int sj = (n == 8 || n == 16) ? n : n + pad_j(n);
+    int sc = ((n == 8 || n == 16) ? n * n : sj * n + pad_k(n)) * n;
     int by_smem = (227 * 1024) / (6 * sc * 8 + 1024);
     int by_thr = 2048 / threads_for(n);
     int b = by_smem < by_thr ? by_smem : by_thr;
@@ -93,101 +118,122 @@ __host__ __device__ constexpr int min_blocks_for(int n)
     if (b > 16) b = 16;
     return b < 1 ? 1 : b;
 }
-
-constexpr int EPI_UNROLL = 4; // nodes per thread whose loads are in flight together
+__host__ __device__ constexpr int epi_unroll_for(int n) { return regs_for(n) >= 160 ? 8 : 4; }
 
 template <int N>
 struct StageParams {
     StageArgs a;
-    double D[N * N]; // dxm1, column-major: D(i,m) at i + N*m  (constant bank operand)
+    double D[N * N]; // dxm1, column-major: D(i,m) at i + N*m
 };
 
-// One pencil phase.  DIR 0/1/2 = r/s/t.  The thread owns the line of N points starting at smem
-// offset `so` (stride SST) / element node `no` (stride GST) and produces outputs O0..O1-1:
-//   d_c   = sum_m D(o,m) u_c(m)                      (mxfK order, left to right)
-//   part  = (d3*my - d2*mz, d1*mz - d3*mx, d2*mx - d1*my)   with this direction's cofactors
-//   DIR 0: R  = part          DIR 1: R = (R + part) * (sg*w3)        DIR 2: R = R + (sg*w3)*part
-template <int N, int DIR, int O0, int O1, int SST, int GST>
+// smem offset / element-node index of point m of the pencil (pa,pb) in direction DIR
+template <int N, int DIR>
+__device__ __forceinline__ int pen_at(int m, int pa, int pb)
+{
+    return DIR == 0 ? Lay<N>::at(m, pa, pb) : (DIR == 1 ? Lay<N>::at(pa, m, pb) : Lay<N>::at(pa, pb, m));
+}
+template <int N, int DIR>
+__device__ __forceinline__ int pen_node(int m, int pa, int pb)
+{
+    return DIR == 0 ? m + N * pa + N * N * pb : (DIR == 1 ? pa + N * m + N * N * pb : pa + N * pb + N * N * m);
+}
+
+__device__ __forceinline__ void curl_part(const double (&d)[3], double mx, double my, double mz,
+                                          double (&c)[3])
+{
+    c[0] = d[2] * my - d[1] * mz;
+    c[1] = d[0] * mz - d[2] * mx;
+    c[2] = d[1] * mx - d[0] * my;
+}
+
+// One pencil phase.  DIR 0/1/2 = r/s/t.  The thread owns the line of N points of pencil (pa,pb)
+// and produces outputs O0..O1-1 of it:
+//   d_c = sum_m D(o,m) u_c(m)                               (mxfK order, left to right)
+//   DIR 0: R = d                                             (raw r-derivatives)
+//   DIR 1: R = (curl_part(R; rx,ry,rz) + curl_part(d; sx,sy,sz)) * (sg*w3)
+//   DIR 2: R = R + (sg*w3) * curl_part(d; tx,ty,tz)
+// with curl_part(d; mx,my,mz) = (d3*my - d2*mz, d1*mz - d3*mx, d2*mx - d1*my).
+template <int N, int DIR, int O0, int O1, int PB>
 __device__ __forceinline__ void pencil_phase(const double (&D)[N * N], const StageArgs &a,
-                                             const double *U, double *R, int SC, int so, int no,
+                                             const double *U, double *R, int pa, int pb,
                                              long long ebase, double sg)
 {
-    constexpr int NO = O1 - O0;
+    constexpr int NO = O1 - O0, SC = Lay<N>::SC;
     if constexpr (NO > 0) {
-        // cofactors (and weight) of every output first: NO*3(+1) independent loads in flight
-        double mx[NO], my[NO], mz[NO], wv[NO];
-        const long long g0 = ebase + no + (long long)GST * O0;
-        if constexpr (DIR == 0 && N % 2 == 0 && O0 % 2 == 0 && NO % 2 == 0) {
-            // outputs are contiguous in memory: 16-byte loads
-#pragma unroll
-            for (int o = 0; o < NO; o += 2) {
-                const double2 vx = __ldg(reinterpret_cast<const double2 *>(a.met[0] + g0 + o));
-                const double2 vy = __ldg(reinterpret_cast<const double2 *>(a.met[1] + g0 + o));
-                const double2 vz = __ldg(reinterpret_cast<const double2 *>(a.met[2] + g0 + o));
-                mx[o] = vx.x; mx[o + 1] = vx.y;
-                my[o] = vy.x; my[o + 1] = vy.y;
-                mz[o] = vz.x; mz[o + 1] = vz.y;
-            }
-        } else {
-#pragma unroll
-            for (int o = 0; o < NO; o++) {
-                mx[o] = ldg(a.met[3 * DIR] + g0 + GST * o);
-                my[o] = ldg(a.met[3 * DIR + 1] + g0 + GST * o);
-                mz[o] = ldg(a.met[3 * DIR + 2] + g0 + GST * o);
-            }
-        }
-        if constexpr (DIR != 0) {
-#pragma unroll
-            for (int o = 0; o < NO; o++) wv[o] = ldg(a.w3 + no + GST * (O0 + o));
-        }
         double u[3][N];
 #pragma unroll
-        for (int c = 0; c < 3; c++)
+        for (int m = 0; m < N; m++) {
+            const int so = pen_at<N, DIR>(m, pa, pb);
 #pragma unroll
-            for (int m = 0; m < N; m++) u[c][m] = U[c * SC + so + SST * m];
+            for (int c = 0; c < 3; c++) u[c][m] = U[c * SC + so];
+        }
 #pragma unroll
-        for (int o = 0; o < NO; o++) {
-            double d[3];
+        for (int b0 = 0; b0 < NO; b0 += PB) {
+            constexpr int NCOF = DIR == 1 ? 6 : 3;
+            double cof[PB][NCOF], wv[PB];
+            if constexpr (DIR != 0) { // cofactors and weight of the whole batch first
 #pragma unroll
-            for (int c = 0; c < 3; c++) d[c] = D[O0 + o] * u[c][0];
+                for (int x = 0; x < PB; x++) {
+                    const int o = O0 + b0 + x < O1 ? O0 + b0 + x : O1 - 1;
+                    const int nd = pen_node<N, DIR>(o, pa, pb);
+                    const long long gi = ebase + nd;
+                    if constexpr (DIR == 1) {
 #pragma unroll
-            for (int m = 1; m < N; m++) {
+                        for (int q = 0; q < 6; q++) cof[x][q] = ldg(a.met[q] + gi);
+                    } else {
 #pragma unroll
-                for (int c = 0; c < 3; c++) d[c] = d[c] + D[(O0 + o) + N * m] * u[c][m];
+                        for (int q = 0; q < 3; q++) cof[x][q] = ldg(a.met[6 + q] + gi);
+                    }
+                    wv[x] = sg * ldg(a.w3 + nd);
+                }
             }
-            const double c0 = d[2] * my[o] - d[1] * mz[o];
-            const double c1 = d[0] * mz[o] - d[2] * mx[o];
-            const double c2 = d[1] * mx[o] - d[0] * my[o];
-            double *Ro = R + so + SST * (O0 + o);
-            if constexpr (DIR == 0) {
-                Ro[0] = c0; Ro[SC] = c1; Ro[2 * SC] = c2;
-            } else if constexpr (DIR == 1) {
-                const double w = sg * wv[o];
-                Ro[0] = (Ro[0] + c0) * w;
-                Ro[SC] = (Ro[SC] + c1) * w;
-                Ro[2 * SC] = (Ro[2 * SC] + c2) * w;
-            } else {
-                const double w = sg * wv[o];
-                Ro[0] = Ro[0] + w * c0;
-                Ro[SC] = Ro[SC] + w * c1;
-                Ro[2 * SC] = Ro[2 * SC] + w * c2;
+#pragma unroll
+            for (int x = 0; x < PB; x++) {
+                const int o = O0 + b0 + x; // compile-time after unrolling
+                if (o < O1) {
+                    double d[3], c[3];
+#pragma unroll
+                    for (int q = 0; q < 3; q++) d[q] = D[o] * u[q][0];
+#pragma unroll
+                    for (int m = 1; m < N; m++) {
+#pragma unroll
+                        for (int q = 0; q < 3; q++) d[q] = d[q] + D[o + N * m] * u[q][m];
+                    }
+                    double *Ro = R + pen_at<N, DIR>(o, pa, pb);
+                    if constexpr (DIR == 0) {
+                        Ro[0] = d[0]; Ro[SC] = d[1]; Ro[2 * SC] = d[2];
+                    } else if constexpr (DIR == 1) {
+                        const double dr[3] = {Ro[0], Ro[SC], Ro[2 * SC]};
+                        double cr[3];
+                        curl_part(dr, cof[x][0], cof[x][1], cof[x][2], cr);
+                        curl_part(d, cof[x][3], cof[x][4], cof[x][5], c);
+                        Ro[0] = (cr[0] + c[0]) * wv[x];
+                        Ro[SC] = (cr[1] + c[1]) * wv[x];
+                        Ro[2 * SC] = (cr[2] + c[2]) * wv[x];
+                    } else {
+                        curl_part(d, cof[x][0], cof[x][1], cof[x][2], c);
+                        Ro[0] = Ro[0] + wv[x] * c[0];
+                        Ro[SC] = Ro[SC] + wv[x] * c[1];
+                        Ro[2 * SC] = Ro[2 * SC] + wv[x] * c[2];
+                    }
+                }
             }
         }
     }
 }
 
 // dispatch on the thread's output range (h = which 1/SPLIT of the outputs)
-template <int N, int DIR, int SPLIT, int SST, int GST>
+template <int N, int DIR, int SPLIT, int PB>
 __device__ __forceinline__ void pencil_split(const double (&D)[N * N], const StageArgs &a,
-                                             const double *U, double *R, int SC, int so, int no,
+                                             const double *U, double *R, int pa, int pb,
                                              long long ebase, double sg, int h)
 {
     constexpr int HN = (N + SPLIT - 1) / SPLIT;
     constexpr int E1 = HN < N ? HN : N, E2 = 2 * HN < N ? 2 * HN : N, E3 = 3 * HN < N ? 3 * HN : N;
-    if (h == 0) pencil_phase<N, DIR, 0, E1, SST, GST>(D, a, U, R, SC, so, no, ebase, sg);
-    if (SPLIT > 1 && h == 1) pencil_phase<N, DIR, E1, E2, SST, GST>(D, a, U, R, SC, so, no, ebase, sg);
-    if (SPLIT > 2 && h == 2) pencil_phase<N, DIR, E2, E3, SST, GST>(D, a, U, R, SC, so, no, ebase, sg);
-    if (SPLIT > 3 && h == 3) pencil_phase<N, DIR, E3, N, SST, GST>(D, a, U, R, SC, so, no, ebase, sg);
+    if (h == 0) pencil_phase<N, DIR, 0, E1, PB>(D, a, U, R, pa, pb, ebase, sg);
+    if (SPLIT > 1 && h == 1) pencil_phase<N, DIR, E1, E2, PB>(D, a, U, R, pa, pb, ebase, sg);
+    if (SPLIT > 2 && h == 2) pencil_phase<N, DIR, E2, E3, PB>(D, a, U, R, pa, pb, ebase, sg);
+    if (SPLIT > 3 && h == 3) pencil_phase<N, DIR, E3, N, PB>(D, a, U, R, pa, pb, ebase, sg);
 }
 
 template <int N, bool PML>
@@ -195,8 +241,7 @@ __global__ void __launch_bounds__(threads_for(N), min_blocks_for(N))
     stage_kernel(const __grid_constant__ StageParams<N> prm)
 {
     constexpr int N2 = N * N, N3 = N2 * N, NF = 6 * N2;
-    constexpr int SPLIT = split_for(N), NT = threads_for(N);
-    constexpr int SJ = N + pad_j(N), SK = SJ * N + pad_k(N), SC = SK * N;
+    constexpr int SPLIT = split_for(N), NT = threads_for(N), SC = Lay<N>::SC;
     constexpr int FPT = (2 * N2 + NT - 1) / NT; // face points per thread and flux round
     const StageArgs &a = prm.a;
     extern __shared__ double smem[];
@@ -212,7 +257,18 @@ __global__ void __launch_bounds__(threads_for(N), min_blocks_for(N))
     const double *__restrict__ oth = a.u_in + cold;
     const double sg = g == 0 ? 1.0 : -1.0;
 
-    // ---- prologue: put every HBM request of this half-task in flight now ------------------
+    // ---- P0: stage the source components (loads issued before anything else) -----------------
+    constexpr int SPER = (3 * N3 + NT - 1) / NT;
+    constexpr int SUNR = SPER < 24 ? SPER : 24;
+    double sv[SUNR];
+#pragma unroll
+    for (int x = 0; x < SUNR; x++) {
+        const int q = tid + x * NT;
+        const int c = q / N3, r = q - c * N3;
+        sv[x] = q < 3 * N3 ? ldg(src + c * a.ld + ebase + r) : 0.0;
+    }
+
+    // ---- prologue: put every other HBM request of this half-task in flight now -------------
     // (a) L2 prefetch of the element's metric, mass, RK-register, old-field and face arrays:
     //     one warp per array, no registers or shared memory held while the data travels
     {
@@ -262,27 +318,23 @@ __global__ void __launch_bounds__(threads_for(N), min_blocks_for(N))
             vpn[2][f] = ldg(a.vmapP + fb + (hi ? 5 : 4) * N2);
         }
     }
-
-    // ---- P0: stage the source components ---------------------------------------------------
-    {
-        constexpr int PER = (3 * N3 + NT - 1) / NT;
-        constexpr int UNR = PER < 12 ? PER : 12;
+    // staged values -> smem
 #pragma unroll 1
-        for (int q0 = 0; q0 < PER; q0 += UNR) {
-            double v[UNR];
+    for (int q0 = 0; q0 < SPER; q0 += SUNR) {
+        if (q0 > 0) {
 #pragma unroll
-            for (int x = 0; x < UNR; x++) {
+            for (int x = 0; x < SUNR; x++) {
                 const int q = tid + (q0 + x) * NT;
                 const int c = q / N3, r = q - c * N3;
-                v[x] = q < 3 * N3 ? ldg(src + c * a.ld + ebase + r) : 0.0;
+                sv[x] = q < 3 * N3 ? ldg(src + c * a.ld + ebase + r) : 0.0;
             }
+        }
 #pragma unroll
-            for (int x = 0; x < UNR; x++) {
-                const int q = tid + (q0 + x) * NT;
-                const int c = q / N3, r = q - c * N3;
-                const int i = r % N, j = (r / N) % N, k = r / N2;
-                if (q < 3 * N3) U[c * SC + i + SJ * j + SK * k] = v[x];
-            }
+        for (int x = 0; x < SUNR; x++) {
+            const int q = tid + (q0 + x) * NT;
+            const int c = q / N3, r = q - c * N3;
+            const int i = r % N, j = (r / N) % N, k = r / N2;
+            if (q < 3 * N3) U[c * SC + Lay<N>::at(i, j, k)] = sv[x];
         }
     }
     // (d) neighbour traces of those face points -> L2
@@ -299,48 +351,59 @@ __global__ void __launch_bounds__(threads_for(N), min_blocks_for(N))
     const int p = tid % N2, h = tid / N2;
     const int pa = p % N, pb = p / N;
 
-    // ---- P1: r-pencils, thread (j,k) = (pa,pb) ------------------------------------------------
-    if (h < SPLIT)
-        pencil_split<N, 0, SPLIT, 1, 1>(prm.D, a, U, R, SC, SJ * pa + SK * pb, N * pa + N2 * pb,
-                                        ebase, sg, h);
+    // ---- P1: r-pencils, thread (j,k) = (pa,pb): raw derivatives --------------------------------
+    if (h < SPLIT) pencil_split<N, 0, SPLIT, outputs_for(N)>(prm.D, a, U, R, pa, pb, ebase, sg, h);
     __syncthreads();
-    // ---- P2: s-pencils, thread (i,k) = (pa,pb) ------------------------------------------------
-    if (h < SPLIT)
-        pencil_split<N, 1, SPLIT, SJ, N>(prm.D, a, U, R, SC, pa + SK * pb, pa + N2 * pb, ebase, sg,
-                                         h);
+    // ---- P2: s-pencils, thread (i,k) = (pa,pb): r- and s-parts of the weighted curl -----------
+    if (h < SPLIT) pencil_split<N, 1, SPLIT, batch_s(N)>(prm.D, a, U, R, pa, pb, ebase, sg, h);
     __syncthreads();
 
     // ---- P3: surface flux, three rounds of two opposite faces ---------------------------------
     // slot order of the reference (cemface, cem_common.F:234-260): -y,+x,+y,-x,-z,+z
-#pragma unroll
+#pragma unroll 1
     for (int rd = 0; rd < 3; rd++) {
+        double fn[FPT][3], far[FPT], fi0[FPT], fi1[FPT], fo[FPT][3], fnb[FPT][6];
+        int fsn[FPT];
+        // all loads of the round first ...
+#pragma unroll
+        for (int f = 0; f < FPT; f++) {
+            const int q = tid + f * NT;
+            const int qq = q < 2 * N2 ? q : 0;
+            const int hi = qq / N2, fp0 = qq - hi * N2;
+            const int fa = fp0 % N, fb = fp0 / N;
+            const int ex = hi ? N - 1 : 0;
+            int s, ci, cj, ck;
+            if (rd == 0) { s = hi ? 1 : 3; ci = ex; cj = fa; ck = fb; }      // +-x
+            else if (rd == 1) { s = hi ? 2 : 0; ci = fa; cj = ex; ck = fb; } // +-y
+            else { s = hi ? 5 : 4; ci = fa; cj = fb; ck = ex; }              // +-z
+            fsn[f] = Lay<N>::at(ci, cj, ck);
+            const long long gn = ebase + ci + N * cj + N2 * ck;
+            const long long jf = (long long)e * NF + s * N2 + fp0;
+            fn[f][0] = ldg(a.unx + jf); fn[f][1] = ldg(a.uny + jf); fn[f][2] = ldg(a.unz + jf);
+            far[f] = ldg(a.area + jf);
+            fi0[f] = ldg((g == 0 ? a.hZ : a.hY) + jf);
+            fi1[f] = ldg((g == 0 ? a.Z1 : a.Y1) + jf);
+#pragma unroll
+            for (int c = 0; c < 3; c++) fo[f][c] = ldg(oth + c * a.ld + gn);
+            const int vp = rd == 0 ? vpn[0][f] : (rd == 1 ? vpn[1][f] : vpn[2][f]);
+            // neighbour trace: volume node, halo slot, or (unused) the own node
+            const double *nb = vp >= 0 ? a.u_in + vp
+                                       : (vp <= -3 ? a.halo + 6ll * (long long)(-(vp + 3))
+                                                   : a.u_in + gn);
+            const long long st = vp <= -3 ? 1 : a.ld;
+#pragma unroll
+            for (int c = 0; c < 6; c++) fnb[f][c] = ldg(nb + c * st);
+        }
+        // ... then the flux arithmetic and the lift into the smem residual
 #pragma unroll
         for (int f = 0; f < FPT; f++) {
             const int q = tid + f * NT;
             if (q < 2 * N2) {
-                const int hi = q / N2, fp0 = q - hi * N2;
-                const int fa = fp0 % N, fb = fp0 / N;
-                int s, node, sn;
-                if (rd == 0) { // +-x
-                    s = hi ? 1 : 3;
-                    node = (hi ? N - 1 : 0) + N * fa + N2 * fb;
-                    sn = (hi ? N - 1 : 0) + SJ * fa + SK * fb;
-                } else if (rd == 1) { // +-y
-                    s = hi ? 2 : 0;
-                    node = fa + N * (hi ? N - 1 : 0) + N2 * fb;
-                    sn = fa + SJ * (hi ? N - 1 : 0) + SK * fb;
-                } else { // +-z
-                    s = hi ? 5 : 4;
-                    node = fa + N * fb + N2 * (hi ? N - 1 : 0);
-                    sn = fa + SJ * fb + SK * (hi ? N - 1 : 0);
-                }
-                const long long jf = (long long)e * NF + s * N2 + fp0;
-                const double unx = ldg(a.unx + jf), uny = ldg(a.uny + jf), unz = ldg(a.unz + jf);
-                const int vp = vpn[rd][f];
+                const int sn = fsn[f];
+                const int vp = rd == 0 ? vpn[0][f] : (rd == 1 ? vpn[1][f] : vpn[2][f]);
+                const double unx = fn[f][0], uny = fn[f][1], unz = fn[f][2];
                 const double S0 = U[sn], S1 = U[SC + sn], S2 = U[2 * SC + sn];
-                const long long gn = ebase + node;
-                const double O0 = ldg(oth + gn), O1 = ldg(oth + a.ld + gn),
-                             O2 = ldg(oth + 2 * a.ld + gn);
+                const double O0 = fo[f][0], O1 = fo[f][1], O2 = fo[f][2];
                 // own (H,E)
                 const double Hx = g == 0 ? S0 : O0, Hy = g == 0 ? S1 : O1, Hz = g == 0 ? S2 : O2;
                 const double Ex = g == 0 ? O0 : S0, Ey = g == 0 ? O1 : S1, Ez = g == 0 ? O2 : S2;
@@ -352,19 +415,8 @@ __global__ void __launch_bounds__(threads_for(N), min_blocks_for(N))
                 double s4 = -unz * Hx + unx * Hz;
                 double s5 = -unx * Hy + uny * Hx;
                 if (vp >= 0 || vp <= -3) {
-                    double pHx, pHy, pHz, pEx, pEy, pEz;
-                    if (vp >= 0) {
-                        pHx = ldg(a.u_in + vp);
-                        pHy = ldg(a.u_in + a.ld + vp);
-                        pHz = ldg(a.u_in + 2 * a.ld + vp);
-                        pEx = ldg(a.u_in + 3 * a.ld + vp);
-                        pEy = ldg(a.u_in + 4 * a.ld + vp);
-                        pEz = ldg(a.u_in + 5 * a.ld + vp);
-                    } else {
-                        const double *hp = a.halo + 6ll * (long long)(-(vp + 3));
-                        pHx = hp[0]; pHy = hp[1]; pHz = hp[2];
-                        pEx = hp[3]; pEy = hp[4]; pEz = hp[5];
-                    }
+                    const double pHx = fnb[f][0], pHy = fnb[f][1], pHz = fnb[f][2];
+                    const double pEx = fnb[f][3], pEy = fnb[f][4], pEz = fnb[f][5];
                     // neighbour's (-n+ x E+) with n+ = -n-  (the gs_op_fields sum of :962)
                     s0 = s0 - (-uny * pEz + unz * pEy);
                     s1 = s1 - (-unz * pEx + unx * pEz);
@@ -376,20 +428,18 @@ __global__ void __launch_bounds__(threads_for(N), min_blocks_for(N))
                     s0 = 2.0 * s0; s1 = 2.0 * s1; s2 = 2.0 * s2;
                     s3 = 0.0; s4 = 0.0; s5 = 0.0;
                 }
-                const double ar = ldg(a.area + jf);
+                const double ar = far[f];
                 double f0, f1, f2;
-                if (g == 1) { // flux into resH (:976-986)
-                    const double hY = ldg(a.hY + jf), Y1 = ldg(a.Y1 + jf);
-                    const double Y02 = -(hY * Y1), C02Y = hY * a.C0;
+                if (g == 1) { // flux into resH (:976-986): fi0 = 0.5/Y_0, fi1 = Y_1
+                    const double Y02 = -(fi0[f] * fi1[f]), C02Y = fi0[f] * a.C0;
                     const double fu1 = uny * s5 - unz * s4;
                     const double fu2 = unz * s3 - unx * s5;
                     const double fu3 = unx * s4 - uny * s3;
                     f0 = ar * (Y02 * s0 - C02Y * fu1);
                     f1 = ar * (Y02 * s1 - C02Y * fu2);
                     f2 = ar * (Y02 * s2 - C02Y * fu3);
-                } else { // flux into resE (:987-997)
-                    const double hZ = ldg(a.hZ + jf), Z1 = ldg(a.Z1 + jf);
-                    const double Z02 = hZ * Z1, C02Z = hZ * a.C0;
+                } else { // flux into resE (:987-997): fi0 = 0.5/Z_0, fi1 = Z_1
+                    const double Z02 = fi0[f] * fi1[f], C02Z = fi0[f] * a.C0;
                     const double fw1 = uny * s2 - unz * s1;
                     const double fw2 = unz * s0 - unx * s2;
                     const double fw3 = unx * s1 - uny * s0;
@@ -406,15 +456,13 @@ __global__ void __launch_bounds__(threads_for(N), min_blocks_for(N))
     }
 
     // ---- P4: t-pencils, thread (i,j) = (pa,pb) ------------------------------------------------
-    if (h < SPLIT)
-        pencil_split<N, 2, SPLIT, SK, N2>(prm.D, a, U, R, SC, pa + SJ * pb, pa + N * pb, ebase, sg,
-                                          h);
+    if (h < SPLIT) pencil_split<N, 2, SPLIT, batch_t(N)>(prm.D, a, U, R, pa, pb, ebase, sg, h);
     __syncthreads();
 
     // ---- P5: streaming epilogue ------------------------------------------------------------------
     {
         constexpr int PER = (N3 + NT - 1) / NT;
-        constexpr int UNR = PER < EPI_UNROLL ? PER : EPI_UNROLL;
+        constexpr int UNR = PER < epi_unroll_for(N) ? PER : epi_unroll_for(N);
         double *__restrict__ kfp = a.kf + cold + ebase;
         double *__restrict__ uop = a.u_out + cold + ebase;
         const double *__restrict__ mbp = (g == 0 ? a.ebm1 : a.hbm1) + ebase;
@@ -437,7 +485,7 @@ __global__ void __launch_bounds__(threads_for(N), min_blocks_for(N))
                 const int node = tid + (q0 + x) * NT;
                 if (node < N3) {
                     const int i = node % N, j = (node / N) % N, k = node / N2;
-                    const int sn = i + SJ * j + SK * k;
+                    const int sn = Lay<N>::at(i, j, k);
                     const long long gi = ebase + node;
                     double r[3] = {R[sn], R[SC + sn], R[2 * SC + sn]};
                     if (PML) { // pml_step (src/cem_maxwell_pml.F:540-585) + PML half of rk_maxwell_ab
@@ -475,10 +523,10 @@ __global__ void __launch_bounds__(threads_for(N), min_blocks_for(N))
                     if (a.src_prof != nullptr) { // usersrc hook: res(comp) -= profile*(tfac*bm)
                         const int cs = a.src_comp - (g == 0 ? 3 : 0);
                         if (cs >= 0 && cs < 3) {
-                            const double sv = ldg(a.src_prof + gi) * (a.src_tfac * ldg(a.bmn + gi));
-                            if (cs == 0) r[0] -= sv;
-                            else if (cs == 1) r[1] -= sv;
-                            else r[2] -= sv;
+                            const double sv2 = ldg(a.src_prof + gi) * (a.src_tfac * ldg(a.bmn + gi));
+                            if (cs == 0) r[0] -= sv2;
+                            else if (cs == 1) r[1] -= sv2;
+                            else r[2] -= sv2;
                         }
                     }
 #pragma unroll
@@ -496,8 +544,7 @@ __global__ void __launch_bounds__(threads_for(N), min_blocks_for(N))
 template <int N>
 static int launch_n(const StageArgs &a, const double *Dhost, bool pml, cudaStream_t st)
 {
-    constexpr int SJ = N + pad_j(N), SK = SJ * N + pad_k(N), SC = SK * N;
-    constexpr size_t smem = sizeof(double) * 6 * SC;
+    constexpr size_t smem = sizeof(double) * 6 * Lay<N>::SC;
     static bool configured = false;
     if (!configured) {
         cudaError_t e1 = cudaFuncSetAttribute(stage_kernel<N, false>,
