@@ -1,0 +1,180 @@
+!> ISO_C_BINDING interface to libnekcem_b200.so (include/nekcem_b200.h).
+!!
+!! This is the thin C-ABI layer BASELINE.json's north_star asks for: NekCEM's host code
+!! stays Fortran and calls the hand-written sm_100a kernels through these bindings.  One
+!! `bind(C)` interface per entry point of the header; the array ids mirror
+!! `enum nekcem_b200_array`.  fortran/cem_maxwell_b200.F shows the three call sites that
+!! change in the reference (src/cem_drive.F:161-165, 628; src/cem_maxwell.F:327-345).
+!!
+!! Build: compile with the reference's own flags (-fdefault-real-8 -fdefault-double-8 or -r8,
+!! bin/configurenek:117-123) and link -lnekcem_b200 -lcudart -lnccl (INTEGRATION.md).
+!! This image has no Fortran compiler, so this file is shipped unverified by a compiler; the
+!! same symbols are exercised through ctypes by tests/test_abi.py.
+module nekcem_b200
+  use, intrinsic :: iso_c_binding
+  implicit none
+  private :: c_int, c_double, c_char, c_int64_t, c_int32_t, c_float
+
+  integer(c_int), parameter :: NEKCEM_B200_ABI_VERSION = 1
+
+  ! enum nekcem_b200_array
+  integer(c_int), parameter :: NKB_DXM1 = 0, NKB_W3MN = 1,                       &
+       NKB_RXMN = 2, NKB_RYMN = 3, NKB_RZMN = 4, NKB_SXMN = 5, NKB_SYMN = 6,      &
+       NKB_SZMN = 7, NKB_TXMN = 8, NKB_TYMN = 9, NKB_TZMN = 10, NKB_BMN = 11,     &
+       NKB_HBM1 = 12, NKB_EBM1 = 13, NKB_UNXM = 14, NKB_UNYM = 15, NKB_UNZM = 16, &
+       NKB_AREAM = 17, NKB_Y_0 = 18, NKB_Y_1 = 19, NKB_Z_0 = 20, NKB_Z_1 = 21,    &
+       NKB_HN = 22, NKB_EN = 23, NKB_KHN = 24, NKB_KEN = 25,                      &
+       NKB_PERMITTIVITY = 26, NKB_PERMEABILITY = 27, NKB_PMLSIGMA = 28,           &
+       NKB_PMLBN = 29, NKB_PMLDN = 30, NKB_KPMLBN = 31, NKB_KPMLDN = 32
+
+  type, bind(C) :: nekcem_b200_desc
+     integer(c_int32_t) :: abi_version, ldim, nx1, nelt, imode, ifupwind, ifpec, ifpml
+     integer(c_int32_t) :: device, strict, rank, nranks
+  end type nekcem_b200_desc
+
+  interface
+     integer(c_int) function nekcem_b200_create(desc, handle) bind(C, name='nekcem_b200_create')
+       import :: c_int, nekcem_b200_desc
+       type(nekcem_b200_desc), intent(in) :: desc
+       integer(c_int), intent(out) :: handle
+     end function
+     integer(c_int) function nekcem_b200_destroy(handle) bind(C, name='nekcem_b200_destroy')
+       import :: c_int
+       integer(c_int), value :: handle
+     end function
+     integer(c_int) function nekcem_b200_set_array(handle, which, host, count) &
+          bind(C, name='nekcem_b200_set_array')
+       import :: c_int, c_double, c_int64_t
+       integer(c_int), value :: handle, which
+       real(c_double), intent(in) :: host(*)
+       integer(c_int64_t), value :: count
+     end function
+     integer(c_int) function nekcem_b200_get_array(handle, which, host, count) &
+          bind(C, name='nekcem_b200_get_array')
+       import :: c_int, c_double, c_int64_t
+       integer(c_int), value :: handle, which
+       real(c_double), intent(out) :: host(*)
+       integer(c_int64_t), value :: count
+     end function
+     integer(c_int) function nekcem_b200_set_faces(handle, glo_num, nxzfl, cempec, ncempec) &
+          bind(C, name='nekcem_b200_set_faces')
+       import :: c_int, c_int64_t, c_int32_t
+       integer(c_int), value :: handle
+       integer(c_int64_t), intent(in) :: glo_num(*)
+       integer(c_int64_t), value :: nxzfl
+       integer(c_int32_t), intent(in) :: cempec(*)
+       integer(c_int32_t), value :: ncempec
+     end function
+     integer(c_int) function nekcem_b200_set_pml(handle, pmlptr, maxpml) &
+          bind(C, name='nekcem_b200_set_pml')
+       import :: c_int, c_int32_t
+       integer(c_int), value :: handle
+       integer(c_int32_t), intent(in) :: pmlptr(*)
+       integer(c_int32_t), value :: maxpml
+     end function
+     integer(c_int) function nekcem_b200_comm_unique_id(id) bind(C, name='nekcem_b200_comm_unique_id')
+       import :: c_int, c_char
+       character(kind=c_char) :: id(128)
+     end function
+     integer(c_int) function nekcem_b200_comm_init(handle, id) bind(C, name='nekcem_b200_comm_init')
+       import :: c_int, c_char
+       integer(c_int), value :: handle
+       character(kind=c_char), intent(in) :: id(128)
+     end function
+     integer(c_int) function nekcem_b200_setup(handle) bind(C, name='nekcem_b200_setup')
+       import :: c_int
+       integer(c_int), value :: handle
+     end function
+     integer(c_int) function nekcem_b200_set_incident(handle, nface, facepts, fh, fe) &
+          bind(C, name='nekcem_b200_set_incident')
+       import :: c_int, c_int32_t, c_double
+       integer(c_int), value :: handle
+       integer(c_int32_t), value :: nface
+       integer(c_int32_t), intent(in) :: facepts(*)
+       real(c_double), intent(in) :: fh(*), fe(*)
+     end function
+     integer(c_int) function nekcem_b200_set_volume_source(handle, comp, profile, amp, omega, phase) &
+          bind(C, name='nekcem_b200_set_volume_source')
+       import :: c_int, c_double
+       integer(c_int), value :: handle, comp
+       real(c_double), intent(in) :: profile(*)
+       real(c_double), value :: amp, omega, phase
+     end function
+     integer(c_int) function nekcem_b200_set_option(handle, name, value) &
+          bind(C, name='nekcem_b200_set_option')
+       import :: c_int, c_char
+       integer(c_int), value :: handle, value
+       character(kind=c_char), intent(in) :: name(*)
+     end function
+     integer(c_int) function nekcem_b200_set_time(handle, time, dt) bind(C, name='nekcem_b200_set_time')
+       import :: c_int, c_double
+       integer(c_int), value :: handle
+       real(c_double), value :: time, dt
+     end function
+     integer(c_int) function nekcem_b200_get_time(handle, time) bind(C, name='nekcem_b200_get_time')
+       import :: c_int, c_double
+       integer(c_int), value :: handle
+       real(c_double), intent(out) :: time
+     end function
+     integer(c_int) function nekcem_b200_step(handle, nsteps) bind(C, name='nekcem_b200_step')
+       import :: c_int
+       integer(c_int), value :: handle, nsteps
+     end function
+     integer(c_int) function nekcem_b200_stage(handle, rkstep) bind(C, name='nekcem_b200_stage')
+       import :: c_int
+       integer(c_int), value :: handle, rkstep
+     end function
+     integer(c_int) function nekcem_b200_synchronize(handle) bind(C, name='nekcem_b200_synchronize')
+       import :: c_int
+       integer(c_int), value :: handle
+     end function
+     integer(c_int) function nekcem_b200_error_sums(handle, exact_hn, exact_en, sumsq, linf) &
+          bind(C, name='nekcem_b200_error_sums')
+       import :: c_int, c_double
+       integer(c_int), value :: handle
+       real(c_double), intent(in) :: exact_hn(*), exact_en(*)
+       real(c_double), intent(out) :: sumsq(6), linf(6)
+     end function
+     integer(c_int) function nekcem_b200_last_step_ms(handle, ms, launches) &
+          bind(C, name='nekcem_b200_last_step_ms')
+       import :: c_int, c_float, c_int64_t
+       integer(c_int), value :: handle
+       real(c_float), intent(out) :: ms
+       integer(c_int64_t), intent(out) :: launches
+     end function
+     integer(c_int) function nekcem_b200_algorithmic_bytes(handle, bytes_per_stage) &
+          bind(C, name='nekcem_b200_algorithmic_bytes')
+       import :: c_int, c_double
+       integer(c_int), value :: handle
+       real(c_double), intent(out) :: bytes_per_stage
+     end function
+  end interface
+
+contains
+
+  !> reference error behaviour: print and exitt (src/nek5_comm_mpi.F:650-692)
+  subroutine nkb_check(rc, what)
+    integer(c_int), intent(in) :: rc
+    character(len=*), intent(in) :: what
+    interface
+       function nekcem_b200_last_error() bind(C, name='nekcem_b200_last_error') result(p)
+         import :: c_ptr
+         type(c_ptr) :: p
+       end function
+       function c_strlen(p) bind(C, name='strlen') result(n)
+         import :: c_ptr, c_size_t
+         type(c_ptr), value :: p
+         integer(c_size_t) :: n
+       end function
+    end interface
+    character(kind=c_char), pointer :: msg(:)
+    type(c_ptr) :: p
+    if (rc /= 0) then
+       p = nekcem_b200_last_error()
+       call c_f_pointer(p, msg, [c_strlen(p)])
+       write (6, *) 'nekcem_b200: ', what, ' failed: ', msg
+       call exitt(1)
+    end if
+  end subroutine nkb_check
+
+end module nekcem_b200

@@ -123,6 +123,16 @@ int nekcem_b200_plan_elements(int handle, int32_t *n_interior, int32_t *n_bounda
  * cem_maxwell_init that depends on connectivity (src/cem_maxwell.F:165-186). */
 int nekcem_b200_setup(int handle);
 
+/* Incident-field hook (8f rank 1; covers `userinc` of tests/3ddielectric/3ddielectric.usr:6-50,
+ * called at src/cem_maxwell.F:498 after restrict_to_face): on the ninc face points
+ * facepts[] (1-based indices into the (nxzf,nfaces,nelt) face arrays, the reference's
+ * `incindex`) the own trace gets, in every stage,
+ *     f(comp)(j) += amp[comp*ninc + q] * cos(phase[q] - omega*rktime),   comp 0..2 = H, 3..5 = E
+ * before the flux is formed; the neighbour sees the modified trace exactly as through the
+ * reference's gs_op_fields sum.  Call before nekcem_b200_setup; ninc = 0 removes it. */
+int nekcem_b200_set_incident(int handle, int32_t ninc, const int32_t *facepts, const double *amp,
+                             const double *phase, double omega);
+
 /* Volume source hook (8f rank 1; covers tests/3dboxpml/3dboxpml.usr:30-88):
  * res(comp) -= profile(i) * (amp*sin(omega*rktime+phase) * bmn(i)) inside every stage,
  * at the reference's `usersrc` position (src/cem_maxwell.F:503).  comp: 0..2 = H, 3..5 = E. */

@@ -79,6 +79,7 @@ def lib():
         L.nekcem_b200_plan_vmap.argtypes = [C.c_int, c_i32p, C.c_int64]
         L.nekcem_b200_plan_elements.argtypes = [C.c_int, c_i32p, c_i32p]
         L.nekcem_b200_setup.argtypes = [C.c_int]
+        L.nekcem_b200_set_incident.argtypes = [C.c_int, C.c_int32, c_i32p, c_dp, c_dp, C.c_double]
         L.nekcem_b200_set_volume_source.argtypes = [C.c_int, C.c_int, c_dp, C.c_double,
                                                     C.c_double, C.c_double]
         L.nekcem_b200_set_option.argtypes = [C.c_int, C.c_char_p, C.c_int]
@@ -251,6 +252,17 @@ class MaxwellB200:
 
     def setup(self):
         _chk(self.L.nekcem_b200_setup(self.h))
+
+    def set_incident(self, facepts0, amp, phase, omega):
+        """userinc hook: on the 0-based face points ``facepts0`` the own trace gets
+        ``amp[comp, q] * cos(phase[q] - omega*rktime)`` added in every stage (comp 0..2 = H,
+        3..5 = E), as tests/3ddielectric/3ddielectric.usr:6-50 does.  Call before setup()."""
+        fp = np.ascontiguousarray(np.asarray(facepts0, dtype=np.int64) + 1, dtype=np.int32)
+        a = np.ascontiguousarray(amp, dtype=np.float64).reshape(-1)
+        ph = np.ascontiguousarray(phase, dtype=np.float64).reshape(-1)
+        assert a.size == 6 * fp.size and ph.size == fp.size
+        _chk(self.L.nekcem_b200_set_incident(self.h, fp.size, fp.ctypes.data_as(c_i32p), _dp(a),
+                                             _dp(ph), float(omega)))
 
     def set_volume_source(self, comp, profile, amp, omega, phase):
         p = None if profile is None else _dp(np.ascontiguousarray(profile, dtype=np.float64))

@@ -95,6 +95,19 @@ NKB_EXPORT void nekcem_b200_set_volume_source_(const int *h, const int *comp,
           "nekcem_b200_set_volume_source");
 }
 
+NKB_EXPORT void nekcem_b200_set_incident_(const int *h, const int *ninc, const int *facepts,
+                                          const double *amp, const double *phase,
+                                          const double *omega)
+{
+    check(nekcem_b200_set_incident(*h, *ninc, facepts, amp, phase, *omega),
+          "nekcem_b200_set_incident");
+}
+
+NKB_EXPORT void nekcem_b200_set_option_(const int *h, const char *name, const int *value)
+{
+    check(nekcem_b200_set_option(*h, name, *value), "nekcem_b200_set_option");
+}
+
 NKB_EXPORT void nekcem_b200_error_sums_(const int *h, const double *exact_hn,
                                         const double *exact_en, double *sumsq, double *linf)
 {

@@ -100,6 +100,13 @@ struct Ctx {
     // time stepping
     double time = 0.0, dt = 0.0;
     double rk4a[5], rk4b[5], rk4c[6];
+    // incident field (userinc hook)
+    std::vector<int32_t> inc_fp;   // 0-based face points
+    std::vector<int64_t> pairfp;   // local face point paired with each face point (-1: none)
+    int *inc_own_d = nullptr, *inc_nbr_d = nullptr, *inc_send_d = nullptr;
+    double *inc_amp_d = nullptr, *inc_phase_d = nullptr;
+    std::vector<double> inc_amp, inc_phase;
+    double inc_omega = 0.0;
     // volume source
     double *src_prof = nullptr;
     int src_comp = 0;
@@ -187,14 +194,22 @@ __global__ void half_inverse_kernel(const double *x, double *y, long long n)
 }
 
 // pack the traces of the send face points: sendbuf[q][c] = u[c][send_node[q]]
+// (+ the incident field of tagged send face points, so that the peer sees the same trace the
+// reference's gs_op_fields sum would give it)
 __global__ void pack_kernel(const double *u, long long ld, const int *send_node, double *sendbuf,
-                            long long nsend)
+                            long long nsend, const int *inc_send, const double *inc_amp,
+                            const double *inc_phase, int inc_n, double inc_wt)
 {
     long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (t >= nsend * 6) return;
     long long q = t / 6;
     int c = (int)(t - q * 6);
-    sendbuf[t] = u[c * ld + send_node[q]];
+    double v = u[c * ld + send_node[q]];
+    if (inc_send != nullptr) {
+        const int qi = inc_send[q];
+        if (qi >= 0) v += inc_amp[c * inc_n + qi] * cos(inc_phase[qi] - inc_wt);
+    }
+    sendbuf[t] = v;
 }
 
 // cem_error partial sums (src/cem_common.F:1335-1355): per block, per component
@@ -237,6 +252,7 @@ int match_local(Ctx *c)
     const int64_t nf = c->nxzfl;
     const int n = c->n, nfp = c->nxzf * c->nfaces;
     c->vmapP.assign(nf, -2);
+    c->pairfp.assign(nf, -1);
     std::vector<std::pair<int64_t, int64_t>> v;
     v.reserve(nf);
     for (int64_t j = 0; j < nf; j++)
@@ -254,6 +270,8 @@ int match_local(Ctx *c)
             const int64_t n1 = e1 * c->nxyz + face_node(n, f1 / c->nxzf, f1 % c->nxzf);
             c->vmapP[j0] = (int32_t)n1;
             c->vmapP[j1] = (int32_t)n0;
+            c->pairfp[j0] = j1;
+            c->pairfp[j1] = j0;
         } else if (b - a == 1) {
             c->singles.emplace_back(v[a].first, v[a].second);
         } else {
@@ -420,6 +438,10 @@ int run_stage(Ctx *c, int rkstep /*1..5*/)
     // rk_c (src/cem_common.F:12): rktime = time + dt*rk4c(i)
     const double rktime = c->time + c->dt * c->rk4c[rkstep - 1];
     a.src_tfac = c->src_prof ? c->src_amp * sin(c->src_omega * rktime + c->src_phase) : 0.0;
+    a.inc_own = c->inc_own_d; a.inc_nbr = c->inc_nbr_d;
+    a.inc_amp = c->inc_amp_d; a.inc_phase = c->inc_phase_d;
+    a.inc_n = (int)c->inc_fp.size();
+    a.inc_wt = c->inc_omega * rktime;
 
     auto launch_list = [&](int q) -> int {
         if (c->list_n[q] == 0) return 0;
@@ -441,7 +463,8 @@ int run_stage(Ctx *c, int rkstep /*1..5*/)
         CUDA_OK(cudaStreamWaitEvent(c->s_comm, c->ev_stage, 0));
         const long long tot = c->nhalo * 6;
         pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c->s_comm>>>(
-            a.u_in, c->ld, c->send_node, c->sendbuf, c->nhalo);
+            a.u_in, c->ld, c->send_node, c->sendbuf, c->nhalo, c->inc_send_d, c->inc_amp_d,
+            c->inc_phase_d, (int)c->inc_fp.size(), a.inc_wt);
         c->last_launches++;
         NCCL_OK(ncclGroupStart());
         for (auto &p : c->peers) {
@@ -544,6 +567,8 @@ int nekcem_b200_destroy(int handle)
         cudaFree(c->hY); cudaFree(c->hZ); cudaFree(c->vmapP_d); cudaFree(c->elist_d);
         cudaFree(c->sendbuf); cudaFree(c->halo); cudaFree(c->send_node);
         cudaFree(c->src_prof); cudaFree(c->red_d);
+        cudaFree(c->inc_own_d); cudaFree(c->inc_nbr_d); cudaFree(c->inc_send_d);
+        cudaFree(c->inc_amp_d); cudaFree(c->inc_phase_d);
         cudaEventDestroy(c->ev_stage); cudaEventDestroy(c->ev_halo);
         cudaEventDestroy(c->ev_t0); cudaEventDestroy(c->ev_t1);
         cudaStreamDestroy(c->s_compute); cudaStreamDestroy(c->s_comm);
@@ -771,12 +796,57 @@ int nekcem_b200_setup(int handle)
         CUDA_OK(cudaMalloc(&c->halo, sizeof(double) * 6 * c->nhalo));
         CUDA_OK(cudaMemset(c->halo, 0, sizeof(double) * 6 * c->nhalo));
     }
+    cudaFree(c->inc_own_d); cudaFree(c->inc_nbr_d); cudaFree(c->inc_send_d);
+    cudaFree(c->inc_amp_d); cudaFree(c->inc_phase_d);
+    c->inc_own_d = c->inc_nbr_d = c->inc_send_d = nullptr;
+    c->inc_amp_d = c->inc_phase_d = nullptr;
+    if (!c->inc_fp.empty()) {
+        const size_t ni = c->inc_fp.size();
+        std::vector<int32_t> own(c->nxzfl, -1), nbr(c->nxzfl, -1);
+        for (size_t q = 0; q < ni; q++) own[c->inc_fp[q]] = (int32_t)q;
+        for (int64_t j = 0; j < c->nxzfl; j++)
+            if (c->pairfp[j] >= 0) nbr[j] = own[c->pairfp[j]];
+        CUDA_OK(cudaMalloc(&c->inc_own_d, sizeof(int) * c->nxzfl));
+        CUDA_OK(cudaMalloc(&c->inc_nbr_d, sizeof(int) * c->nxzfl));
+        CUDA_OK(cudaMemcpy(c->inc_own_d, own.data(), sizeof(int) * c->nxzfl, cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMemcpy(c->inc_nbr_d, nbr.data(), sizeof(int) * c->nxzfl, cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMalloc(&c->inc_amp_d, sizeof(double) * 6 * ni));
+        CUDA_OK(cudaMalloc(&c->inc_phase_d, sizeof(double) * ni));
+        CUDA_OK(cudaMemcpy(c->inc_amp_d, c->inc_amp.data(), sizeof(double) * 6 * ni, cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMemcpy(c->inc_phase_d, c->inc_phase.data(), sizeof(double) * ni, cudaMemcpyHostToDevice));
+        if (c->nhalo > 0) {
+            std::vector<int32_t> snd(c->nhalo, -1);
+            for (auto &p : c->peers)
+                for (size_t q = 0; q < p.send_fp.size(); q++) snd[p.off + q] = own[p.send_fp[q]];
+            CUDA_OK(cudaMalloc(&c->inc_send_d, sizeof(int) * c->nhalo));
+            CUDA_OK(cudaMemcpy(c->inc_send_d, snd.data(), sizeof(int) * c->nhalo, cudaMemcpyHostToDevice));
+        }
+    }
     if (!c->red_d) {
         c->red_blocks = 1024;
         CUDA_OK(cudaMalloc(&c->red_d, sizeof(double) * 12 * c->red_blocks));
     }
     CUDA_OK(cudaDeviceSynchronize());
     c->setup_done = true;
+    return 0;
+}
+
+int nekcem_b200_set_incident(int handle, int32_t ninc, const int32_t *facepts, const double *amp,
+                             const double *phase, double omega)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (ninc < 0 || (ninc > 0 && (!facepts || !amp || !phase))) return fail("bad incident arguments");
+    c->inc_fp.clear();
+    for (int q = 0; q < ninc; q++) {
+        if (facepts[q] < 1 || facepts[q] > c->nxzfl)
+            return fail("incident face point %d out of range 1..%lld", facepts[q], (long long)c->nxzfl);
+        c->inc_fp.push_back(facepts[q] - 1);
+    }
+    c->inc_amp.assign(amp, amp + 6 * (size_t)ninc);
+    c->inc_phase.assign(phase, phase + ninc);
+    c->inc_omega = omega;
+    c->setup_done = false;
     return 0;
 }
 

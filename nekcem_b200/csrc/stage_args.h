@@ -29,6 +29,12 @@ struct StageArgs {
     const double *sig, *eps, *mu;
     double *pB, *pD, *kB, *kD;
     long long npts;
+    // incident field (userinc hook): slot of the own / the neighbour's face point in the
+    // incident list (-1: none), amplitudes [6][inc_n], phases [inc_n], inc_wt = omega*rktime
+    const int *inc_own, *inc_nbr;
+    const double *inc_amp, *inc_phase;
+    int inc_n;
+    double inc_wt;
     // separable volume source (usersrc hook)
     const double *src_prof;
     int src_comp;

@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(threads_for(N), min_blocks_for(N))
 #pragma unroll 1
     for (int rd = 0; rd < 3; rd++) {
         double fn[FPT][3], far[FPT], fi0[FPT], fi1[FPT], fo[FPT][3], fnb[FPT][6];
-        int fsn[FPT];
+        int fsn[FPT], fjs[FPT];
         // all loads of the round first ...
 #pragma unroll
         for (int f = 0; f < FPT; f++) {
@@ -379,6 +379,7 @@ __global__ void __launch_bounds__(threads_for(N), min_blocks_for(N))
             fsn[f] = Lay<N>::at(ci, cj, ck);
             const long long gn = ebase + ci + N * cj + N2 * ck;
             const long long jf = (long long)e * NF + s * N2 + fp0;
+            fjs[f] = s * N2 + fp0;
             fn[f][0] = ldg(a.unx + jf); fn[f][1] = ldg(a.uny + jf); fn[f][2] = ldg(a.unz + jf);
             far[f] = ldg(a.area + jf);
             fi0[f] = ldg((g == 0 ? a.hZ : a.hY) + jf);
@@ -405,8 +406,30 @@ __global__ void __launch_bounds__(threads_for(N), min_blocks_for(N))
                 const double S0 = U[sn], S1 = U[SC + sn], S2 = U[2 * SC + sn];
                 const double O0 = fo[f][0], O1 = fo[f][1], O2 = fo[f][2];
                 // own (H,E)
-                const double Hx = g == 0 ? S0 : O0, Hy = g == 0 ? S1 : O1, Hz = g == 0 ? S2 : O2;
-                const double Ex = g == 0 ? O0 : S0, Ey = g == 0 ? O1 : S1, Ez = g == 0 ? O2 : S2;
+                double Hx = g == 0 ? S0 : O0, Hy = g == 0 ? S1 : O1, Hz = g == 0 ? S2 : O2;
+                double Ex = g == 0 ? O0 : S0, Ey = g == 0 ? O1 : S1, Ez = g == 0 ? O2 : S2;
+                double pHx = fnb[f][0], pHy = fnb[f][1], pHz = fnb[f][2];
+                double pEx = fnb[f][3], pEy = fnb[f][4], pEz = fnb[f][5];
+                if (a.inc_own != nullptr) { // userinc hook (src/cem_maxwell.F:498)
+                    const long long jf = (long long)e * NF + fjs[f];
+                    const int qo = a.inc_own[jf], qn = a.inc_nbr[jf];
+                    if (qo >= 0) {
+                        const double ui = cos(a.inc_phase[qo] - a.inc_wt);
+                        Hx += a.inc_amp[qo] * ui; Hy += a.inc_amp[a.inc_n + qo] * ui;
+                        Hz += a.inc_amp[2 * a.inc_n + qo] * ui;
+                        Ex += a.inc_amp[3 * a.inc_n + qo] * ui;
+                        Ey += a.inc_amp[4 * a.inc_n + qo] * ui;
+                        Ez += a.inc_amp[5 * a.inc_n + qo] * ui;
+                    }
+                    if (qn >= 0) {
+                        const double ui = cos(a.inc_phase[qn] - a.inc_wt);
+                        pHx += a.inc_amp[qn] * ui; pHy += a.inc_amp[a.inc_n + qn] * ui;
+                        pHz += a.inc_amp[2 * a.inc_n + qn] * ui;
+                        pEx += a.inc_amp[3 * a.inc_n + qn] * ui;
+                        pEy += a.inc_amp[4 * a.inc_n + qn] * ui;
+                        pEz += a.inc_amp[5 * a.inc_n + qn] * ui;
+                    }
+                }
                 // -n x E, -n x H of the own side (flux3d :946-955)
                 double s0 = -uny * Ez + unz * Ey;
                 double s1 = -unz * Ex + unx * Ez;
@@ -415,8 +438,6 @@ __global__ void __launch_bounds__(threads_for(N), min_blocks_for(N))
                 double s4 = -unz * Hx + unx * Hz;
                 double s5 = -unx * Hy + uny * Hx;
                 if (vp >= 0 || vp <= -3) {
-                    const double pHx = fnb[f][0], pHy = fnb[f][1], pHz = fnb[f][2];
-                    const double pEx = fnb[f][3], pEy = fnb[f][4], pEz = fnb[f][5];
                     // neighbour's (-n+ x E+) with n+ = -n-  (the gs_op_fields sum of :962)
                     s0 = s0 - (-uny * pEz + unz * pEy);
                     s1 = s1 - (-unz * pEx + unx * pEz);

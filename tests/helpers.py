@@ -43,10 +43,38 @@ def arrays_from_refcase(c, elems=None):
     return d
 
 
-def solver_from_refcase(c, device=0):
+def incident_3ddielectric(c, elems=None):
+    """The 3ddielectric `userinc` (tests/3ddielectric/3ddielectric.usr:6-50) as the arguments of
+    MaxwellB200.set_incident: (face points, amp[6, ninc], phase, omega).  ``elems`` restricts
+    and renumbers to one rank's partition."""
+    u = c.user
+    j = u.incindex
+    k = c.cemface[j]
+    eps = c.permittivity[k]; mu = c.permeability[k]
+    eta = np.sqrt(mu / eps)
+    ky = u.omega * np.sqrt(mu * eps)
+    amp = np.zeros((6, j.size))
+    amp[0] = -1.0 / eta   # incfhx -= uinc/eta
+    amp[2] = 1.0          # incfhz += uinc
+    amp[3] = eta          # incfex += eta*uinc
+    amp[5] = 1.0          # incfez += uinc
+    phase = -ky * c.ym1[k]
+    if elems is not None:
+        nfp = c.nxzf * c.nfaces
+        loc = -np.ones(c.nelt, dtype=np.int64)
+        loc[np.asarray(elems)] = np.arange(len(elems))
+        keep = loc[j // nfp] >= 0
+        j = loc[j[keep] // nfp] * nfp + j[keep] % nfp
+        amp = amp[:, keep]; phase = phase[keep]
+    return j, amp, phase, u.omega
+
+
+def solver_from_refcase(c, device=0, incident=None):
     s = MaxwellB200(c.ldim, c.nx1, c.nelt, imode=c.imode, upwind=bool(c.s.ifupwind),
                     ifpec=c.ifpec, ifpml=c.ifpml, device=device)
     s.cem_maxwell_init(arrays_from_refcase(c))
+    if incident is not None:
+        s.set_incident(*incident)
     s.setup()
     s.set_time(c.s.time, c.s.dt)
     return s

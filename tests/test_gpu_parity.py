@@ -4,7 +4,7 @@ result.  Tolerance: north_star asks for <= 1e-12 relative L2 in FP64."""
 import numpy as np
 import pytest
 
-from helpers import arrays_from_refcase, rel_l2, solver_from_refcase
+from helpers import arrays_from_refcase, incident_3ddielectric, rel_l2, solver_from_refcase
 
 pytestmark = pytest.mark.gpu
 
@@ -88,6 +88,26 @@ def test_dielectric_pml_parity(twomat):
     assert rel_l2(s.get_array("pmlbn"), c.pmlbn) <= TOL
     assert rel_l2(s.get_array("pmldn"), c.pmldn) <= TOL
     assert rel_l2(s.get_array("kpmlbn"), c.kpmlbn) <= TOL
+    s.close()
+
+
+@pytest.mark.parametrize("twomat", [False, True])
+def test_kat_3ddielectric_on_gpu(twomat):
+    """tests/3ddielectric as shipped: heterogeneous eps/mu, PML, and the `userinc` plane-wave
+    injection running on the device (incident-field hook).  Parity with the oracle after 100
+    steps and the .usr tolerances 5e-4 / 5e-3 (zero components 5e-14 / 1e-12)."""
+    from oracle import cases
+    c = cases.case_3ddielectric(twomat)
+    s = solver_from_refcase(c, incident=incident_3ddielectric(c))
+    s.step(100); c.step(100)
+    assert rel_l2(_fields(s), _fields(c)) <= TOL
+    assert rel_l2(s.get_array("pmlbn"), c.pmlbn) <= TOL
+    shn, sen = c.usersol(c, s.time)
+    l2, linf = s.cem_error(shn, sen)
+    for comp in (0, 2, 3, 5):
+        assert l2[comp] <= 5e-4 and linf[comp] <= 5e-3, (comp, l2, linf)
+    for comp in (1, 4):
+        assert l2[comp] <= 5e-14 and linf[comp] <= 1e-12, (comp, l2, linf)
     s.close()
 
 
