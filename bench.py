@@ -303,8 +303,8 @@ def main():
     ap.add_argument("--elems", type=int, default=64, help="elements per direction per GPU")
     ap.add_argument("--order", type=int, default=7, help="polynomial order N (nx1 = N+1)")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-elems", type=int, default=16)
-    ap.add_argument("--cpu-steps", type=int, default=10)
+    ap.add_argument("--cpu-elems", type=int, default=24)
+    ap.add_argument("--cpu-steps", type=int, default=30)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

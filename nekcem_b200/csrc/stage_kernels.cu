@@ -82,7 +82,7 @@ struct Lay {
     }
 };
 // threads per pencil: each computes ceil(n/split) of the pencil's n outputs
-__host__ __device__ constexpr int split_for(int n) { return n <= 5 ? 4 : (n <= 13 ? 2 : 1); }
+__host__ __device__ constexpr int split_for(int n) { return n <= 5 ? 4 : 2; }
 __host__ __device__ constexpr int threads_for(int n)
 {
     return ((n * n * split_for(n) + 31) / 32) * 32;
@@ -101,8 +101,8 @@ __host__ __device__ constexpr int batch_t(int n)
 }
 __host__ __device__ constexpr int regs_for(int n)
 {
-    // pencil of 3 components (6n) + cofactor batch + working set
-    int r = 6 * n + 14 * batch_s(n) + 40;
+    // 3*NO accumulators + cofactor batch + working set
+    int r = 6 * outputs_for(n) + 14 * batch_s(n) + 44;
     return r > 255 ? 255 : r;
 }
 __host__ __device__ constexpr int min_blocks_for(int n)
@@ -146,8 +146,66 @@ __device__ __forceinline__ void curl_part(const double (&d)[3], double mx, doubl
     c[2] = d[1] * mx - d[0] * my;
 }
 
-// One pencil phase.  DIR 0/1/2 = r/s/t.  The thread owns the line of N points of pencil (pa,pb)
-// and produces outputs O0..O1-1 of it:
+// cofactors (and signed weight) of outputs O0+b0 .. O0+b0+PB-1 of a pencil
+template <int N, int DIR, int O0, int O1, int PB, int NCOF, int B0>
+__device__ __forceinline__ void load_cof(const StageArgs &a, double (&cof)[PB][NCOF],
+                                         double (&wv)[PB], int pa, int pb, long long ebase,
+                                         double sg)
+{
+#pragma unroll
+    for (int x = 0; x < PB; x++) {
+        const int o = O0 + B0 + x < O1 ? O0 + B0 + x : O1 - 1;
+        const int nd = pen_node<N, DIR>(o, pa, pb);
+        const long long gi = ebase + nd;
+        if constexpr (DIR == 1) {
+#pragma unroll
+            for (int q = 0; q < 6; q++) cof[x][q] = ldg(a.met[q] + gi);
+        } else {
+#pragma unroll
+            for (int q = 0; q < 3; q++) cof[x][q] = ldg(a.met[6 + q] + gi);
+        }
+        wv[x] = sg * ldg(a.w3 + nd);
+    }
+}
+
+// combine the derivatives of outputs O0+B0 .. with their cofactors into the smem residual
+template <int N, int DIR, int O0, int O1, int PB, int NCOF, int B0>
+__device__ __forceinline__ void finish_batch(const double (&acc)[3][O1 - O0],
+                                             const double (&cof)[PB][NCOF],
+                                             const double (&wv)[PB], double *R, int pa, int pb)
+{
+    constexpr int NO = O1 - O0, SC = Lay<N>::SC;
+#pragma unroll
+    for (int x = 0; x < PB; x++) {
+        if constexpr (true) {
+            const int oo = B0 + x;
+            if (oo < NO) {
+                const double d[3] = {acc[0][oo], acc[1][oo], acc[2][oo]};
+                double c[3];
+                double *Ro = R + pen_at<N, DIR>(O0 + oo, pa, pb);
+                if constexpr (DIR == 0) {
+                    Ro[0] = d[0]; Ro[SC] = d[1]; Ro[2 * SC] = d[2];
+                } else if constexpr (DIR == 1) {
+                    const double dr[3] = {Ro[0], Ro[SC], Ro[2 * SC]};
+                    double cr[3];
+                    curl_part(dr, cof[x][0], cof[x][1], cof[x][2], cr);
+                    curl_part(d, cof[x][3], cof[x][4], cof[x][5], c);
+                    Ro[0] = (cr[0] + c[0]) * wv[x];
+                    Ro[SC] = (cr[1] + c[1]) * wv[x];
+                    Ro[2 * SC] = (cr[2] + c[2]) * wv[x];
+                } else {
+                    curl_part(d, cof[x][0], cof[x][1], cof[x][2], c);
+                    Ro[0] = Ro[0] + wv[x] * c[0];
+                    Ro[SC] = Ro[SC] + wv[x] * c[1];
+                    Ro[2 * SC] = Ro[2 * SC] + wv[x] * c[2];
+                }
+            }
+        }
+    }
+}
+
+// One pencil phase.  DIR 0/1/2 = r/s/t.  The thread streams the line of N points of pencil
+// (pa,pb) from shared memory and produces outputs O0..O1-1 of it:
 //   d_c = sum_m D(o,m) u_c(m)                               (mxfK order, left to right)
 //   DIR 0: R = d                                             (raw r-derivatives)
 //   DIR 1: R = (curl_part(R; rx,ry,rz) + curl_part(d; sx,sy,sz)) * (sg*w3)
@@ -159,65 +217,36 @@ __device__ __forceinline__ void pencil_phase(const double (&D)[N * N], const Sta
                                              long long ebase, double sg)
 {
     constexpr int NO = O1 - O0, SC = Lay<N>::SC;
+    constexpr int NCOF = DIR == 1 ? 6 : 3;
     if constexpr (NO > 0) {
-        double u[3][N];
+        // cofactors and weight of the first batch of outputs: in flight during the contraction
+        double cof[PB][NCOF], wv[PB];
+        if constexpr (DIR != 0) load_cof<N, DIR, O0, O1, PB, NCOF, 0>(a, cof, wv, pa, pb, ebase, sg);
+        // output-stationary contraction: the line is streamed from smem once, each point feeds
+        // the 3*NO accumulators of this thread (sum over m left to right, as mxfK)
+        double acc[3][NO];
 #pragma unroll
         for (int m = 0; m < N; m++) {
             const int so = pen_at<N, DIR>(m, pa, pb);
+            const double u0 = U[so], u1 = U[SC + so], u2 = U[2 * SC + so];
 #pragma unroll
-            for (int c = 0; c < 3; c++) u[c][m] = U[c * SC + so];
+            for (int o = 0; o < NO; o++) {
+                const double dv = D[(O0 + o) + N * m];
+                if (m == 0) {
+                    acc[0][o] = dv * u0; acc[1][o] = dv * u1; acc[2][o] = dv * u2;
+                } else {
+                    acc[0][o] = acc[0][o] + dv * u0;
+                    acc[1][o] = acc[1][o] + dv * u1;
+                    acc[2][o] = acc[2][o] + dv * u2;
+                }
+            }
         }
-#pragma unroll
-        for (int b0 = 0; b0 < NO; b0 += PB) {
-            constexpr int NCOF = DIR == 1 ? 6 : 3;
-            double cof[PB][NCOF], wv[PB];
-            if constexpr (DIR != 0) { // cofactors and weight of the whole batch first
-#pragma unroll
-                for (int x = 0; x < PB; x++) {
-                    const int o = O0 + b0 + x < O1 ? O0 + b0 + x : O1 - 1;
-                    const int nd = pen_node<N, DIR>(o, pa, pb);
-                    const long long gi = ebase + nd;
-                    if constexpr (DIR == 1) {
-#pragma unroll
-                        for (int q = 0; q < 6; q++) cof[x][q] = ldg(a.met[q] + gi);
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < 3; q++) cof[x][q] = ldg(a.met[6 + q] + gi);
-                    }
-                    wv[x] = sg * ldg(a.w3 + nd);
-                }
-            }
-#pragma unroll
-            for (int x = 0; x < PB; x++) {
-                const int o = O0 + b0 + x; // compile-time after unrolling
-                if (o < O1) {
-                    double d[3], c[3];
-#pragma unroll
-                    for (int q = 0; q < 3; q++) d[q] = D[o] * u[q][0];
-#pragma unroll
-                    for (int m = 1; m < N; m++) {
-#pragma unroll
-                        for (int q = 0; q < 3; q++) d[q] = d[q] + D[o + N * m] * u[q][m];
-                    }
-                    double *Ro = R + pen_at<N, DIR>(o, pa, pb);
-                    if constexpr (DIR == 0) {
-                        Ro[0] = d[0]; Ro[SC] = d[1]; Ro[2 * SC] = d[2];
-                    } else if constexpr (DIR == 1) {
-                        const double dr[3] = {Ro[0], Ro[SC], Ro[2 * SC]};
-                        double cr[3];
-                        curl_part(dr, cof[x][0], cof[x][1], cof[x][2], cr);
-                        curl_part(d, cof[x][3], cof[x][4], cof[x][5], c);
-                        Ro[0] = (cr[0] + c[0]) * wv[x];
-                        Ro[SC] = (cr[1] + c[1]) * wv[x];
-                        Ro[2 * SC] = (cr[2] + c[2]) * wv[x];
-                    } else {
-                        curl_part(d, cof[x][0], cof[x][1], cof[x][2], c);
-                        Ro[0] = Ro[0] + wv[x] * c[0];
-                        Ro[SC] = Ro[SC] + wv[x] * c[1];
-                        Ro[2 * SC] = Ro[2 * SC] + wv[x] * c[2];
-                    }
-                }
-            }
+        finish_batch<N, DIR, O0, O1, PB, NCOF, 0>(acc, cof, wv, R, pa, pb);
+        if constexpr (PB < NO) {
+            static_assert(2 * PB >= NO, "at most two cofactor batches");
+            if constexpr (DIR != 0)
+                load_cof<N, DIR, O0, O1, PB, NCOF, PB>(a, cof, wv, pa, pb, ebase, sg);
+            finish_batch<N, DIR, O0, O1, PB, NCOF, PB>(acc, cof, wv, R, pa, pb);
         }
     }
 }

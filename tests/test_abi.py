@@ -21,7 +21,11 @@ def test_library_exports_every_declared_symbol():
     L = C.CDLL(LIBPATH)
     for n in sorted(names):
         assert hasattr(L, n), f"{n} declared in the header but not exported"
-    for n in ("nekcem_b200_create_", "nekcem_b200_step_", "nekcem_b200_set_array_"):
+    for n in ("nekcem_b200_create_", "nekcem_b200_step_", "nekcem_b200_set_array_",
+              "nekcem_b200_get_array_", "nekcem_b200_set_faces_", "nekcem_b200_set_pml_",
+              "nekcem_b200_setup_", "nekcem_b200_set_time_", "nekcem_b200_set_incident_",
+              "nekcem_b200_set_volume_source_", "nekcem_b200_error_sums_",
+              "nekcem_b200_comm_unique_id_", "nekcem_b200_comm_init_"):
         assert hasattr(L, n), f"Fortran twin {n} missing"
 
 
