@@ -26,6 +26,7 @@
 
 namespace nkb {
 int launch_stage(const StageArgs &a, const double *Dhost, int nx1, bool pml, void *stream);
+int launch_stage_slab(const StageArgs &a, const double *Dhost, int nx1, bool pml, void *stream);
 }
 
 namespace {
@@ -115,6 +116,7 @@ struct Ctx {
     float last_ms = 0.f;
     int64_t last_launches = 0;
     int pf_dist = 0;
+    int variant = 1; // 1: element-slab kernel (stage_slab.cu); 0: half-task pencil kernel
     double *red_d = nullptr; // reduction scratch
     int red_blocks = 0;
 };
@@ -448,7 +450,9 @@ int run_stage(Ctx *c, int rkstep /*1..5*/)
         nkb::StageArgs b = a;
         b.elist = c->elist_d + c->list_off[q];
         b.nel = c->list_n[q];
-        int rc = nkb::launch_stage(b, c->D_host.data(), c->n, (q & 1) != 0, c->s_compute);
+        int rc = c->variant == 1
+                     ? nkb::launch_stage_slab(b, c->D_host.data(), c->n, (q & 1) != 0, c->s_compute)
+                     : nkb::launch_stage(b, c->D_host.data(), c->n, (q & 1) != 0, c->s_compute);
         if (rc < 0) return fail("nx1=%d is not supported by the stage kernels (2..16)", c->n);
         if (rc > 0) return fail("stage kernel launch failed: %s",
                                 cudaGetErrorString(cudaGetLastError()));
@@ -881,6 +885,11 @@ int nekcem_b200_set_option(int handle, const char *name, int value)
     if (strcmp(name, "pf_dist") == 0) {
         if (value < 0) return fail("pf_dist must be >= 0");
         c->pf_dist = value;
+        return 0;
+    }
+    if (strcmp(name, "variant") == 0) {
+        if (value < 0 || value > 1) return fail("variant must be 0 or 1");
+        c->variant = value;
         return 0;
     }
     return fail("unknown option '%s'", name);

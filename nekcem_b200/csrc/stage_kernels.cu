@@ -35,52 +35,10 @@
 // Arithmetic: same products as the reference; the 6-term curl sum is associated by
 // direction ((r-part + s-part)*w + lift) + w*t-part, and nvcc contracts a*b+c into FMA --
 // both are <= 1e-15 relative effects per operation (DESIGN.md "Numerics").
-#include <cuda_runtime.h>
-
-#include "stage_args.h"
+#include "stage_common.h"
 
 namespace nkb {
 
-// read-only data (everything except the RK registers and the PML auxiliaries) goes through
-// ld.global.nc so that the compiler may hoist the loads above earlier stores
-__device__ __forceinline__ double ldg(const double *p) { return __ldg(p); }
-__device__ __forceinline__ int ldg(const int *p) { return __ldg(p); }
-
-// pull a 128-byte line into L2 without occupying a register or shared memory
-__device__ __forceinline__ void prefetch_l2(const void *p)
-{
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-// one warp prefetches `bytes` starting at base (any alignment)
-__device__ __forceinline__ void prefetch_chunk(const void *base, int bytes, int lane)
-{
-    const char *b = (const char *)base;
-    for (int off = lane * 128; off < bytes; off += 32 * 128) prefetch_l2(b + off);
-    if (lane == 0) prefetch_l2(b + bytes - 8);
-}
-
-// ---- compile-time geometry of one half-task --------------------------------------------
-__host__ __device__ constexpr int pad_j(int n) { return (n == 6 || n == 14) ? 3 : (n == 12 ? 1 : 0); }
-__host__ __device__ constexpr int pad_k(int n)
-{
-    return (n == 3 || n == 4 || n == 7) ? 3 : (n == 10 ? 7 : 0);
-}
-// Shared-memory layout of one component of an element.  n = 8 and n = 16 use an XOR swizzle
-// (no padding) that makes the r-, s-, t-pencil and the linear access patterns all free of
-// 64-bit bank conflicts; other orders use the padding found by scripts/smem_banks.py.
-template <int N>
-struct Lay {
-    static constexpr bool SWZ = (N == 8 || N == 16);
-    static constexpr int SJ = SWZ ? N : N + pad_j(N);
-    static constexpr int SK = SWZ ? N * N : SJ * N + pad_k(N);
-    static constexpr int SC = SK * N;
-    __device__ __forceinline__ static int at(int i, int j, int k)
-    {
-        if constexpr (N == 8) return (i ^ ((j >> 1) + 4 * (k & 1))) + 8 * (j ^ (k & 1)) + 64 * k;
-        else if constexpr (N == 16) return (i ^ j) + 16 * j + 256 * k;
-        else return i + SJ * j + SK * k;
-    }
-};
 // threads per pencil: each computes ceil(n/split) of the pencil's n outputs
 __host__ __device__ constexpr int split_for(int n) { return n <= 5 ? 4 : 2; }
 __host__ __device__ constexpr int threads_for(int n)
@@ -120,12 +78,6 @@ __host__ __device__ constexpr int min_blocks_for(int n)
 }
 __host__ __device__ constexpr int epi_unroll_for(int n) { return regs_for(n) >= 160 ? 8 : 4; }
 
-template <int N>
-struct StageParams {
-    StageArgs a;
-    double D[N * N]; // dxm1, column-major: D(i,m) at i + N*m
-};
-
 // smem offset / element-node index of point m of the pencil (pa,pb) in direction DIR
 template <int N, int DIR>
 __device__ __forceinline__ int pen_at(int m, int pa, int pb)
@@ -136,14 +88,6 @@ template <int N, int DIR>
 __device__ __forceinline__ int pen_node(int m, int pa, int pb)
 {
     return DIR == 0 ? m + N * pa + N * N * pb : (DIR == 1 ? pa + N * m + N * N * pb : pa + N * pb + N * N * m);
-}
-
-__device__ __forceinline__ void curl_part(const double (&d)[3], double mx, double my, double mz,
-                                          double (&c)[3])
-{
-    c[0] = d[2] * my - d[1] * mz;
-    c[1] = d[0] * mz - d[2] * mx;
-    c[2] = d[1] * mx - d[0] * my;
 }
 
 // cofactors (and signed weight) of outputs O0+b0 .. O0+b0+PB-1 of a pencil

@@ -1,0 +1,634 @@
+// Fused Maxwell RK-stage kernel for sm_100a, "element-slab" formulation, 2 <= nx1 <= 16.
+//
+// One launch = one RK stage over a list of elements.  One CTA = one k-SLAB of one element
+// (slab = all nodes with k0 <= k < k0+kb; KS slabs per element, KS = 1 for nx1 <= 10), and it
+// updates ALL SIX components of those nodes, so every array of the stage crosses L2->SM once per
+// node: fields, RK registers, the nine cofactors, the two masses, and one neighbour trace per
+// face point.  The slabs of an element are adjacent CTAs; what they
+// share (the t-lines through the other slabs) is served by L2.
+//
+//   P0  stage H,E of the slab in shared memory U[6]
+//   P1  r-pencils: thread (g,j,k) holds nothing but 3*NO accumulators; the line of 3 source
+//       components streams from smem, D(i,m) is a constant-bank operand; raw r-derivatives -> R
+//       [local_grad3, src/nek5_grad.F:2-19; mxfK left-to-right sums, src/nek5_mxm_std.F:173-190]
+//       g = 0: resE <- curl H,  g = 1: resH <- -curl E      [cem_maxwell :510-602]
+//   P2  s-pencils: thread (g,i,k): s-derivatives, then the r- and s-parts of the weighted curl
+//       with the cofactors rx..sz (coalesced along i) and w3mn  [maxwell_wght_curl :1428-1497]
+//   P3  surface flux: one thread per face point of the slab computes BOTH numerical fluxes from
+//       one gather of the neighbour trace (vmapP = the gs_op_fields pair-sum of :962, or the
+//       NCCL halo), own trace from smem, PEC mirror, upwind/central; the lifts are added to R in
+//       three barrier-separated rounds (x-, y-, z-faces) so that edge nodes are race-free
+//       [restrict_to_face :604-652, flux3d :922-1002, flux_pec :1368-1426, add_flux_to_res :725-735]
+//   P4  t-pencils: thread (g,i,j) adds the weighted t-part for the slab's k; the line comes from
+//       smem (KS = 1) or from global memory/L2 (KS > 1: the other slabs' nodes)
+//   P5  streaming epilogue: PML ADEs [pml_step, src/cem_maxwell_pml.F:508-592], volume source
+//       [usersrc hook :503], inverse mass [invqmass :1878-1886], low-storage RK update
+//       [rk4_upd, src/cem_common.F:18-76]; old fields come from smem, k/masses are loaded
+//       EPI nodes ahead, results go to the ping-pong buffer.
+//
+// Arithmetic: same products as the reference; the 6-term curl sum is associated by direction
+// ((r-part + s-part)*w + lift) + w*t-part, and nvcc contracts a*b+c into FMA -- both are
+// <= 1e-15 relative effects per operation (DESIGN.md "Numerics").
+#include "stage_common.h"
+
+namespace nkb {
+namespace {
+
+// ---- compile-time geometry -----------------------------------------------------------------
+__host__ __device__ constexpr int ks_for(int n) { return n <= 10 ? 1 : (n <= 12 ? 2 : (n == 13 ? 3 : 4)); }
+__host__ __device__ constexpr int rsplit_for(int n) { return n <= 5 ? 4 : 2; }
+__host__ __device__ constexpr int round32(int x) { return ((x + 31) / 32) * 32; }
+__host__ __device__ constexpr int nt_for(int items)
+{
+    if (items <= 288) return round32(items);
+    int passes = (items + 255) / 256;
+    return round32((items + passes - 1) / passes);
+}
+
+template <int N, int KS>
+struct Slab {
+    static constexpr int N2 = N * N;
+    static constexpr int KB = (N + KS - 1) / KS; // thickest slab
+    static constexpr int SPLIT = rsplit_for(N);  // threads per r/s pencil
+    static constexpr int NO = (N + SPLIT - 1) / SPLIT;
+    static constexpr int RS_ITEMS = 2 * SPLIT * N * KB;
+    static constexpr int TSPLIT = KS == 1 ? SPLIT : 1; // threads per t pencil
+    static constexpr int T_ITEMS = 2 * TSPLIT * N2;
+    static constexpr int NT = nt_for(RS_ITEMS);
+    static constexpr int SC = Lay<N>::SK * KB; // component stride in smem
+    static constexpr int FXY = 4 * N * KB;     // face points on the x/y faces of a slab
+    static constexpr int FZ = KS == 1 ? 2 * N2 : N2;
+    static constexpr int F_ITEMS = FXY + FZ;
+    static constexpr int FPT = (F_ITEMS + NT - 1) / NT;
+    static constexpr size_t SMEM = sizeof(double) * 12 * SC;
+    __host__ __device__ static constexpr int k0(int s) { return s * N / KS; }
+    __host__ __device__ static constexpr int kb(int s) { return (s + 1) * N / KS - s * N / KS; }
+    // cofactor batches: outputs whose cofactors are loaded together
+    static constexpr int PB_S = NO <= 2 ? NO : (NO <= 6 ? (NO + 1) / 2 : (NO + 3) / 4);
+    static constexpr int REG_CAP = NO >= 7 ? 128 : (NO >= 5 ? 112 : 96);
+    static constexpr int MINB_SMEM = (227 * 1024) / ((int)SMEM + 1024);
+    static constexpr int MINB_THR = 2048 / NT;
+    static constexpr int MINB_REG = 65536 / (NT * REG_CAP);
+    static constexpr int MINB0 = MINB_SMEM < MINB_THR ? MINB_SMEM : MINB_THR;
+    static constexpr int MINB1 = MINB0 < MINB_REG ? MINB0 : MINB_REG;
+    static constexpr int MINB = MINB1 < 1 ? 1 : (MINB1 > 8 ? 8 : MINB1);
+    static constexpr int EPI = 4; // nodes in flight per thread in the epilogue
+};
+
+// ---- one pencil phase -------------------------------------------------------------------------
+// DIR 0/1/2 = r/s/t.  The thread produces outputs O0..O1-1 (positions along the pencil; for
+// DIR 2 these are element k indices, and KOFF = k0 of the slab) of pencil (pa,pb):
+//   d_c = sum_m D(o,m) u_c(m)                               (mxfK order, left to right)
+//   DIR 0: R = d                                             (raw r-derivatives)
+//   DIR 1: R = (curl_part(R; rx,ry,rz) + curl_part(d; sx,sy,sz)) * (sg*w3)
+//   DIR 2: R = R + (sg*w3) * curl_part(d; tx,ty,tz)
+// gsrc != nullptr (DIR 2 only): the line is read from global memory (3 components, stride ld).
+template <int N, int DIR, int KOFF>
+__device__ __forceinline__ int s_at(int m, int pa, int pb)
+{
+    return DIR == 0 ? Lay<N>::at(m, pa, pb)
+                    : (DIR == 1 ? Lay<N>::at(pa, m, pb) : Lay<N>::at(pa, pb, m - KOFF));
+}
+template <int N, int DIR>
+__device__ __forceinline__ int n_at(int m, int pa, int pb)
+{
+    return DIR == 0 ? m + N * pa + N * N * pb : (DIR == 1 ? pa + N * m + N * N * pb : pa + N * pb + N * N * m);
+}
+
+template <int N, int DIR, int KOFF, int O0, int O1, int PB, int SC, bool GSRC>
+__device__ __forceinline__ void pencil_phase(const double (&D)[N * N], const StageArgs &a,
+                                             const double *U, const double *gsrc, double *R,
+                                             int pa, int pb, long long gbase, int wbase, double sg)
+{
+    constexpr int NO = O1 - O0;
+    constexpr int NCOF = DIR == 1 ? 6 : 3;
+    if constexpr (NO > 0) {
+        double cof[PB][NCOF], wv[PB];
+        auto load_cof = [&](int b0) {
+#pragma unroll
+            for (int x = 0; x < PB; x++) {
+                const int o = O0 + b0 + x < O1 ? O0 + b0 + x : O1 - 1;
+                const int nd = n_at<N, DIR>(o, pa, pb);
+                const long long gi = gbase + nd;
+                if constexpr (DIR == 1) {
+#pragma unroll
+                    for (int q = 0; q < 6; q++) cof[x][q] = ldg(a.met[q] + gi);
+                } else if constexpr (DIR == 2) {
+#pragma unroll
+                    for (int q = 0; q < 3; q++) cof[x][q] = ldg(a.met[6 + q] + gi);
+                }
+                if constexpr (DIR != 0) wv[x] = sg * ldg(a.w3 + wbase + nd);
+            }
+        };
+        // cofactors of the first batch: in flight during the contraction
+        if constexpr (DIR != 0) load_cof(0);
+        // output-stationary contraction: the line streams by once, each point feeds the 3*NO
+        // accumulators of this thread (sum over m left to right, as mxfK)
+        double acc[3][NO];
+#pragma unroll
+        for (int m = 0; m < N; m++) {
+            double u0, u1, u2;
+            if constexpr (GSRC) {
+                const double *gp = gsrc + n_at<N, DIR>(m, pa, pb);
+                u0 = ldg(gp); u1 = ldg(gp + a.ld); u2 = ldg(gp + 2 * a.ld);
+            } else {
+                const int so = s_at<N, DIR, KOFF>(m, pa, pb);
+                u0 = U[so]; u1 = U[SC + so]; u2 = U[2 * SC + so];
+            }
+#pragma unroll
+            for (int o = 0; o < NO; o++) {
+                const double dv = D[(O0 + o) + N * m];
+                if (m == 0) {
+                    acc[0][o] = dv * u0; acc[1][o] = dv * u1; acc[2][o] = dv * u2;
+                } else {
+                    acc[0][o] = acc[0][o] + dv * u0;
+                    acc[1][o] = acc[1][o] + dv * u1;
+                    acc[2][o] = acc[2][o] + dv * u2;
+                }
+            }
+        }
+#pragma unroll
+        for (int b0 = 0; b0 < NO; b0 += PB) {
+            if (b0 > 0) {
+                if constexpr (DIR != 0) load_cof(b0);
+            }
+#pragma unroll
+            for (int x = 0; x < PB; x++) {
+                const int oo = b0 + x;
+                if (oo < NO) {
+                    const double d[3] = {acc[0][oo], acc[1][oo], acc[2][oo]};
+                    double c[3];
+                    double *Ro = R + s_at<N, DIR, KOFF>(O0 + oo, pa, pb);
+                    if constexpr (DIR == 0) {
+                        Ro[0] = d[0]; Ro[SC] = d[1]; Ro[2 * SC] = d[2];
+                    } else if constexpr (DIR == 1) {
+                        const double dr[3] = {Ro[0], Ro[SC], Ro[2 * SC]};
+                        double cr[3];
+                        curl_part(dr, cof[x][0], cof[x][1], cof[x][2], cr);
+                        curl_part(d, cof[x][3], cof[x][4], cof[x][5], c);
+                        Ro[0] = (cr[0] + c[0]) * wv[x];
+                        Ro[SC] = (cr[1] + c[1]) * wv[x];
+                        Ro[2 * SC] = (cr[2] + c[2]) * wv[x];
+                    } else {
+                        curl_part(d, cof[x][0], cof[x][1], cof[x][2], c);
+                        Ro[0] = Ro[0] + wv[x] * c[0];
+                        Ro[SC] = Ro[SC] + wv[x] * c[1];
+                        Ro[2 * SC] = Ro[2 * SC] + wv[x] * c[2];
+                    }
+                }
+            }
+        }
+    }
+}
+
+// dispatch on the thread's share h of the outputs LO..HI-1 (compile-time ranges)
+template <int N, int DIR, int KOFF, int LO, int HI, int SPLIT, int PB, int SC, bool GSRC>
+__device__ __forceinline__ void pencil_split(const double (&D)[N * N], const StageArgs &a,
+                                             const double *U, const double *gsrc, double *R,
+                                             int pa, int pb, long long gbase, int wbase,
+                                             double sg, int h)
+{
+    constexpr int L = HI - LO, HN = (L + SPLIT - 1) / SPLIT;
+    constexpr int E1 = LO + (HN < L ? HN : L), E2 = LO + (2 * HN < L ? 2 * HN : L),
+                  E3 = LO + (3 * HN < L ? 3 * HN : L);
+    if (h == 0) pencil_phase<N, DIR, KOFF, LO, E1, PB, SC, GSRC>(D, a, U, gsrc, R, pa, pb, gbase, wbase, sg);
+    if (SPLIT > 1 && h == 1)
+        pencil_phase<N, DIR, KOFF, E1, E2, PB, SC, GSRC>(D, a, U, gsrc, R, pa, pb, gbase, wbase, sg);
+    if (SPLIT > 2 && h == 2)
+        pencil_phase<N, DIR, KOFF, E2, E3, PB, SC, GSRC>(D, a, U, gsrc, R, pa, pb, gbase, wbase, sg);
+    if (SPLIT > 3 && h == 3)
+        pencil_phase<N, DIR, KOFF, E3, HI, PB, SC, GSRC>(D, a, U, gsrc, R, pa, pb, gbase, wbase, sg);
+}
+
+// t-pencils of slab S (compile-time k range)
+template <int N, int KS, int S>
+__device__ __forceinline__ void t_phase(const double (&D)[N * N], const StageArgs &a, const double *U,
+                                        double *R, long long ebase, int tid)
+{
+    using C = Slab<N, KS>;
+    constexpr int K0 = C::k0(S), K1 = K0 + C::kb(S);
+    constexpr int NOT = (K1 - K0 + C::TSPLIT - 1) / C::TSPLIT;
+    constexpr int PB_T = NOT <= 8 ? NOT : (NOT + 1) / 2;
+#pragma unroll 1
+    for (int w = tid; w < C::T_ITEMS; w += C::NT) {
+        const int p = w % C::N2, hg = w / C::N2;
+        const int h = hg % C::TSPLIT, g = hg / C::TSPLIT;
+        const int pa = p % N, pb = p / N;
+        const double *Us = U + (g ? 3 : 0) * C::SC;
+        double *Rd = R + (g ? 0 : 3) * C::SC;
+        const double *gs = a.u_in + (g ? 3 : 0) * a.ld + ebase;
+        pencil_split<N, 2, K0, K0, K1, C::TSPLIT, PB_T, C::SC, (KS > 1)>(
+            D, a, Us, gs, Rd, pa, pb, ebase, 0, g ? -1.0 : 1.0, h);
+    }
+}
+
+template <int N, int KS, bool PML>
+__global__ void __launch_bounds__(Slab<N, KS>::NT, Slab<N, KS>::MINB)
+    slab_kernel(const __grid_constant__ StageParams<N> prm)
+{
+    using C = Slab<N, KS>;
+    constexpr int N2 = N * N, N3 = N2 * N, NF = 6 * N2;
+    constexpr int NT = C::NT, SC = C::SC, KB = C::KB, FPT = C::FPT;
+    const StageArgs &a = prm.a;
+    extern __shared__ double smem[];
+    double *U = smem;          // [6][SC] H,E of the slab at stage start
+    double *R = smem + 6 * SC; // [6][SC] residuals resH,resE
+
+    const int tid = threadIdx.x;
+    const int e = a.elist[blockIdx.x / KS];
+    const int s = blockIdx.x % KS;
+    const int k0 = C::k0(s), kb = C::kb(s);
+    const long long ebase = (long long)e * N3;
+    const long long sbase = ebase + k0 * N2; // first node of the slab
+    const int nslab = N2 * kb;
+
+    // ---- P0: stage the six field components of the slab (loads issued before anything else) ----
+    constexpr int SPER = (6 * N2 * KB + NT - 1) / NT;
+    constexpr int SUNR = SPER < 24 ? SPER : 24;
+    double sv[SUNR];
+#pragma unroll
+    for (int x = 0; x < SUNR; x++) {
+        const int q = tid + x * NT;
+        const int c = q / (N2 * KB), r = q - c * (N2 * KB);
+        sv[x] = (q < 6 * N2 * KB && r < nslab) ? ldg(a.u_in + c * a.ld + sbase + r) : 0.0;
+    }
+
+    // ---- prologue: put every other HBM request of this slab in flight now -----------------------
+    // (a) L2 prefetch of the slab's metric, mass and RK-register arrays: one warp per array
+    {
+        const int warp = tid >> 5, lane = tid & 31;
+        constexpr int NW = NT / 32;
+        for (int arr = warp; arr < 17; arr += NW) {
+            const double *base;
+            if (arr < 9) base = a.met[arr];
+            else if (arr < 15) base = a.kf + (arr - 9) * a.ld;
+            else base = arr == 15 ? a.hbm1 : a.ebm1;
+            prefetch_chunk(base + sbase, nslab * 8, lane);
+        }
+        // face geometry / impedances / vmapP of the slab's part of the four x/y faces and of
+        // its z face(s): 9 arrays x (4 strips of N*kb points + whole z faces)
+        constexpr int LXY = (N * KB * 8 + 127) / 128 + 1; // lines per strip (any alignment)
+        constexpr int LZ = (N2 * 8 + 127) / 128 + 1;
+        const long long fbase = (long long)e * NF;
+        for (int t = tid; t < 9 * 4 * LXY; t += NT) {
+            const int arr = t / (4 * LXY), r = t - arr * (4 * LXY), f = r / LXY, ln = r - f * LXY;
+            const long long off = fbase + f * N2 + N * k0;
+            const int bytes = (arr == 8 ? 4 : 8) * N * kb;
+            const char *b;
+            if (arr == 8) b = (const char *)(a.vmapP + off);
+            else {
+                const double *fa = arr == 0 ? a.unx : arr == 1 ? a.uny : arr == 2 ? a.unz
+                                 : arr == 3 ? a.area : arr == 4 ? a.hY : arr == 5 ? a.Y1
+                                 : arr == 6 ? a.hZ : a.Z1;
+                b = (const char *)(fa + off);
+            }
+            if (ln * 128 < bytes + 127) prefetch_l2(b + (ln * 128 < bytes ? ln * 128 : bytes - 4));
+        }
+        if (s == 0 || s == KS - 1) {
+            for (int t = tid; t < 9 * 2 * LZ; t += NT) {
+                const int arr = t / (2 * LZ), r = t - arr * (2 * LZ), zf = r / LZ, ln = r - zf * LZ;
+                if ((zf == 0 && s != 0) || (zf == 1 && s != KS - 1)) continue;
+                const long long off = fbase + (4 + zf) * N2;
+                const int bytes = (arr == 8 ? 4 : 8) * N2;
+                const char *b;
+                if (arr == 8) b = (const char *)(a.vmapP + off);
+                else {
+                    const double *fa = arr == 0 ? a.unx : arr == 1 ? a.uny : arr == 2 ? a.unz
+                                     : arr == 3 ? a.area : arr == 4 ? a.hY : arr == 5 ? a.Y1
+                                     : arr == 6 ? a.hZ : a.Z1;
+                    b = (const char *)(fa + off);
+                }
+                if (ln * 128 < bytes + 127) prefetch_l2(b + (ln * 128 < bytes ? ln * 128 : bytes - 4));
+            }
+        }
+    }
+    // (b) this thread's face points: slot, smem node, round; neighbour ids
+    //     face slots in the reference's order (cemface, cem_common.F:234-260): -y,+x,+y,-x,-z,+z
+    int fvp[FPT], fsn[FPT], fjs[FPT];
+#pragma unroll
+    for (int f = 0; f < FPT; f++) {
+        const int q = tid + f * NT;
+        int slot = -1, fp0 = 0, ci = 0, cj = 0, kl = 0;
+        if (q < C::FXY) {
+            const int f4 = q / (N * KB), r = q - f4 * (N * KB);
+            const int fa = r % N;
+            kl = r / N;
+            if (kl < kb) {
+                fp0 = fa + N * (k0 + kl);
+                if (f4 == 0) { slot = 3; ci = 0; cj = fa; }
+                else if (f4 == 1) { slot = 1; ci = N - 1; cj = fa; }
+                else if (f4 == 2) { slot = 0; ci = fa; cj = 0; }
+                else { slot = 2; ci = fa; cj = N - 1; }
+            }
+        } else if (q < C::F_ITEMS) {
+            const int q2 = q - C::FXY, zf = q2 / N2;
+            fp0 = q2 - zf * N2;
+            ci = fp0 % N; cj = fp0 / N;
+            if (KS == 1) { slot = 4 + zf; kl = zf ? N - 1 : 0; }
+            else if (s == 0) { slot = 4; kl = 0; }
+            else if (s == KS - 1) { slot = 5; kl = kb - 1; }
+        }
+        fjs[f] = slot < 0 ? -1 : slot * N2 + fp0;
+        fsn[f] = Lay<N>::at(ci, cj, kl);
+        fvp[f] = slot < 0 ? -2 : ldg(a.vmapP + (long long)e * NF + fjs[f]);
+    }
+    // staged values -> smem
+#pragma unroll 1
+    for (int q0 = 0; q0 < SPER; q0 += SUNR) {
+        if (q0 > 0) {
+#pragma unroll
+            for (int x = 0; x < SUNR; x++) {
+                const int q = tid + (q0 + x) * NT;
+                const int c = q / (N2 * KB), r = q - c * (N2 * KB);
+                sv[x] = (q < 6 * N2 * KB && r < nslab) ? ldg(a.u_in + c * a.ld + sbase + r) : 0.0;
+            }
+        }
+#pragma unroll
+        for (int x = 0; x < SUNR; x++) {
+            const int q = tid + (q0 + x) * NT;
+            const int c = q / (N2 * KB), r = q - c * (N2 * KB);
+            const int i = r % N, j = (r / N) % N, k = r / N2;
+            if (q < 6 * N2 * KB && r < nslab) U[c * SC + Lay<N>::at(i, j, k)] = sv[x];
+        }
+    }
+    // (c) neighbour traces of those face points -> L2
+#pragma unroll
+    for (int f = 0; f < FPT; f++)
+        if (fvp[f] >= 0) {
+#pragma unroll
+            for (int c = 0; c < 6; c++) prefetch_l2(a.u_in + c * a.ld + fvp[f]);
+        }
+    __syncthreads();
+
+    // ---- P1: r-pencils, thread (g,h,j,k): raw derivatives ----------------------------------------
+#pragma unroll 1
+    for (int w = tid; w < C::RS_ITEMS; w += NT) {
+        const int p = w % (N * KB), hg = w / (N * KB);
+        const int h = hg % C::SPLIT, g = hg / C::SPLIT;
+        const int pa = p % N, pb = p / N;
+        if (pb < kb)
+            pencil_split<N, 0, 0, 0, N, C::SPLIT, C::NO, SC, false>(
+                prm.D, a, U + (g ? 3 : 0) * SC, nullptr, R + (g ? 0 : 3) * SC, pa, pb, sbase,
+                k0 * N2, g ? -1.0 : 1.0, h);
+    }
+    __syncthreads();
+    // ---- P2: s-pencils, thread (g,h,i,k): r- and s-parts of the weighted curl ------------------
+#pragma unroll 1
+    for (int w = tid; w < C::RS_ITEMS; w += NT) {
+        const int p = w % (N * KB), hg = w / (N * KB);
+        const int h = hg % C::SPLIT, g = hg / C::SPLIT;
+        const int pa = p % N, pb = p / N;
+        if (pb < kb)
+            pencil_split<N, 1, 0, 0, N, C::SPLIT, C::PB_S, SC, false>(
+                prm.D, a, U + (g ? 3 : 0) * SC, nullptr, R + (g ? 0 : 3) * SC, pa, pb, sbase,
+                k0 * N2, g ? -1.0 : 1.0, h);
+    }
+    __syncthreads();
+
+    // ---- P3: surface flux: both fluxes of a face point from one neighbour gather ---------------
+    {
+        double fl[FPT][6];
+#pragma unroll
+        for (int f = 0; f < FPT; f++) {
+            const bool valid = fjs[f] >= 0;
+            const long long jf = (long long)e * NF + (valid ? fjs[f] : 0);
+            const int vp = fvp[f];
+            const int sn = fsn[f];
+            // all loads first
+            const double unx = ldg(a.unx + jf), uny = ldg(a.uny + jf), unz = ldg(a.unz + jf);
+            const double ar = ldg(a.area + jf);
+            const double hY = ldg(a.hY + jf), Y1 = ldg(a.Y1 + jf);
+            const double hZ = ldg(a.hZ + jf), Z1 = ldg(a.Z1 + jf);
+            // neighbour trace: volume node, halo slot, or (unused) the first node of the slab
+            const double *nb = vp >= 0 ? a.u_in + vp
+                                       : (vp <= -3 ? a.halo + 6ll * (long long)(-(vp + 3))
+                                                   : a.u_in + sbase);
+            const long long st = vp <= -3 ? 1 : a.ld;
+            double pv[6];
+#pragma unroll
+            for (int c = 0; c < 6; c++) pv[c] = ldg(nb + c * st);
+            double Hx = U[sn], Hy = U[SC + sn], Hz = U[2 * SC + sn];
+            double Ex = U[3 * SC + sn], Ey = U[4 * SC + sn], Ez = U[5 * SC + sn];
+            double pHx = pv[0], pHy = pv[1], pHz = pv[2], pEx = pv[3], pEy = pv[4], pEz = pv[5];
+            if (a.inc_own != nullptr && valid) { // userinc hook (src/cem_maxwell.F:498)
+                const int qo = a.inc_own[jf], qn = a.inc_nbr[jf];
+                if (qo >= 0) {
+                    const double ui = cos(a.inc_phase[qo] - a.inc_wt);
+                    Hx += a.inc_amp[qo] * ui; Hy += a.inc_amp[a.inc_n + qo] * ui;
+                    Hz += a.inc_amp[2 * a.inc_n + qo] * ui;
+                    Ex += a.inc_amp[3 * a.inc_n + qo] * ui;
+                    Ey += a.inc_amp[4 * a.inc_n + qo] * ui;
+                    Ez += a.inc_amp[5 * a.inc_n + qo] * ui;
+                }
+                if (qn >= 0) {
+                    const double ui = cos(a.inc_phase[qn] - a.inc_wt);
+                    pHx += a.inc_amp[qn] * ui; pHy += a.inc_amp[a.inc_n + qn] * ui;
+                    pHz += a.inc_amp[2 * a.inc_n + qn] * ui;
+                    pEx += a.inc_amp[3 * a.inc_n + qn] * ui;
+                    pEy += a.inc_amp[4 * a.inc_n + qn] * ui;
+                    pEz += a.inc_amp[5 * a.inc_n + qn] * ui;
+                }
+            }
+            // -n x E, -n x H of the own side (flux3d :946-955)
+            double s0 = -uny * Ez + unz * Ey;
+            double s1 = -unz * Ex + unx * Ez;
+            double s2 = -unx * Ey + uny * Ex;
+            double s3 = -uny * Hz + unz * Hy;
+            double s4 = -unz * Hx + unx * Hz;
+            double s5 = -unx * Hy + uny * Hx;
+            if (vp >= 0 || vp <= -3) {
+                // neighbour's (-n+ x E+) with n+ = -n-  (the gs_op_fields sum of :962)
+                s0 = s0 - (-uny * pEz + unz * pEy);
+                s1 = s1 - (-unz * pEx + unx * pEz);
+                s2 = s2 - (-unx * pEy + uny * pEx);
+                s3 = s3 - (-uny * pHz + unz * pHy);
+                s4 = s4 - (-unz * pHx + unx * pHz);
+                s5 = s5 - (-unx * pHy + uny * pHx);
+            } else if (vp == -1) { // 'PEC' / 'PML' outer face: cem_maxwell_flux_pec :1397-1405
+                s0 = 2.0 * s0; s1 = 2.0 * s1; s2 = 2.0 * s2;
+                s3 = 0.0; s4 = 0.0; s5 = 0.0;
+            }
+            { // flux into resH (:976-986)
+                const double Y02 = -(hY * Y1), C02Y = hY * a.C0;
+                const double fu1 = uny * s5 - unz * s4;
+                const double fu2 = unz * s3 - unx * s5;
+                const double fu3 = unx * s4 - uny * s3;
+                fl[f][0] = ar * (Y02 * s0 - C02Y * fu1);
+                fl[f][1] = ar * (Y02 * s1 - C02Y * fu2);
+                fl[f][2] = ar * (Y02 * s2 - C02Y * fu3);
+            }
+            { // flux into resE (:987-997)
+                const double Z02 = hZ * Z1, C02Z = hZ * a.C0;
+                const double fw1 = uny * s2 - unz * s1;
+                const double fw2 = unz * s0 - unx * s2;
+                const double fw3 = unx * s1 - uny * s0;
+                fl[f][3] = ar * (Z02 * s3 - C02Z * fw1);
+                fl[f][4] = ar * (Z02 * s4 - C02Z * fw2);
+                fl[f][5] = ar * (Z02 * s5 - C02Z * fw3);
+            }
+        }
+        // lifts into the residual: x-, y-, z-faces in turn (edge/corner nodes get 2/3 of them)
+#pragma unroll
+        for (int rd = 0; rd < 3; rd++) {
+#pragma unroll
+            for (int f = 0; f < FPT; f++) {
+                const int slot = fjs[f] < 0 ? -1 : fjs[f] / N2;
+                const int myrd = (slot == 1 || slot == 3) ? 0 : ((slot == 0 || slot == 2) ? 1 : 2);
+                if (slot >= 0 && myrd == rd) {
+                    const int sn = fsn[f];
+#pragma unroll
+                    for (int c = 0; c < 6; c++) R[c * SC + sn] += fl[f][c];
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- P4: t-pencils, thread (g,h,i,j) ---------------------------------------------------------
+    if constexpr (KS == 1) t_phase<N, KS, 0>(prm.D, a, U, R, ebase, tid);
+    else {
+        if (s == 0) t_phase<N, KS, 0>(prm.D, a, U, R, ebase, tid);
+        if (KS > 1 && s == 1) t_phase<N, KS, (KS > 1 ? 1 : 0)>(prm.D, a, U, R, ebase, tid);
+        if (KS > 2 && s == 2) t_phase<N, KS, (KS > 2 ? 2 : 0)>(prm.D, a, U, R, ebase, tid);
+        if (KS > 3 && s == 3) t_phase<N, KS, (KS > 3 ? 3 : 0)>(prm.D, a, U, R, ebase, tid);
+    }
+    __syncthreads();
+
+    // ---- P5: streaming epilogue --------------------------------------------------------------------
+    {
+        constexpr int ITEMS = 2 * N2 * KB;
+        constexpr int PER = (ITEMS + NT - 1) / NT;
+        constexpr int UNR = PER < C::EPI ? PER : C::EPI;
+#pragma unroll 1
+        for (int q0 = 0; q0 < PER; q0 += UNR) {
+            double kk[UNR][3], mb[UNR];
+#pragma unroll
+            for (int x = 0; x < UNR; x++) {
+                const int q = tid + (q0 + x) * NT;
+                const int g = q / (N2 * KB) ? 1 : 0;
+                int nl = q - g * (N2 * KB);
+                nl = nl < nslab ? nl : nslab - 1;
+                const long long cold = (g == 0 ? 3 : 0) * a.ld;
+#pragma unroll
+                for (int c = 0; c < 3; c++) kk[x][c] = a.kf[cold + c * a.ld + sbase + nl];
+                mb[x] = ldg((g == 0 ? a.ebm1 : a.hbm1) + sbase + nl);
+            }
+#pragma unroll
+            for (int x = 0; x < UNR; x++) {
+                const int q = tid + (q0 + x) * NT;
+                const int g = q / (N2 * KB) ? 1 : 0;
+                const int nl = q - g * (N2 * KB);
+                if (q < ITEMS && nl < nslab) {
+                    const int i = nl % N, j = (nl / N) % N, k = nl / N2;
+                    const int sn = Lay<N>::at(i, j, k);
+                    const long long gi = sbase + nl;
+                    const int cb0 = g == 0 ? 3 : 0; // components being updated
+                    double r[3] = {R[cb0 * SC + sn], R[(cb0 + 1) * SC + sn], R[(cb0 + 2) * SC + sn]};
+                    const double o[3] = {U[cb0 * SC + sn], U[(cb0 + 1) * SC + sn], U[(cb0 + 2) * SC + sn]};
+                    if (PML) { // pml_step (src/cem_maxwell_pml.F:540-585) + PML half of rk_maxwell_ab
+                        const double bm1 = ldg(a.bmn + gi);
+                        const double bm1inv = 1.0 / bm1;
+                        const double sigx = a.sig[gi], sigy = a.sig[a.npts + gi],
+                                     sigz = a.sig[2 * a.npts + gi];
+                        const double permitt = a.eps[gi];
+                        const double sxp = sigx / permitt, syp = sigy / permitt, szp = sigz / permitt;
+                        double *pF = g == 0 ? a.pD : a.pB;
+                        double *kF = g == 0 ? a.kD : a.kB;
+                        const double b0 = pF[gi], b1 = pF[a.npts + gi], b2 = pF[2 * a.npts + gi];
+                        const double rb0 = r[0] * bm1inv - syp * b0;
+                        const double rb1 = r[1] * bm1inv - szp * b1;
+                        const double rb2 = r[2] * bm1inv - sxp * b2;
+                        double p0, p1, p2;
+                        if (g == 0) {
+                            p0 = -syp * b0 + sxp * b0 - sigz * o[0];
+                            p1 = -szp * b1 + syp * b1 - sigx * o[1];
+                            p2 = -sxp * b2 + szp * b2 - sigy * o[2];
+                        } else {
+                            const double permeab = a.mu[gi];
+                            p0 = -syp * b0 + sxp * b0 - szp * permeab * o[0];
+                            p1 = -szp * b1 + syp * b1 - sxp * permeab * o[1];
+                            p2 = -sxp * b2 + szp * b2 - syp * permeab * o[2];
+                        }
+                        r[0] = r[0] + p0 * bm1; r[1] = r[1] + p1 * bm1; r[2] = r[2] + p2 * bm1;
+                        double t;
+                        t = a.ca * kF[gi] + a.dt * rb0; kF[gi] = t; pF[gi] = b0 + a.cb * t;
+                        t = a.ca * kF[a.npts + gi] + a.dt * rb1; kF[a.npts + gi] = t;
+                        pF[a.npts + gi] = b1 + a.cb * t;
+                        t = a.ca * kF[2 * a.npts + gi] + a.dt * rb2; kF[2 * a.npts + gi] = t;
+                        pF[2 * a.npts + gi] = b2 + a.cb * t;
+                    }
+                    if (a.src_prof != nullptr) { // usersrc hook: res(comp) -= profile*(tfac*bm)
+                        const int cs = a.src_comp - cb0;
+                        if (cs >= 0 && cs < 3) {
+                            const double sv2 = ldg(a.src_prof + gi) * (a.src_tfac * ldg(a.bmn + gi));
+                            if (cs == 0) r[0] -= sv2;
+                            else if (cs == 1) r[1] -= sv2;
+                            else r[2] -= sv2;
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const double t = a.ca * kk[x][c] + a.dt * (r[c] * mb[x]);
+                        a.kf[(cb0 + c) * a.ld + gi] = t;
+                        a.u_out[(cb0 + c) * a.ld + gi] = o[c] + a.cb * t;
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int N>
+int launch_n(const StageArgs &a, const double *Dhost, bool pml, cudaStream_t st)
+{
+    constexpr int KS = ks_for(N);
+    using C = Slab<N, KS>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e1 = cudaFuncSetAttribute(slab_kernel<N, KS, false>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)C::SMEM);
+        cudaError_t e2 = cudaFuncSetAttribute(slab_kernel<N, KS, true>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)C::SMEM);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) return 1;
+        configured = true;
+    }
+    if (a.nel <= 0) return 0;
+    StageParams<N> prm;
+    prm.a = a;
+    for (int q = 0; q < N * N; q++) prm.D[q] = Dhost[q];
+    if (pml)
+        slab_kernel<N, KS, true><<<KS * a.nel, C::NT, C::SMEM, st>>>(prm);
+    else
+        slab_kernel<N, KS, false><<<KS * a.nel, C::NT, C::SMEM, st>>>(prm);
+    return cudaGetLastError() == cudaSuccess ? 0 : 2;
+}
+
+} // namespace
+
+// returns 0 ok, -1 unsupported order, >0 CUDA failure.  Dhost = dxm1 (n*n, column-major).
+int launch_stage_slab(const StageArgs &a, const double *Dhost, int nx1, bool pml, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (nx1) {
+    case 2: return launch_n<2>(a, Dhost, pml, st);
+    case 3: return launch_n<3>(a, Dhost, pml, st);
+    case 4: return launch_n<4>(a, Dhost, pml, st);
+    case 5: return launch_n<5>(a, Dhost, pml, st);
+    case 6: return launch_n<6>(a, Dhost, pml, st);
+    case 7: return launch_n<7>(a, Dhost, pml, st);
+    case 8: return launch_n<8>(a, Dhost, pml, st);
+    case 9: return launch_n<9>(a, Dhost, pml, st);
+    case 10: return launch_n<10>(a, Dhost, pml, st);
+    case 11: return launch_n<11>(a, Dhost, pml, st);
+    case 12: return launch_n<12>(a, Dhost, pml, st);
+    case 13: return launch_n<13>(a, Dhost, pml, st);
+    case 14: return launch_n<14>(a, Dhost, pml, st);
+    case 15: return launch_n<15>(a, Dhost, pml, st);
+    case 16: return launch_n<16>(a, Dhost, pml, st);
+    default: return -1;
+    }
+}
+
+} // namespace nkb
