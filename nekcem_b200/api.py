@@ -23,7 +23,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(_HERE, "lib", "libnekcem_b200.so")
+LIBPATH = os.environ.get("NEKCEM_B200_LIB") or os.path.join(_HERE, "lib", "libnekcem_b200.so")
 ABI_VERSION = 1
 
 ARRAY_IDS = {name: i for i, name in enumerate([

@@ -1,7 +1,7 @@
 // Fused Maxwell RK-stage kernel for sm_100a, "element-slab" formulation, 2 <= nx1 <= 16.
 //
 // One launch = one RK stage over a list of elements.  One CTA = one k-SLAB of one element
-// (slab = all nodes with k0 <= k < k0+kb; KS slabs per element, KS = 1 for nx1 <= 10), and it
+// (slab = all nodes with k0 <= k < k0+kb; KS slabs per element, KS = 1 for nx1 <= 8), and it
 // updates ALL SIX components of those nodes, so every array of the stage crosses L2->SM once per
 // node: fields, RK registers, the nine cofactors, the two masses, and one neighbour trace per
 // face point.  The slabs of an element are adjacent CTAs; what they
@@ -35,12 +35,31 @@ namespace nkb {
 namespace {
 
 // ---- compile-time geometry -----------------------------------------------------------------
-__host__ __device__ constexpr int ks_for(int n) { return n <= 10 ? 1 : (n <= 12 ? 2 : (n == 13 ? 3 : 4)); }
+// Build-time tunables (developer sweeps: scripts/build_variants.sh)
+#ifndef SLAB_EPI
+#define SLAB_EPI 4
+#endif
+#ifndef SLAB_PF_MODE
+#define SLAB_PF_MODE 1 // 0: prefetch everything at CTA start; 1: staged (just in time); 2: none
+#endif
+#ifndef SLAB_ST_CS
+#define SLAB_ST_CS 1 // 1: streaming (evict-first) stores of the results
+#endif
+#ifndef SLAB_COF_SLOTS
+#define SLAB_COF_SLOTS 1
+#endif
+__host__ __device__ constexpr int ks_for(int n)
+{
+#ifdef KS_OVERRIDE_N
+    if (n == KS_OVERRIDE_N) return KS_OVERRIDE;
+#endif
+    return n <= 8 ? 1 : (n <= 12 ? 2 : 4);
+}
 __host__ __device__ constexpr int rsplit_for(int n) { return n <= 5 ? 4 : 2; }
 __host__ __device__ constexpr int round32(int x) { return ((x + 31) / 32) * 32; }
 __host__ __device__ constexpr int nt_for(int items)
 {
-    if (items <= 288) return round32(items);
+    if (items <= 320) return round32(items);
     int passes = (items + 255) / 256;
     return round32((items + passes - 1) / passes);
 }
@@ -51,10 +70,19 @@ struct Slab {
     static constexpr int KB = (N + KS - 1) / KS; // thickest slab
     static constexpr int SPLIT = rsplit_for(N);  // threads per r/s pencil
     static constexpr int NO = (N + SPLIT - 1) / SPLIT;
-    static constexpr int RS_ITEMS = 2 * SPLIT * N * KB;
+    // work items of a pencil phase: (h, g, pencil) with the output share h slowest and the
+    // (g, pencil) block padded to whole warps, so that h -- the only index that selects
+    // different code -- is warp-uniform
+    static constexpr int RS_BLK = round32(2 * N * KB);
+    static constexpr int RS_ITEMS = SPLIT * RS_BLK;
     static constexpr int TSPLIT = KS == 1 ? SPLIT : 1; // threads per t pencil
-    static constexpr int T_ITEMS = 2 * TSPLIT * N2;
+    static constexpr int T_BLK = round32(2 * N2);
+    static constexpr int T_ITEMS = TSPLIT * T_BLK;
+#ifdef SLAB_NT
+    static constexpr int NT = SLAB_NT;
+#else
     static constexpr int NT = nt_for(RS_ITEMS);
+#endif
     static constexpr int SC = Lay<N>::SK * KB; // component stride in smem
     static constexpr int FXY = 4 * N * KB;     // face points on the x/y faces of a slab
     static constexpr int FZ = KS == 1 ? 2 * N2 : N2;
@@ -64,15 +92,23 @@ struct Slab {
     __host__ __device__ static constexpr int k0(int s) { return s * N / KS; }
     __host__ __device__ static constexpr int kb(int s) { return (s + 1) * N / KS - s * N / KS; }
     // cofactor batches: outputs whose cofactors are loaded together
+#ifdef SLAB_PB_S
+    static constexpr int PB_S = SLAB_PB_S < NO ? SLAB_PB_S : NO;
+#else
     static constexpr int PB_S = NO <= 2 ? NO : (NO <= 6 ? (NO + 1) / 2 : (NO + 3) / 4);
-    static constexpr int REG_CAP = NO >= 7 ? 128 : (NO >= 5 ? 112 : 96);
+#endif
+#ifdef SLAB_REG_CAP
+    static constexpr int REG_CAP = SLAB_REG_CAP;
+#else
+    static constexpr int REG_CAP = NO >= 7 ? 128 : 96;
+#endif
     static constexpr int MINB_SMEM = (227 * 1024) / ((int)SMEM + 1024);
     static constexpr int MINB_THR = 2048 / NT;
     static constexpr int MINB_REG = 65536 / (NT * REG_CAP);
     static constexpr int MINB0 = MINB_SMEM < MINB_THR ? MINB_SMEM : MINB_THR;
     static constexpr int MINB1 = MINB0 < MINB_REG ? MINB0 : MINB_REG;
     static constexpr int MINB = MINB1 < 1 ? 1 : (MINB1 > 8 ? 8 : MINB1);
-    static constexpr int EPI = 4; // nodes in flight per thread in the epilogue
+    static constexpr int EPI = SLAB_EPI; // nodes in flight per thread in the epilogue
 };
 
 // ---- one pencil phase -------------------------------------------------------------------------
@@ -103,58 +139,73 @@ __device__ __forceinline__ void pencil_phase(const double (&D)[N * N], const Sta
     constexpr int NO = O1 - O0;
     constexpr int NCOF = DIR == 1 ? 6 : 3;
     if constexpr (NO > 0) {
-        double cof[PB][NCOF], wv[PB];
-        auto load_cof = [&](int b0) {
+        constexpr int NB = (NO + PB - 1) / PB;                   // cofactor batches
+        constexpr int NS = SLAB_COF_SLOTS < NB ? SLAB_COF_SLOTS : NB; // batches in flight
+        double cof[NS][PB][NCOF], wv[NS][PB];
+        auto load_cof = [&](int b, int sl) {
 #pragma unroll
             for (int x = 0; x < PB; x++) {
-                const int o = O0 + b0 + x < O1 ? O0 + b0 + x : O1 - 1;
+                const int o = O0 + b * PB + x < O1 ? O0 + b * PB + x : O1 - 1;
                 const int nd = n_at<N, DIR>(o, pa, pb);
                 const long long gi = gbase + nd;
                 if constexpr (DIR == 1) {
 #pragma unroll
-                    for (int q = 0; q < 6; q++) cof[x][q] = ldg(a.met[q] + gi);
+                    for (int q = 0; q < 6; q++) cof[sl][x][q] = ldg(a.met[q] + gi);
                 } else if constexpr (DIR == 2) {
 #pragma unroll
-                    for (int q = 0; q < 3; q++) cof[x][q] = ldg(a.met[6 + q] + gi);
+                    for (int q = 0; q < 3; q++) cof[sl][x][q] = ldg(a.met[6 + q] + gi);
                 }
-                if constexpr (DIR != 0) wv[x] = sg * ldg(a.w3 + wbase + nd);
+                if constexpr (DIR != 0) wv[sl][x] = sg * ldg(a.w3 + wbase + nd);
             }
         };
-        // cofactors of the first batch: in flight during the contraction
-        if constexpr (DIR != 0) load_cof(0);
+        // cofactors of the first batch(es): in flight during the contraction
+        if constexpr (DIR != 0) {
+#pragma unroll
+            for (int b = 0; b < NS; b++) load_cof(b, b);
+        }
         // output-stationary contraction: the line streams by once, each point feeds the 3*NO
         // accumulators of this thread (sum over m left to right, as mxfK)
         double acc[3][NO];
+        if constexpr (GSRC) {
+            // line from global memory: all N loads of a component are issued before its FMAs
 #pragma unroll
-        for (int m = 0; m < N; m++) {
-            double u0, u1, u2;
-            if constexpr (GSRC) {
-                const double *gp = gsrc + n_at<N, DIR>(m, pa, pb);
-                u0 = ldg(gp); u1 = ldg(gp + a.ld); u2 = ldg(gp + 2 * a.ld);
-            } else {
-                const int so = s_at<N, DIR, KOFF>(m, pa, pb);
-                u0 = U[so]; u1 = U[SC + so]; u2 = U[2 * SC + so];
+            for (int c = 0; c < 3; c++) {
+                double ul[N];
+#pragma unroll
+                for (int m = 0; m < N; m++) ul[m] = ldg(gsrc + c * a.ld + n_at<N, DIR>(m, pa, pb));
+#pragma unroll
+                for (int m = 0; m < N; m++)
+#pragma unroll
+                    for (int o = 0; o < NO; o++) {
+                        const double dv = D[(O0 + o) + N * m];
+                        if (m == 0) acc[c][o] = dv * ul[m];
+                        else acc[c][o] = acc[c][o] + dv * ul[m];
+                    }
             }
+        } else {
 #pragma unroll
-            for (int o = 0; o < NO; o++) {
-                const double dv = D[(O0 + o) + N * m];
-                if (m == 0) {
-                    acc[0][o] = dv * u0; acc[1][o] = dv * u1; acc[2][o] = dv * u2;
-                } else {
-                    acc[0][o] = acc[0][o] + dv * u0;
-                    acc[1][o] = acc[1][o] + dv * u1;
-                    acc[2][o] = acc[2][o] + dv * u2;
+            for (int m = 0; m < N; m++) {
+                const int so = s_at<N, DIR, KOFF>(m, pa, pb);
+                const double u0 = U[so], u1 = U[SC + so], u2 = U[2 * SC + so];
+#pragma unroll
+                for (int o = 0; o < NO; o++) {
+                    const double dv = D[(O0 + o) + N * m];
+                    if (m == 0) {
+                        acc[0][o] = dv * u0; acc[1][o] = dv * u1; acc[2][o] = dv * u2;
+                    } else {
+                        acc[0][o] = acc[0][o] + dv * u0;
+                        acc[1][o] = acc[1][o] + dv * u1;
+                        acc[2][o] = acc[2][o] + dv * u2;
+                    }
                 }
             }
         }
 #pragma unroll
-        for (int b0 = 0; b0 < NO; b0 += PB) {
-            if (b0 > 0) {
-                if constexpr (DIR != 0) load_cof(b0);
-            }
+        for (int b = 0; b < NB; b++) {
+            const int sl = b % NS;
 #pragma unroll
             for (int x = 0; x < PB; x++) {
-                const int oo = b0 + x;
+                const int oo = b * PB + x;
                 if (oo < NO) {
                     const double d[3] = {acc[0][oo], acc[1][oo], acc[2][oo]};
                     double c[3];
@@ -164,18 +215,22 @@ __device__ __forceinline__ void pencil_phase(const double (&D)[N * N], const Sta
                     } else if constexpr (DIR == 1) {
                         const double dr[3] = {Ro[0], Ro[SC], Ro[2 * SC]};
                         double cr[3];
-                        curl_part(dr, cof[x][0], cof[x][1], cof[x][2], cr);
-                        curl_part(d, cof[x][3], cof[x][4], cof[x][5], c);
-                        Ro[0] = (cr[0] + c[0]) * wv[x];
-                        Ro[SC] = (cr[1] + c[1]) * wv[x];
-                        Ro[2 * SC] = (cr[2] + c[2]) * wv[x];
+                        curl_part(dr, cof[sl][x][0], cof[sl][x][1], cof[sl][x][2], cr);
+                        curl_part(d, cof[sl][x][3], cof[sl][x][4], cof[sl][x][5], c);
+                        Ro[0] = (cr[0] + c[0]) * wv[sl][x];
+                        Ro[SC] = (cr[1] + c[1]) * wv[sl][x];
+                        Ro[2 * SC] = (cr[2] + c[2]) * wv[sl][x];
                     } else {
-                        curl_part(d, cof[x][0], cof[x][1], cof[x][2], c);
-                        Ro[0] = Ro[0] + wv[x] * c[0];
-                        Ro[SC] = Ro[SC] + wv[x] * c[1];
-                        Ro[2 * SC] = Ro[2 * SC] + wv[x] * c[2];
+                        curl_part(d, cof[sl][x][0], cof[sl][x][1], cof[sl][x][2], c);
+                        Ro[0] = Ro[0] + wv[sl][x] * c[0];
+                        Ro[SC] = Ro[SC] + wv[sl][x] * c[1];
+                        Ro[2 * SC] = Ro[2 * SC] + wv[sl][x] * c[2];
                     }
                 }
+            }
+            // refill the slot just consumed with the batch NS ahead
+            if constexpr (DIR != 0) {
+                if (b + NS < NB) load_cof(b + NS, sl);
             }
         }
     }
@@ -211,8 +266,9 @@ __device__ __forceinline__ void t_phase(const double (&D)[N * N], const StageArg
     constexpr int PB_T = NOT <= 8 ? NOT : (NOT + 1) / 2;
 #pragma unroll 1
     for (int w = tid; w < C::T_ITEMS; w += C::NT) {
-        const int p = w % C::N2, hg = w / C::N2;
-        const int h = hg % C::TSPLIT, g = hg / C::TSPLIT;
+        const int h = w / C::T_BLK, r = w - h * C::T_BLK;
+        const int g = r / C::N2, p = r - g * C::N2;
+        if (g > 1) continue;
         const int pa = p % N, pb = p / N;
         const double *Us = U + (g ? 3 : 0) * C::SC;
         double *Rd = R + (g ? 0 : 3) * C::SC;
@@ -242,29 +298,40 @@ __global__ void __launch_bounds__(Slab<N, KS>::NT, Slab<N, KS>::MINB)
     const long long sbase = ebase + k0 * N2; // first node of the slab
     const int nslab = N2 * kb;
 
-    // ---- P0: stage the six field components of the slab (loads issued before anything else) ----
-    constexpr int SPER = (6 * N2 * KB + NT - 1) / NT;
-    constexpr int SUNR = SPER < 24 ? SPER : 24;
-    double sv[SUNR];
-#pragma unroll
-    for (int x = 0; x < SUNR; x++) {
-        const int q = tid + x * NT;
-        const int c = q / (N2 * KB), r = q - c * (N2 * KB);
-        sv[x] = (q < 6 * N2 * KB && r < nslab) ? ldg(a.u_in + c * a.ld + sbase + r) : 0.0;
-    }
-
-    // ---- prologue: put every other HBM request of this slab in flight now -----------------------
-    // (a) L2 prefetch of the slab's metric, mass and RK-register arrays: one warp per array
-    {
+    // L2 prefetch of the slab's share of the volume arrays [first,last) of the list
+    // rx..sz (0-5), tx..tz (6-8), kH,kE (9-14), hbm1, ebm1 (15,16): one warp per array
+    auto pf_vol = [&](int first, int last) {
         const int warp = tid >> 5, lane = tid & 31;
-        constexpr int NW = NT / 32;
-        for (int arr = warp; arr < 17; arr += NW) {
+        for (int arr = first + warp; arr < last; arr += NT / 32) {
             const double *base;
             if (arr < 9) base = a.met[arr];
             else if (arr < 15) base = a.kf + (arr - 9) * a.ld;
             else base = arr == 15 ? a.hbm1 : a.ebm1;
             prefetch_chunk(base + sbase, nslab * 8, lane);
         }
+    };
+
+    // ---- P0: stage the six field components of the slab (loads issued before anything else) ----
+    // plane mapping (no per-value index arithmetic): thread = (plane slot ps, node (pi,pj) of an
+    // i-j plane); the 6*KB planes (component c, local k) of the slab are handled NPL at a time
+    constexpr int NPL = NT / N2;
+    static_assert(NPL >= 1, "block smaller than one i-j plane");
+    const int ps = tid / N2, pnd = tid - ps * N2;
+    const int pi = pnd % N, pj = pnd / N;
+    const bool pok = ps < NPL;
+    constexpr int SPER = (6 * KB + NPL - 1) / NPL;
+    constexpr int SUNR = SPER < 24 ? SPER : 24;
+    double sv[SUNR];
+#pragma unroll
+    for (int x = 0; x < SUNR; x++) {
+        const int pl = ps + NPL * x, c = pl / KB, kl = pl - c * KB;
+        sv[x] = (pok && pl < 6 * KB && kl < kb) ? ldg(a.u_in + c * a.ld + sbase + kl * N2 + pnd) : 0.0;
+    }
+
+    // ---- prologue: put every other HBM request of this slab in flight now -----------------------
+    // (a) L2 prefetch of the slab's metric, mass and RK-register arrays: one warp per array
+    {
+        pf_vol(SLAB_PF_MODE == 0 ? 0 : 0, SLAB_PF_MODE == 0 ? 17 : (SLAB_PF_MODE == 1 ? 6 : 0));
         // face geometry / impedances / vmapP of the slab's part of the four x/y faces and of
         // its z face(s): 9 arrays x (4 strips of N*kb points + whole z faces)
         constexpr int LXY = (N * KB * 8 + 127) / 128 + 1; // lines per strip (any alignment)
@@ -338,17 +405,14 @@ __global__ void __launch_bounds__(Slab<N, KS>::NT, Slab<N, KS>::MINB)
         if (q0 > 0) {
 #pragma unroll
             for (int x = 0; x < SUNR; x++) {
-                const int q = tid + (q0 + x) * NT;
-                const int c = q / (N2 * KB), r = q - c * (N2 * KB);
-                sv[x] = (q < 6 * N2 * KB && r < nslab) ? ldg(a.u_in + c * a.ld + sbase + r) : 0.0;
+                const int pl = ps + NPL * (q0 + x), c = pl / KB, kl = pl - c * KB;
+                sv[x] = (pok && pl < 6 * KB && kl < kb) ? ldg(a.u_in + c * a.ld + sbase + kl * N2 + pnd) : 0.0;
             }
         }
 #pragma unroll
         for (int x = 0; x < SUNR; x++) {
-            const int q = tid + (q0 + x) * NT;
-            const int c = q / (N2 * KB), r = q - c * (N2 * KB);
-            const int i = r % N, j = (r / N) % N, k = r / N2;
-            if (q < 6 * N2 * KB && r < nslab) U[c * SC + Lay<N>::at(i, j, k)] = sv[x];
+            const int pl = ps + NPL * (q0 + x), c = pl / KB, kl = pl - c * KB;
+            if (pok && pl < 6 * KB && kl < kb) U[c * SC + Lay<N>::at(pi, pj, kl)] = sv[x];
         }
     }
     // (c) neighbour traces of those face points -> L2
@@ -363,27 +427,29 @@ __global__ void __launch_bounds__(Slab<N, KS>::NT, Slab<N, KS>::MINB)
     // ---- P1: r-pencils, thread (g,h,j,k): raw derivatives ----------------------------------------
 #pragma unroll 1
     for (int w = tid; w < C::RS_ITEMS; w += NT) {
-        const int p = w % (N * KB), hg = w / (N * KB);
-        const int h = hg % C::SPLIT, g = hg / C::SPLIT;
+        const int h = w / C::RS_BLK, r = w - h * C::RS_BLK;
+        const int g = r / (N * KB), p = r - g * (N * KB);
         const int pa = p % N, pb = p / N;
-        if (pb < kb)
+        if (g < 2 && pb < kb)
             pencil_split<N, 0, 0, 0, N, C::SPLIT, C::NO, SC, false>(
                 prm.D, a, U + (g ? 3 : 0) * SC, nullptr, R + (g ? 0 : 3) * SC, pa, pb, sbase,
                 k0 * N2, g ? -1.0 : 1.0, h);
     }
     __syncthreads();
+    if (SLAB_PF_MODE == 1) pf_vol(6, 9);
     // ---- P2: s-pencils, thread (g,h,i,k): r- and s-parts of the weighted curl ------------------
 #pragma unroll 1
     for (int w = tid; w < C::RS_ITEMS; w += NT) {
-        const int p = w % (N * KB), hg = w / (N * KB);
-        const int h = hg % C::SPLIT, g = hg / C::SPLIT;
+        const int h = w / C::RS_BLK, r = w - h * C::RS_BLK;
+        const int g = r / (N * KB), p = r - g * (N * KB);
         const int pa = p % N, pb = p / N;
-        if (pb < kb)
+        if (g < 2 && pb < kb)
             pencil_split<N, 1, 0, 0, N, C::SPLIT, C::PB_S, SC, false>(
                 prm.D, a, U + (g ? 3 : 0) * SC, nullptr, R + (g ? 0 : 3) * SC, pa, pb, sbase,
                 k0 * N2, g ? -1.0 : 1.0, h);
     }
     __syncthreads();
+    if (SLAB_PF_MODE == 1) pf_vol(9, 17);
 
     // ---- P3: surface flux: both fluxes of a face point from one neighbour gather ---------------
     {
@@ -496,18 +562,17 @@ __global__ void __launch_bounds__(Slab<N, KS>::NT, Slab<N, KS>::MINB)
 
     // ---- P5: streaming epilogue --------------------------------------------------------------------
     {
-        constexpr int ITEMS = 2 * N2 * KB;
-        constexpr int PER = (ITEMS + NT - 1) / NT;
+        constexpr int PER = (2 * KB + NPL - 1) / NPL; // (g, local k) planes per thread
         constexpr int UNR = PER < C::EPI ? PER : C::EPI;
 #pragma unroll 1
         for (int q0 = 0; q0 < PER; q0 += UNR) {
             double kk[UNR][3], mb[UNR];
 #pragma unroll
             for (int x = 0; x < UNR; x++) {
-                const int q = tid + (q0 + x) * NT;
-                const int g = q / (N2 * KB) ? 1 : 0;
-                int nl = q - g * (N2 * KB);
-                nl = nl < nslab ? nl : nslab - 1;
+                const int pl = ps + NPL * (q0 + x), g = pl / KB ? 1 : 0;
+                int kl = pl - g * KB;
+                kl = kl < kb ? kl : kb - 1;
+                const int nl = (pok ? pnd : 0) + kl * N2;
                 const long long cold = (g == 0 ? 3 : 0) * a.ld;
 #pragma unroll
                 for (int c = 0; c < 3; c++) kk[x][c] = a.kf[cold + c * a.ld + sbase + nl];
@@ -515,12 +580,11 @@ __global__ void __launch_bounds__(Slab<N, KS>::NT, Slab<N, KS>::MINB)
             }
 #pragma unroll
             for (int x = 0; x < UNR; x++) {
-                const int q = tid + (q0 + x) * NT;
-                const int g = q / (N2 * KB) ? 1 : 0;
-                const int nl = q - g * (N2 * KB);
-                if (q < ITEMS && nl < nslab) {
-                    const int i = nl % N, j = (nl / N) % N, k = nl / N2;
-                    const int sn = Lay<N>::at(i, j, k);
+                const int pl = ps + NPL * (q0 + x), g = pl / KB ? 1 : 0;
+                const int kl = pl - g * KB;
+                if (pok && pl < 2 * KB && kl < kb) {
+                    const int nl = pnd + kl * N2;
+                    const int sn = Lay<N>::at(pi, pj, kl);
                     const long long gi = sbase + nl;
                     const int cb0 = g == 0 ? 3 : 0; // components being updated
                     double r[3] = {R[cb0 * SC + sn], R[(cb0 + 1) * SC + sn], R[(cb0 + 2) * SC + sn]};
@@ -569,8 +633,13 @@ __global__ void __launch_bounds__(Slab<N, KS>::NT, Slab<N, KS>::MINB)
 #pragma unroll
                     for (int c = 0; c < 3; c++) {
                         const double t = a.ca * kk[x][c] + a.dt * (r[c] * mb[x]);
-                        a.kf[(cb0 + c) * a.ld + gi] = t;
-                        a.u_out[(cb0 + c) * a.ld + gi] = o[c] + a.cb * t;
+                        if (SLAB_ST_CS) {
+                            __stcs(a.kf + (cb0 + c) * a.ld + gi, t);
+                            __stcs(a.u_out + (cb0 + c) * a.ld + gi, o[c] + a.cb * t);
+                        } else {
+                            a.kf[(cb0 + c) * a.ld + gi] = t;
+                            a.u_out[(cb0 + c) * a.ld + gi] = o[c] + a.cb * t;
+                        }
                     }
                 }
             }
@@ -611,6 +680,10 @@ int launch_n(const StageArgs &a, const double *Dhost, bool pml, cudaStream_t st)
 int launch_stage_slab(const StageArgs &a, const double *Dhost, int nx1, bool pml, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
+#ifdef SLAB_ONLY_N
+    if (nx1 == SLAB_ONLY_N) return launch_n<SLAB_ONLY_N>(a, Dhost, pml, st);
+    return -1;
+#else
     switch (nx1) {
     case 2: return launch_n<2>(a, Dhost, pml, st);
     case 3: return launch_n<3>(a, Dhost, pml, st);
@@ -629,6 +702,7 @@ int launch_stage_slab(const StageArgs &a, const double *Dhost, int nx1, bool pml
     case 16: return launch_n<16>(a, Dhost, pml, st);
     default: return -1;
     }
+#endif
 }
 
 } // namespace nkb
