@@ -61,7 +61,7 @@ enum nekcem_b200_array {
 /* ---- problem description (the scalars the hot path reads from COMMON) -------------- */
 typedef struct nekcem_b200_desc {
     int32_t abi_version; /* NEKCEM_B200_ABI_VERSION */
-    int32_t ldim;        /* 3 (2D TE/TM path: see DESIGN.md "next")                  */
+    int32_t ldim;        /* 3, or 2 for the TE/TM modes (cem_maxwell_flux2d path)     */
     int32_t nx1;         /* points per direction, N+1 (SIZE: lx1)                    */
     int32_t nelt;        /* local element count (SIZE/DIMN)                          */
     int32_t imode;       /* 3 = 3D, 2 = TM, 1 = TE (src/INPUT:18-47, cem_param.F)    */
@@ -139,6 +139,23 @@ int nekcem_b200_set_incident(int handle, int32_t ninc, const int32_t *facepts, c
 int nekcem_b200_set_volume_source(int handle, int comp, const double *profile, double amp,
                                   double omega, double phase);
 
+/* Drude / Lorentz auxiliary differential equations.  Replace the per-stage calls
+ * `cem_maxwell_drude(jn,kjn,resjn,params,dindex,n)` (src/cem_maxwell.F:3095-3147) and
+ * `cem_maxwell_lorentz(jn,kjn,resjn,params,lindex,n)` (:3149-3211) that the reference's .usr
+ * files make from `usersrc` (tests/drude/drude.usr:153-170, tests/lorentz/lorentz.usr): the
+ * polarisation current is kept on the device and advanced inside the fused stage kernel at the
+ * reference's position (after pml_step, before the inverse mass):
+ *     Drude:   resE -= J*bm;  dJ/dt = -a*J + b*E;                    params(npts,2) = (a,b)
+ *     Lorentz: resE -= J*bm;  dJ/dt = -a*J - b*P + c*E;  dP/dt = J;   params(npts,3) = (a,b,c)
+ * jn,kjn: (npts,3) Drude, (npts,3,2) Lorentz (the user's COMMON arrays; NULL = zeros); index:
+ * the user's 1-based node list; n = 0 removes the ADE.  Call before nekcem_b200_setup.
+ * get_ade downloads jn and/or kjn (the `!$ACC UPDATE HOST` seam). */
+int nekcem_b200_set_drude(int handle, const double *jn, const double *kjn, const double *params,
+                          const int32_t *dindex, int32_t n);
+int nekcem_b200_set_lorentz(int handle, const double *jn, const double *kjn, const double *params,
+                            const int32_t *lindex, int32_t n);
+int nekcem_b200_get_ade(int handle, double *jn, double *kjn);
+
 /* The hot path.  Replaces `cem_maxwell_op_rk` (src/cem_maxwell.F:327-345): nsteps time
  * steps of 5 x {rk_c; cem_maxwell_op; rk_maxwell_ab}; advances the context's time by
  * nsteps*dt like time_advancing_pde (src/cem_drive.F:618-654). */
@@ -159,8 +176,7 @@ int nekcem_b200_error_sums(int handle, const double *exact_hn, const double *exa
  * compute stream) and the number of kernels it launched. */
 int nekcem_b200_last_step_ms(int handle, float *ms, int64_t *launches);
 
-/* Performance tunables (no effect on results).  "pf_dist": how many half-task CTAs ahead the
- * stage kernel prefetches the staged field components into L2 (0 = off). */
+/* Performance tunables (no effect on results).  "pf_dist": reserved (accepted, ignored). */
 int nekcem_b200_set_option(int handle, const char *name, int value);
 
 /* Algorithmic HBM bytes per stage for this context: 280 B/node +

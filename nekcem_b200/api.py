@@ -82,6 +82,9 @@ def lib():
         L.nekcem_b200_set_incident.argtypes = [C.c_int, C.c_int32, c_i32p, c_dp, c_dp, C.c_double]
         L.nekcem_b200_set_volume_source.argtypes = [C.c_int, C.c_int, c_dp, C.c_double,
                                                     C.c_double, C.c_double]
+        L.nekcem_b200_set_drude.argtypes = [C.c_int, c_dp, c_dp, c_dp, c_i32p, C.c_int32]
+        L.nekcem_b200_set_lorentz.argtypes = [C.c_int, c_dp, c_dp, c_dp, c_i32p, C.c_int32]
+        L.nekcem_b200_get_ade.argtypes = [C.c_int, c_dp, c_dp]
         L.nekcem_b200_set_option.argtypes = [C.c_int, C.c_char_p, C.c_int]
         L.nekcem_b200_set_time.argtypes = [C.c_int, C.c_double, C.c_double]
         L.nekcem_b200_get_time.argtypes = [C.c_int, c_dp]
@@ -267,6 +270,40 @@ class MaxwellB200:
     def set_volume_source(self, comp, profile, amp, omega, phase):
         p = None if profile is None else _dp(np.ascontiguousarray(profile, dtype=np.float64))
         _chk(self.L.nekcem_b200_set_volume_source(self.h, comp, p, amp, omega, phase))
+
+    def _set_ade(self, fn, ncomp, npar, jn, kjn, params, index0):
+        idx = np.ascontiguousarray(np.asarray(index0, dtype=np.int64) + 1, dtype=np.int32)
+        par = np.ascontiguousarray(params, dtype=np.float64).reshape(-1)
+        assert par.size == npar * self.npts
+        ptr = []
+        for a in (jn, kjn):
+            if a is None:
+                ptr.append(None)
+            else:
+                a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+                assert a.size == ncomp * self.npts
+                ptr.append(a)
+        self._ade_ncomp = ncomp
+        _chk(fn(self.h, None if ptr[0] is None else _dp(ptr[0]),
+                None if ptr[1] is None else _dp(ptr[1]), _dp(par),
+                idx.ctypes.data_as(c_i32p), idx.size))
+
+    def cem_maxwell_drude(self, jn, kjn, params, dindex0):
+        """Registers the Drude ADE that the reference's usersrc runs every stage through
+        ``cem_maxwell_drude(jn,kjn,resjn,params,dindex,n)`` (src/cem_maxwell.F:3095-3147):
+        jn,kjn (npts,3) or None, params (npts,2), dindex0 0-based nodes.  Call before setup()."""
+        self._set_ade(self.L.nekcem_b200_set_drude, 3, 2, jn, kjn, params, dindex0)
+
+    def cem_maxwell_lorentz(self, jn, kjn, params, lindex0):
+        """``cem_maxwell_lorentz`` (src/cem_maxwell.F:3149-3211): jn,kjn (npts,3,2), params
+        (npts,3)."""
+        self._set_ade(self.L.nekcem_b200_set_lorentz, 6, 3, jn, kjn, params, lindex0)
+
+    def get_ade(self):
+        """(jn, kjn) of the registered ADE, downloaded from the device."""
+        jn = np.zeros(self._ade_ncomp * self.npts); kjn = np.zeros_like(jn)
+        _chk(self.L.nekcem_b200_get_ade(self.h, _dp(jn), _dp(kjn)))
+        return jn, kjn
 
     def set_option(self, name: str, value: int):
         _chk(self.L.nekcem_b200_set_option(self.h, name.encode(), int(value)))

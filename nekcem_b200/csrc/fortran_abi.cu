@@ -113,3 +113,62 @@ NKB_EXPORT void nekcem_b200_error_sums_(const int *h, const double *exact_hn,
 {
     check(nekcem_b200_error_sums(*h, exact_hn, exact_en, sumsq, linf), "nekcem_b200_error_sums");
 }
+
+NKB_EXPORT void nekcem_b200_set_drude_(const int *h, const double *jn, const double *kjn,
+                                       const double *params, const int *dindex, const int *n)
+{
+    check(nekcem_b200_set_drude(*h, jn, kjn, params, dindex, *n), "nekcem_b200_set_drude");
+}
+
+NKB_EXPORT void nekcem_b200_set_lorentz_(const int *h, const double *jn, const double *kjn,
+                                         const double *params, const int *lindex, const int *n)
+{
+    check(nekcem_b200_set_lorentz(*h, jn, kjn, params, lindex, *n), "nekcem_b200_set_lorentz");
+}
+
+NKB_EXPORT void nekcem_b200_get_ade_(const int *h, double *jn, double *kjn)
+{
+    check(nekcem_b200_get_ade(*h, jn, kjn), "nekcem_b200_get_ade");
+}
+
+// Drop-in twins of the reference's ADE entry points, same names and argument lists
+// (src/cem_maxwell.F:3095, 3149).  The reference's .usr calls them from `usersrc` in every
+// stage; with the fused kernel the stage loop lives on the device, so the FIRST call registers
+// the user's COMMON arrays with the context selected by nekcem_b200_bind_ (the ADE then advances
+// inside nekcem_b200_step), and later calls are no-ops.  resjn is scratch in the reference and
+// is not needed here.
+static int g_bound_handle = -1;
+static int g_ade_registered = 0;
+
+NKB_EXPORT void nekcem_b200_bind_(const int *h)
+{
+    g_bound_handle = *h;
+    g_ade_registered = 0;
+}
+
+NKB_EXPORT void cem_maxwell_drude_(const double *jn, const double *kjn, double *resjn,
+                                   const double *params, const int *dindex, const int *n)
+{
+    (void)resjn;
+    if (g_bound_handle < 0) {
+        fprintf(stderr, "nekcem_b200: cem_maxwell_drude called before nekcem_b200_bind\n");
+        exit(1);
+    }
+    if (g_ade_registered) return;
+    check(nekcem_b200_set_drude(g_bound_handle, jn, kjn, params, dindex, *n), "cem_maxwell_drude");
+    g_ade_registered = 1;
+}
+
+NKB_EXPORT void cem_maxwell_lorentz_(const double *jn, const double *kjn, double *resjn,
+                                     const double *params, const int *lindex, const int *n)
+{
+    (void)resjn;
+    if (g_bound_handle < 0) {
+        fprintf(stderr, "nekcem_b200: cem_maxwell_lorentz called before nekcem_b200_bind\n");
+        exit(1);
+    }
+    if (g_ade_registered) return;
+    check(nekcem_b200_set_lorentz(g_bound_handle, jn, kjn, params, lindex, *n),
+          "cem_maxwell_lorentz");
+    g_ade_registered = 1;
+}

@@ -25,8 +25,8 @@
 #include "stage_args.h"
 
 namespace nkb {
-int launch_stage(const StageArgs &a, const double *Dhost, int nx1, bool pml, void *stream);
-int launch_stage_slab(const StageArgs &a, const double *Dhost, int nx1, bool pml, void *stream);
+int launch_stage_slab(const StageArgs &a, const double *Dhost, int nx1, bool aux, void *stream);
+int launch_stage2d(const StageArgs &a, const double *Dhost, int nx1, bool aux, void *stream);
 }
 
 namespace {
@@ -80,7 +80,7 @@ struct Ctx {
     std::vector<double> D_host; // dxm1: passed to the stage kernel by value (constant bank)
     int *vmapP_d = nullptr;
     int *elist_d = nullptr; // concatenated lists
-    int list_off[4] = {}, list_n[4] = {}; // [interior plain, interior pml, boundary plain, boundary pml]
+    int list_off[4] = {}, list_n[4] = {}; // [interior plain, interior aux, boundary plain, boundary aux]; aux = PML and/or ADE elements
     // host planning data
     std::vector<int64_t> glo;
     std::vector<int32_t> cempec;
@@ -115,8 +115,12 @@ struct Ctx {
     // diagnostics
     float last_ms = 0.f;
     int64_t last_launches = 0;
-    int pf_dist = 0;
-    int variant = 1; // 1: element-slab kernel (stage_slab.cu); 0: half-task pencil kernel
+    // Drude / Lorentz ADE state (user COMMON arrays, mirrored on the device)
+    int ade_kind = 0; // 0 none, 1 Drude, 2 Lorentz
+    double *ade_j = nullptr, *ade_k = nullptr, *ade_par = nullptr;
+    unsigned char *ade_mask = nullptr;
+    unsigned char *elflag_d = nullptr; // per element: bit 0 PML, bit 1 ADE
+    std::vector<char> ade_el; // per element: contains ADE nodes
     double *red_d = nullptr; // reduction scratch
     int red_blocks = 0;
 };
@@ -338,6 +342,9 @@ int build_lists(Ctx *c, std::vector<int32_t> &lists)
     for (auto &p : c->peers)
         for (int64_t fp : p.send_fp) is_b[fp / nfp] = 1;
     for (int32_t e : c->pml_el) is_pml[e] = 1;
+    if (c->ade_kind)
+        for (int e = 0; e < c->d.nelt; e++)
+            if (c->ade_el[e]) is_pml[e] = 1;
     std::vector<int32_t> L[4];
     for (int e = 0; e < c->d.nelt; e++) L[(is_b[e] ? 2 : 0) + (is_pml[e] ? 1 : 0)].push_back(e);
     lists.clear();
@@ -418,7 +425,6 @@ int run_stage(Ctx *c, int rkstep /*1..5*/)
     a.kf = c->kf;
     a.ld = c->ld;
     for (int q = 0; q < 9; q++) a.met[q] = c->dev[NKB_RXMN + q];
-    a.pf_dist = c->pf_dist;
     a.hbm1 = c->dev[NKB_HBM1]; a.ebm1 = c->dev[NKB_EBM1]; a.bmn = c->dev[NKB_BMN];
     a.D = c->dev[NKB_DXM1];
     a.w3 = c->dev[NKB_W3MN];
@@ -435,6 +441,10 @@ int run_stage(Ctx *c, int rkstep /*1..5*/)
     a.pB = c->dev[NKB_PMLBN]; a.pD = c->dev[NKB_PMLDN];
     a.kB = c->dev[NKB_KPMLBN]; a.kD = c->dev[NKB_KPMLDN];
     a.npts = c->npts;
+    a.elflag = c->elflag_d;
+    a.ade_kind = c->ade_kind;
+    a.ade_j = c->ade_j; a.ade_k = c->ade_k; a.ade_par = c->ade_par; a.ade_mask = c->ade_mask;
+    a.imode = c->d.imode;
     a.src_prof = c->src_prof;
     a.src_comp = c->src_comp;
     // rk_c (src/cem_common.F:12): rktime = time + dt*rk4c(i)
@@ -450,9 +460,9 @@ int run_stage(Ctx *c, int rkstep /*1..5*/)
         nkb::StageArgs b = a;
         b.elist = c->elist_d + c->list_off[q];
         b.nel = c->list_n[q];
-        int rc = c->variant == 1
+        int rc = c->d.ldim == 3
                      ? nkb::launch_stage_slab(b, c->D_host.data(), c->n, (q & 1) != 0, c->s_compute)
-                     : nkb::launch_stage(b, c->D_host.data(), c->n, (q & 1) != 0, c->s_compute);
+                     : nkb::launch_stage2d(b, c->D_host.data(), c->n, (q & 1) != 0, c->s_compute);
         if (rc < 0) return fail("nx1=%d is not supported by the stage kernels (2..16)", c->n);
         if (rc > 0) return fail("stage kernel launch failed: %s",
                                 cudaGetErrorString(cudaGetLastError()));
@@ -505,9 +515,10 @@ int nekcem_b200_create(const nekcem_b200_desc *desc, int *handle)
     if (desc->abi_version != NEKCEM_B200_ABI_VERSION)
         return fail("ABI version mismatch: caller %d, library %d", desc->abi_version,
                     NEKCEM_B200_ABI_VERSION);
-    if (desc->ldim != 3 || desc->imode != 3)
-        return fail("only the 3D path (ldim=3, imode=3) is implemented; got ldim=%d imode=%d",
-                    desc->ldim, desc->imode);
+    if (!((desc->ldim == 3 && desc->imode == 3) ||
+          (desc->ldim == 2 && (desc->imode == 1 || desc->imode == 2))))
+        return fail("need ldim=3 with imode=3, or ldim=2 with imode=1 (TE) / 2 (TM); got ldim=%d "
+                    "imode=%d", desc->ldim, desc->imode);
     if (desc->nx1 < 2 || desc->nx1 > 16)
         return fail("nx1=%d outside the supported range 2..16", desc->nx1);
     if (desc->nelt < 1) return fail("nelt must be >= 1");
@@ -517,9 +528,9 @@ int nekcem_b200_create(const nekcem_b200_desc *desc, int *handle)
     auto c = std::make_unique<Ctx>();
     c->d = *desc;
     c->n = desc->nx1;
-    c->nxyz = c->n * c->n * c->n;
-    c->nxzf = c->n * c->n;
-    c->nfaces = 6;
+    c->nxyz = desc->ldim == 3 ? c->n * c->n * c->n : c->n * c->n;
+    c->nxzf = desc->ldim == 3 ? c->n * c->n : c->n;
+    c->nfaces = 2 * desc->ldim;
     c->npts = (int64_t)c->nxyz * desc->nelt;
     c->nxzfl = (int64_t)c->nxzf * c->nfaces * desc->nelt;
     if (c->npts > 2147483647LL - 64) return fail("npts exceeds 32-bit node indexing");
@@ -571,6 +582,7 @@ int nekcem_b200_destroy(int handle)
         cudaFree(c->hY); cudaFree(c->hZ); cudaFree(c->vmapP_d); cudaFree(c->elist_d);
         cudaFree(c->sendbuf); cudaFree(c->halo); cudaFree(c->send_node);
         cudaFree(c->src_prof); cudaFree(c->red_d);
+        cudaFree(c->ade_j); cudaFree(c->ade_k); cudaFree(c->ade_par); cudaFree(c->ade_mask);
         cudaFree(c->inc_own_d); cudaFree(c->inc_nbr_d); cudaFree(c->inc_send_d);
         cudaFree(c->inc_amp_d); cudaFree(c->inc_phase_d);
         cudaEventDestroy(c->ev_stage); cudaEventDestroy(c->ev_halo);
@@ -599,6 +611,11 @@ int nekcem_b200_set_array(int handle, int which, const double *host, int64_t cou
         CUDA_OK(cudaMemcpy2D(base + c0 * c->ld, sizeof(double) * c->ld, host,
                              sizeof(double) * c->npts, sizeof(double) * c->npts, 3,
                              cudaMemcpyHostToDevice));
+        // 2D modes never write the inactive components: keep both ping-pong buffers alike
+        if (c->d.ldim == 2 && (which == NKB_HN || which == NKB_EN))
+            CUDA_OK(cudaMemcpy2D(c->u[c->cur ^ 1] + c0 * c->ld, sizeof(double) * c->ld, host,
+                                 sizeof(double) * c->npts, sizeof(double) * c->npts, 3,
+                                 cudaMemcpyHostToDevice));
     } else {
         if (ensure_dev(c, which)) return 1;
         CUDA_OK(cudaMemcpy(c->dev[which], host, sizeof(double) * count, cudaMemcpyHostToDevice));
@@ -761,10 +778,11 @@ int nekcem_b200_setup(int handle)
     if (!c->local_matched) return fail("nekcem_b200_set_faces has not been called");
     if (c->host_only) return fail("host-only planning context cannot be set up for compute");
     CUDA_OK(cudaSetDevice(c->d.device));
-    if (require(c, {NKB_DXM1, NKB_W3MN, NKB_RXMN, NKB_RYMN, NKB_RZMN, NKB_SXMN, NKB_SYMN,
-                    NKB_SZMN, NKB_TXMN, NKB_TYMN, NKB_TZMN, NKB_BMN, NKB_HBM1, NKB_EBM1,
-                    NKB_UNXM, NKB_UNYM, NKB_UNZM, NKB_AREAM, NKB_Y_0, NKB_Y_1, NKB_Z_0,
-                    NKB_Z_1}))
+    if (require(c, {NKB_DXM1, NKB_W3MN, NKB_RXMN, NKB_RYMN, NKB_SXMN, NKB_SYMN, NKB_BMN, NKB_HBM1,
+                    NKB_EBM1, NKB_UNXM, NKB_UNYM, NKB_AREAM, NKB_Y_0, NKB_Y_1, NKB_Z_0, NKB_Z_1}))
+        return 1;
+    if (c->d.ldim == 3 &&
+        require(c, {NKB_RZMN, NKB_SZMN, NKB_TXMN, NKB_TYMN, NKB_TZMN, NKB_UNZM}))
         return 1;
     if (!c->pml_el.empty()) {
         if (require(c, {NKB_PERMITTIVITY, NKB_PERMEABILITY, NKB_PMLSIGMA})) return 1;
@@ -782,6 +800,17 @@ int nekcem_b200_setup(int handle)
     c->vmapP_d = nullptr; c->elist_d = nullptr; c->sendbuf = c->halo = nullptr; c->send_node = nullptr;
     CUDA_OK(cudaMalloc(&c->vmapP_d, sizeof(int) * c->nxzfl));
     CUDA_OK(cudaMemcpy(c->vmapP_d, c->vmapP.data(), sizeof(int) * c->nxzfl, cudaMemcpyHostToDevice));
+    {
+        std::vector<unsigned char> ef(c->d.nelt, 0);
+        for (int32_t e : c->pml_el) ef[e] |= 1;
+        if (c->ade_kind)
+            for (int e = 0; e < c->d.nelt; e++)
+                if (c->ade_el[e]) ef[e] |= 2;
+        cudaFree(c->elflag_d);
+        c->elflag_d = nullptr;
+        CUDA_OK(cudaMalloc(&c->elflag_d, ef.size()));
+        CUDA_OK(cudaMemcpy(c->elflag_d, ef.data(), ef.size(), cudaMemcpyHostToDevice));
+    }
     CUDA_OK(cudaMalloc(&c->elist_d, sizeof(int) * std::max<size_t>(lists.size(), 1)));
     CUDA_OK(cudaMemcpy(c->elist_d, lists.data(), sizeof(int) * lists.size(), cudaMemcpyHostToDevice));
     if (c->nhalo > 0) {
@@ -877,6 +906,70 @@ int nekcem_b200_set_volume_source(int handle, int comp, const double *profile, d
     return 0;
 }
 
+static int set_ade(int handle, int kind, const double *jn, const double *kjn, const double *params,
+                   const int32_t *index, int32_t n)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (c->host_only) return fail("host-only planning context");
+    if (n < 0 || (n > 0 && (!index || !params))) return fail("bad ADE arguments");
+    CUDA_OK(cudaSetDevice(c->d.device));
+    CUDA_OK(cudaStreamSynchronize(c->s_compute));
+    cudaFree(c->ade_j); cudaFree(c->ade_k); cudaFree(c->ade_par); cudaFree(c->ade_mask);
+    c->ade_j = c->ade_k = c->ade_par = nullptr;
+    c->ade_mask = nullptr;
+    c->ade_kind = 0;
+    c->setup_done = false;
+    if (n == 0) return 0;
+    const int nj = kind == 1 ? 3 : 6, np = kind == 1 ? 2 : 3;
+    std::vector<unsigned char> mask(c->npts, 0);
+    c->ade_el.assign(c->d.nelt, 0);
+    for (int q = 0; q < n; q++) {
+        if (index[q] < 1 || index[q] > c->npts)
+            return fail("ADE index(%d)=%d out of range 1..%lld", q + 1, index[q], (long long)c->npts);
+        mask[index[q] - 1] = 1;
+        c->ade_el[(index[q] - 1) / c->nxyz] = 1;
+    }
+    const size_t bj = sizeof(double) * nj * c->npts, bp = sizeof(double) * np * c->npts;
+    CUDA_OK(cudaMalloc(&c->ade_j, bj));
+    CUDA_OK(cudaMalloc(&c->ade_k, bj));
+    CUDA_OK(cudaMalloc(&c->ade_par, bp));
+    CUDA_OK(cudaMalloc(&c->ade_mask, c->npts));
+    if (jn) CUDA_OK(cudaMemcpy(c->ade_j, jn, bj, cudaMemcpyHostToDevice));
+    else CUDA_OK(cudaMemset(c->ade_j, 0, bj));
+    if (kjn) CUDA_OK(cudaMemcpy(c->ade_k, kjn, bj, cudaMemcpyHostToDevice));
+    else CUDA_OK(cudaMemset(c->ade_k, 0, bj));
+    CUDA_OK(cudaMemcpy(c->ade_par, params, bp, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(c->ade_mask, mask.data(), c->npts, cudaMemcpyHostToDevice));
+    c->ade_kind = kind;
+    return 0;
+}
+
+int nekcem_b200_set_drude(int handle, const double *jn, const double *kjn, const double *params,
+                          const int32_t *dindex, int32_t n)
+{
+    return set_ade(handle, 1, jn, kjn, params, dindex, n);
+}
+
+int nekcem_b200_set_lorentz(int handle, const double *jn, const double *kjn, const double *params,
+                            const int32_t *lindex, int32_t n)
+{
+    return set_ade(handle, 2, jn, kjn, params, lindex, n);
+}
+
+int nekcem_b200_get_ade(int handle, double *jn, double *kjn)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (!c->ade_kind) return fail("no Drude/Lorentz state has been set");
+    CUDA_OK(cudaSetDevice(c->d.device));
+    CUDA_OK(cudaStreamSynchronize(c->s_compute));
+    const size_t bj = sizeof(double) * (c->ade_kind == 1 ? 3 : 6) * c->npts;
+    if (jn) CUDA_OK(cudaMemcpy(jn, c->ade_j, bj, cudaMemcpyDeviceToHost));
+    if (kjn) CUDA_OK(cudaMemcpy(kjn, c->ade_k, bj, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 int nekcem_b200_set_option(int handle, const char *name, int value)
 {
     Ctx *c = get(handle);
@@ -884,13 +977,7 @@ int nekcem_b200_set_option(int handle, const char *name, int value)
     if (!name) return fail("null option name");
     if (strcmp(name, "pf_dist") == 0) {
         if (value < 0) return fail("pf_dist must be >= 0");
-        c->pf_dist = value;
-        return 0;
-    }
-    if (strcmp(name, "variant") == 0) {
-        if (value < 0 || value > 1) return fail("variant must be 0 or 1");
-        c->variant = value;
-        return 0;
+        return 0; // reserved
     }
     return fail("unknown option '%s'", name);
 }
@@ -997,8 +1084,22 @@ int nekcem_b200_algorithmic_bytes(int handle, double *bytes_per_stage)
     Ctx *c = get(handle);
     if (!c) return 1;
     // volume 280 B/node, 116 B/face point; PML element node +240 B
-    double b = 280.0 * (double)c->npts + 116.0 * (double)c->nxzfl;
-    b += 240.0 * (double)c->pml_el.size() * (double)c->nxyz;
+    double b;
+    if (c->d.ldim == 3) {
+        b = 280.0 * (double)c->npts + 116.0 * (double)c->nxzfl;
+        b += 240.0 * (double)c->pml_el.size() * (double)c->nxyz;
+    } else {
+        // 2D: 3 active components (read, write, k read+write) 96 B, rx,ry,sx,sy 32 B, masses 16 B;
+        // per face point 2 normals + area + 4 impedances + 3 neighbour values + vmapP = 84 B
+        b = 144.0 * (double)c->npts + 84.0 * (double)c->nxzfl;
+        b += 120.0 * (double)c->pml_el.size() * (double)c->nxyz;
+    }
+    if (c->ade_kind) {
+        // Drude node: J,kJ read+write (3 comps) + 2 params + bm = 120 B; Lorentz twice the currents
+        double nade = 0;
+        for (char f : c->ade_el) nade += f ? 1.0 : 0.0;
+        b += (c->ade_kind == 1 ? 120.0 : 224.0) * nade * (double)c->nxyz;
+    }
     *bytes_per_stage = b;
     return 0;
 }

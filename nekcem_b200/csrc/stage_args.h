@@ -23,7 +23,6 @@ struct StageArgs {
     const double *halo; // [nhalo][6] traces received from peer ranks
     const int *elist;   // element ids handled by this launch
     int nel;
-    int pf_dist;        // L2 prefetch distance (in half-tasks) for the staged source components
     double ca, cb, dt, C0;
     // PML auxiliary fields (PML launches only) -- src/PML
     const double *sig, *eps, *mu;
@@ -35,6 +34,17 @@ struct StageArgs {
     const double *inc_amp, *inc_phase;
     int inc_n;
     double inc_wt;
+    // Drude / Lorentz auxiliary differential equations (cem_maxwell_drude / _lorentz,
+    // src/cem_maxwell.F:3095-3211), AUX launches only.  ade_kind 0 none, 1 Drude, 2 Lorentz;
+    // ade_j, ade_k: (npts,3) or (npts,3,2); ade_par: (npts,2) or (npts,3); ade_mask: 1 on the
+    // nodes of the user's dindex list
+    const unsigned char *elflag; // per element: bit 0 = PML element, bit 1 = has ADE nodes
+    int ade_kind;
+    double *ade_j, *ade_k;
+    const double *ade_par;
+    const unsigned char *ade_mask;
+    // 2D: imode 2 = TM (Hx,Hy,Ez), 1 = TE (Ex,Ey,Hz)
+    int imode;
     // separable volume source (usersrc hook)
     const double *src_prof;
     int src_comp;

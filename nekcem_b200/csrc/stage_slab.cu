@@ -21,7 +21,8 @@
 //       [restrict_to_face :604-652, flux3d :922-1002, flux_pec :1368-1426, add_flux_to_res :725-735]
 //   P4  t-pencils: thread (g,i,j) adds the weighted t-part for the slab's k; the line comes from
 //       smem (KS = 1) or from global memory/L2 (KS > 1: the other slabs' nodes)
-//   P5  streaming epilogue: PML ADEs [pml_step, src/cem_maxwell_pml.F:508-592], volume source
+//   P5  streaming epilogue: PML ADEs [pml_step, src/cem_maxwell_pml.F:508-592], Drude/Lorentz
+//       currents [cem_maxwell_drude/_lorentz, src/cem_maxwell.F:3095-3211], volume source
 //       [usersrc hook :503], inverse mass [invqmass :1878-1886], low-storage RK update
 //       [rk4_upd, src/cem_common.F:18-76]; old fields come from smem, k/masses are loaded
 //       EPI nodes ahead, results go to the ping-pong buffer.
@@ -29,7 +30,7 @@
 // Arithmetic: same products as the reference; the 6-term curl sum is associated by direction
 // ((r-part + s-part)*w + lift) + w*t-part, and nvcc contracts a*b+c into FMA -- both are
 // <= 1e-15 relative effects per operation (DESIGN.md "Numerics").
-#include "stage_common.h"
+#include "stage_aux.h"
 
 namespace nkb {
 namespace {
@@ -589,37 +590,17 @@ __global__ void __launch_bounds__(Slab<N, KS>::NT, Slab<N, KS>::MINB)
                     const int cb0 = g == 0 ? 3 : 0; // components being updated
                     double r[3] = {R[cb0 * SC + sn], R[(cb0 + 1) * SC + sn], R[(cb0 + 2) * SC + sn]};
                     const double o[3] = {U[cb0 * SC + sn], U[(cb0 + 1) * SC + sn], U[(cb0 + 2) * SC + sn]};
-                    if (PML) { // pml_step (src/cem_maxwell_pml.F:540-585) + PML half of rk_maxwell_ab
-                        const double bm1 = ldg(a.bmn + gi);
-                        const double bm1inv = 1.0 / bm1;
-                        const double sigx = a.sig[gi], sigy = a.sig[a.npts + gi],
-                                     sigz = a.sig[2 * a.npts + gi];
-                        const double permitt = a.eps[gi];
-                        const double sxp = sigx / permitt, syp = sigy / permitt, szp = sigz / permitt;
-                        double *pF = g == 0 ? a.pD : a.pB;
-                        double *kF = g == 0 ? a.kD : a.kB;
-                        const double b0 = pF[gi], b1 = pF[a.npts + gi], b2 = pF[2 * a.npts + gi];
-                        const double rb0 = r[0] * bm1inv - syp * b0;
-                        const double rb1 = r[1] * bm1inv - szp * b1;
-                        const double rb2 = r[2] * bm1inv - sxp * b2;
-                        double p0, p1, p2;
-                        if (g == 0) {
-                            p0 = -syp * b0 + sxp * b0 - sigz * o[0];
-                            p1 = -szp * b1 + syp * b1 - sigx * o[1];
-                            p2 = -sxp * b2 + szp * b2 - sigy * o[2];
-                        } else {
-                            const double permeab = a.mu[gi];
-                            p0 = -syp * b0 + sxp * b0 - szp * permeab * o[0];
-                            p1 = -szp * b1 + syp * b1 - sxp * permeab * o[1];
-                            p2 = -sxp * b2 + szp * b2 - syp * permeab * o[2];
+                    if (PML) { // auxiliary ODEs of this node, in the reference's order:
+                        // pml_step (+ PML half of rk_maxwell_ab), then the usersrc ADEs
+                        const int ef = a.elflag[e];
+                        if (ef & 1) {
+#pragma unroll
+                            for (int c = 0; c < 3; c++) r[c] = pml_component(a, gi, c, g == 0, r[c], o[c]);
                         }
-                        r[0] = r[0] + p0 * bm1; r[1] = r[1] + p1 * bm1; r[2] = r[2] + p2 * bm1;
-                        double t;
-                        t = a.ca * kF[gi] + a.dt * rb0; kF[gi] = t; pF[gi] = b0 + a.cb * t;
-                        t = a.ca * kF[a.npts + gi] + a.dt * rb1; kF[a.npts + gi] = t;
-                        pF[a.npts + gi] = b1 + a.cb * t;
-                        t = a.ca * kF[2 * a.npts + gi] + a.dt * rb2; kF[2 * a.npts + gi] = t;
-                        pF[2 * a.npts + gi] = b2 + a.cb * t;
+                        if ((ef & 2) && g == 0 && a.ade_mask[gi]) {
+#pragma unroll
+                            for (int c = 0; c < 3; c++) r[c] = ade_component(a, gi, c, r[c], o[c]);
+                        }
                     }
                     if (a.src_prof != nullptr) { // usersrc hook: res(comp) -= profile*(tfac*bm)
                         const int cs = a.src_comp - cb0;

@@ -310,3 +310,251 @@ def case_3dboxpml(nx1=9, nel=(6, 6, 6)):
     c.tol = dict(l2=[1.0] * 6, linf=[1.0] * 6)
     c.nsteps = 2000
     return c
+
+
+# ------------------------------------------------------------------------------------
+# tests/2dboxper, tests/2dboxpec : 2D TE / TM standing modes
+# ------------------------------------------------------------------------------------
+def usersol_2dboxper(case, tt):
+    """tests/2dboxper/2dboxper.usr:33-105 (omega = sqrt(2); TM: hx,hy,ez; TE: hz,ex,ey)."""
+    n = case.npts
+    xx, yy = case.xm1, case.ym1
+    omega = math.sqrt(2.0)
+    shn = np.zeros(3 * n); sen = np.zeros(3 * n)
+    if case.imode == 2:
+        tmph = math.sin(omega * tt) / omega; tmpe = math.cos(omega * tt)
+        shn[0:n] = np.cos(xx) * np.sin(yy) * tmph
+        shn[n:2 * n] = -np.sin(xx) * np.cos(yy) * tmph
+        sen[2 * n:] = np.cos(xx) * np.cos(yy) * tmpe
+    else:
+        tmph = math.cos(omega * tt); tmpe = math.sin(omega * tt) / omega
+        shn[2 * n:] = np.sin(xx) * np.sin(yy) * tmph
+        sen[0:n] = np.sin(xx) * np.cos(yy) * tmpe
+        sen[n:2 * n] = -np.cos(xx) * np.sin(yy) * tmpe
+    return shn, sen
+
+
+def case_2dboxper(imode=1, nx1=9, nel=(3, 3), dt=-0.005):
+    """tests/2dboxper (9 elements, N=8, dt=5e-3, 1000 steps; usrdat2 :155-187 maps onto
+    [0,2pi]^2; userchk tolerances 5e-8 / 5e-7 on the three active components, :199-231)."""
+    mesh = O.box_mesh(nel, ((0.0, 1.0),) * 2, ("P  ",) * 4)
+    c = O.RefCase(mesh, nx1, imode=imode, upwind=True,
+                  usrdat2=lambda case: _rescale(case, (0.0, 0.0), (2 * math.pi, 2 * math.pi)))
+    c.set_dt(dt)
+    c.usersol = usersol_2dboxper
+    shn, sen = usersol_2dboxper(c, 0.0)
+    c.hn[:] = shn; c.en[:] = sen
+    act = [0, 0, 1, 1, 1, 0] if imode == 1 else [1, 1, 0, 0, 0, 1]
+    c.tol = dict(l2=[5e-8 * a for a in act], linf=[5e-7 * a for a in act])
+    c.nsteps = 1000
+    return c
+
+
+def usersol_2dboxpec(case, tt):
+    """tests/2dboxpec/2dboxpec.usr:40-108 (ww = 1.5 pi, omega = sqrt(2))."""
+    n = case.npts
+    xx, yy = case.xm1, case.ym1
+    ww = 1.5 * math.pi
+    omega = math.sqrt(2.0)
+    tmph = math.sin(ww * omega * tt) / omega
+    tmpe = math.cos(ww * omega * tt)
+    shn = np.zeros(3 * n); sen = np.zeros(3 * n)
+    if case.imode == 2:
+        shn[0:n] = np.cos(ww * xx) * np.sin(ww * yy) * tmph
+        shn[n:2 * n] = -np.sin(ww * xx) * np.cos(ww * yy) * tmph
+        sen[2 * n:] = np.cos(ww * xx) * np.cos(ww * yy) * tmpe
+    else:
+        shn[2 * n:] = np.sin(ww * xx) * np.sin(ww * yy) * tmpe
+        sen[0:n] = np.sin(ww * xx) * np.cos(ww * yy) * tmph
+        sen[n:2 * n] = -np.cos(ww * xx) * np.sin(ww * yy) * tmph
+    return shn, sen
+
+
+def case_2dboxpec(imode=1, nx1=9, nel=(3, 3), dt=-0.005):
+    """tests/2dboxpec (9 elements, PEC walls, usrdat2 :176-187 maps onto [-1,1]^2; tolerances
+    1e-6 / 1e-5, :204-231)."""
+    mesh = O.box_mesh(nel, ((0.0, 1.0),) * 2, ("PEC",) * 4)
+    c = O.RefCase(mesh, nx1, imode=imode, upwind=True,
+                  usrdat2=lambda case: _rescale(case, (-1.0, -1.0), (1.0, 1.0)))
+    c.set_dt(dt)
+    c.usersol = usersol_2dboxpec
+    shn, sen = usersol_2dboxpec(c, 0.0)
+    c.hn[:] = shn; c.en[:] = sen
+    act = [0, 0, 1, 1, 1, 0] if imode == 1 else [1, 1, 0, 0, 0, 1]
+    c.tol = dict(l2=[1e-6 * a for a in act], linf=[1e-5 * a for a in act])
+    c.nsteps = 1000
+    return c
+
+
+# ------------------------------------------------------------------------------------
+# tests/drude, tests/lorentz : 2D TE plane wave onto a dispersive half space, ADE for J
+# ------------------------------------------------------------------------------------
+class _Dispersive:
+    """tests/drude/drude.usr and tests/lorentz/lorentz.usr (uservp, usrdat2, userinc, userini,
+    usersol, usersrc).  kind = 'drude' | 'lorentz'."""
+
+    def __init__(self, kind: str):
+        self.kind = kind
+        self.omega = 5.0
+        self.mu1 = self.mu2 = 1.0
+        self.eps1 = 1.0
+        om = self.omega
+        if kind == "drude":
+            self.pa, self.pb = 0.0, 100.0  # mydrudea, mydrudeb (drude.usr:236-237)
+            self.eps2 = 1.0 - self.pb / (om * (om + 1j * self.pa))
+        else:
+            self.pa = 0.0
+            self.pb = 0.9 * om ** 2
+            self.pc = 1.0 * self.pb  # lorentz.usr:242-244
+            self.eps2 = 1.0 + self.pc / (self.pb - 1j * self.pa * om - om ** 2)
+        import cmath
+        self.eta1 = math.sqrt(self.mu1 / self.eps1)
+        eta2 = cmath.sqrt(self.mu2 / self.eps2)
+        if eta2.real == 0.0 and eta2.imag > 0.0:  # branch fix (drude.usr:243-247)
+            eta2 = -eta2
+        self.eta2 = eta2
+        self.k1 = om * math.sqrt(self.mu1 * self.eps1)
+        k2 = om * cmath.sqrt(self.mu2 * self.eps2)
+        if k2.imag < 0:  # Fortran's csqrt(-x + 0i) = +i sqrt(x): the decaying branch
+            k2 = -k2
+        self.k2 = k2
+        self.refl = (self.eta1 - eta2) / (self.eta1 + eta2)
+        self.tran = 2 * self.eta1 / (self.eta1 + eta2)
+
+    def usrdat2(self, case):
+        for arr, s in zip((case.xm1, case.ym1), (5.0, 10.0)):
+            mn, mx = arr.min(), arr.max()
+            arr[:] = s * (arr - mn) / (mx - mn) - (s / 2.0)
+
+    def _mid(self, case):
+        h = case.nx1 // 2 - 1
+        return h + case.nx1 * h
+
+    def uservp(self, case):
+        ym = case.ym1.reshape(case.nelt, case.nxyz)
+        upper = ym[:, self._mid(case)] > 0
+        self.upper = upper
+        case.permittivity[:] = np.repeat(np.where(upper, self.eps1, 1.0), case.nxyz)
+        case.permeability[:] = np.repeat(np.where(upper, self.mu1, self.mu2), case.nxyz)
+        n = case.npts
+        low = np.repeat(~upper, case.nxyz)
+        self.index = np.nonzero(low)[0].astype(np.int32)  # 0-based node list
+        npar = 2 if self.kind == "drude" else 3
+        self.params = np.zeros(npar * n)
+        self.params[0:n][low] = self.pa
+        self.params[n:2 * n][low] = self.pb
+        if npar == 3:
+            self.params[2 * n:][low] = self.pc
+        nj = 3 if self.kind == "drude" else 6
+        self.jn = np.zeros(nj * n); self.kjn = np.zeros(nj * n); self.resjn = np.zeros(nj * n)
+        inc = []
+        for e in range(case.nelt):
+            if upper[e]:
+                markinc = True  # never reset per face, like the reference (drude.usr:289-305)
+                for f in range(case.nfaces):
+                    base = e * case.nxzf * case.nfaces + case.nxzf * f
+                    js = np.arange(base, base + case.nxzf)
+                    if np.any(np.abs(case.ym1[case.cemface[js]]) > 1e-8):
+                        markinc = False
+                    if markinc:
+                        inc.extend(js.tolist())
+        self.incindex = np.array(inc, dtype=np.int64)
+
+    def userinc(self, case):
+        j = self.incindex
+        yy = case.ym1[case.cemface[j]]
+
+        def cb(tt, fhx, fhy, fhz, fex, fey, fez):
+            uinc = np.cos(-self.k1 * yy - self.omega * tt)
+            fhz[j] = fhz[j] + uinc
+            fex[j] = fex[j] + self.eta1 * uinc
+
+        return cb
+
+    def incident(self, case):
+        """the same userinc as arguments of MaxwellB200.set_incident"""
+        j = self.incindex
+        yy = case.ym1[case.cemface[j]]
+        amp = np.zeros((6, j.size))
+        amp[2] = 1.0
+        amp[3] = self.eta1
+        return j, amp, -self.k1 * yy, self.omega
+
+    def usersol(self, case, tt):
+        n = case.npts
+        yy = case.ym1
+        upper = np.repeat(self.upper, case.nxyz)
+        inpml = np.repeat(case.pmltag != 0, case.nxyz)
+        d = case.pmlouter[3] - case.pmlinner[3]
+        smax = -(case.pmlorder + 1) * math.log(case.pmlreferr) / (2.0 * self.eta1 * d)
+        with np.errstate(invalid="ignore"):
+            pf = (smax * d / (case.pmlorder + 1)) * ((yy - case.pmlinner[3]) / d) ** (case.pmlorder + 1)
+        pmlfac = np.where(inpml & upper, pf, 0.0)
+        usc_u = self.refl * np.exp(1j * (self.k1 * yy - self.omega * tt) - self.eta1 * pmlfac)
+        usc_l = self.tran * np.exp(1j * (-self.k2 * yy - self.omega * tt))
+        shn = np.zeros(3 * n); sen = np.zeros(3 * n)
+        shn[2 * n:] = np.where(upper, usc_u.real, usc_l.real)
+        sen[0:n] = np.where(upper, (-self.eta1 * usc_u).real, (self.eta2 * usc_l).real)
+        return shn, sen
+
+    def userini(self, case):
+        n = case.npts
+        shn, sen = self.usersol(case, 0.0)
+        case.hn[:] = shn; case.en[:] = sen
+        for k in range(3):
+            case.pmlbn[k * n:(k + 1) * n] = case.permeability * shn[k * n:(k + 1) * n]
+            case.pmldn[k * n:(k + 1) * n] = case.permittivity * sen[k * n:(k + 1) * n]
+        j = self.index
+        yy = case.ym1[j]
+        efac = self.tran * self.eta2 * np.exp(1j * (-self.k2 * yy - self.omega * 0.0))
+        if self.kind == "drude":
+            sigma = self.params[n:2 * n][j] / (self.params[0:n][j] - 1j * self.omega)
+            self.jn[0:n][j] = (sigma * efac).real
+        else:
+            a, b, c = self.params[0:n][j], self.params[n:2 * n][j], self.params[2 * n:][j]
+            sigma = 1j * c * self.omega / (self.omega ** 2 + 1j * a * self.omega - b)
+            jf = sigma * efac
+            self.jn[0:n][j] = jf.real
+            self.jn[3 * n:4 * n][j] = ((1j / self.omega) * jf).real
+
+    def usersrc(self, case):
+        fn = (case.L.ora_cem_maxwell_drude if self.kind == "drude"
+              else case.L.ora_cem_maxwell_lorentz)
+        import ctypes as C
+
+        def cb(tt, *res):
+            fn(C.byref(case.s), O.dp(self.jn), O.dp(self.kjn), O.dp(self.resjn),
+               O.dp(self.params), O.ip(self.index), int(self.index.size))
+
+        return cb
+
+
+def _case_dispersive(kind, nx1, nel, thick):
+    mesh = O.box_mesh(nel, ((-1500.0, 1500.0),) * 2, ("P  ", "P  ", "PEC", "PML"))
+    u = _Dispersive(kind)
+    c = O.RefCase(mesh, nx1, imode=1, upwind=True, usrdat2=u.usrdat2, uservp=u.uservp,
+                  param={77: thick, 78: 3.0, 79: 1e-15})
+    c.user = u
+    c.set_dt(-0.005)
+    c.usersol = lambda case, tt: u.usersol(case, tt)
+    u.userini(c)
+    c.set_callback("userinc", u.userinc(c))
+    c.set_callback("usersrc", u.usersrc(c))
+    c.nsteps = 1000
+    return c
+
+
+def case_drude(nx1=9, nel=(4, 32), thick=6):
+    """tests/drude (.box 4x32, BC P,P,PEC,PML; N=8; dt=5e-3; 1000 steps; PML thick 6, order 3,
+    referr 1e-15).  Tolerances 1e-7 / 5e-6 on hz, ex, ey (drude.usr userchk)."""
+    c = _case_dispersive("drude", nx1, nel, thick)
+    c.tol = dict(l2=[0, 0, 1e-7, 1e-7, 1e-7, 0], linf=[0, 0, 5e-6, 5e-6, 5e-6, 0])
+    return c
+
+
+def case_lorentz(nx1=9, nel=(4, 32), thick=6):
+    """tests/lorentz (same mesh as drude).  Tolerances 5e-6 / 5e-5 on hz, ex; 5e-10 on ey
+    (lorentz.usr:373-387)."""
+    c = _case_dispersive("lorentz", nx1, nel, thick)
+    c.tol = dict(l2=[0, 0, 5e-6, 5e-6, 5e-10, 0], linf=[0, 0, 5e-5, 5e-5, 5e-10, 0])
+    return c

@@ -7,13 +7,13 @@ cd "$(dirname "$0")/../nekcem_b200/csrc"
 NVCC=/usr/local/cuda/bin/nvcc
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 FLAGS="$ARCH -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -ccbin /usr/bin/g++"
-make -s _obj/nekcem_b200.o _obj/stage_kernels.o _obj/fortran_abi.o
+make -s _obj/nekcem_b200.o _obj/stage2d.o _obj/fortran_abi.o
 mkdir -p ../lib/variants _obj/variants
 for spec in "$@"; do
   name="${spec%%=*}"; defs="${spec#*=}"
   (
     $NVCC $FLAGS $defs -Xptxas -v -c stage_slab.cu -o _obj/variants/$name.o 2> _obj/variants/$name.log
-    $NVCC $ARCH -shared -o ../lib/variants/$name.so _obj/nekcem_b200.o _obj/stage_kernels.o _obj/variants/$name.o _obj/fortran_abi.o -lnccl -lcudart
+    $NVCC $ARCH -shared -o ../lib/variants/$name.so _obj/nekcem_b200.o _obj/stage2d.o _obj/variants/$name.o _obj/fortran_abi.o -lnccl -lcudart
     grep -E "Used|spill" _obj/variants/$name.log | paste - - | awk -v n=$name '{print n": "$0}' | sed 's/ptxas info    ://g' | head -4
   ) &
 done

@@ -69,12 +69,16 @@ def incident_3ddielectric(c, elems=None):
     return j, amp, phase, u.omega
 
 
-def solver_from_refcase(c, device=0, incident=None):
+def solver_from_refcase(c, device=0, incident=None, ade=None):
+    """ade = (kind, jn, kjn, params, index0) registers a Drude/Lorentz ADE."""
     s = MaxwellB200(c.ldim, c.nx1, c.nelt, imode=c.imode, upwind=bool(c.s.ifupwind),
                     ifpec=c.ifpec, ifpml=c.ifpml, device=device)
     s.cem_maxwell_init(arrays_from_refcase(c))
     if incident is not None:
         s.set_incident(*incident)
+    if ade is not None:
+        kind, jn, kjn, params, index0 = ade
+        (s.cem_maxwell_drude if kind == "drude" else s.cem_maxwell_lorentz)(jn, kjn, params, index0)
     s.setup()
     s.set_time(c.s.time, c.s.dt)
     return s

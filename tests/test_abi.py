@@ -25,7 +25,9 @@ def test_library_exports_every_declared_symbol():
               "nekcem_b200_get_array_", "nekcem_b200_set_faces_", "nekcem_b200_set_pml_",
               "nekcem_b200_setup_", "nekcem_b200_set_time_", "nekcem_b200_set_incident_",
               "nekcem_b200_set_volume_source_", "nekcem_b200_error_sums_",
-              "nekcem_b200_comm_unique_id_", "nekcem_b200_comm_init_"):
+              "nekcem_b200_comm_unique_id_", "nekcem_b200_comm_init_",
+              "nekcem_b200_set_drude_", "nekcem_b200_set_lorentz_", "nekcem_b200_get_ade_",
+              "nekcem_b200_bind_", "cem_maxwell_drude_", "cem_maxwell_lorentz_"):
         assert hasattr(L, n), f"Fortran twin {n} missing"
 
 
@@ -41,8 +43,10 @@ def test_array_enum_matches_header():
 def test_bad_arguments_fail_loudly():
     with pytest.raises(NekcemB200Error, match="nx1"):
         MaxwellB200(3, 40, 8, device=-1)
-    with pytest.raises(NekcemB200Error, match="3D path"):
-        MaxwellB200(2, 8, 8, imode=1, device=-1)
+    with pytest.raises(NekcemB200Error, match="imode"):
+        MaxwellB200(2, 8, 8, imode=3, device=-1)
+    with pytest.raises(NekcemB200Error, match="imode"):
+        MaxwellB200(3, 8, 8, imode=1, device=-1)
     s = MaxwellB200(3, 4, 27, device=-1)
     with pytest.raises(NekcemB200Error, match="host-only"):
         s.set_array("rxmn", np.zeros(s.npts))
@@ -101,4 +105,29 @@ def test_host_plan_pec_box_codes():
     s.set_faces(g, np.zeros(0))  # unpaired and not PEC -> code -2
     vm = s.plan()[0]
     assert np.all(vm[g == 0] == -2)
+    s.close()
+
+
+def test_host_plan_2d_box():
+    """2D face numbering: slot s, point p of an element sits at node (p,0), (n-1,p), (p,n-1),
+    (0,p) -- the reference's cemface (src/cem_common.F:262-283) as restated by the oracle."""
+    from oracle import cases
+    c = cases.case_2dboxper(1, nx1=5, nel=(3, 4))
+    s = MaxwellB200(2, 5, c.nelt, imode=1, device=-1)
+    s.set_faces(c.glo_num, np.zeros(0))
+    vm = s.plan()[0]
+    assert vm.min() >= 0
+    # partner of partner: vmapP of the partner face point is the own node = cemface
+    own = c.cemface.astype(np.int64)
+    inv = {}
+    for j, o in enumerate(own):
+        inv.setdefault(int(o), []).append(j)
+    for j in range(vm.size):
+        partners = inv[int(vm[j])]
+        assert any(vm[q] == own[j] for q in partners)
+    # geometric check: partner nodes coincide modulo the period
+    for arr in (c.xm1, c.ym1):
+        d = np.abs(arr[own] - arr[vm])
+        d = np.minimum(d, np.abs(d - 2 * np.pi))
+        assert d.max() < 1e-12
     s.close()

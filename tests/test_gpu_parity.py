@@ -201,3 +201,123 @@ def test_full_size_properties():
     l2, linf = s.cem_error(shn, sen)
     assert np.all(l2 <= 5e-10) and np.all(linf <= 5e-9)
     s.close()
+
+
+# ---- 2D TE / TM path (cem_maxwell_flux2d, local_grad2) -------------------------------------------
+@pytest.mark.parametrize("imode", [1, 2])
+@pytest.mark.parametrize("nx1", [2, 3, 5, 8, 9, 12, 16])
+def test_2d_periodic_every_mode(imode, nx1):
+    from oracle import cases
+    c = cases.case_2dboxper(imode, nx1=nx1, nel=(4, 3), dt=-1e-3)
+    s = solver_from_refcase(c)
+    c.step(3); s.step(3)
+    assert rel_l2(_fields(s), _fields(c)) <= TOL
+    # the inactive components stay exactly zero
+    inactive = (0, 1, 5) if imode == 1 else (2, 3, 4)
+    f = _fields(s).reshape(6, -1)
+    assert all(np.all(f[k] == 0.0) for k in inactive)
+    s.close()
+
+
+@pytest.mark.parametrize("imode", [1, 2])
+def test_kat_2dboxper_2dboxpec_on_gpu(imode):
+    """tests/2dboxper and tests/2dboxpec on the GPU: stage parity, then 200 steps with the .usr
+    tolerances evaluated by the device-side cem_error."""
+    from oracle import cases
+    for make in (cases.case_2dboxper, cases.case_2dboxpec):
+        c = make(imode)
+        s = solver_from_refcase(c)
+        for rk in range(1, 6):
+            c.stage(rk); s.stage(rk)
+            s.synchronize()
+            assert rel_l2(_fields(s), _fields(c)) <= TOL, rk
+        s.close()
+        c = make(imode)
+        s = solver_from_refcase(c)
+        for _ in range(2):
+            s.step(100); c.step(100)
+            shn, sen = c.usersol(c, s.time)
+            l2, linf = s.cem_error(shn, sen)
+            assert np.all(l2 <= np.array(c.tol["l2"]) + 1e-300), (make.__name__, l2)
+            assert np.all(linf <= np.array(c.tol["linf"]) + 1e-300), (make.__name__, linf)
+            assert rel_l2(_fields(s), _fields(c)) <= TOL
+        s.close()
+
+
+def test_2d_central_flux_deformed():
+    """central flux on a sheared 2D mesh with PEC walls (all four metric terms, oblique normals)"""
+    from oracle import cases, oracle as O
+    mesh = O.box_mesh((4, 4), ((-1.0, 1.0),) * 2, ("PEC",) * 4)
+
+    def warp(case):
+        x, y = case.xm1.copy(), case.ym1.copy()
+        case.xm1[:] = x + 0.07 * np.sin(np.pi * y)
+        case.ym1[:] = y + 0.05 * np.sin(np.pi * x) * np.cos(0.5 * np.pi * y)
+
+    for imode in (1, 2):
+        c = O.RefCase(mesh, 7, imode=imode, upwind=False, usrdat2=warp)
+        c.set_dt(-2e-3)
+        c.hn[:], c.en[:] = cases.usersol_2dboxpec(c, 0.0)
+        s = solver_from_refcase(c)
+        s.step(5); c.step(5)
+        assert rel_l2(_fields(s), _fields(c)) <= TOL
+        s.close()
+
+
+# ---- Drude / Lorentz auxiliary differential equations ------------------------------------------------
+@pytest.mark.parametrize("kind", ["drude", "lorentz"])
+def test_kat_dispersive_on_gpu(kind):
+    """tests/drude and tests/lorentz as shipped: 2D TE, PML, plane-wave injection (incident hook)
+    and the polarisation-current ADE fused into the stage kernel.  Parity with the oracle (fields,
+    J, kJ, PML fields) and the .usr tolerances at steps 1..10, 50, 100."""
+    from oracle import cases
+    c = getattr(cases, "case_" + kind)()
+    u = c.user
+    s = solver_from_refcase(c, incident=u.incident(c), ade=(kind, u.jn, u.kjn, u.params, u.index))
+    done = 0
+    for target in list(range(1, 11)) + [50, 100]:
+        s.step(target - done); c.step(target - done)
+        done = target
+        shn, sen = c.usersol(c, s.time)
+        l2, linf = s.cem_error(shn, sen)
+        assert np.all(l2 <= np.array(c.tol["l2"]) + 1e-300), (target, l2)
+        assert np.all(linf <= np.array(c.tol["linf"]) + 1e-300), (target, linf)
+    assert rel_l2(_fields(s), _fields(c)) <= TOL
+    jn, kjn = s.get_ade()
+    assert rel_l2(jn, u.jn) <= TOL and rel_l2(kjn, u.kjn) <= TOL
+    assert rel_l2(s.get_array("pmlbn"), c.pmlbn) <= TOL
+    assert rel_l2(s.get_array("pmldn"), c.pmldn) <= TOL
+    s.close()
+
+
+@pytest.mark.parametrize("kind", ["drude", "lorentz"])
+def test_ade_in_3d(kind):
+    """the same ADEs in the 3D kernel: a periodic box whose lower half is dispersive"""
+    import ctypes as C
+    from oracle import cases, oracle as O
+    c = cases.case_boxper((3, 4, 3), 6, dt=-2e-3)
+    n = c.npts
+    low = c.ym1 < np.pi
+    low = np.repeat(low.reshape(c.nelt, -1).all(axis=1), c.nxyz)  # whole elements
+    index = np.nonzero(low)[0].astype(np.int32)
+    npar, nj = (2, 3) if kind == "drude" else (3, 6)
+    params = np.zeros(npar * n)
+    params[0:n][low] = 0.3
+    params[n:2 * n][low] = 4.0
+    if npar == 3:
+        params[2 * n:][low] = 2.5
+    rng = np.random.default_rng(7)
+    jn = np.zeros(nj * n)
+    for k in range(nj):
+        jn[k * n:(k + 1) * n][low] = 0.1 * rng.standard_normal(int(low.sum()))
+    kjn = np.zeros(nj * n); resjn = np.zeros(nj * n)
+    j_gpu = jn.copy()
+    fn = c.L.ora_cem_maxwell_drude if kind == "drude" else c.L.ora_cem_maxwell_lorentz
+    c.set_callback("usersrc", lambda tt, *res: fn(C.byref(c.s), O.dp(jn), O.dp(kjn), O.dp(resjn),
+                                                    O.dp(params), O.ip(index), int(index.size)))
+    s = solver_from_refcase(c, ade=(kind, j_gpu, None, params, index))
+    s.step(4); c.step(4)
+    assert rel_l2(_fields(s), _fields(c)) <= TOL
+    jg, kg = s.get_ade()
+    assert rel_l2(jg, jn) <= TOL and rel_l2(kg, kjn) <= TOL
+    s.close()

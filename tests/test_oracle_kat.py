@@ -63,3 +63,40 @@ def test_kat_3dboxpml_stability():
     assert np.all(np.isfinite(c.hn)) and np.all(np.isfinite(c.en))
     assert np.max(np.abs(c.en)) < 1.0 and np.max(np.abs(c.hn)) < 1.0
     assert np.max(np.abs(c.en)) > 1e-6  # the source did radiate
+
+
+@pytest.mark.parametrize("imode", [1, 2])
+def test_kat_2dboxper(imode):
+    """tests/2dboxper TE (param(4)=1) and TM (=2): 9 elements, N=8, 1000 steps of dt=5e-3;
+    userchk at steps 1..10 and every 100 with L2 <= 5e-8, Linf <= 5e-7 on the three active
+    components and exact zeros elsewhere (2dboxper.usr:199-231)."""
+    c = cases.case_2dboxper(imode)
+    assert c.ldim == 2 and c.nelt == 9 and c.npts == 9 * 81
+    _check(c, list(range(1, 11)) + list(range(100, 1001, 100)), 1000)
+
+
+@pytest.mark.parametrize("imode", [1, 2])
+def test_kat_2dboxpec(imode):
+    """tests/2dboxpec TE/TM: PEC walls, tolerances 1e-6 / 1e-5 (2dboxpec.usr:204-231)."""
+    c = cases.case_2dboxpec(imode)
+    assert c.ifpec and c.ncempec == 12 * 9
+    _check(c, list(range(1, 11)) + list(range(100, 1001, 100)), 1000)
+
+
+def test_kat_drude():
+    """tests/drude: 2D TE, 4x32 elements, PEC bottom / PML top, plane-wave injection, Drude ADE
+    through usersrc -> cem_maxwell_drude; 1e-7 / 5e-6 on hz, ex, ey at steps 1..10 and every 50
+    (drude.usr userchk).  400 of the 1000 steps."""
+    c = cases.case_drude()
+    assert c.nelt == 128 and c.maxpml == 24 and c.user.index.size == 64 * 81
+    _check(c, list(range(1, 11)) + list(range(50, 401, 50)), 400)
+    assert np.max(np.abs(c.user.jn)) > 0.1  # the current is alive
+
+
+def test_kat_lorentz():
+    """tests/lorentz: as drude with the two-pole ADE; 5e-6 / 5e-5 on hz, ex and 5e-10 on ey
+    (lorentz.usr:373-387).  400 of the 1000 steps."""
+    c = cases.case_lorentz()
+    _check(c, list(range(1, 11)) + list(range(100, 401, 100)), 400)
+    n = c.npts
+    assert np.max(np.abs(c.user.jn[3 * n:4 * n])) > 1e-3  # the polarisation variable too
