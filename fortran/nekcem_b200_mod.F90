@@ -142,6 +142,27 @@ module nekcem_b200
        real(c_float), intent(out) :: ms
        integer(c_int64_t), intent(out) :: launches
      end function
+     !> Drude / Lorentz ADE state (replaces the per-stage cem_maxwell_drude / cem_maxwell_lorentz
+     !> calls of the .usr usersrc, src/cem_maxwell.F:3095-3211)
+     integer(c_int) function nekcem_b200_set_drude(handle, jn, kjn, params, dindex, n) &
+          bind(C, name='nekcem_b200_set_drude')
+       import :: c_int, c_double
+       integer(c_int), value :: handle, n
+       real(c_double), intent(in) :: jn(*), kjn(*), params(*)
+       integer(c_int), intent(in) :: dindex(*)
+     end function
+     integer(c_int) function nekcem_b200_set_lorentz(handle, jn, kjn, params, lindex, n) &
+          bind(C, name='nekcem_b200_set_lorentz')
+       import :: c_int, c_double
+       integer(c_int), value :: handle, n
+       real(c_double), intent(in) :: jn(*), kjn(*), params(*)
+       integer(c_int), intent(in) :: lindex(*)
+     end function
+     integer(c_int) function nekcem_b200_get_ade(handle, jn, kjn) bind(C, name='nekcem_b200_get_ade')
+       import :: c_int, c_double
+       integer(c_int), value :: handle
+       real(c_double), intent(out) :: jn(*), kjn(*)
+     end function
      integer(c_int) function nekcem_b200_algorithmic_bytes(handle, bytes_per_stage) &
           bind(C, name='nekcem_b200_algorithmic_bytes')
        import :: c_int, c_double
