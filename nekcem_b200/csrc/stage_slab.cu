@@ -46,6 +46,9 @@ namespace {
 #ifndef SLAB_ST_CS
 #define SLAB_ST_CS 1 // 1: streaming (evict-first) stores of the results
 #endif
+#ifndef SLAB_T_PIPE
+#define SLAB_T_PIPE 1 // 1: software-pipelined t-lines from global memory (KS > 1)
+#endif
 #ifndef SLAB_COF_SLOTS
 #define SLAB_COF_SLOTS 1
 #endif
@@ -263,19 +266,83 @@ __device__ __forceinline__ void t_phase(const double (&D)[N * N], const StageArg
 {
     using C = Slab<N, KS>;
     constexpr int K0 = C::k0(S), K1 = K0 + C::kb(S);
-    constexpr int NOT = (K1 - K0 + C::TSPLIT - 1) / C::TSPLIT;
-    constexpr int PB_T = NOT <= 8 ? NOT : (NOT + 1) / 2;
+    if constexpr (KS == 1 || !SLAB_T_PIPE) {
+        constexpr int NOT = (K1 - K0 + C::TSPLIT - 1) / C::TSPLIT;
+        constexpr int PB_T = NOT <= 8 ? NOT : (NOT + 1) / 2;
 #pragma unroll 1
-    for (int w = tid; w < C::T_ITEMS; w += C::NT) {
-        const int h = w / C::T_BLK, r = w - h * C::T_BLK;
-        const int g = r / C::N2, p = r - g * C::N2;
-        if (g > 1) continue;
-        const int pa = p % N, pb = p / N;
-        const double *Us = U + (g ? 3 : 0) * C::SC;
-        double *Rd = R + (g ? 0 : 3) * C::SC;
-        const double *gs = a.u_in + (g ? 3 : 0) * a.ld + ebase;
-        pencil_split<N, 2, K0, K0, K1, C::TSPLIT, PB_T, C::SC, (KS > 1)>(
-            D, a, Us, gs, Rd, pa, pb, ebase, 0, g ? -1.0 : 1.0, h);
+        for (int w = tid; w < C::T_ITEMS; w += C::NT) {
+            const int h = w / C::T_BLK, r = w - h * C::T_BLK;
+            const int g = r / C::N2, p = r - g * C::N2;
+            if (g > 1) continue;
+            const int pa = p % N, pb = p / N;
+            const double *Us = U + (g ? 3 : 0) * C::SC;
+            double *Rd = R + (g ? 0 : 3) * C::SC;
+            const double *gs = a.u_in + (g ? 3 : 0) * a.ld + ebase;
+            pencil_split<N, 2, K0, K0, K1, C::TSPLIT, PB_T, C::SC, (KS > 1)>(
+                D, a, Us, gs, Rd, pa, pb, ebase, 0, g ? -1.0 : 1.0, h);
+        }
+    } else {
+        // KS > 1: the lines come from global memory (L2).  Software pipeline over the flat
+        // sequence of (item, component) steps: the N loads of step+1 are issued before the FMAs
+        // of step, so one line is always in flight behind the arithmetic.
+        constexpr int NO = K1 - K0;
+        constexpr int NPASS = (C::T_ITEMS + C::NT - 1) / C::NT;
+        constexpr int NSTEP = 3 * NPASS;
+        double ul[2][N];
+        auto item = [&](int ps, int &g, int &nd, bool &ok) {
+            const int w = tid + ps * C::NT;
+            g = w / C::N2;
+            nd = w - g * C::N2; // = pa + N*pb
+            ok = w < 2 * C::N2;
+            if (!ok) { g = 0; nd = 0; }
+        };
+        auto issue = [&](int step, int buf) {
+            int g, nd; bool ok;
+            item(step / 3, g, nd, ok);
+            const double *gp = a.u_in + ((g ? 3 : 0) + step % 3) * a.ld + ebase + nd;
+#pragma unroll
+            for (int m = 0; m < N; m++) ul[buf][m] = ok ? ldg(gp + C::N2 * m) : 0.0;
+        };
+        issue(0, 0);
+        double acc[3][NO], cof[NO][3], wv[NO];
+#pragma unroll
+        for (int step = 0; step < NSTEP; step++) {
+            const int c = step % 3, buf = step & 1;
+            int g, nd; bool ok;
+            item(step / 3, g, nd, ok);
+            if (step + 1 < NSTEP) issue(step + 1, buf ^ 1);
+            if (c == 0) { // cofactors and weight of this item's outputs
+#pragma unroll
+                for (int o = 0; o < NO; o++) {
+                    const long long gi = ebase + nd + C::N2 * (K0 + o);
+#pragma unroll
+                    for (int q = 0; q < 3; q++) cof[o][q] = ldg(a.met[6 + q] + gi);
+                    wv[o] = (g ? -1.0 : 1.0) * ldg(a.w3 + nd + C::N2 * (K0 + o));
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < N; m++)
+#pragma unroll
+                for (int o = 0; o < NO; o++) {
+                    const double dv = D[(K0 + o) + N * m];
+                    if (m == 0) acc[c][o] = dv * ul[buf][m];
+                    else acc[c][o] = acc[c][o] + dv * ul[buf][m];
+                }
+            if (c == 2 && ok) {
+                double *Rd = R + (g ? 0 : 3) * C::SC;
+                const int pa = nd % N, pb = nd / N;
+#pragma unroll
+                for (int o = 0; o < NO; o++) {
+                    const double d[3] = {acc[0][o], acc[1][o], acc[2][o]};
+                    double cc[3];
+                    curl_part(d, cof[o][0], cof[o][1], cof[o][2], cc);
+                    double *Ro = Rd + Lay<N>::at(pa, pb, o);
+                    Ro[0] = Ro[0] + wv[o] * cc[0];
+                    Ro[C::SC] = Ro[C::SC] + wv[o] * cc[1];
+                    Ro[2 * C::SC] = Ro[2 * C::SC] + wv[o] * cc[2];
+                }
+            }
+        }
     }
 }
 
