@@ -156,7 +156,9 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     E, nx1 = args.elems, args.order + 1
-    nel = (E, E, E * world)  # weak scaling: one E^3 slab per GPU
+    strong = args.scaling == "strong"
+    # weak scaling (default): one E^3 slab per GPU; strong: the global E^3 box split over the GPUs
+    nel = (E, E, E) if strong else (E, E, E * world)
     case = BoxCase(nel, nx1, rank=rank, nranks=world, length=2 * math.pi)
     slv = MaxwellB200(3, nx1, case.nelt, device=local, rank=rank, nranks=world)
     t_setup = time.perf_counter()
@@ -252,7 +254,8 @@ def run_gpu(args):
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get(f"N{args.order}_E{E}")
+                traffic = None if strong and world > 1 else \
+                    json.load(open(tpath)).get(f"N{args.order}_E{E}")
             except Exception:
                 traffic = None
         cpu = None
@@ -264,10 +267,12 @@ def run_gpu(args):
                              "(reference needs gfortran+MPI, absent on this box)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
-            "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
+            "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": f"synthetic 3D periodic box, {E}^3 hex elements per GPU at N={args.order} "
+                "workload": f"synthetic 3D periodic box, {E}^3 hex elements "
+                            f"{'in total' if strong else 'per GPU'} at N={args.order} "
                             f"(global {nel[0]}x{nel[1]}x{nel[2]}), 3dboxper initial condition, "
                             "upwind flux, LSRK(5,4)",
                 "nodes_global": npts_global, "dof_unit": "grid node (6 field components)",
@@ -306,6 +311,8 @@ def main():
     ap.add_argument("--cpu-elems", type=int, default=24)
     ap.add_argument("--cpu-steps", type=int, default=30)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --elems^3 per GPU (default); strong: --elems^3 in total")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

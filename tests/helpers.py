@@ -89,3 +89,19 @@ def rel_l2(a, b):
     a = np.asarray(a); b = np.asarray(b)
     den = np.sqrt(np.sum(b * b))
     return float(np.sqrt(np.sum((a - b) ** 2)) / (den if den > 0 else 1.0))
+
+
+def restrict_to_elems(c, elems, facepts=None, nodes=None):
+    """Renumber global face points / nodes of RefCase ``c`` to the local numbering of the
+    partition ``elems`` (sorted global element ids).  Returns (keep_mask, local_ids)."""
+    elems = np.asarray(elems)
+    loc = -np.ones(c.nelt, dtype=np.int64)
+    loc[elems] = np.arange(elems.size)
+    if facepts is not None:
+        nfp = c.nxzf * c.nfaces
+        j = np.asarray(facepts, dtype=np.int64)
+        keep = loc[j // nfp] >= 0
+        return keep, loc[j[keep] // nfp] * nfp + j[keep] % nfp
+    j = np.asarray(nodes, dtype=np.int64)
+    keep = loc[j // c.nxyz] >= 0
+    return keep, loc[j[keep] // c.nxyz] * c.nxyz + j[keep] % c.nxyz

@@ -9,12 +9,15 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_two_gpu_parity():
+@pytest.mark.parametrize("case", ["boxper3d", "drude", "lorentz"])
+def test_two_gpu_parity(case):
+    """3D periodic box, and the 2D drude / lorentz tests (PML + incident field + ADE), cut over
+    two ranks with the NCCL face exchange"""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", "29611",
-           os.path.join(ROOT, "scripts", "mgpu_parity.py")]
+           os.path.join(ROOT, "scripts", "mgpu_parity.py"), case]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
