@@ -1,0 +1,88 @@
+"""Recipe for oracle/_ref/libnekcem_ref.so -- the REFERENCE'S OWN hot path, executable here.
+
+TEST INFRASTRUCTURE ONLY.  The reference's Maxwell path is Fortran + one C library; this image
+has gcc but no Fortran compiler.  The recipe therefore
+
+  1. translates the reference's own Fortran routines on the path, read from
+     /root/reference/src where they lie, into C with oracle/f2c_lite.py (mechanical,
+     statement by statement, same arithmetic order; see that file's header),
+  2. compiles the translation together with the reference's own gather-scatter library
+     (src/jl/gs.c and its dependencies, compiled unchanged, single process, no MPI) and the
+     small harness oracle/ref_harness.c,
+  3. writes everything to oracle/_ref/ (git-ignored; the .so travels to the GPU box).
+
+Preprocessor configuration: -DMPI -DMPIIO -DMAXWELL as bin/configurenek sets them, plus
+-DNOTIMER (a switch of the reference itself, src/nek5_mxm_wrapper.F:16: it removes only the
+flop counters of mxm).  `real` is 8 bytes as with -fdefault-real-8 (bin/configurenek:117).
+
+Run:  python oracle/build_ref.py          (needs /root/reference; a no-op without it)
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("NEKCEM_REFERENCE", "/root/reference")
+OUT = os.path.join(HERE, "_ref")
+LIB = os.path.join(OUT, "libnekcem_ref.so")
+
+# reference file -> the program units on the path
+UNITS = [
+    ("src/cem_maxwell.F", [
+        "cem_maxwell_op_rk", "cem_maxwell_op", "cem_maxwell", "maxwell_wght_curl",
+        "cem_maxwell_restrict_to_face", "cem_maxwell_flux", "cem_maxwell_flux2d",
+        "cem_maxwell_flux3d", "cem_maxwell_flux_pec", "cem_maxwell_add_flux_to_res",
+        "cem_maxwell_invqmass", "rk_maxwell_ab", "cem_maxwell_drude", "cem_maxwell_lorentz"]),
+    ("src/cem_maxwell_pml.F", ["pml_step"]),
+    ("src/cem_common.F", ["rk_c", "rk4_upd", "rk_storage", "cem_set_fc_ptr"]),
+    ("src/nek5_grad.F", ["local_grad3", "local_grad2"]),
+    ("src/nek5_mxm_wrapper.F", ["mxm"]),
+    ("src/nek5_mxm_std.F", ["mxmf2"] + ["mxf%d" % k for k in range(1, 25)] + ["mxm44_0"]),
+    ("src/nek5_mat1.F", ["chsign"]),
+    # setup routines that define the face numbering the path relies on
+    ("src/nek5_connect11.F", ["initds", "dsset"]),
+]
+# reference gather-scatter library, compiled unchanged (flags of bin/configurenek:132-139
+# without -DMPI: single process)
+JL = ["gs.c", "gs_local.c", "comm.c", "crystal.c", "sarray_transfer.c", "sarray_sort.c",
+      "sort.c", "fail.c", "tensor.c"]
+JL_FLAGS = ["-DUNDERSCORE", "-DGLOBAL_LONG_LONG", "-DUSE_NAIVE_BLAS"]
+DEFINES = ("MPI", "MPIIO", "MAXWELL", "NOTIMER")
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(REF, "src"))
+
+
+def build(force: bool = False, verbose: bool = False) -> str | None:
+    """returns the library path, or None when the reference tree is absent and no prebuilt
+    library exists"""
+    if not available():
+        return LIB if os.path.exists(LIB) else None
+    srcs = [os.path.join(REF, p) for p, _ in UNITS] + [os.path.join(REF, "src/jl", f) for f in JL]
+    mine = [os.path.join(HERE, f) for f in ("f2c_lite.py", "build_ref.py", "ref_harness.c")]
+    if not force and os.path.exists(LIB):
+        t = os.path.getmtime(LIB)
+        if all(os.path.getmtime(s) < t for s in srcs + mine):
+            return LIB
+    sys.path.insert(0, HERE)
+    import f2c_lite
+    os.makedirs(OUT, exist_ok=True)
+    inc = [os.path.join(REF, "tests/3dboxper"), os.path.join(REF, "src")]
+    ctext, em = f2c_lite.translate([(os.path.join(REF, p), u) for p, u in UNITS], inc, DEFINES)
+    gen = os.path.join(OUT, "ref_gen.c")
+    with open(gen, "w") as f:
+        f.write(ctext)
+    cmd = (["gcc", "-O2", "-std=gnu11", "-ffp-contract=off", "-fPIC", "-shared", "-w",
+            "-I" + os.path.join(REF, "src/jl")] + JL_FLAGS +
+           ["-o", LIB, gen, os.path.join(HERE, "ref_harness.c")] +
+           [os.path.join(REF, "src/jl", f) for f in JL] + ["-lm"])
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return LIB
+
+
+if __name__ == "__main__":
+    p = build(force=True, verbose=True)
+    print("built" if p else "reference tree absent", p)

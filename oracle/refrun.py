@@ -1,0 +1,186 @@
+"""Driver for oracle/_ref/libnekcem_ref.so: the reference's own hot path (its Fortran
+translated mechanically by oracle/f2c_lite.py + its own src/jl gather-scatter library,
+recipe oracle/build_ref.py) run on the inputs of an oracle case.  TEST INFRASTRUCTURE ONLY.
+
+What is the reference here and what is not: everything from `cem_maxwell_op_rk` down
+(rk_c, cem_maxwell_op, cem_maxwell, maxwell_wght_curl, local_grad3/2, mxm -> mxfK,
+restrict_to_face, flux2d/3d, gs_op_fields, flux_pec, add_flux_to_res, pml_step, invqmass,
+rk_maxwell_ab, rk4_upd, rk_storage, cem_maxwell_drude/lorentz, cem_set_fc_ptr) executes the
+reference's statements.  The COMMON-block inputs (geometry, masses, impedances, index lists,
+initial fields) are filled from the oracle's setup, exactly as the drop-in library receives
+them from the Fortran COMMONs; the .usr callbacks are supplied by the test.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build_ref
+
+c_dp = C.POINTER(C.c_double)
+USERCB = C.CFUNCTYPE(None, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp)
+
+_lib = None
+
+
+def available() -> bool:
+    return build_ref.build() is not None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = build_ref.build()
+        if path is None:
+            raise RuntimeError("oracle/_ref is not built and /root/reference is absent")
+        L = C.CDLL(path)
+        L.ref_set_param.argtypes = [C.c_char_p, C.c_long]
+        L.ref_sym.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_long)]
+        L.ref_sym.restype = C.c_void_p
+        L.ref_set_user.argtypes = [C.c_int, USERCB]
+        L.ref_units.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+class ReferenceRun:
+    """One process-wide instance at a time (the reference's state is global COMMON storage)."""
+
+    def __init__(self, case):
+        L = lib()
+        self.L, self.case = L, case
+        ldim, nx1, nelt = case.ldim, case.nx1, case.nelt
+        # SIZE: parameter (ldim, lxi, lelg ...) of this case; lelt = nelt exactly so that the
+        # (lpts1,3) arrays have the oracle's layout (the reference pads lelt by 3 unused
+        # elements, tests/3dboxper/SIZE:15)
+        for k, v in (("ldim", ldim), ("lxi", nx1 - 1), ("lelg", nelt), ("lpmin", 1),
+                     ("lelv", nelt), ("lelt", nelt), ("lpts10", case.npts),
+                     ("lxzfl10", case.nxzfl)):
+            L.ref_set_param(k.encode(), v)
+        L.ref_alloc()
+        npts, nxzfl = case.npts, case.nxzfl
+        assert self.get("lpts1") == npts and self.get("lxzfl1") == nxzfl
+        nz1 = nx1 if ldim == 3 else 1
+        # /DIMN/ (src/cem_drive.F:697-707)
+        for k, v in (("nelt", nelt), ("nelv", nelt), ("nx1", nx1), ("ny1", nx1), ("nz1", nz1),
+                     ("ndim", ldim), ("nxyz", case.nxyz), ("npts", npts), ("nxzf", case.nxzf),
+                     ("nxzfl", nxzfl), ("nfaces", case.nfaces), ("imode", case.imode),
+                     ("ifupwind", int(case.s.ifupwind)), ("ifcentral", int(case.s.ifcentral)),
+                     ("ifpml", int(case.ifpml)), ("ifpec", int(case.ifpec)), ("ifrk45", 1),
+                     ("ifrk22", 0), ("iffilter", 0), ("ifdealias", 0),
+                     ("ncemface", nxzfl), ("ncempec", case.ncempec), ("maxpml", case.maxpml),
+                     ("istep", 0)):
+            try:
+                self.set(k, v)
+            except KeyError:
+                pass  # a COMMON scalar none of the translated routines reads
+        self.set("dt", case.s.dt)
+        self.set("time", case.s.time)
+        # geometry, masses, impedances, fields: same names as the COMMON blocks
+        for name in ("dxm1", "dxtm1", "w3mn", "rxmn", "rymn", "rzmn", "sxmn", "symn", "szmn",
+                     "txmn", "tymn", "tzmn", "bmn", "unxm", "unym", "unzm", "aream", "hbm1",
+                     "ebm1", "hn", "en", "khn", "ken", "permittivity", "permeability",
+                     "pmlsigma", "pmlbn", "pmldn", "kpmlbn", "kpmldn"):
+            try:
+                self.put(name, getattr(case, name))
+            except KeyError:
+                pass
+        for name in ("Y_0", "Y_1", "Z_0", "Z_1"):
+            self.put(name.lower(), getattr(case, name))
+        self.put("bm1", case.bmn)
+        # index lists are 1-based in the reference
+        self.put("cemface", case.cemface + 1)
+        if case.ncempec:
+            self.put("cempec", case.cempec[:case.ncempec] + 1)
+        if case.maxpml:
+            self.put("pmlptr", case.pmlptr[:case.maxpml] + 1)
+        # gs_setup(gsh_face, glo_num, nxzfl, comm, np)  (src/nek5_connect11.F:2217-2223)
+        h = C.c_int(-1)
+        n = C.c_int(nxzfl)
+        comm, np_ = C.c_int(0), C.c_int(1)
+        ids = np.ascontiguousarray(case.glo_num, dtype=np.int64)
+        L.gs_setup_(C.byref(h), ids.ctypes.data_as(C.c_void_p), C.byref(n), C.byref(comm),
+                    C.byref(np_))
+        self.gsh = h.value
+        self.set("gsh_face", self.gsh)
+        L.rk_storage_()
+        self._cbs = {}
+        self.istep = 0
+
+    # ---- COMMON access ------------------------------------------------------------------
+    def _sym(self, name):
+        isint, cnt = C.c_int(), C.c_long()
+        p = self.L.ref_sym(name.encode(), C.byref(isint), C.byref(cnt))
+        if not p:
+            raise KeyError(name)
+        return p, bool(isint.value), cnt.value
+
+    def view(self, name):
+        p, isint, cnt = self._sym(name)
+        t = C.c_int if isint else C.c_double
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(t)), shape=(cnt,))
+
+    def get(self, name):
+        return self.view(name)[0]
+
+    def set(self, name, v):
+        self.view(name)[0] = v
+
+    def put(self, name, arr):
+        v = self.view(name)
+        a = np.asarray(arr).reshape(-1)
+        assert a.size <= v.size, (name, a.size, v.size)
+        v[:a.size] = a
+
+    # ---- callbacks ------------------------------------------------------------------------
+    def set_callback(self, which: str, fn):
+        """fn(tt, a1..a6): numpy views, argument order of the reference's call site"""
+        n = self.case.nxzfl if which in ("userinc", "userfsrc") else self.case.npts
+
+        def tramp(t, a1, a2, a3, a4, a5, a6):
+            arrs = [np.ctypeslib.as_array(a, shape=(n,)) for a in (a1, a2, a3, a4, a5, a6)]
+            fn(t[0], *arrs)
+
+        cb = USERCB(tramp)
+        self._cbs[which] = cb
+        self.L.ref_set_user({"userinc": 0, "usersrc": 1, "userfsrc": 2}[which], cb)
+
+    def clear_callbacks(self):
+        for k in (0, 1, 2):
+            self.L.ref_set_user(k, C.cast(None, USERCB))
+        self._cbs = {}
+
+    # ---- stepping -------------------------------------------------------------------------
+    def step(self, nsteps: int = 1):
+        """the body of the time loop, src/cem_drive.F:622-640"""
+        for _ in range(nsteps):
+            self.istep += 1
+            try:
+                self.set("istep", self.istep)
+            except KeyError:
+                pass
+            self.L.cem_maxwell_op_rk_()
+            self.set("time", self.get("time") + self.get("dt"))
+
+    def stage(self, rkstep: int):
+        """one pass of the loop in cem_maxwell_op_rk (src/cem_maxwell.F:337-341)"""
+        i = C.c_int(rkstep)
+        self.set("rkstep", rkstep)
+        self.L.rk_c_(C.byref(i))
+        self.L.cem_maxwell_op_()
+        self.L.rk_maxwell_ab_(C.byref(i))
+
+    @property
+    def hn(self):
+        return self.view("hn")[:3 * self.case.npts]
+
+    @property
+    def en(self):
+        return self.view("en")[:3 * self.case.npts]
+
+    def close(self):
+        self.clear_callbacks()
+        h = C.c_int(self.gsh)
+        self.L.gs_free_(C.byref(h))

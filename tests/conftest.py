@@ -3,6 +3,9 @@ import sys
 
 import pytest
 
+# the oracle's OpenMP team must not spin while pytest-xdist / gloo workers share the cores
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
