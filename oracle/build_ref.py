@@ -32,15 +32,34 @@ UNITS = [
         "cem_maxwell_op_rk", "cem_maxwell_op", "cem_maxwell", "maxwell_wght_curl",
         "cem_maxwell_restrict_to_face", "cem_maxwell_flux", "cem_maxwell_flux2d",
         "cem_maxwell_flux3d", "cem_maxwell_flux_pec", "cem_maxwell_add_flux_to_res",
-        "cem_maxwell_invqmass", "rk_maxwell_ab", "cem_maxwell_drude", "cem_maxwell_lorentz"]),
-    ("src/cem_maxwell_pml.F", ["pml_step"]),
-    ("src/cem_common.F", ["rk_c", "rk4_upd", "rk_storage", "cem_set_fc_ptr"]),
+        "cem_maxwell_invqmass", "rk_maxwell_ab", "cem_maxwell_drude", "cem_maxwell_lorentz",
+        "cem_maxwell_materials", "cem_maxwell_pec_init"]),
+    ("src/cem_maxwell_pml.F", ["pml_step", "pml_faces", "march_faces", "pml_fill_faceary",
+                               "dir_local_to_global", "pml_extent_and_tags", "pml_calc_sigma"]),
+    ("src/cem_common.F", ["rk_c", "rk4_upd", "rk_storage", "cem_set_fc_ptr", "cem_error"]),
+    ("src/nek5_courant.F", ["get_dxmin"]),
     ("src/nek5_grad.F", ["local_grad3", "local_grad2"]),
     ("src/nek5_mxm_wrapper.F", ["mxm"]),
     ("src/nek5_mxm_std.F", ["mxmf2"] + ["mxf%d" % k for k in range(1, 25)] + ["mxm44_0"]),
-    ("src/nek5_mat1.F", ["chsign"]),
+    ("src/nek5_mat1.F", ["chsign", "rzero", "rone", "copy", "addcol3", "addcol4", "subcol3",
+                         "subcol4", "ascol5", "col2", "col3", "invcol1", "invcol3", "invers2",
+                         "vdot2", "vdot3", "vcross", "unitvec", "rzero3", "cmult", "sub3",
+                         "izero", "vlmax", "vlmin", "glsc3", "glamax", "glmin"]),
+    # setup routines whose OUTPUT the path consumes: GLL nodes/weights and
+    # derivative matrix, metric cofactors / Jacobian / mass, face areas and normals
+    ("src/nek5_speclib.F", ["zwgll", "zwglj", "zwgljd", "jacg", "jacobf", "zwgjd", "endw1",
+                            "endw2", "gammaf", "pnormj", "dgll", "pnleg", "pndleg"]),
+    ("src/nek5_coef.F", ["xyzrst", "glmapm1", "chkjac", "geodat1", "setarea", "area2", "area3",
+                         "setwgtr", "set_unr"]),
+    ("src/nek5_subs2.F", ["facexv", "setaxdy", "setaxw1"]),
     # setup routines that define the face numbering the path relies on
     ("src/nek5_connect11.F", ["initds", "dsset"]),
+    # the analytic solutions the reference's own tests check against: the
+    # usersol of each shipped case, emitted as usersol__<case>_
+    ("tests/3dboxper/3dboxper.usr", ["usersol"], "__3dboxper"),
+    ("tests/3dboxpec/3dboxpec.usr", ["usersol"], "__3dboxpec"),
+    ("tests/2dboxper/2dboxper.usr", ["usersol"], "__2dboxper"),
+    ("tests/2dboxpec/2dboxpec.usr", ["usersol"], "__2dboxpec"),
 ]
 # reference gather-scatter library, compiled unchanged (flags of bin/configurenek:132-139
 # without -DMPI: single process)
@@ -59,7 +78,7 @@ def build(force: bool = False, verbose: bool = False) -> str | None:
     library exists"""
     if not available():
         return LIB if os.path.exists(LIB) else None
-    srcs = [os.path.join(REF, p) for p, _ in UNITS] + [os.path.join(REF, "src/jl", f) for f in JL]
+    srcs = [os.path.join(REF, u[0]) for u in UNITS] + [os.path.join(REF, "src/jl", f) for f in JL]
     mine = [os.path.join(HERE, f) for f in ("f2c_lite.py", "build_ref.py", "ref_harness.c")]
     if not force and os.path.exists(LIB):
         t = os.path.getmtime(LIB)
@@ -69,7 +88,8 @@ def build(force: bool = False, verbose: bool = False) -> str | None:
     import f2c_lite
     os.makedirs(OUT, exist_ok=True)
     inc = [os.path.join(REF, "tests/3dboxper"), os.path.join(REF, "src")]
-    ctext, em = f2c_lite.translate([(os.path.join(REF, p), u) for p, u in UNITS], inc, DEFINES)
+    ctext, em = f2c_lite.translate([(os.path.join(REF, u[0]),) + tuple(u[1:]) for u in UNITS], inc,
+                                   DEFINES)
     gen = os.path.join(OUT, "ref_gen.c")
     with open(gen, "w") as f:
         f.write(ctext)

@@ -402,6 +402,7 @@ class Sym:
         self.static = False    # SAVE / DATA
         self.init = None
         self.data_unsupported = False
+        self.init_list = None
 
     def ctype(self):
         return {"real": "double", "integer": "int", "logical": "int", "character": "char"}[self.ftype]
@@ -466,13 +467,15 @@ class Translator:
         for lab, s in lines:
             m = re.match(r"^include\s*'([^']+)'", s)
             if m:
-                out.extend(self.read_include(m.group(1)))
+                out.extend([("@" + l.lstrip("@"), t) for l, t in self.read_include(m.group(1))])
             else:
                 out.append((lab, s))
         return out
 
-    def load(self, path, wanted=None):
-        """parse a source file; keep the units named in `wanted` (all if None)"""
+    def load(self, path, wanted=None, suffix=""):
+        """parse a source file; keep the units named in `wanted` (all if None).  With a
+        suffix the kept units are emitted as <name><suffix>_ (several .usr files define the
+        same callback names) and calls between them follow the renaming."""
         txt = preprocess(open(path, errors="replace").read(), self.defines)
         lines = logical_lines(txt)
         cur = None
@@ -491,16 +494,25 @@ class Translator:
                 continue
             if s == "end" or re.match(r"^end\s*(subroutine|function|program)(\s+\w+)?$", s):
                 if wanted is None or cur.name in wanted:
-                    self.units[cur.name] = cur
-                    self.order.append(cur.name)
-                    found.append(cur.name)
+                    cur.fname = cur.name          # Fortran name (function result variable)
+                    cur.rename = {}
+                    key = cur.name + suffix
+                    self.units[key] = cur
+                    self.order.append(key)
+                    found.append(key)
                 cur = None
                 continue
             cur.raw.append((lab, s))
+        if suffix:
+            ren = {self.units[k].fname: k for k in found}
+            for k in found:
+                self.units[k].rename = ren
         for name in found:
             u = self.units[name]
             u.raw = self.expand_includes(u.raw)
             self.declare(u)
+            u.name = name if not suffix else u.name
+            u.cname = name
         return found
 
     # ---- declarations
@@ -551,6 +563,11 @@ class Translator:
                 else:
                     vals.append(v)
             names = [n for n in names if n]
+            if len(names) == 1 and "(" not in names[0] and len(vals) > 1:
+                sy = u.sym(names[0])     # whole array: DATA a /v1,v2,.../
+                sy.static = True
+                sy.init_list = [parse_expr(v) for v in vals]
+                continue
             if len(names) != len(vals) or any("(" in n for n in names):
                 for n in names:
                     u.sym(re.match(r"[a-z_0-9$]+", n).group(0)).data_unsupported = True
@@ -565,6 +582,8 @@ class Translator:
             u.sym(a).kind = "dummy"
         body_started = False
         for lab, s in u.raw:
+            from_inc = lab.startswith("@")
+            lab = lab.lstrip("@")
             if not body_started:
                 if s.startswith("implicit"):
                     if "none" in s:
@@ -593,8 +612,12 @@ class Translator:
                         j = top_level_eq(d)
                         name, val = d[:j].strip(), parse_expr(d[j + 1:])
                         sy = u.sym(name)
-                        sy.kind, sy.value = "param", val
-                        u.decl_order.append(name)
+                        sy.value = val
+                        if not from_inc:
+                            sy.kind = "lparam"  # a constant of this unit only
+                            u.decl_order.append(name)
+                            continue
+                        sy.kind = "param"
                         if name not in self.param_names:
                             self.param_names.add(name)
                             self.params.append((name, val, u))
@@ -828,6 +851,9 @@ class Emitter:
                 return "f_powi(%s,%s)" % (self.ex(u, b), self.ex(u, x))
             return "pow(%s,%s)" % (self.ex(u, b), self.ex(u, x))
         if k == "bin":
+            if e[1] in ("==", "!=") and "char" in (self.typ(u, e[2]), self.typ(u, e[3])):
+                (pa, la), (pb, lb) = self.chref(u, e[2]), self.chref(u, e[3])
+                return "(f_chcmp(%s,%d,%s,%d)%s0)" % (pa, la, pb, lb, e[1])
             return "(%s%s%s)" % (self.ex(u, e[2]), e[1], self.ex(u, e[3]))
         if k == "var":
             sy = self.lookup(u, e[1])
@@ -843,9 +869,30 @@ class Emitter:
                 return self.intrinsic(u, name, args)
             # external function
             ft = (sy.ftype if sy and sy.ftype else implicit_type(name))
+            name = u.rename.get(name, name)
             self.called[name] = ft
             return "%s_(%s)" % (name, ", ".join(self.argref(u, a) for a in args))
         raise F2CError("ex: " + str(e))
+
+    def chref(self, u, e):
+        """character operand -> (C pointer expression, length) ; literals have length -1"""
+        if e[0] == "paren":
+            return self.chref(u, e[1])
+        if e[0] == "str":
+            return self.ex(u, e), -1
+        if e[0] == "var":
+            sy = self.lookup(u, e[1])
+            if sy.ftype != "character" or sy.dims is not None:
+                raise F2CError("character operand expected: %s in %s" % (e[1], u.name))
+            if sy.kind == "common":
+                self.note_global(u, sy)
+            return self.vname(e[1]), sy.charlen
+        if e[0] == "call":
+            sy = u.syms.get(e[1])
+            if sy is None or sy.dims is None or sy.ftype != "character":
+                raise F2CError("character operand expected: %s in %s" % (e[1], u.name))
+            return "(%s+(long)%d*%s)" % (self.base(u, sy), sy.charlen, self.index(u, sy, e[2])), sy.charlen
+        raise F2CError("unsupported character expression in %s: %s" % (u.name, e))
 
     def intrinsic(self, u, name, args):
         a = [self.ex(u, x) for x in args]
@@ -888,6 +935,8 @@ class Emitter:
             return ("f_dsign(%s,%s)" if isd else "f_isign(%s,%s)") % (a[0], a[1])
         if name == "iand":
             return "((%s)&(%s))" % (a[0], a[1])
+        if name == "ishft":
+            return "f_ishft(%s,%s)" % (a[0], a[1])
         if name == "ior":
             return "((%s)|(%s))" % (a[0], a[1])
         raise F2CError("intrinsic not supported: " + name)
@@ -902,6 +951,8 @@ class Emitter:
                 if sy.external:
                     return self.vname(e[1])
                 return self.vname(e[1])
+            if sy.kind == "lparam":
+                return "&(%s){%s}" % (sy.ctype(), self.vname(e[1]))
             if sy.kind == "param":
                 self.used_params.add(e[1])
                 return "&(int){%s}" % self.vname(e[1]) if sy.ftype != "real" else "&(double){%s}" % self.vname(e[1])
@@ -937,7 +988,11 @@ class Emitter:
                 params.append("void (*%s)()" % self.vname(a))
             else:
                 params.append("%s *%s" % (sy.ctype(), self.vname(a)))
-        out.append("%s %s_(%s)\n{" % (rt, u.name, ", ".join(params) if params else "void"))
+        out.append("%s %s_(%s)\n{" % (rt, u.cname, ", ".join(params) if params else "void"))
+        # constants of this unit (PARAMETER in the unit's own text), in definition order
+        for name in u.decl_order:
+            sy = u.syms[name]
+            out.append("    const %s %s = %s;" % (sy.ctype(), self.vname(name), self.ex(u, sy.value)))
         # locals
         for name, sy in sorted(u.syms.items()):
             if sy.kind != "local" or name == u.name:
@@ -947,7 +1002,12 @@ class Emitter:
             if sy.ftype == "character":
                 out.append("    char %s[%d] = {0};" % (self.vname(name), sy.charlen + 1))
                 continue
-            if sy.dims is not None:
+            if sy.data_unsupported:
+                raise F2CError("unsupported DATA for %s in %s" % (name, u.name))
+            if sy.dims is not None and sy.init_list is not None:
+                out.append("    static %s %s[] = {%s};" % (sy.ctype(), self.vname(name),
+                           ", ".join(self.ex(u, v) for v in sy.init_list)))
+            elif sy.dims is not None:
                 n = "*".join("(long)(%s)" % self.extent(u, sy, d) for d in range(len(sy.dims)))
                 out.append("    %s *%s = (%s*)f_scratch(sizeof(%s)*(%s));" %
                            (sy.ctype(), self.vname(name), sy.ctype(), sy.ctype(), n))
@@ -1104,6 +1164,7 @@ class Emitter:
             sy = u.syms.get(name)
             if sy is not None and sy.kind == "dummy":
                 return ["%s(%s);" % (self.vname(name), ", ".join(self.argref(u, a) for a in args))]
+            name = u.rename.get(name, name)
             self.called.setdefault(name, None)
             return ["%s_(%s);" % (name, ", ".join(self.argref(u, a) for a in args))]
         j = top_level_eq(s)
@@ -1111,21 +1172,22 @@ class Emitter:
             lhs, rhs = s[:j].strip(), s[j + 1:].strip()
             le = parse_expr(lhs)
             re_ = parse_expr(rhs)
+            if (le[0] == "var" and self.lookup(u, le[1]).ftype == "character") or \
+               (le[0] == "call" and u.syms.get(le[1]) is not None and u.syms[le[1]].dims is not None
+                    and u.syms[le[1]].ftype == "character"):
+                (pa, la), (pb, lb) = self.chref(u, le), self.chref(u, re_)
+                return ["f_chassign(%s,%d,%s,%d);" % (pa, la, pb, lb)]
             if le[0] == "var":
                 sy = self.lookup(u, le[1])
-                if sy.ftype == "character":
-                    raise F2CError("character assignment in %s: %s" % (u.name, s))
                 if sy.dims is not None:
                     raise F2CError("whole-array assignment in %s: %s" % (u.name, s))
-                if sy.kind == "param":
+                if sy.kind in ("param", "lparam"):
                     raise F2CError("assignment to parameter: " + s)
                 return ["%s = %s;" % (self.ref(u, le[1]), self.ex(u, re_))]
             if le[0] == "call":
                 sy = u.syms.get(le[1])
                 if sy is None or sy.dims is None:
                     raise F2CError("statement function or undeclared array in %s: %s" % (u.name, s))
-                if sy.ftype == "character":
-                    raise F2CError("character assignment in %s: %s" % (u.name, s))
                 return ["%s[%s] = %s;" % (self.base(u, sy), self.index(u, sy, le[2]), self.ex(u, re_))]
         raise F2CError("unsupported statement in %s: %s" % (u.name, s))
 
@@ -1151,9 +1213,9 @@ class Emitter:
             out.append("%s %s;" % (sy.ctype(), self.vname(name)))
         # commons
         for name, (sy, u) in sorted(self.used_globals.items()):
-            if sy.ftype == "character":
-                raise F2CError("character common variable used: " + name)
-            if sy.dims is None:
+            if sy.ftype == "character" and sy.dims is None:
+                out.append("char %s[%d];" % (self.vname(name), sy.charlen + 1))
+            elif sy.dims is None:
                 out.append("%s %s;" % (sy.ctype(), self.vname(name)))
             else:
                 out.append("%s *%s;" % (sy.ctype(), self.vname(name)))
@@ -1182,15 +1244,26 @@ class Emitter:
         for name, (sy, u) in sorted(self.used_globals.items()):
             if sy.dims is not None:
                 n = "*".join("(long)(%s)" % self.extent(u, sy, d) for d in range(len(sy.dims)))
-                out.append("    free(%s); %s = (%s*)calloc((size_t)(%s) + 1, sizeof(%s));" %
+                if sy.ftype == "character":
+                    n = "(%s)*%d" % (n, sy.charlen)
+                # 2x slack: the reference zeroes some face arrays past their end in 2D (SETAREA
+                # clears 6 faces of arrays dimensioned 2*ldim, src/nek5_coef.F:1003-1007), which
+                # in the Fortran image lands in the following members of the COMMON block
+                out.append("    free(%s); %s = (%s*)calloc(2 * (size_t)(%s) + 64, sizeof(%s));" %
                            (self.vname(name), self.vname(name), sy.ctype(), n, sy.ctype()))
+                if sy.ftype == "character":
+                    out.append("    memset(%s, ' ', (size_t)(%s));" % (self.vname(name), n))
         out.append("}")
         out.append("EXPORT void *ref_sym(const char *name, int *isint, long *count)\n{")
         for name, val, u in pnames:
             out.append("    if (!strcmp(name, \"%s\")) { *isint = 1; *count = 1; return &%s; }" % (name, self.vname(name)))
         for name, (sy, u) in sorted(self.used_globals.items()):
-            isint = 0 if sy.ftype == "real" else 1
-            if sy.dims is None:
+            isint = 0 if sy.ftype == "real" else (2 if sy.ftype == "character" else 1)
+            if sy.ftype == "character":
+                n = "*".join("(long)(%s)" % self.extent(u, sy, d) for d in range(len(sy.dims))) if sy.dims else "1"
+                out.append("    if (!strcmp(name, \"%s\")) { *isint = 2; *count = (%s)*%d; return %s; }" %
+                           (name, n, sy.charlen, self.vname(name)))
+            elif sy.dims is None:
                 out.append("    if (!strcmp(name, \"%s\")) { *isint = %d; *count = 1; return &%s; }" %
                            (name, isint, self.vname(name)))
             else:
@@ -1226,8 +1299,26 @@ static inline double f_dmin(double a, double b) { return a < b ? a : b; }
 static inline int f_imax(int a, int b) { return a > b ? a : b; }
 static inline int f_imin(int a, int b) { return a < b ? a : b; }
 static inline int f_imodulo(int a, int p) { int r = a % p; return (r != 0 && ((r < 0) != (p < 0))) ? r + p : r; }
+static inline int f_ishft(int a, int s) { return s >= 0 ? (int)((unsigned)a << s) : (int)((unsigned)a >> (-s)); }
 static inline double f_dsign(double a, double b) { return b >= 0 ? fabs(a) : -fabs(a); }
 static inline int f_isign(int a, int b) { return b >= 0 ? abs(a) : -abs(a); }
+/* character assignment / comparison with blank padding (Fortran semantics) */
+static void f_chassign(char *d, int ld, const char *s, int ls)
+{
+    if (ls < 0) ls = (int)strlen(s);
+    for (int i = 0; i < ld; i++) d[i] = i < ls ? s[i] : ' ';
+}
+static int f_chcmp(const char *a, int la, const char *b, int lb)
+{
+    if (la < 0) la = (int)strlen(a);
+    if (lb < 0) lb = (int)strlen(b);
+    int n = la > lb ? la : lb;
+    for (int i = 0; i < n; i++) {
+        char ca = i < la ? a[i] : ' ', cb = i < lb ? b[i] : ' ';
+        if (ca != cb) return ca < cb ? -1 : 1;
+    }
+    return 0;
+}
 /* scratch stack for local (non-COMMON) arrays */
 static char *f_scr; static long f_scr_cap, f_scr_top;
 static long f_scratch_mark(void) { return f_scr_top; }
@@ -1248,11 +1339,13 @@ def translate(sources, include_dirs, defines=()):
     """sources: [(path, [unit names])] -> C text"""
     tr = Translator(include_dirs, defines)
     names = []
-    for path, wanted in sources:
-        got = tr.load(path, set(wanted))
-        missing = set(wanted) - set(got)
+    for src in sources:
+        path, wanted = src[0], src[1]
+        suffix = src[2] if len(src) > 2 else ""
+        got = tr.load(path, set(wanted), suffix)
+        missing = set(w + suffix for w in wanted) - set(got)
         if missing:
             raise F2CError("units not found in %s: %s" % (path, sorted(missing)))
-        names.extend([w for w in wanted])
+        names.extend([w + suffix for w in wanted])
     em = Emitter(tr)
     return em.emit_all(names), em

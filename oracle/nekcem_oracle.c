@@ -6,12 +6,15 @@
  * arithmetic grouping.  Every routine cites the reference file:line it follows
  * (paths relative to the NekCEM source tree).
  *
- * PARITY STATUS: "parity unpinned" against the reference binary -- the
- * reference is Fortran+MPI and neither gfortran nor MPI exist in the build
- * container or on the GPU box, and the reference ships no golden field dumps.
- * The oracle is pinned instead by the reference's own known-answer tests: the
- * analytic solutions and L2/Linf tolerances compiled into tests/<case>/<case>.usr
- * (see tests/test_oracle_kat.py).
+ * PARITY STATUS: PINNED against the reference's own code run here: oracle/_ref
+ * (the reference's Fortran routines of the path translated statement by statement
+ * by oracle/f2c_lite.py -- no Fortran compiler exists in this image -- plus its own
+ * src/jl gather-scatter library; recipe oracle/build_ref.py).  This restatement
+ * must reproduce it bit for bit (tests/test_reference_pin.py); both are compiled
+ * with -ffp-contract=off.  Unpinned remainder: the code generation of a real
+ * Fortran compiler (<= 1e-15 relative per operation).  The reference's known-answer
+ * tests (analytic solutions and L2/Linf tolerances of tests/<case>/<case>.usr) are
+ * checked besides (tests/test_oracle_kat.py).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load this library.  The product path

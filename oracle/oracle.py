@@ -4,10 +4,18 @@ ctypes binding of ``nekcem_oracle.c`` plus numpy restatements of the reference's
 setup-time routines (mesh, face numbering, BC flags, materials, PML layout) that feed
 the hot path.  Each function cites the NekCEM file:line it follows.
 
-PARITY STATUS: "parity unpinned" against the reference binary (no Fortran/MPI toolchain
-exists here or on the GPU box; the reference ships no golden field dumps).  The oracle is
-pinned by the reference's own known-answer tests -- the analytic solutions and L2/Linf
-tolerances in tests/<case>/<case>.usr -- see tests/test_oracle_kat.py.
+PARITY STATUS: PINNED against the reference's own code executed in this container.
+`oracle/_ref/libnekcem_ref.so` (recipe oracle/build_ref.py) holds the reference's Fortran
+routines of the path -- translated statement by statement from /root/reference/src by
+oracle/f2c_lite.py, since no Fortran compiler exists here -- linked with the reference's own
+src/jl gather-scatter library compiled unchanged.  tests/test_reference_pin.py requires this
+oracle to reproduce it BIT FOR BIT (fields, RK registers, PML/ADE state) on every shipped case
+of the path and for nx1 = 2..17, and pins the setup it feeds the path (GLL nodes/weights/D,
+cofactors, Jacobian, mass, face areas/normals, cemface, impedances, PEC list, PML tags/extents/
+sigma, error norms, dxmin) and the .usr analytic solutions the same way.  What stays unpinned:
+the reference compiled by a real Fortran compiler (gfortran/ifort code generation, e.g. FMA
+contraction with -march=native) -- a <= 1e-15 relative effect per operation.  The reference's
+known-answer tolerances are checked besides (tests/test_oracle_kat.py).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
 may import this module.  All index arrays are 0-based.
@@ -661,8 +669,12 @@ class RefCase:
                     sigmamax = -(order + 1) * math.log(referr) / (2 * eta * width)
                     zero2one = (coords[axis - 1][sl] - self.pmlinner[face - 1]) / (
                         self.pmlouter[face - 1] - self.pmlinner[face - 1])
+                    # zero2one**order with a REAL exponent is libm pow() in the reference;
+                    # numpy's vectorised power is not correctly rounded (1 ulp off in ~10 %
+                    # of the points against oracle/_ref), so call libm element by element
+                    z2o = np.array([math.pow(v, order) for v in zero2one])
                     self.pmlsigma[(axis - 1) * npts + sl.start:(axis - 1) * npts + sl.stop] = (
-                        sigmamax * zero2one ** order)
+                        sigmamax * z2o)
 
     def sync_pml_state(self):
         """Refresh the struct after setup helpers changed counts."""

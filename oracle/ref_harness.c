@@ -43,3 +43,7 @@ EXPORT void exitt_(int *rc) { fprintf(stderr, "reference called exitt(%d)\n", rc
 EXPORT void q_filter_(double *w) { (void)w; fprintf(stderr, "q_filter is outside the path\n"); exit(1); }
 /* dealiased curl (src/cem_maxwell.F:1541-1729): ifdealias is off in every case of the path */
 EXPORT void maxwell_wght_dcurl_(void) { fprintf(stderr, "maxwell_wght_dcurl is outside the path\n"); exit(1); }
+/* global integer sum over ranks (src/nek5_mat1.F): one process here */
+EXPORT int iglsum_(int *a, int *n) { (void)n; return *a; }
+/* global reduction over ranks (src/nek5_comm_mpi.F:379-420): the identity on one process */
+EXPORT void gop_(double *x, double *w, const char *op, int *n) { (void)x; (void)w; (void)op; (void)n; }

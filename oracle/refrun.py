@@ -70,6 +70,7 @@ class ReferenceRun:
                      ("ifupwind", int(case.s.ifupwind)), ("ifcentral", int(case.s.ifcentral)),
                      ("ifpml", int(case.ifpml)), ("ifpec", int(case.ifpec)), ("ifrk45", 1),
                      ("ifrk22", 0), ("iffilter", 0), ("ifdealias", 0),
+                     ("ifte", int(case.imode == 1)), ("iftm", int(case.imode == 2)),
                      ("ncemface", nxzfl), ("ncempec", case.ncempec), ("maxpml", case.maxpml),
                      ("istep", 0)):
             try:
@@ -78,6 +79,10 @@ class ReferenceRun:
                 pass  # a COMMON scalar none of the translated routines reads
         self.set("dt", case.s.dt)
         self.set("time", case.s.time)
+        try:
+            self.set("pi", 4.0 * np.arctan(1.0))  # src/cem_drive.F: pi = 4.*atan(1.)
+        except KeyError:
+            pass
         # geometry, masses, impedances, fields: same names as the COMMON blocks
         for name in ("dxm1", "dxtm1", "w3mn", "rxmn", "rymn", "rzmn", "sxmn", "symn", "szmn",
                      "txmn", "tymn", "tzmn", "bmn", "unxm", "unym", "unzm", "aream", "hbm1",
@@ -106,16 +111,27 @@ class ReferenceRun:
         self.gsh = h.value
         self.set("gsh_face", self.gsh)
         L.rk_storage_()
+        # setup_topo's face tables (src/nek5_connect11.F:1046-1093, 1440-1528).  dsset keeps
+        # the dimensions of its last call in SAVEd variables and returns early when they
+        # repeat; ref_alloc has just re-created the COMMON arrays, so force a refresh.
+        L.initds_()
+        one = C.c_int(1)
+        L.dsset_(C.byref(one), C.byref(one), C.byref(one))
+        L.dsset_(C.byref(C.c_int(nx1)), C.byref(C.c_int(nx1)), C.byref(C.c_int(nz1)))
         self._cbs = {}
         self.istep = 0
 
     # ---- COMMON access ------------------------------------------------------------------
-    def _sym(self, name):
+    def _sym_kind(self, name):
         isint, cnt = C.c_int(), C.c_long()
         p = self.L.ref_sym(name.encode(), C.byref(isint), C.byref(cnt))
         if not p:
             raise KeyError(name)
-        return p, bool(isint.value), cnt.value
+        return p, isint.value, cnt.value
+
+    def _sym(self, name):
+        p, kind, cnt = self._sym_kind(name)
+        return p, kind == 1, cnt
 
     def view(self, name):
         p, isint, cnt = self._sym(name)
@@ -133,6 +149,29 @@ class ReferenceRun:
         a = np.asarray(arr).reshape(-1)
         assert a.size <= v.size, (name, a.size, v.size)
         v[:a.size] = a
+
+    def view_char(self, name):
+        p, kind, cnt = self._sym_kind(name)
+        assert kind == 2, name
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(cnt,))
+
+    def set_cbc(self, cbc):
+        """CBC(6,LELT,0:LDIMT1) character*3 (src/INPUT:147-150), field 1 = the E&M boundary
+        conditions; cbc[e][f] are the 3-character flags in preprocessor face order"""
+        v = self.view_char("cbc")
+        lelt = self.case.nelt
+        v[:] = ord(" ")
+        for e, row in enumerate(cbc):
+            for f, s in enumerate(row):
+                off = (f + 6 * (e + lelt * 1)) * 3
+                v[off:off + 3] = np.frombuffer(s.ljust(3)[:3].encode(), dtype=np.uint8)
+
+    def put_opt(self, name, arr):
+        """put() for a COMMON array that the translated routines may not reference"""
+        try:
+            self.put(name, arr)
+        except KeyError:
+            pass
 
     # ---- callbacks ------------------------------------------------------------------------
     def set_callback(self, which: str, fn):

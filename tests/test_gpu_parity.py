@@ -321,3 +321,56 @@ def test_ade_in_3d(kind):
     jg, kg = s.get_ade()
     assert rel_l2(jg, jn) <= TOL and rel_l2(kg, kjn) <= TOL
     s.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU vs the reference's own hot path (oracle/_ref: the reference's Fortran translated by
+# oracle/f2c_lite.py + its src/jl gs library; built here, the .so travels to the GPU box)
+# ---------------------------------------------------------------------------------------------
+def _refrun_or_skip():
+    from oracle import refrun
+    if not refrun.available():
+        pytest.skip("oracle/_ref/libnekcem_ref.so did not travel with the tree")
+    return refrun
+
+
+def test_gpu_vs_translated_reference_3dboxper():
+    """north_star's clause 'fields after K steps ... match the reference's own CPU build within
+    1e-12 relative L2', checked against the translated reference directly: tests/3dboxper as
+    shipped, 50 steps."""
+    from oracle import cases
+    refrun = _refrun_or_skip()
+    c = cases.case_3dboxper()
+    r = refrun.ReferenceRun(c)
+    s = solver_from_refcase(c)
+    r.step(50); s.step(50)
+    assert rel_l2(_fields(s), np.concatenate([r.hn, r.en])) <= TOL
+    r.close(); s.close()
+
+
+def test_gpu_vs_translated_reference_pml_dielectric():
+    """tests/3ddielectric (two materials, PML, userinc injection): GPU with the device-side
+    incident hook vs the translated reference with the .usr callback"""
+    from oracle import cases
+    refrun = _refrun_or_skip()
+    c = cases.case_3ddielectric(True)
+    r = refrun.ReferenceRun(c)
+    r.set_callback("userinc", c.user.userinc(c))
+    s = solver_from_refcase(c, incident=incident_3ddielectric(c))
+    r.step(20); s.step(20)
+    assert rel_l2(_fields(s), np.concatenate([r.hn, r.en])) <= TOL
+    for name in ("pmlbn", "pmldn"):
+        assert rel_l2(s.get_array(name), r.view(name)[:3 * c.npts]) <= TOL, name
+    r.close(); s.close()
+
+
+@pytest.mark.parametrize("nx1", [8, 12, 16])
+def test_gpu_vs_translated_reference_orders(nx1):
+    from oracle import cases
+    refrun = _refrun_or_skip()
+    c = cases.case_boxper((3, 3, 4), nx1, dt=-1e-3)
+    r = refrun.ReferenceRun(c)
+    s = solver_from_refcase(c)
+    r.step(3); s.step(3)
+    assert rel_l2(_fields(s), np.concatenate([r.hn, r.en])) <= TOL
+    r.close(); s.close()

@@ -190,3 +190,213 @@ def test_pin_cemface_numbering():
         assert r.get("ncemface") == c.nxzfl
         assert np.array_equal(r.view("cemface")[:c.nxzfl], c.cemface + 1)
         r.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# setup routines whose output the path consumes: also translated from the
+# reference, so the oracle's restated setup is pinned too
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", list(range(2, 18)))
+def test_pin_gll_nodes_weights_and_dgll(n):
+    """ZWGLL (-> ZWGLJ -> ZWGLJD -> JACG/JACOBF, ENDW1/2, GAMMAF, PNORMJ) and DGLL (PNLEG),
+    src/nek5_speclib.F:107-122, 240-283, 423-521, 807-912"""
+    from oracle import oracle as O
+    L = refrun.lib()
+    z, w = np.zeros(n), np.zeros(n)
+    nn = C.c_int(n)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    L.zwgll_(dp(z), dp(w), C.byref(nn))
+    zo, wo = O.zwgll(n)
+    assert np.array_equal(z, zo) and np.array_equal(w, wo)
+    d, dt = np.zeros(n * n), np.zeros(n * n)
+    L.dgll_(dp(d), dp(dt), dp(z), C.byref(nn), C.byref(nn))
+    do, dto = O.dgll(zo)
+    assert np.array_equal(d, do) and np.array_equal(dt, dto)
+
+
+def _geometry_case(which):
+    from oracle import oracle as O
+    if which == "3dboxper":
+        return cases.case_3dboxper()
+    if which == "3ddielectric":
+        return cases.case_3ddielectric(True)
+    if which == "drude2d":
+        return cases.case_drude()
+    # sheared, non-affine 3D elements (curved-metric terms all non-zero)
+    mesh = O.box_mesh((2, 2, 2), ((0.0, 1.0),) * 3, ("P  ",) * 6)
+
+    def warp(c):
+        x, y, z = c.xm1.copy(), c.ym1.copy(), c.zm1.copy()
+        c.xm1[:] = x + 0.05 * np.sin(3 * y) * np.cos(2 * z)
+        c.ym1[:] = y + 0.04 * np.sin(2 * x + z)
+        c.zm1[:] = z + 0.03 * x * y
+
+    return O.RefCase(mesh, 6, usrdat2=warp)
+
+
+@pytest.mark.parametrize("which", ["3dboxper", "3ddielectric", "drude2d", "warped"])
+def test_pin_geometry(which):
+    """GLMAPM1 (XYZRST + cofactors + Jacobian), GEODAT1 (mass bm1 = jac*w3m1) and SETAREA
+    (AREA2/AREA3 + UNITVEC): src/nek5_coef.F:555-636, 637-785, 877-925, 992-1237, run on
+    the oracle's node coordinates; the cofactors, Jacobian, mass, face areas and normals the
+    oracle hands to the path must be the reference's, bit for bit."""
+    c = _geometry_case(which)
+    r = refrun.ReferenceRun(c)
+    n = c.nx1
+    nz1 = n if c.ldim == 3 else 1
+    for name in ("xm1", "ym1", "zm1"):
+        r.put(name, getattr(c, name))
+    for name in ("dxm1", "dym1"):
+        r.put_opt(name, c.dxm1)
+    for name in ("dxtm1", "dytm1"):
+        r.put_opt(name, c.dxtm1)
+    if c.ldim == 3:
+        r.put_opt("dzm1", c.dxm1); r.put_opt("dztm1", c.dxtm1)
+    r.put("w3m1", c.w3mn)
+    for name in ("wxm1", "wym1"):
+        r.put_opt(name, c.wxm1)
+    r.put_opt("wzm1", c.wxm1 if c.ldim == 3 else np.ones(1))
+    r.put_opt("zgm1", np.concatenate([c.zgm1, c.zgm1, c.zgm1 if c.ldim == 3 else np.zeros(n)]))
+    for name in ("rxm1", "rym1", "rzm1", "sxm1", "sym1", "szm1", "txm1", "tym1", "tzm1",
+                 "jacm1", "bm1", "area", "unx", "uny", "unz"):
+        r.view(name)[:] = -7.0  # poison
+    r.L.initds_()
+    r.L.glmapm1_()
+    r.L.geodat1_()
+    for a, b in (("rxmn", "rxm1"), ("rymn", "rym1"), ("sxmn", "sxm1"), ("symn", "sym1"),
+                 ("jacm", "jacm1"), ("bmn", "bm1")) + ((("rzmn", "rzm1"), ("szmn", "szm1"),
+                 ("txmn", "txm1"), ("tymn", "tym1"), ("tzmn", "tzm1")) if c.ldim == 3 else ()):
+        x, y = getattr(c, a), r.view(b)[:c.npts]
+        assert np.array_equal(x, y), (a, float(np.abs(x - y).max()))
+    for a, b in (("aream", "area"), ("unxm", "unx"), ("unym", "uny")) + (
+            (("unzm", "unz"),) if c.ldim == 3 else ()):
+        x, y = getattr(c, a), r.view(b)[:c.nxzfl]
+        assert np.array_equal(x, y), (a, float(np.abs(x - y).max()))
+    r.close()
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+@pytest.mark.parametrize("which", ["3dboxpec", "3ddielectric", "drude2d"])
+def test_pin_materials_and_pec_list(which):
+    """cem_maxwell_materials (impedances Y_0,Y_1,Z_0,Z_1 via the reference's gs_op, PEC
+    doubling, src/cem_maxwell.F:262-325) and cem_maxwell_pec_init (:1338-1366)"""
+    c = {"3dboxpec": cases.case_3dboxpec, "3ddielectric": lambda: cases.case_3ddielectric(True),
+         "drude2d": cases.case_drude}[which]()
+    r = refrun.ReferenceRun(c)
+    r.set_cbc(c.mesh.cbc)
+    for name in ("y_0", "y_1", "z_0", "z_1"):
+        r.view(name)[:] = 0.0
+    r.L.cem_maxwell_materials_()
+    for name in ("Y_0", "Y_1", "Z_0", "Z_1"):
+        assert np.array_equal(getattr(c, name), r.view(name.lower())[:c.nxzfl]), name
+    r.view("cempec")[:] = 0
+    r.L.cem_maxwell_pec_init_()
+    assert r.get("ncempec") == c.ncempec
+    assert np.array_equal(r.view("cempec")[:c.ncempec], c.cempec[:c.ncempec] + 1)
+    r.close()
+
+
+@pytest.mark.parametrize("which", ["3ddielectric", "3dboxpml", "drude2d"])
+def test_pin_pml_setup(which):
+    """pml_fill_faceary / march_faces (gs_op max) / pml_extent_and_tags / pml_calc_sigma,
+    src/cem_maxwell_pml.F:85-506: PML element list, tags, extents and the sigma profile"""
+    c = {"3ddielectric": lambda: cases.case_3ddielectric(True),
+         "3dboxpml": lambda: cases.case_3dboxpml(nx1=6, nel=(5, 5, 5)),
+         "drude2d": cases.case_drude}[which]()
+    r = refrun.ReferenceRun(c)
+    r.set_cbc(c.mesh.cbc)
+    for name in ("xm1", "ym1", "zm1"):
+        r.put(name, getattr(c, name))
+    for a, b in (("rxmn", "rxm1"), ("rymn", "rym1"), ("rzmn", "rzm1"), ("sxmn", "sxm1"),
+                 ("symn", "sym1"), ("szmn", "szm1"), ("txmn", "txm1"), ("tymn", "tym1"),
+                 ("tzmn", "tzm1")):
+        r.put_opt(b, getattr(c, a))
+    # the reference passes its COMMON arrays as the actual arguments (src/cem_maxwell.F:164-175)
+    faceary = np.zeros(c.nxzfl)  # /scratch/ faceary: not named by any translated routine
+    tag = r.view("pmltag")
+    inner, outer = np.zeros(2 * c.ldim), np.zeros(2 * c.ldim)
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+    thick = C.c_int(c.pmlthick)
+    r.L.pml_fill_faceary_(_dp(faceary), C.byref(thick))
+    r.L.pml_extent_and_tags_(_dp(inner), _dp(outer), ip(tag), _dp(faceary))
+    assert np.array_equal(tag[:c.nelt], c.pmltag)
+    assert np.array_equal(inner[:2 * c.ldim], c.pmlinner)
+    assert np.array_equal(outer[:2 * c.ldim], c.pmlouter)
+    r.view("pmlsigma")[:] = 0.0
+    order, referr = C.c_double(c.pmlorder), C.c_double(c.pmlreferr)
+    r.L.pml_calc_sigma_(_dp(inner), _dp(outer), ip(tag), C.byref(order), C.byref(referr))
+    assert r.get("maxpml") == c.maxpml
+    assert np.array_equal(r.view("pmlptr")[:c.maxpml], c.pmlptr[:c.maxpml] + 1)
+    assert np.array_equal(r.view("pmlsigma")[:3 * c.npts], c.pmlsigma)
+    r.close()
+
+
+def test_pin_error_norms_and_dxmin():
+    """cem_error (src/cem_common.F:1335-1355: the L2 / Linf norms userchk prints) and get_dxmin
+    (src/nek5_courant.F:2-79: the CFL length of set_dt)"""
+    from oracle import oracle as O
+    c = cases.case_3dboxper()
+    r = refrun.ReferenceRun(c)
+    c.step(3)
+    shn, sen = c.usersol(c, c.time)
+    r.set("volvm1", c.volvm1)
+    n = C.c_int(c.npts)
+    err = np.zeros(c.npts)
+    for arr, sol in ((c.hn, shn), (c.en, sen)):
+        for k in range(3):
+            u = np.ascontiguousarray(c.comp(arr, k)); ex = np.ascontiguousarray(c.comp(sol, k))
+            l2, linf = C.c_double(), C.c_double()
+            r.L.cem_error_(_dp(u), _dp(ex), _dp(err), C.byref(n), C.byref(l2), C.byref(linf))
+            a, b = c.cem_error(u, ex)
+            assert (a, b) == (l2.value, linf.value)
+            assert l2.value > 0
+    for name in ("xm1", "ym1", "zm1"):
+        r.put(name, getattr(c, name))
+    d = C.c_double()
+    r.L.get_dxmin_(C.byref(d))
+    assert d.value == c.L.ora_get_dxmin(c.ldim, c.nx1, c.nelt, O.dp(c.xm1), O.dp(c.ym1), O.dp(c.zm1))
+    r.close()
+
+
+@pytest.mark.parametrize("which", ["3dboxper", "3dboxpec", "2dboxper-te", "2dboxper-tm",
+                                   "2dboxpec-te", "2dboxpec-tm"])
+def test_pin_usersol_and_error_norms(which):
+    """The analytic solutions compiled into the reference's .usr files (usersol of
+    tests/3dboxper, 3dboxpec, 2dboxper, 2dboxpec), translated from those files: the oracle's
+    numpy restatements agree to round-off of the libm / numpy sin and cos (<= 4 ulp of an O(1)
+    value), and the L2 / Linf errors the reference's userchk would print for the oracle's
+    fields -- reference usersol + reference cem_error -- equal the oracle's own."""
+    name, _, mode = which.partition("-")
+    imode = {"te": 1, "tm": 2}.get(mode, 3)
+    c = {"3dboxper": cases.case_3dboxper, "3dboxpec": cases.case_3dboxpec,
+         "2dboxper": lambda: cases.case_2dboxper(imode),
+         "2dboxpec": lambda: cases.case_2dboxpec(imode)}[name]()
+    r = refrun.ReferenceRun(c)
+    for nm in ("xm1", "ym1", "zm1"):
+        r.put_opt(nm, getattr(c, nm))
+    c.step(7)
+    n = c.npts
+    sol = [np.zeros(n) for _ in range(6)]
+    tt = C.c_double(c.time)
+    getattr(r.L, "usersol__%s_" % name)(C.byref(tt), *[_dp(a) for a in sol])
+    shn, sen = c.usersol(c, c.time)
+    mine = [c.comp(shn, k) for k in range(3)] + [c.comp(sen, k) for k in range(3)]
+    for k in range(6):
+        assert np.max(np.abs(sol[k] - mine[k])) <= 1e-15, (k, np.max(np.abs(sol[k] - mine[k])))
+    assert max(np.abs(a).max() for a in sol) > 0.1
+    # userchk: cem_error of every component against the reference's usersol
+    r.set("volvm1", c.volvm1)
+    l2o, linfo = c.errors(c.usersol)
+    err = np.zeros(n)
+    nn = C.c_int(n)
+    for k in range(6):
+        u = np.ascontiguousarray(c.comp(c.hn if k < 3 else c.en, k % 3))
+        l2, linf = C.c_double(), C.c_double()
+        r.L.cem_error_(_dp(u), _dp(sol[k]), _dp(err), C.byref(nn), C.byref(l2), C.byref(linf))
+        assert l2.value <= c.tol["l2"][k] and linf.value <= c.tol["linf"][k]
+        assert abs(l2.value - l2o[k]) <= 1e-3 * l2o[k] + 1e-15
+        assert abs(linf.value - linfo[k]) <= 1e-3 * linfo[k] + 1e-14
+    r.close()
