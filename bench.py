@@ -3,7 +3,8 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--elems E] [--order P]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
-    python bench.py --impl reference ...      (CPU arm: the oracle port on the host cores)
+    python bench.py --impl reference ...      (CPU arm: the reference's own path, oracle/_ref,
+                                               on all host cores; the oracle port if absent)
 
 Workload (BASELINE.json configs[4]): synthetic 3D periodic box, 64^3 hex elements at N=7 per
 GPU (weak scaling: the global box is 64 x 64 x 64*N elements, split into z-slabs by the
@@ -59,15 +60,73 @@ def cpu_oracle_rate(elems: int, nx1: int, steps: int, warmup: int):
     return rate, threads, dt, c.npts
 
 
+def _ref_worker(elems: int, nx1: int, steps: int, warmup: int, sync_dir: str, idx: int):
+    """one replica of the translated reference (oracle/_ref): setup, warm-up, file barrier,
+    then `steps` timed calls of the reference's cem_maxwell_op_rk"""
+    os.environ["OMP_NUM_THREADS"] = "1"
+    from oracle import cases, refrun
+    c = cases.case_boxper((elems,) * 3, nx1)
+    r = refrun.ReferenceRun(c)
+    r.step(max(warmup, 1))
+    open(os.path.join(sync_dir, f"ready_{idx}"), "w").close()
+    go = os.path.join(sync_dir, "go")
+    while not os.path.exists(go):
+        time.sleep(0.005)
+    t0 = time.perf_counter()
+    r.step(steps)
+    dt = time.perf_counter() - t0
+    print(json.dumps({"dt": dt, "npts": int(c.npts)}), flush=True)
+
+
+def cpu_reference_rate(elems: int, nx1: int, steps: int, warmup: int):
+    """The reference's own hot path (oracle/_ref: its Fortran translated to C + its src/jl gs
+    library) on all host cores.  This image has no MPI, so the cores are filled the way
+    `mpiexec -np P` would fill them but without the inter-rank exchange: P independent
+    single-process replicas, each advancing its own periodic box of elems^3 elements
+    (an upper bound on what the MPI reference could reach on the same cores).
+    Returns None when oracle/_ref is not available."""
+    from oracle import refrun
+    if not refrun.available():
+        return None
+    procs = len(os.sched_getaffinity(0))
+    sync_dir = tempfile.mkdtemp(prefix="nekcem_ref_")
+    ws = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--ref-worker",
+                            f"{elems},{nx1},{steps},{warmup},{sync_dir},{i}"],
+                           stdout=subprocess.PIPE, text=True) for i in range(procs)]
+    while sum(os.path.exists(os.path.join(sync_dir, f"ready_{i}")) for i in range(procs)) < procs:
+        if any(w.poll() not in (None, 0) for w in ws):
+            for w in ws:
+                w.kill()
+            return None
+        time.sleep(0.01)
+    open(os.path.join(sync_dir, "go"), "w").close()
+    outs = [json.loads(w.communicate()[0].strip().splitlines()[-1]) for w in ws]
+    import shutil
+    shutil.rmtree(sync_dir, ignore_errors=True)
+    dt = max(o["dt"] for o in outs)
+    npts = sum(o["npts"] for o in outs)
+    return npts * 5.0 * steps / dt / 1e9, procs, dt, npts
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     nx1 = args.order + 1
-    elems = args.cpu_elems
-    rate, threads, dt, npts = cpu_oracle_rate(elems, nx1, args.steps, args.warmup)
-    sample = (f"periodic box {elems}^3 elements, N={args.order} ({npts} nodes), "
-              f"{args.steps} steps per run")
+    ref = cpu_reference_rate(args.ref_elems, nx1, args.steps, args.warmup)
+    if ref is not None:
+        rate, threads, dt, npts = ref
+        kind = "reference"
+        sample = (f"{threads} independent single-process replicas of the reference's own path "
+                  f"(oracle/_ref: its Fortran translated to C + its src/jl gs library; no MPI in "
+                  f"this image), each a periodic box of {args.ref_elems}^3 elements at "
+                  f"N={args.order} ({npts} nodes in total), {args.steps} steps per run")
+    else:
+        elems = args.cpu_elems
+        rate, threads, dt, npts = cpu_oracle_rate(elems, nx1, args.steps, args.warmup)
+        kind = "port"
+        sample = (f"periodic box {elems}^3 elements, N={args.order} ({npts} nodes), "
+                  f"{args.steps} steps per run; oracle port (oracle/_ref did not travel)")
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
@@ -76,7 +135,7 @@ def run_reference(args):
         "config": {"workload": f"synthetic 3D periodic box, 64^3 hex elements/GPU at N={args.order}"
                                " (CPU arm runs a bounded sample of it)",
                    "sample": sample},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
                          "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -260,11 +319,21 @@ def run_gpu(args):
                 traffic = None
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            rate, threads, dtc, nptc = cpu_oracle_rate(args.cpu_elems, nx1, args.cpu_steps, 1)
-            cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                   "sample": f"periodic box {args.cpu_elems}^3 elements, N={args.order} "
-                             f"({nptc} nodes), {args.cpu_steps} steps, {dtc:.1f} s; oracle port "
-                             "(reference needs gfortran+MPI, absent on this box)"}
+            ref = cpu_reference_rate(args.ref_elems, nx1, args.ref_steps, 1)
+            if ref is not None:
+                rate, threads, dtc, nptc = ref
+                cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "reference",
+                       "sample": f"{threads} independent single-process replicas of the "
+                                 "reference's own path (oracle/_ref: its Fortran translated to C "
+                                 "+ its src/jl gs library; no MPI in this image), each a periodic "
+                                 f"box of {args.ref_elems}^3 elements at N={args.order} ({nptc} "
+                                 f"nodes in total), {args.ref_steps} steps, {dtc:.1f} s"}
+            else:
+                rate, threads, dtc, nptc = cpu_oracle_rate(args.cpu_elems, nx1, args.cpu_steps, 1)
+                cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                       "sample": f"periodic box {args.cpu_elems}^3 elements, N={args.order} "
+                                 f"({nptc} nodes), {args.cpu_steps} steps, {dtc:.1f} s; oracle "
+                                 "port (oracle/_ref did not travel with the tree)"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True,
@@ -310,10 +379,18 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-elems", type=int, default=24)
     ap.add_argument("--cpu-steps", type=int, default=30)
+    ap.add_argument("--ref-elems", type=int, default=12,
+                    help="elements per direction of each replica of the reference CPU arm")
+    ap.add_argument("--ref-steps", type=int, default=12)
+    ap.add_argument("--ref-worker", default=None, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --elems^3 per GPU (default); strong: --elems^3 in total")
     args = ap.parse_args()
+    if args.ref_worker:
+        e, n, k, w, d, i = args.ref_worker.split(",")
+        _ref_worker(int(e), int(n), int(k), int(w), d, int(i))
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

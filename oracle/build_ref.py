@@ -93,7 +93,7 @@ def build(force: bool = False, verbose: bool = False) -> str | None:
     gen = os.path.join(OUT, "ref_gen.c")
     with open(gen, "w") as f:
         f.write(ctext)
-    cmd = (["gcc", "-O2", "-std=gnu11", "-ffp-contract=off", "-fPIC", "-shared", "-w",
+    cmd = (["gcc", "-O3", "-std=gnu11", "-ffp-contract=off", "-fPIC", "-shared", "-w",
             "-I" + os.path.join(REF, "src/jl")] + JL_FLAGS +
            ["-o", LIB, gen, os.path.join(HERE, "ref_harness.c")] +
            [os.path.join(REF, "src/jl", f) for f in JL] + ["-lm"])
