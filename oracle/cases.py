@@ -558,3 +558,85 @@ def case_lorentz(nx1=9, nel=(4, 32), thick=6):
     c = _case_dispersive("lorentz", nx1, nel, thick)
     c.tol = dict(l2=[0, 0, 5e-6, 5e-6, 5e-10, 0], linf=[0, 0, 5e-5, 5e-5, 5e-10, 0])
     return c
+
+
+# ------------------------------------------------------------------------------------
+# rotated elements: the same physical mesh with every element's local (r,s,t) frame turned by
+# one of the 24 proper rotations -- neighbouring face lattices then run in different directions,
+# which is what unstructured meshes (tests/cylwave, graphene) look like to the face pairing
+# (SURVEY.md 8f rank 3).  Pure relabelling: the physical solution must not change.
+# ------------------------------------------------------------------------------------
+_PRE2SYM = (0, 1, 3, 2, 4, 5, 7, 6)  # preprocessor corner p -> symmetric index i+2j+4k
+_FACE_SLOT = {(0, 0): 3, (0, 1): 1, (1, 0): 0, (1, 1): 2, (2, 0): 4, (2, 1): 5}  # (axis, side)
+
+
+def proper_rotations():
+    """the 24 signed axis permutations with determinant +1: list of (perm, sign), meaning the
+    new local axis a runs along old axis perm[a], reversed if sign[a] < 0"""
+    import itertools
+    out = []
+    for perm in itertools.permutations(range(3)):
+        for sign in itertools.product((1, -1), repeat=3):
+            m = np.zeros((3, 3))
+            for a in range(3):
+                m[a, perm[a]] = sign[a]
+            if round(np.linalg.det(m)) == 1:
+                out.append((perm, sign))
+    return out
+
+
+def rotate_elements(mesh, rot_of_elem):
+    """new Mesh whose element e uses the local frame rot_of_elem[e] = (perm, sign)"""
+    assert mesh.ldim == 3
+    xc, yc, zc = mesh.xc.copy(), mesh.yc.copy(), mesh.zc.copy()
+    vertex = mesh.vertex.copy()
+    cbc = [list(r) for r in mesh.cbc]
+    for e, (perm, sign) in enumerate(rot_of_elem):
+        old_sym = {}
+        for p in range(8):
+            old_sym[_PRE2SYM[p]] = (mesh.xc[e, p], mesh.yc[e, p], mesh.zc[e, p])
+        for p in range(8):
+            ls = _PRE2SYM[p]
+            new = (ls & 1, (ls >> 1) & 1, (ls >> 2) & 1)
+            old = [0, 0, 0]
+            for a in range(3):
+                old[perm[a]] = new[a] if sign[a] > 0 else 1 - new[a]
+            lo = old[0] + 2 * old[1] + 4 * old[2]
+            xc[e, p], yc[e, p], zc[e, p] = old_sym[lo]
+            vertex[e, ls] = mesh.vertex[e, lo]
+        for a in range(3):
+            for side in (0, 1):
+                oside = side if sign[a] > 0 else 1 - side
+                cbc[e][_FACE_SLOT[(a, side)]] = mesh.cbc[e][_FACE_SLOT[(perm[a], oside)]]
+    return O.Mesh(3, xc, yc, zc, cbc, vertex)
+
+
+def rotated_node_map(nx1, nelt, rot_of_elem):
+    """index array m with new_field[m] == old_field: m[old flat node] = new flat node"""
+    n = nx1
+    m = np.zeros(n ** 3 * nelt, dtype=np.int64)
+    idx = np.indices((n, n, n))  # idx[a][i',j',k'] new indices, array order [i'][j'][k']
+    for e, (perm, sign) in enumerate(rot_of_elem):
+        old = [None, None, None]
+        for a in range(3):
+            old[perm[a]] = idx[a] if sign[a] > 0 else (n - 1 - idx[a])
+        new_flat = idx[0] + n * idx[1] + n * n * idx[2]
+        old_flat = old[0] + n * old[1] + n * n * old[2]
+        m[e * n ** 3 + old_flat.ravel()] = e * n ** 3 + new_flat.ravel()
+    return m
+
+
+def case_boxper_rotated(nel=(3, 3, 3), nx1=5, dt=-1e-3, seed=7):
+    """case_boxper with every element's local frame turned by a (deterministic) pseudo-random
+    proper rotation.  Returns (case, rot_of_elem)."""
+    pi2 = 2 * 4.0 * math.atan(1.0)
+    base = O.box_mesh(nel, ((0.0, pi2),) * 3, ("P  ",) * 6)
+    rots = proper_rotations()
+    rot_of_elem = [rots[(5 * e + seed) % 24] for e in range(base.nelt)]  # all 24 occur
+    mesh = rotate_elements(base, rot_of_elem)
+    c = O.RefCase(mesh, nx1, upwind=True)
+    c.set_dt(dt)
+    c.usersol = usersol_3dboxper
+    shn, sen = usersol_3dboxper(c, 0.0)
+    c.hn[:] = shn; c.en[:] = sen
+    return c, rot_of_elem

@@ -20,9 +20,15 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 case = sys.argv[1] if len(sys.argv) > 1 else "boxper3d"
 ade = None
-if case == "boxper3d":
+if case in ("boxper3d", "rotated3d"):
     nel, nx1, nsteps = (4, 4, 4 * world), 8, 5
-    ref = cases.case_boxper(nel, nx1, dt=-1e-3)
+    if case == "rotated3d":
+        # every element's local frame turned by one of the 24 proper rotations: the per-peer
+        # pack lists must pair face points whose lattices run in different directions
+        nx1 = 6
+        ref, _ = cases.case_boxper_rotated(nel, nx1, dt=-1e-3)
+    else:
+        ref = cases.case_boxper(nel, nx1, dt=-1e-3)
     elems = np.nonzero(gllnid_box(*nel, world) == rank)[0]
     s = MaxwellB200(3, nx1, elems.size, device=local, rank=rank, nranks=world)
     s.cem_maxwell_init(arrays_from_refcase(ref, elems))

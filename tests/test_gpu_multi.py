@@ -9,9 +9,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("case", ["boxper3d", "drude", "lorentz"])
+@pytest.mark.parametrize("case", ["boxper3d", "rotated3d", "drude", "lorentz"])
 def test_two_gpu_parity(case):
-    """3D periodic box, and the 2D drude / lorentz tests (PML + incident field + ADE), cut over
+    """3D periodic box, the same with randomly rotated element frames, and the 2D drude / lorentz tests (PML + incident field + ADE), cut over
     two ranks with the NCCL face exchange"""
     import torch
     if torch.cuda.device_count() < 2:

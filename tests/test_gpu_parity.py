@@ -374,3 +374,25 @@ def test_gpu_vs_translated_reference_orders(nx1):
     r.step(3); s.step(3)
     assert rel_l2(_fields(s), np.concatenate([r.hn, r.en])) <= TOL
     r.close(); s.close()
+
+
+def test_rotated_element_frames():
+    """the face topology (vmapP) is built from the reference's face ids
+    only, so it must not care how an element's local (r,s,t) frame is oriented.  Every element of
+    a periodic box gets one of the 24 proper rotations; GPU vs oracle <= 1e-12, and the result
+    equals the unrotated run node for node (pure relabelling)."""
+    from oracle import cases
+    nel, nx1 = (3, 3, 3), 7
+    c, rots = cases.case_boxper_rotated(nel, nx1, dt=-1e-3)
+    assert len(set(rots)) == 24
+    s = solver_from_refcase(c)
+    c.step(5); s.step(5)
+    assert rel_l2(_fields(s), _fields(c)) <= TOL
+    c0 = cases.case_boxper(nel, nx1, dt=-1e-3)
+    s0 = solver_from_refcase(c0)
+    s0.step(5)
+    m = cases.rotated_node_map(nx1, c.nelt, rots)
+    n = c.npts
+    a = np.concatenate([s.hn.reshape(3, n)[:, m].ravel(), s.en.reshape(3, n)[:, m].ravel()])
+    assert rel_l2(a, _fields(s0)) <= TOL
+    s.close(); s0.close()

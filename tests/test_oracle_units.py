@@ -96,3 +96,20 @@ def test_pencil_map():
     assert np.all(g[: 4 * 4 * 4] == 0) and np.all(g[4 * 4 * 4:] == 1)  # z-slabs
     g = gllnid_box(2, 3, 5, 4)  # uneven: 15 pencils over 4 ranks, boustrophedon order
     assert sorted(np.bincount(g) // 2) == [3, 4, 4, 4]
+
+
+def test_rotated_element_frames_leave_the_solution_unchanged():
+    """Relabelling every element's local frame by a proper rotation must not change the physical
+    solution: checks the oracle's orientation handling in face_glo_num (setup_dgds2 semantics)
+    and in the metric/normal computation independently of any other implementation."""
+    from oracle import cases
+    nel, nx1 = (3, 3, 3), 5
+    c0 = cases.case_boxper(nel, nx1, dt=-1e-3)
+    c1, rots = cases.case_boxper_rotated(nel, nx1, dt=-1e-3)
+    assert len(set(rots)) == 24
+    m = cases.rotated_node_map(nx1, c0.nelt, rots)
+    assert np.abs(c1.xm1[m] - c0.xm1).max() < 1e-14
+    c0.step(10); c1.step(10)
+    n = c0.npts
+    for a, b in ((c1.hn, c0.hn), (c1.en, c0.en)):
+        assert np.abs(a.reshape(3, n)[:, m] - b.reshape(3, n)).max() < 1e-13

@@ -400,3 +400,13 @@ def test_pin_usersol_and_error_norms(which):
         assert abs(l2.value - l2o[k]) <= 1e-3 * l2o[k] + 1e-15
         assert abs(linf.value - linfo[k]) <= 1e-3 * linfo[k] + 1e-14
     r.close()
+
+
+def test_pin_rotated_element_frames():
+    """elements with arbitrarily oriented local frames (all 24 proper rotations): the reference's
+    gs_op_fields pairs the face points through the ids alone; oracle == translated reference"""
+    c, rots = cases.case_boxper_rotated((3, 3, 3), 5, dt=-1e-3)
+    r = refrun.ReferenceRun(c)
+    c.step(5); r.step(5)
+    _assert_same(c, r)
+    r.close()
