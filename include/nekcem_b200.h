@@ -176,8 +176,16 @@ int nekcem_b200_error_sums(int handle, const double *exact_hn, const double *exa
  * compute stream) and the number of kernels it launched. */
 int nekcem_b200_last_step_ms(int handle, float *ms, int64_t *launches);
 
-/* Performance tunables (no effect on results).  "pf_dist": reserved (accepted, ignored). */
+/* Performance tunables (no effect on results).  "pf_dist": reserved (accepted, ignored).
+ * "const_metrics" (default 1): exploit exact, bitwise redundancy found in the geometry at setup
+ * -- elements whose nine cofactors rxmn..tzmn (src/GEOM:30-45) hold one value each over the
+ * whole element read them once per element instead of once per node, and bitwise identical
+ * hbm1/ebm1 (src/cem_maxwell.F:183-186 with eps = mu) share one array.  The numbers entering
+ * the arithmetic are the same, so results do not change by a single bit; 0 streams every
+ * array per node exactly as the reference's loops do. */
 int nekcem_b200_set_option(int handle, const char *name, int value);
+/* What the setup scan found: elements with constant cofactors, and whether hbm1 == ebm1. */
+int nekcem_b200_geometry_info(int handle, int64_t *n_const_metric_elements, int32_t *masses_shared);
 
 /* Algorithmic HBM bytes per stage for this context: 280 B/node +
  * 116 B/face point (+ PML add-on for PML elements). */

@@ -86,6 +86,7 @@ def lib():
         L.nekcem_b200_set_lorentz.argtypes = [C.c_int, c_dp, c_dp, c_dp, c_i32p, C.c_int32]
         L.nekcem_b200_get_ade.argtypes = [C.c_int, c_dp, c_dp]
         L.nekcem_b200_set_option.argtypes = [C.c_int, C.c_char_p, C.c_int]
+        L.nekcem_b200_geometry_info.argtypes = [C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
         L.nekcem_b200_set_time.argtypes = [C.c_int, C.c_double, C.c_double]
         L.nekcem_b200_get_time.argtypes = [C.c_int, c_dp]
         L.nekcem_b200_step.argtypes = [C.c_int, C.c_int]
@@ -331,6 +332,12 @@ class MaxwellB200:
 
     def synchronize(self):
         _chk(self.L.nekcem_b200_synchronize(self.h))
+
+    def geometry_info(self):
+        """(elements with constant cofactors, hbm1 == ebm1) found by the setup scan"""
+        n, m = C.c_int64(), C.c_int32()
+        _chk(self.L.nekcem_b200_geometry_info(self.h, C.byref(n), C.byref(m)))
+        return int(n.value), bool(m.value)
 
     def last_step_ms(self):
         ms = C.c_float(0); n = C.c_int64(0)

@@ -25,7 +25,7 @@
 #include "stage_args.h"
 
 namespace nkb {
-int launch_stage_slab(const StageArgs &a, const double *Dhost, int nx1, bool aux, void *stream);
+int launch_stage_slab(const StageArgs &a, const double *Dhost, int nx1, bool aux, bool cm, void *stream);
 int launch_stage2d(const StageArgs &a, const double *Dhost, int nx1, bool aux, void *stream);
 }
 
@@ -80,7 +80,9 @@ struct Ctx {
     std::vector<double> D_host; // dxm1: passed to the stage kernel by value (constant bank)
     int *vmapP_d = nullptr;
     int *elist_d = nullptr; // concatenated lists
-    int list_off[4] = {}, list_n[4] = {}; // [interior plain, interior aux, boundary plain, boundary aux]; aux = PML and/or ADE elements
+    // element lists, index = 4*boundary + 2*constant-metrics + aux (aux = PML and/or ADE elements)
+    int list_off[8] = {}, list_n[8] = {};
+    std::vector<unsigned char> elflag_h; // host copy of elflag_d after the geometry scan
     // host planning data
     std::vector<int64_t> glo;
     std::vector<int32_t> cempec;
@@ -119,8 +121,14 @@ struct Ctx {
     int ade_kind = 0; // 0 none, 1 Drude, 2 Lorentz
     double *ade_j = nullptr, *ade_k = nullptr, *ade_par = nullptr;
     unsigned char *ade_mask = nullptr;
-    unsigned char *elflag_d = nullptr; // per element: bit 0 PML, bit 1 ADE
+    unsigned char *elflag_d = nullptr; // per element: bit 0 PML, bit 1 ADE, bit 2 constant metrics
     std::vector<char> ade_el; // per element: contains ADE nodes
+    // redundancy found in the geometry at setup (exact, bitwise): elements whose nine cofactors
+    // do not vary over the element read them once per element; identical hbm1/ebm1 share one array
+    bool opt_const_metrics = true;
+    bool masses_same = false;
+    bool geom_scanned = false;
+    int64_t n_const_metric_el = 0;
     double *red_d = nullptr; // reduction scratch
     int red_blocks = 0;
 };
@@ -197,6 +205,40 @@ __global__ void half_inverse_kernel(const double *x, double *y, long long n)
 {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i < n) y[i] = 0.5 / x[i];
+}
+
+// Setup scan: element e has "constant metrics" when each of its cofactor arrays holds one
+// bit pattern over the whole element (affine elements whose metrics were generated without
+// round-off noise).  The stage kernel then reads 9 values per element instead of 9 per node --
+// the same numbers, so the results are unchanged bit for bit.
+__global__ void metric_const_kernel(const double *m0, const double *m1, const double *m2,
+                                    const double *m3, const double *m4, const double *m5,
+                                    const double *m6, const double *m7, const double *m8,
+                                    int nxyz, unsigned char *elflag, unsigned long long *count)
+{
+    const double *met[9] = {m0, m1, m2, m3, m4, m5, m6, m7, m8};
+    const long long base = (long long)blockIdx.x * nxyz;
+    int same = 1;
+    for (int q = 0; q < 9; q++) {
+        const long long ref = __double_as_longlong(met[q][base]);
+        for (int i = threadIdx.x; i < nxyz; i += blockDim.x)
+            same &= (__double_as_longlong(met[q][base + i]) == ref);
+    }
+    same = __syncthreads_and(same);
+    if (threadIdx.x == 0) {
+        unsigned char f = elflag[blockIdx.x] & (unsigned char)~4;
+        if (same) { f |= 4; atomicAdd(count, 1ull); }
+        elflag[blockIdx.x] = f;
+    }
+}
+
+__global__ void arrays_differ_kernel(const double *a, const double *b, long long n, int *differ)
+{
+    int d = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        d |= (__double_as_longlong(a[i]) != __double_as_longlong(b[i]));
+    if (__syncthreads_or(d) && threadIdx.x == 0) *differ = 1;
 }
 
 // pack the traces of the send face points: sendbuf[q][c] = u[c][send_node[q]]
@@ -345,16 +387,20 @@ int build_lists(Ctx *c, std::vector<int32_t> &lists)
     if (c->ade_kind)
         for (int e = 0; e < c->d.nelt; e++)
             if (c->ade_el[e]) is_pml[e] = 1;
-    std::vector<int32_t> L[4];
-    for (int e = 0; e < c->d.nelt; e++) L[(is_b[e] ? 2 : 0) + (is_pml[e] ? 1 : 0)].push_back(e);
+    const bool have_flags = (int)c->elflag_h.size() == c->d.nelt;
+    std::vector<int32_t> L[8];
+    for (int e = 0; e < c->d.nelt; e++) {
+        const int cm = have_flags && (c->elflag_h[e] & 4) ? 2 : 0;
+        L[(is_b[e] ? 4 : 0) + cm + (is_pml[e] ? 1 : 0)].push_back(e);
+    }
     lists.clear();
-    for (int q = 0; q < 4; q++) {
+    for (int q = 0; q < 8; q++) {
         c->list_off[q] = (int)lists.size();
         c->list_n[q] = (int)L[q].size();
         lists.insert(lists.end(), L[q].begin(), L[q].end());
     }
-    c->n_interior = c->list_n[0] + c->list_n[1];
-    c->n_boundary = c->list_n[2] + c->list_n[3];
+    c->n_interior = c->list_n[0] + c->list_n[1] + c->list_n[2] + c->list_n[3];
+    c->n_boundary = c->list_n[4] + c->list_n[5] + c->list_n[6] + c->list_n[7];
     return 0;
 }
 
@@ -417,15 +463,68 @@ int ensure_dev(Ctx *c, int which)
     return 0;
 }
 
+// (re)scan the geometry for exact redundancy; called from setup and lazily after a geometry
+// array was replaced
+int scan_geometry(Ctx *c)
+{
+    c->geom_scanned = true;
+    c->masses_same = false;
+    c->n_const_metric_el = 0;
+    if (!c->elflag_d) return 0;
+    unsigned long long *cnt = nullptr;
+    int *differ = nullptr;
+    CUDA_OK(cudaMalloc(&cnt, sizeof(unsigned long long)));
+    CUDA_OK(cudaMalloc(&differ, sizeof(int)));
+    CUDA_OK(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), c->s_compute));
+    CUDA_OK(cudaMemsetAsync(differ, 0, sizeof(int), c->s_compute));
+    if (c->d.ldim == 3 && c->opt_const_metrics) {
+        const double *m[9];
+        for (int q = 0; q < 9; q++) m[q] = c->dev[NKB_RXMN + q];
+        metric_const_kernel<<<c->d.nelt, 128, 0, c->s_compute>>>(
+            m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], c->nxyz, c->elflag_d, cnt);
+    } else if (c->d.ldim == 3) {
+        // option switched off: clear bit 2
+        std::vector<unsigned char> ef(c->d.nelt);
+        CUDA_OK(cudaStreamSynchronize(c->s_compute));
+        CUDA_OK(cudaMemcpy(ef.data(), c->elflag_d, ef.size(), cudaMemcpyDeviceToHost));
+        for (auto &f : ef) f &= (unsigned char)~4;
+        CUDA_OK(cudaMemcpy(c->elflag_d, ef.data(), ef.size(), cudaMemcpyHostToDevice));
+    }
+    if (c->opt_const_metrics)
+        arrays_differ_kernel<<<1184, 256, 0, c->s_compute>>>(c->dev[NKB_HBM1], c->dev[NKB_EBM1],
+                                                            c->npts, differ);
+    unsigned long long hc = 0;
+    int hd = 1;
+    CUDA_OK(cudaStreamSynchronize(c->s_compute));
+    CUDA_OK(cudaMemcpy(&hc, cnt, sizeof(hc), cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaMemcpy(&hd, differ, sizeof(hd), cudaMemcpyDeviceToHost));
+    cudaFree(cnt); cudaFree(differ);
+    c->n_const_metric_el = (int64_t)hc;
+    c->masses_same = c->opt_const_metrics && hd == 0;
+    // the element lists depend on the flags: rebuild and upload them
+    c->elflag_h.resize(c->d.nelt);
+    CUDA_OK(cudaMemcpy(c->elflag_h.data(), c->elflag_d, c->elflag_h.size(), cudaMemcpyDeviceToHost));
+    std::vector<int32_t> lists;
+    build_lists(c, lists);
+    cudaFree(c->elist_d);
+    c->elist_d = nullptr;
+    CUDA_OK(cudaMalloc(&c->elist_d, sizeof(int) * std::max<size_t>(lists.size(), 1)));
+    CUDA_OK(cudaMemcpy(c->elist_d, lists.data(), sizeof(int) * lists.size(), cudaMemcpyHostToDevice));
+    return 0;
+}
+
 int run_stage(Ctx *c, int rkstep /*1..5*/)
 {
+    if (!c->geom_scanned && scan_geometry(c)) return 1;
     nkb::StageArgs a{};
     a.u_in = c->u[c->cur];
     a.u_out = c->u[c->cur ^ 1];
     a.kf = c->kf;
     a.ld = c->ld;
     for (int q = 0; q < 9; q++) a.met[q] = c->dev[NKB_RXMN + q];
-    a.hbm1 = c->dev[NKB_HBM1]; a.ebm1 = c->dev[NKB_EBM1]; a.bmn = c->dev[NKB_BMN];
+    a.hbm1 = c->dev[NKB_HBM1]; a.bmn = c->dev[NKB_BMN];
+    // bitwise identical inverse masses (eps = mu): both reads hit the same lines
+    a.ebm1 = c->masses_same ? c->dev[NKB_HBM1] : c->dev[NKB_EBM1];
     a.D = c->dev[NKB_DXM1];
     a.w3 = c->dev[NKB_W3MN];
     a.unx = c->dev[NKB_UNXM]; a.uny = c->dev[NKB_UNYM]; a.unz = c->dev[NKB_UNZM];
@@ -461,7 +560,8 @@ int run_stage(Ctx *c, int rkstep /*1..5*/)
         b.elist = c->elist_d + c->list_off[q];
         b.nel = c->list_n[q];
         int rc = c->d.ldim == 3
-                     ? nkb::launch_stage_slab(b, c->D_host.data(), c->n, (q & 1) != 0, c->s_compute)
+                     ? nkb::launch_stage_slab(b, c->D_host.data(), c->n, (q & 1) != 0, (q & 2) != 0,
+                                              c->s_compute)
                      : nkb::launch_stage2d(b, c->D_host.data(), c->n, (q & 1) != 0, c->s_compute);
         if (rc < 0) return fail("nx1=%d is not supported by the stage kernels (2..16)", c->n);
         if (rc > 0) return fail("stage kernel launch failed: %s",
@@ -489,11 +589,11 @@ int run_stage(Ctx *c, int rkstep /*1..5*/)
         NCCL_OK(ncclGroupEnd());
         CUDA_OK(cudaEventRecord(c->ev_halo, c->s_comm));
     }
-    if (launch_list(0)) return 1;
-    if (launch_list(1)) return 1;
+    for (int q = 0; q < 4; q++)
+        if (launch_list(q)) return 1;
     if (exchange) CUDA_OK(cudaStreamWaitEvent(c->s_compute, c->ev_halo, 0));
-    if (launch_list(2)) return 1;
-    if (launch_list(3)) return 1;
+    for (int q = 4; q < 8; q++)
+        if (launch_list(q)) return 1;
     CUDA_OK(cudaEventRecord(c->ev_stage, c->s_compute));
     c->cur ^= 1;
     return 0;
@@ -620,6 +720,8 @@ int nekcem_b200_set_array(int handle, int which, const double *host, int64_t cou
         if (ensure_dev(c, which)) return 1;
         CUDA_OK(cudaMemcpy(c->dev[which], host, sizeof(double) * count, cudaMemcpyHostToDevice));
         if (which == NKB_DXM1) c->D_host.assign(host, host + count);
+        if ((which >= NKB_RXMN && which <= NKB_TZMN) || which == NKB_HBM1 || which == NKB_EBM1)
+            c->geom_scanned = false;
         if (which == NKB_Y_0 || which == NKB_Z_0) {
             double *&h = (which == NKB_Y_0) ? c->hY : c->hZ;
             if (!h) CUDA_OK(cudaMalloc(&h, sizeof(double) * count));
@@ -795,9 +897,9 @@ int nekcem_b200_setup(int handle)
     }
     std::vector<int32_t> lists;
     build_lists(c, lists);
-    cudaFree(c->vmapP_d); cudaFree(c->elist_d); cudaFree(c->sendbuf); cudaFree(c->halo);
+    cudaFree(c->vmapP_d); cudaFree(c->sendbuf); cudaFree(c->halo);
     cudaFree(c->send_node);
-    c->vmapP_d = nullptr; c->elist_d = nullptr; c->sendbuf = c->halo = nullptr; c->send_node = nullptr;
+    c->vmapP_d = nullptr; c->sendbuf = c->halo = nullptr; c->send_node = nullptr;
     CUDA_OK(cudaMalloc(&c->vmapP_d, sizeof(int) * c->nxzfl));
     CUDA_OK(cudaMemcpy(c->vmapP_d, c->vmapP.data(), sizeof(int) * c->nxzfl, cudaMemcpyHostToDevice));
     {
@@ -810,9 +912,8 @@ int nekcem_b200_setup(int handle)
         c->elflag_d = nullptr;
         CUDA_OK(cudaMalloc(&c->elflag_d, ef.size()));
         CUDA_OK(cudaMemcpy(c->elflag_d, ef.data(), ef.size(), cudaMemcpyHostToDevice));
+        if (scan_geometry(c)) return 1;
     }
-    CUDA_OK(cudaMalloc(&c->elist_d, sizeof(int) * std::max<size_t>(lists.size(), 1)));
-    CUDA_OK(cudaMemcpy(c->elist_d, lists.data(), sizeof(int) * lists.size(), cudaMemcpyHostToDevice));
     if (c->nhalo > 0) {
         if (!c->has_comm) return fail("inter-rank faces exist but no communicator was initialised");
         const int nfp = c->nxzf * c->nfaces;
@@ -979,7 +1080,27 @@ int nekcem_b200_set_option(int handle, const char *name, int value)
         if (value < 0) return fail("pf_dist must be >= 0");
         return 0; // reserved
     }
+    if (strcmp(name, "const_metrics") == 0) {
+        // 1 (default): exploit exact redundancy of the geometry (constant cofactors per element,
+        // identical hbm1/ebm1); 0: stream every array per node as the reference does
+        c->opt_const_metrics = value != 0;
+        c->geom_scanned = false;
+        return 0;
+    }
     return fail("unknown option '%s'", name);
+}
+
+int nekcem_b200_geometry_info(int handle, int64_t *n_const_metric_elements, int32_t *masses_shared)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (!c->geom_scanned && c->elflag_d) {
+        CUDA_OK(cudaSetDevice(c->d.device));
+        if (scan_geometry(c)) return 1;
+    }
+    if (n_const_metric_elements) *n_const_metric_elements = c->n_const_metric_el;
+    if (masses_shared) *masses_shared = c->masses_same ? 1 : 0;
+    return 0;
 }
 
 int nekcem_b200_set_time(int handle, double time, double dt)

@@ -396,3 +396,33 @@ def test_rotated_element_frames():
     a = np.concatenate([s.hn.reshape(3, n)[:, m].ravel(), s.en.reshape(3, n)[:, m].ravel()])
     assert rel_l2(a, _fields(s0)) <= TOL
     s.close(); s0.close()
+
+
+def test_constant_metric_elements_bitwise():
+    """Setup finds elements whose nine cofactors are bitwise constant over the element (affine
+    elements with noise-free metrics) and identical hbm1/ebm1; the kernel then reads those
+    values once per element / from one array.  Same numbers -> the fields must not change by a
+    single bit against streaming every array per node (option const_metrics=0), and parity with
+    the oracle on the same inputs holds.  Half of the elements keep noisy metrics, so both code
+    paths run in one launch."""
+    from oracle import cases
+    c = cases.case_boxper((3, 3, 4), 8, dt=-1e-3)
+    nxyz = c.nxyz
+    names = ("rxmn", "rymn", "rzmn", "sxmn", "symn", "szmn", "txmn", "tymn", "tzmn")
+    const_el = np.arange(c.nelt) % 2 == 0
+    for k in names:
+        v = getattr(c, k).reshape(c.nelt, nxyz)
+        v[const_el] = np.round(v[const_el, :1], 14)  # one value per element, exact zeros
+    res = {}
+    for opt in (1, 0):
+        s = solver_from_refcase(c)
+        s.set_option("const_metrics", opt)
+        nconst, shared = s.geometry_info()
+        assert nconst == (int(const_el.sum()) if opt else 0)
+        assert shared == bool(opt)   # eps = mu = 1: hbm1 == ebm1
+        s.step(3)
+        res[opt] = _fields(s).copy()
+        s.close()
+    assert np.array_equal(res[1], res[0])
+    c.step(3)
+    assert rel_l2(res[1], _fields(c)) <= TOL
