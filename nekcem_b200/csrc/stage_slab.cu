@@ -112,6 +112,17 @@ struct Slab {
     static constexpr int MINB0 = MINB_SMEM < MINB_THR ? MINB_SMEM : MINB_THR;
     static constexpr int MINB1 = MINB0 < MINB_REG ? MINB0 : MINB_REG;
     static constexpr int MINB = MINB1 < 1 ? 1 : (MINB1 > 8 ? 8 : MINB1);
+    // constant-metric instantiation: no cofactor batches in registers, so 80 registers hold the
+    // pencil phases without spilling and a third CTA fits per SM where shared memory allows
+    // (n <= 10): measured +10 % at n=8, +3..5 % at n=9,10; the general path loses at n=10
+#ifdef SLAB_REG_CAP_CM
+    static constexpr int REG_CAP_CM = SLAB_REG_CAP_CM;
+#else
+    static constexpr int REG_CAP_CM = (MINB_SMEM >= 3 && NO <= 5) ? 80 : REG_CAP;
+#endif
+    static constexpr int MINB_REG_CM = 65536 / (NT * REG_CAP_CM);
+    static constexpr int MINB2 = MINB0 < MINB_REG_CM ? MINB0 : MINB_REG_CM;
+    static constexpr int MINB_CM = MINB2 < 1 ? 1 : (MINB2 > 8 ? 8 : MINB2);
     static constexpr int EPI = SLAB_EPI; // nodes in flight per thread in the epilogue
 };
 
@@ -351,7 +362,7 @@ __device__ __forceinline__ void t_phase(const double (&D)[N * N], const StageArg
 }
 
 template <int N, int KS, bool PML, bool CM>
-__global__ void __launch_bounds__(Slab<N, KS>::NT, Slab<N, KS>::MINB)
+__global__ void __launch_bounds__(Slab<N, KS>::NT, CM ? Slab<N, KS>::MINB_CM : Slab<N, KS>::MINB)
     slab_kernel(const __grid_constant__ StageParams<N> prm)
 {
     using C = Slab<N, KS>;
