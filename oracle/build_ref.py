@@ -68,6 +68,17 @@ JL = ["gs.c", "gs_local.c", "comm.c", "crystal.c", "sarray_transfer.c", "sarray_
 JL_FLAGS = ["-DUNDERSCORE", "-DGLOBAL_LONG_LONG", "-DUSE_NAIVE_BLAS"]
 DEFINES = ("MPI", "MPIIO", "MAXWELL", "NOTIMER")
 
+# Drop-in variant: the same translated reference + THIS REPO'S fixed-form shim
+# (fortran/cem_maxwell_b200_f77.F, translated by the same tool) linked against the product
+# library.  cem_maxwell_drude / cem_maxwell_lorentz are left out so that the .usr's calls
+# resolve to the library's twins, exactly as a -DB200 build of the reference would link.
+LIB_DROPIN = os.path.join(OUT, "libnekcem_ref_dropin.so")
+REPO = os.path.dirname(HERE)
+SHIM = (os.path.join(REPO, "fortran", "cem_maxwell_b200_f77.F"),
+        ["b200_copy_all_in", "b200_update_device", "b200_op_rk", "b200_update_host",
+         "b200_copy_all_out"])
+PRODUCT_LIB_DIR = os.path.join(REPO, "nekcem_b200", "lib")
+
 
 def available() -> bool:
     return os.path.isdir(os.path.join(REF, "src"))
@@ -80,6 +91,7 @@ def build(force: bool = False, verbose: bool = False) -> str | None:
         return LIB if os.path.exists(LIB) else None
     srcs = [os.path.join(REF, u[0]) for u in UNITS] + [os.path.join(REF, "src/jl", f) for f in JL]
     mine = [os.path.join(HERE, f) for f in ("f2c_lite.py", "build_ref.py", "ref_harness.c")]
+    mine += [SHIM[0], os.path.join(REPO, "fortran", "NEKCEM_B200")]
     if not force and os.path.exists(LIB):
         t = os.path.getmtime(LIB)
         if all(os.path.getmtime(s) < t for s in srcs + mine):
@@ -100,7 +112,34 @@ def build(force: bool = False, verbose: bool = False) -> str | None:
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)
+    build_dropin(inc, verbose)
     return LIB
+
+
+def build_dropin(inc, verbose=False):
+    """libnekcem_ref_dropin.so (needs nekcem_b200/lib/libnekcem_b200.so; skipped without it)"""
+    import f2c_lite
+    if not os.path.exists(os.path.join(PRODUCT_LIB_DIR, "libnekcem_b200.so")):
+        return None
+    units = []
+    for u in UNITS:
+        names = [n for n in u[1] if n not in ("cem_maxwell_drude", "cem_maxwell_lorentz")]
+        units.append((os.path.join(REF, u[0]), names) + tuple(u[2:]))
+    units.append(SHIM)
+    ctext, em = f2c_lite.translate(units, inc + [os.path.join(REPO, "fortran")], DEFINES)
+    gen = os.path.join(OUT, "ref_dropin_gen.c")
+    with open(gen, "w") as f:
+        f.write(ctext)
+    cmd = (["gcc", "-O3", "-std=gnu11", "-ffp-contract=off", "-fPIC", "-shared", "-w",
+            "-I" + os.path.join(REF, "src/jl")] + JL_FLAGS +
+           ["-o", LIB_DROPIN, gen, os.path.join(HERE, "ref_harness.c")] +
+           [os.path.join(REF, "src/jl", f) for f in JL] +
+           ["-L" + PRODUCT_LIB_DIR, "-lnekcem_b200",
+            "-Wl,-rpath,$ORIGIN/../../nekcem_b200/lib", "-lm"])
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return LIB_DROPIN
 
 
 if __name__ == "__main__":

@@ -403,8 +403,11 @@ class Sym:
         self.init = None
         self.data_unsupported = False
         self.init_list = None
+        self.kind8 = False     # integer*8
 
     def ctype(self):
+        if self.ftype == "integer" and self.kind8:
+            return "long long"
         return {"real": "double", "integer": "int", "logical": "int", "character": "char"}[self.ftype]
 
 
@@ -541,6 +544,8 @@ class Translator:
             sy.dims = dims
         if ftype:
             sy.ftype = ftype
+            if ftype == "integer" and str(charlen) == "8":
+                sy.kind8 = True
             if ftype == "character":
                 cl = m.group(4) if m.group(3) else charlen
                 sy.charlen = int(cl) if cl and str(cl).isdigit() else 1
@@ -692,7 +697,7 @@ class Emitter:
             if e[1] in ("==", "!=", "<", "<=", ">", ">=", "&&", "||"):
                 return "int"
             a, b = self.typ(u, e[2]), self.typ(u, e[3])
-            return "double" if "double" in (a, b) else "int"
+            return "double" if "double" in (a, b) else ("long long" if "long long" in (a, b) else "int")
         if k == "var":
             sy = self.lookup(u, e[1])
             return sy.ctype()
@@ -1258,7 +1263,7 @@ class Emitter:
         for name, val, u in pnames:
             out.append("    if (!strcmp(name, \"%s\")) { *isint = 1; *count = 1; return &%s; }" % (name, self.vname(name)))
         for name, (sy, u) in sorted(self.used_globals.items()):
-            isint = 0 if sy.ftype == "real" else (2 if sy.ftype == "character" else 1)
+            isint = 0 if sy.ftype == "real" else (2 if sy.ftype == "character" else (3 if sy.kind8 else 1))
             if sy.ftype == "character":
                 n = "*".join("(long)(%s)" % self.extent(u, sy, d) for d in range(len(sy.dims))) if sy.dims else "1"
                 out.append("    if (!strcmp(name, \"%s\")) { *isint = 2; *count = (%s)*%d; return %s; }" %

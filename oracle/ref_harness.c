@@ -47,3 +47,5 @@ EXPORT void maxwell_wght_dcurl_(void) { fprintf(stderr, "maxwell_wght_dcurl is o
 EXPORT int iglsum_(int *a, int *n) { (void)n; return *a; }
 /* global reduction over ranks (src/nek5_comm_mpi.F:379-420): the identity on one process */
 EXPORT void gop_(double *x, double *w, const char *op, int *n) { (void)x; (void)w; (void)op; (void)n; }
+/* MPI broadcast of the NCCL id (src/nek5_comm_mpi.F bcast): never reached on one process */
+EXPORT void bcast_(void *buf, int *len) { (void)buf; (void)len; }

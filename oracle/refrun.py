@@ -22,34 +22,41 @@ from . import build_ref
 c_dp = C.POINTER(C.c_double)
 USERCB = C.CFUNCTYPE(None, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp)
 
-_lib = None
+_libs = {}
 
 
-def available() -> bool:
-    return build_ref.build() is not None
+def available(kind: str = "base") -> bool:
+    path = build_ref.build()
+    if path is None:
+        return False
+    return kind == "base" or os.path.exists(build_ref.LIB_DROPIN)
 
 
-def lib():
-    global _lib
-    if _lib is None:
+def lib(kind: str = "base"):
+    """kind 'base': the translated reference alone.  kind 'dropin': the same plus this repo's
+    fixed-form shim fortran/cem_maxwell_b200_f77.F, linked against libnekcem_b200.so (its own
+    copy of the COMMON blocks: the two libraries do not share state)."""
+    if kind not in _libs:
         path = build_ref.build()
         if path is None:
             raise RuntimeError("oracle/_ref is not built and /root/reference is absent")
+        if kind == "dropin":
+            path = build_ref.LIB_DROPIN
         L = C.CDLL(path)
         L.ref_set_param.argtypes = [C.c_char_p, C.c_long]
         L.ref_sym.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_long)]
         L.ref_sym.restype = C.c_void_p
         L.ref_set_user.argtypes = [C.c_int, USERCB]
         L.ref_units.restype = C.c_char_p
-        _lib = L
-    return _lib
+        _libs[kind] = L
+    return _libs[kind]
 
 
 class ReferenceRun:
     """One process-wide instance at a time (the reference's state is global COMMON storage)."""
 
-    def __init__(self, case):
-        L = lib()
+    def __init__(self, case, kind: str = "base"):
+        L = lib(kind)
         self.L, self.case = L, case
         ldim, nx1, nelt = case.ldim, case.nx1, case.nelt
         # SIZE: parameter (ldim, lxi, lelg ...) of this case; lelt = nelt exactly so that the
@@ -110,6 +117,14 @@ class ReferenceRun:
                     C.byref(np_))
         self.gsh = h.value
         self.set("gsh_face", self.gsh)
+        # what the drop-in shim reads besides the arrays above: the face ids still resident in
+        # COMMON /c_is1/ glo_num (src/nek5_connect11.F:31), and the rank / size
+        self.put_opt("glo_num", ids)
+        for k, v in (("nid", 0), ("np", 1)):
+            try:
+                self.set(k, v)
+            except KeyError:
+                pass
         L.rk_storage_()
         # setup_topo's face tables (src/nek5_connect11.F:1046-1093, 1440-1528).  dsset keeps
         # the dimensions of its last call in SAVEd variables and returns early when they
@@ -134,7 +149,10 @@ class ReferenceRun:
         return p, kind == 1, cnt
 
     def view(self, name):
-        p, isint, cnt = self._sym(name)
+        p, kind, cnt = self._sym_kind(name)
+        isint = kind == 1
+        if kind == 3:
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_longlong)), shape=(cnt,))
         t = C.c_int if isint else C.c_double
         return np.ctypeslib.as_array(C.cast(p, C.POINTER(t)), shape=(cnt,))
 

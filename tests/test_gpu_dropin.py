@@ -1,0 +1,131 @@
+"""The drop-in boundary exercised the way the reference would use it.
+
+`oracle/_ref/libnekcem_ref_dropin.so` holds the reference's own routines (translated from
+/root/reference/src by oracle/f2c_lite.py) together with THIS REPO'S Fortran shim
+`fortran/cem_maxwell_b200_f77.F`, translated by the same tool and linked against
+`libnekcem_b200.so`.  The only interface between the two sides is the reference's COMMON blocks
+(SIZE/TOTAL/EMWAVE/PML, /bdry1/ cempec, /c_is1/ glo_num): the shim's `b200_copy_all_in`
+(replacing acc_copy_all_in, src/cem_drive.F:397-480) uploads them through the `_` twins of the C
+ABI, `b200_op_rk` replaces `call cem_maxwell_op_rk` (src/cem_drive.F:628), `b200_update_host`
+is the `!$ACC UPDATE HOST` seam.  The same COMMON state is then advanced by the reference's own
+cem_maxwell_op_rk, and the fields must agree within 1e-12 relative L2.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _refrun():
+    from oracle import refrun
+    if not refrun.available("dropin"):
+        pytest.skip("oracle/_ref/libnekcem_ref_dropin.so did not travel with the tree")
+    return refrun
+
+
+def _time_loop(r, call, nsteps):
+    """src/cem_drive.F:618-654: istep loop, `call <op_rk>`, time = time + dt"""
+    for _ in range(nsteps):
+        call()
+        r.set("time", r.get("time") + r.get("dt"))
+
+
+def _run_both(case, nsteps, callbacks=None, names=("hn", "en")):
+    refrun = _refrun()
+    n3 = 3 * case.npts
+    # (1) the reference's own path
+    r = refrun.ReferenceRun(case, kind="dropin")
+    for which, fn in (callbacks or {}).items():
+        r.set_callback(which, fn("ref"))
+    _time_loop(r, r.L.cem_maxwell_op_rk_, nsteps)
+    want = {k: r.view(k)[:n3].copy() for k in names}
+    t_end = r.get("time")
+    r.close()
+    # (2) the same COMMON blocks driven through the shim into the GPU library
+    r = refrun.ReferenceRun(case, kind="dropin")
+    for which, fn in (callbacks or {}).items():
+        r.set_callback(which, fn("gpu"))
+    r.L.b200_copy_all_in_()
+    r.L.b200_update_device_()
+    for k in ("hn", "en"):
+        r.view(k)[:] = -7.0                      # the host copies must come back from the device
+    _time_loop(r, r.L.b200_op_rk_, nsteps)
+    r.L.b200_update_host_()
+    got = {k: r.view(k)[:n3].copy() for k in ("hn", "en")}
+    assert r.get("time") == t_end
+    r.L.b200_copy_all_out_()
+    r.close()
+    a = np.concatenate([got["hn"], got["en"]]); b = np.concatenate([want["hn"], want["en"]])
+    assert np.abs(b).max() > 1e-3
+    return rel_l2(a, b)
+
+
+def test_dropin_3dboxper_as_shipped():
+    """tests/3dboxper (mesh from the reference's .re2): 20 steps through the Fortran shim"""
+    from oracle import cases
+    assert _run_both(cases.case_3dboxper(), 20) <= TOL
+
+
+def test_dropin_3dboxpec():
+    """PEC walls: cempec (1-based face points from COMMON /bdry1/) and the doubled impedances"""
+    from oracle import cases
+    assert _run_both(cases.case_3dboxpec(), 20) <= TOL
+
+
+@pytest.mark.parametrize("imode", [1, 2])
+def test_dropin_2dboxper(imode):
+    from oracle import cases
+    assert _run_both(cases.case_2dboxper(imode), 40) <= TOL
+
+
+def test_dropin_pml_two_materials():
+    """tests/3ddielectric geometry, materials and PML (pmlptr, pmlsigma, pmlbn/pmldn from COMMON
+    /pml1-3/); the userinc injection is left out on both sides (the shim has no device-side
+    registration for it; tests/test_gpu_parity.py covers the incident hook)"""
+    from oracle import cases
+    assert _run_both(cases.case_3ddielectric(True), 15) <= TOL
+
+
+def test_dropin_drude_through_the_users_usersrc():
+    """tests/drude: the .usr's usersrc calls cem_maxwell_drude(jn,kjn,resjn,params,dindex,n)
+    (drude.usr:153-170).  In the drop-in build that name resolves to the library's twin: the
+    first call (made by b200_update_device) registers the user's arrays, the ADE then advances
+    inside the fused kernel.  Reference side: the oracle, which equals the translated reference
+    bit for bit on this case (tests/test_reference_pin.py::test_pin_dispersive).  userinc is
+    left out on both sides (no device-side registration in the shim)."""
+    from oracle import cases
+    refrun = _refrun()
+    nsteps = 20
+    c = cases.case_drude()
+    c.set_callback("userinc", lambda tt, *a: None)
+    c.step(nsteps)
+
+    c2 = cases.case_drude()
+    u = c2.user
+    drop = refrun.lib("dropin")      # its cem_maxwell_drude_ is the product library's twin
+    idx1 = (u.index + 1).astype(np.int32)
+    n = C.c_int(idx1.size)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    jn, kjn, resjn, par = u.jn.copy(), u.kjn.copy(), u.resjn.copy(), u.params.copy()
+
+    def usersrc(tt, *res):
+        drop.cem_maxwell_drude_(dp(jn), dp(kjn), dp(resjn), dp(par),
+                                idx1.ctypes.data_as(C.POINTER(C.c_int)), C.byref(n))
+
+    r = refrun.ReferenceRun(c2, kind="dropin")
+    r.set_callback("usersrc", usersrc)
+    r.L.b200_copy_all_in_()
+    r.L.b200_update_device_()
+    _time_loop(r, r.L.b200_op_rk_, nsteps)
+    r.L.b200_update_host_()
+    n3 = 3 * c.npts
+    got = np.concatenate([r.view("hn")[:n3], r.view("en")[:n3]])
+    r.L.b200_copy_all_out_()
+    r.close()
+    assert rel_l2(got, np.concatenate([c.hn, c.en])) <= TOL
+    assert np.abs(c.user.jn).max() > 1e-3
