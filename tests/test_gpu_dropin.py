@@ -129,3 +129,72 @@ def test_dropin_drude_through_the_users_usersrc():
     r.close()
     assert rel_l2(got, np.concatenate([c.hn, c.en])) <= TOL
     assert np.abs(c.user.jn).max() > 1e-3
+
+
+def test_dropin_incident_field_registered_like_a_usr_would():
+    """tests/3ddielectric complete: the reference side runs the .usr's userinc callback between
+    restrict_to_face and the flux (src/cem_maxwell.F:498); the drop-in side registers the same
+    plane wave once through the Fortran twin nekcem_b200_set_incident (as a .usr would do in
+    usrdat2) and the injection happens inside the fused kernel."""
+    from helpers import incident_3ddielectric
+    from oracle import cases
+    refrun = _refrun()
+    nsteps = 15
+    c = cases.case_3ddielectric(True)
+    n3 = 3 * c.npts
+    r = refrun.ReferenceRun(c, kind="dropin")
+    r.set_callback("userinc", c.user.userinc(c))
+    _time_loop(r, r.L.cem_maxwell_op_rk_, nsteps)
+    want = np.concatenate([r.view("hn")[:n3], r.view("en")[:n3]]).copy()
+    r.close()
+
+    r = refrun.ReferenceRun(c, kind="dropin")
+    r.L.b200_copy_all_in_()
+    j, amp, phase, omega = incident_3ddielectric(c)
+    fp1 = np.ascontiguousarray(j + 1, dtype=np.int32)          # 1-based, like incindex
+    amp = np.ascontiguousarray(amp, dtype=np.float64); phase = np.ascontiguousarray(phase)
+    h = C.c_int(int(r.get("b200_handle"))); ninc = C.c_int(fp1.size); om = C.c_double(omega)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    r.L.nekcem_b200_set_incident_(C.byref(h), C.byref(ninc), fp1.ctypes.data_as(C.POINTER(C.c_int)),
+                                  dp(amp), dp(phase), C.byref(om))
+    r.L.b200_update_device_()
+    _time_loop(r, r.L.b200_op_rk_, nsteps)
+    r.L.b200_update_host_()
+    got = np.concatenate([r.view("hn")[:n3], r.view("en")[:n3]]).copy()
+    r.L.b200_copy_all_out_()
+    r.close()
+    assert rel_l2(got, want) <= TOL
+
+
+def test_dropin_volume_source_registered_like_a_usr_would():
+    """tests/3dboxpml: the reference side runs the .usr's usersrc (Gaussian dipole,
+    3dboxpml.usr:30-88) between pml_step and invqmass; the drop-in side registers profile,
+    amplitude and frequency once through nekcem_b200_set_volume_source_."""
+    from oracle import cases
+    refrun = _refrun()
+    nsteps = 15
+    c = cases.case_3dboxpml(nx1=6, nel=(5, 5, 5))
+    n3 = 3 * c.npts
+    fn = cases.usersrc_3dboxpml(c)
+    r = refrun.ReferenceRun(c, kind="dropin")
+    r.set_callback("usersrc", fn)
+    _time_loop(r, r.L.cem_maxwell_op_rk_, nsteps)
+    want = np.concatenate([r.view("hn")[:n3], r.view("en")[:n3]]).copy()
+    r.close()
+
+    r = refrun.ReferenceRun(c, kind="dropin")
+    r.L.b200_copy_all_in_()
+    h = C.c_int(int(r.get("b200_handle")))
+    prof = np.ascontiguousarray(fn.profile, dtype=np.float64)
+    comp, amp, om, ph = C.c_int(5), C.c_double(1.0), C.c_double(-fn.omega), C.c_double(0.0)
+    r.L.nekcem_b200_set_volume_source_(C.byref(h), C.byref(comp),
+                                       prof.ctypes.data_as(C.POINTER(C.c_double)),
+                                       C.byref(amp), C.byref(om), C.byref(ph))
+    r.L.b200_update_device_()
+    _time_loop(r, r.L.b200_op_rk_, nsteps)
+    r.L.b200_update_host_()
+    got = np.concatenate([r.view("hn")[:n3], r.view("en")[:n3]]).copy()
+    r.L.b200_copy_all_out_()
+    r.close()
+    assert np.abs(want).max() > 1e-6
+    assert rel_l2(got, want) <= TOL
