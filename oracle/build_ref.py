@@ -52,6 +52,9 @@ UNITS = [
     ("src/nek5_coef.F", ["xyzrst", "glmapm1", "chkjac", "geodat1", "setarea", "area2", "area3",
                          "setwgtr", "set_unr"]),
     ("src/nek5_subs2.F", ["facexv", "setaxdy", "setaxw1"]),
+    # node coordinates from the element vertices (straight-sided elements; the curved-side
+    # generators sphsrf / gensrf / arcsrf are outside the configs of the path)
+    ("src/nek5_genxyz.F", ["genxyz", "setzgml"]),
     # setup routines that define the face numbering the path relies on
     ("src/nek5_connect11.F", ["initds", "dsset"]),
     # the analytic solutions the reference's own tests check against: the

@@ -49,3 +49,7 @@ EXPORT int iglsum_(int *a, int *n) { (void)n; return *a; }
 EXPORT void gop_(double *x, double *w, const char *op, int *n) { (void)x; (void)w; (void)op; (void)n; }
 /* MPI broadcast of the NCCL id (src/nek5_comm_mpi.F bcast): never reached on one process */
 EXPORT void bcast_(void *buf, int *len) { (void)buf; (void)len; }
+/* curved-side generators (src/nek5_genxyz.F): no case of the path has curved sides */
+EXPORT void sphsrf_(void) { fprintf(stderr, "sphsrf is outside the path\n"); exit(1); }
+EXPORT void gensrf_(void) { fprintf(stderr, "gensrf is outside the path\n"); exit(1); }
+EXPORT void arcsrf_(void) { fprintf(stderr, "arcsrf is outside the path\n"); exit(1); }

@@ -410,3 +410,51 @@ def test_pin_rotated_element_frames():
     c.step(5); r.step(5)
     _assert_same(c, r)
     r.close()
+
+
+@pytest.mark.parametrize("which", ["3dboxper", "drude2d", "box3d"])
+def test_pin_genxyz(which):
+    """GENXYZ (src/nek5_genxyz.F:562-680): GLL node coordinates of every element from its
+    corner vertices xc,yc,zc (trilinear blend in the reference's summation order).  The
+    oracle's coordinates BEFORE the user's usrdat2 rescaling must be the reference's."""
+    from oracle import oracle as O
+    if which == "3dboxper":
+        mesh, _ = cases._load_mesh("3dboxper_mesh.npz")     # vertices of the reference's .re2
+        nx1 = 9
+    elif which == "drude2d":
+        mesh = O.box_mesh((4, 32), ((-1500.0, 1500.0),) * 2, ("P  ", "P  ", "PEC", "PML"))
+        nx1 = 9
+    else:
+        mesh = O.box_mesh((3, 2, 4), ((0.0, 1.0), (-2.0, 5.0), (0.5, 0.75)), ("P  ",) * 6,
+                          gain=(1.0, 1.3, 0.8))
+        nx1 = 6
+    c = O.RefCase(mesh, nx1, imode=1)                        # no usrdat2: raw genxyz output
+    r = refrun.ReferenceRun(c)
+    ldim = c.ldim
+    nc = 2 ** ldim
+    # xc(8,lelt), yc, zc in preprocessor corner order (src/INPUT); zgm1 = GLL points per axis
+    for name, arr in (("xc", mesh.xc), ("yc", mesh.yc), ("zc", mesh.zc)):
+        v = r.view(name).reshape(-1)
+        v[:] = 0.0
+        full = np.zeros((c.nelt, 8))
+        full[:, :nc] = arr[:, :nc]
+        v[:8 * c.nelt] = full.reshape(-1)
+    n = nx1
+    r.put("zgm1", np.concatenate([c.zgm1, c.zgm1, c.zgm1 if ldim == 3 else np.zeros(n)]))
+    for k in ("ifgmsh3", "ifaxis"):
+        try:
+            r.set(k, 0)
+        except KeyError:
+            pass
+    try:
+        r.view_char("ccurve")[:] = ord(" ")
+    except KeyError:
+        pass
+    x, y, z = np.zeros(c.npts), np.zeros(c.npts), np.zeros(c.npts)
+    nz1 = nx1 if ldim == 3 else 1
+    r.L.genxyz_(_dp(x), _dp(y), _dp(z), C.byref(C.c_int(nx1)), C.byref(C.c_int(nx1)),
+                C.byref(C.c_int(nz1)))
+    assert np.array_equal(x, c.xm1) and np.array_equal(y, c.ym1)
+    if ldim == 3:
+        assert np.array_equal(z, c.zm1)
+    r.close()
