@@ -25,7 +25,8 @@ module nekcem_b200
        NKB_AREAM = 17, NKB_Y_0 = 18, NKB_Y_1 = 19, NKB_Z_0 = 20, NKB_Z_1 = 21,    &
        NKB_HN = 22, NKB_EN = 23, NKB_KHN = 24, NKB_KEN = 25,                      &
        NKB_PERMITTIVITY = 26, NKB_PERMEABILITY = 27, NKB_PMLSIGMA = 28,           &
-       NKB_PMLBN = 29, NKB_PMLDN = 30, NKB_KPMLBN = 31, NKB_KPMLDN = 32
+       NKB_PMLBN = 29, NKB_PMLDN = 30, NKB_KPMLBN = 31, NKB_KPMLDN = 32,           &
+       NKB_XMN = 33, NKB_YMN = 34, NKB_ZMN = 35
 
   type, bind(C) :: nekcem_b200_desc
      integer(c_int32_t) :: abi_version, ldim, nx1, nelt, imode, ifupwind, ifpec, ifpml
@@ -133,6 +134,14 @@ module nekcem_b200
        import :: c_int, c_double
        integer(c_int), value :: handle
        real(c_double), intent(in) :: exact_hn(*), exact_en(*)
+       real(c_double), intent(out) :: sumsq(6), linf(6)
+     end function
+     integer(c_int) function nekcem_b200_error_sums_mode(handle, kind, k, ph, amp, sumsq, linf) &
+          bind(C, name='nekcem_b200_error_sums_mode')
+       import :: c_int, c_double, c_int32_t
+       integer(c_int), value :: handle
+       integer(c_int32_t), intent(in) :: kind(18)
+       real(c_double), intent(in) :: k(3), ph(3), amp(6)
        real(c_double), intent(out) :: sumsq(6), linf(6)
      end function
      integer(c_int) function nekcem_b200_last_step_ms(handle, ms, launches) &

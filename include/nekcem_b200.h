@@ -55,6 +55,8 @@ enum nekcem_b200_array {
     NKB_PERMITTIVITY, NKB_PERMEABILITY,      /* (npts) src/EMWAVE:31-32 (PML only)      */
     NKB_PMLSIGMA,      /* (npts,3)             src/PML:11                              */
     NKB_PMLBN, NKB_PMLDN, NKB_KPMLBN, NKB_KPMLDN, /* (npts,3) src/PML:14-28              */
+    NKB_XMN, NKB_YMN, NKB_ZMN, /* xmn,ymn,zmn(npts) node coordinates, src/GEOM:30-33; only needed
+                                  by nekcem_b200_error_sums_mode                             */
     NKB_ARRAY_COUNT
 };
 
@@ -171,6 +173,17 @@ int nekcem_b200_synchronize(int handle);
  * Sums are LOCAL to the rank (the caller reduces like glsc3/glamax). */
 int nekcem_b200_error_sums(int handle, const double *exact_hn, const double *exact_en,
                            double sumsq[6], double linf[6]);
+
+/* The same norms against an analytic solution evaluated ON THE DEVICE (device-side `usersol`,
+ * SURVEY.md 8f rank 1): the separable standing modes of the shipped periodic / PEC box tests
+ * (usersol of tests/3dboxper/3dboxper.usr:45-86, 3dboxpec.usr:64-115, 2dboxper.usr, 2dboxpec.usr),
+ *   exact_c(x,y,z) = amp[c] * f(kind[3c+0], k[0]*x + ph[0]) * f(kind[3c+1], k[1]*y + ph[1])
+ *                           * f(kind[3c+2], k[2]*z + ph[2]),   f(0,.) = 1, f(1,.) = sin, f(2,.) = cos,
+ * c = 0..2 H, 3..5 E; the caller folds the time factor (tmph, tmpe of the .usr) into amp.
+ * Needs NKB_XMN, NKB_YMN (and NKB_ZMN in 3D) uploaded; no host array crosses PCIe. */
+int nekcem_b200_error_sums_mode(int handle, const int32_t kind[18], const double k[3],
+                                const double ph[3], const double amp[6], double sumsq[6],
+                                double linf[6]);
 
 /* Device-time of the last nekcem_b200_step call in milliseconds (CUDA events on the
  * compute stream) and the number of kernels it launched. */

@@ -30,7 +30,7 @@ ARRAY_IDS = {name: i for i, name in enumerate([
     "dxm1", "w3mn", "rxmn", "rymn", "rzmn", "sxmn", "symn", "szmn", "txmn", "tymn", "tzmn",
     "bmn", "hbm1", "ebm1", "unxm", "unym", "unzm", "aream", "Y_0", "Y_1", "Z_0", "Z_1",
     "hn", "en", "khn", "ken", "permittivity", "permeability", "pmlsigma", "pmlbn", "pmldn",
-    "kpmlbn", "kpmldn"])}
+    "kpmlbn", "kpmldn", "xmn", "ymn", "zmn"])}
 
 GEOMETRY_ARRAYS = ["dxm1", "w3mn", "rxmn", "rymn", "rzmn", "sxmn", "symn", "szmn", "txmn",
                    "tymn", "tzmn", "bmn", "hbm1", "ebm1", "unxm", "unym", "unzm", "aream",
@@ -86,6 +86,8 @@ def lib():
         L.nekcem_b200_set_lorentz.argtypes = [C.c_int, c_dp, c_dp, c_dp, c_i32p, C.c_int32]
         L.nekcem_b200_get_ade.argtypes = [C.c_int, c_dp, c_dp]
         L.nekcem_b200_set_option.argtypes = [C.c_int, C.c_char_p, C.c_int]
+        L.nekcem_b200_error_sums_mode.argtypes = [C.c_int, C.POINTER(C.c_int32), c_dp, c_dp, c_dp,
+                                                  c_dp, c_dp]
         L.nekcem_b200_geometry_info.argtypes = [C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
         L.nekcem_b200_set_time.argtypes = [C.c_int, C.c_double, C.c_double]
         L.nekcem_b200_get_time.argtypes = [C.c_int, c_dp]
@@ -356,6 +358,24 @@ class MaxwellB200:
             self.h, _dp(np.ascontiguousarray(exact_hn, dtype=np.float64)),
             _dp(np.ascontiguousarray(exact_en, dtype=np.float64)), _dp(s), _dp(m)))
         return s, m
+
+    def cem_error_mode(self, kind, k, ph, amp, volvm1=None, reduce=None):
+        """cem_error against a standing mode evaluated on the device (device-side usersol):
+        exact_c = amp[c] * f(kind[c][0], k[0] x + ph[0]) * f(kind[c][1], k[1] y + ph[1])
+        * f(kind[c][2], k[2] z + ph[2]), f = 1 / sin / cos for kind 0 / 1 / 2.  Needs the node
+        coordinates uploaded as 'xmn','ymn'(,'zmn')."""
+        kd = np.ascontiguousarray(np.asarray(kind, dtype=np.int32).reshape(18))
+        kk = np.ascontiguousarray(k, dtype=np.float64); pp = np.ascontiguousarray(ph, dtype=np.float64)
+        aa = np.ascontiguousarray(amp, dtype=np.float64)
+        s, m = np.zeros(6), np.zeros(6)
+        _chk(self.L.nekcem_b200_error_sums_mode(self.h, kd.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                _dp(kk), _dp(pp), _dp(aa), _dp(s), _dp(m)))
+        if reduce is not None:
+            s, m = reduce(s, m)
+        vol = self.volvm1 if volvm1 is None else volvm1
+        l2 = s / vol
+        l2 = np.where(l2 > 0, np.sqrt(np.maximum(l2, 0)), l2)
+        return l2, m
 
     def cem_error(self, exact_hn, exact_en, volvm1=None, reduce=None):
         """(l2[6], linf[6]) as cem_error; ``reduce(sums, maxes)`` performs the glsc3/glamax

@@ -114,6 +114,14 @@ NKB_EXPORT void nekcem_b200_error_sums_(const int *h, const double *exact_hn,
     check(nekcem_b200_error_sums(*h, exact_hn, exact_en, sumsq, linf), "nekcem_b200_error_sums");
 }
 
+NKB_EXPORT void nekcem_b200_error_sums_mode_(const int *h, const int *kind, const double *k,
+                                             const double *ph, const double *amp, double *sumsq,
+                                             double *linf)
+{
+    check(nekcem_b200_error_sums_mode(*h, kind, k, ph, amp, sumsq, linf),
+          "nekcem_b200_error_sums_mode");
+}
+
 NKB_EXPORT void nekcem_b200_set_drude_(const int *h, const double *jn, const double *kjn,
                                        const double *params, const int *dindex, const int *n)
 {

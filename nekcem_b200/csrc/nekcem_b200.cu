@@ -9,7 +9,9 @@
 //   step driver       = cem_maxwell_op_rk + rk_c + rk_storage (src/cem_maxwell.F:327-345,
 //                       src/cem_common.F:2-16, 78-114)
 #include <cuda_runtime.h>
-#include <nccl.h>
+#include <nccl.h>  // types and enums only: the entry points are bound at run time (nccl_api below)
+#include <dlfcn.h>
+#include <type_traits>
 
 #include <algorithm>
 #include <cmath>
@@ -55,7 +57,7 @@ int fail(const char *fmt, ...)
     do {                                                                                       \
         ncclResult_t r_ = (call);                                                              \
         if (r_ != ncclSuccess)                                                                 \
-            return fail("NCCL error at %s:%d: %s", __FILE__, __LINE__, ncclGetErrorString(r_)); \
+            return fail("NCCL error at %s:%d: %s", __FILE__, __LINE__, (g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?")); \
     } while (0)
 
 struct Peer {
@@ -63,6 +65,52 @@ struct Peer {
     std::vector<int64_t> send_fp; // local face points, sorted by shared id
     int64_t off = 0;              // offset (in face points) into sendbuf / halo
 };
+
+// NCCL is bound at run time instead of at link time.  A process may already hold another copy
+// of libnccl.so.2 (PyTorch bundles its own, newer than the system's): two copies under one soname
+// cannot coexist, and whichever loads first would break the other.  So the library takes the
+// copy that is already loaded if there is one (RTLD_NOLOAD), else loads libnccl.so.2 itself --
+// only when a communicator is actually requested (single-GPU runs never touch NCCL).
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+NcclApi g_nccl;
+
+int nccl_load()
+{
+    if (g_nccl.ok) return 0;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail("cannot load libnccl.so.2: %s", dlerror());
+    bool all = true;
+    auto bind = [&](auto &fp, const char *name) {
+        fp = reinterpret_cast<std::remove_reference_t<decltype(fp)>>(dlsym(h, name));
+        if (!fp) all = false;
+    };
+    bind(g_nccl.GetUniqueId, "ncclGetUniqueId");
+    bind(g_nccl.CommInitRank, "ncclCommInitRank");
+    bind(g_nccl.CommDestroy, "ncclCommDestroy");
+    bind(g_nccl.AllGather, "ncclAllGather");
+    bind(g_nccl.Send, "ncclSend");
+    bind(g_nccl.Recv, "ncclRecv");
+    bind(g_nccl.GroupStart, "ncclGroupStart");
+    bind(g_nccl.GroupEnd, "ncclGroupEnd");
+    bind(g_nccl.GetErrorString, "ncclGetErrorString");
+    if (!all) return fail("libnccl.so.2 lacks a required entry point");
+    g_nccl.ok = true;
+    return 0;
+}
 
 struct Ctx {
     nekcem_b200_desc d{};
@@ -151,7 +199,7 @@ int64_t array_count(const Ctx *c, int which)
     case NKB_W3MN: return c->nxyz;
     case NKB_RXMN: case NKB_RYMN: case NKB_RZMN: case NKB_SXMN: case NKB_SYMN: case NKB_SZMN:
     case NKB_TXMN: case NKB_TYMN: case NKB_TZMN: case NKB_BMN: case NKB_HBM1: case NKB_EBM1:
-    case NKB_PERMITTIVITY: case NKB_PERMEABILITY:
+    case NKB_PERMITTIVITY: case NKB_PERMEABILITY: case NKB_XMN: case NKB_YMN: case NKB_ZMN:
         return c->npts;
     case NKB_UNXM: case NKB_UNYM: case NKB_UNZM: case NKB_AREAM:
     case NKB_Y_0: case NKB_Y_1: case NKB_Z_0: case NKB_Z_1:
@@ -270,6 +318,50 @@ __global__ void error_kernel(const double *u, long long ld, const double *exact,
         for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npts;
              i += (long long)gridDim.x * blockDim.x) {
             double err = exact[c * npts + i] - u[c * ld + i];
+            sum += err * bm[i] * err;
+            mx = fmax(mx, fabs(err));
+        }
+        ssum[threadIdx.x] = sum;
+        smax[threadIdx.x] = mx;
+        __syncthreads();
+        for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+            if (threadIdx.x < s) {
+                ssum[threadIdx.x] += ssum[threadIdx.x + s];
+                smax[threadIdx.x] = fmax(smax[threadIdx.x], smax[threadIdx.x + s]);
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            part[blockIdx.x * 12 + c] = ssum[0];
+            part[blockIdx.x * 12 + 6 + c] = smax[0];
+        }
+        __syncthreads();
+    }
+}
+
+// cem_error against a separable standing mode evaluated on the fly (device-side usersol)
+struct ModeSol {
+    int kind[18];
+    double k[3], ph[3], amp[6];
+};
+__device__ __forceinline__ double mode_f(int kind, double a)
+{
+    return kind == 0 ? 1.0 : (kind == 1 ? sin(a) : cos(a));
+}
+__global__ void error_mode_kernel(const double *u, long long ld, ModeSol m, const double *x,
+                                  const double *y, const double *z, long long npts,
+                                  const double *bm, double *part /* [blocks][12] */)
+{
+    __shared__ double ssum[256], smax[256];
+    for (int c = 0; c < 6; c++) {
+        double sum = 0.0, mx = 0.0;
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npts;
+             i += (long long)gridDim.x * blockDim.x) {
+            const double zz = z ? z[i] : 0.0;
+            const double ex = m.amp[c] * mode_f(m.kind[3 * c], m.k[0] * x[i] + m.ph[0]) *
+                              mode_f(m.kind[3 * c + 1], m.k[1] * y[i] + m.ph[1]) *
+                              mode_f(m.kind[3 * c + 2], m.k[2] * zz + m.ph[2]);
+            double err = ex - u[c * ld + i];
             sum += err * bm[i] * err;
             mx = fmax(mx, fabs(err));
         }
@@ -412,7 +504,7 @@ int exchange_singletons_nccl(Ctx *c)
     int64_t *d_cnt = nullptr;
     CUDA_OK(cudaMalloc(&d_cnt, sizeof(int64_t) * (R + 1)));
     CUDA_OK(cudaMemcpy(d_cnt + R, &mycnt, sizeof(int64_t), cudaMemcpyHostToDevice));
-    NCCL_OK(ncclAllGather(d_cnt + R, d_cnt, 1, ncclInt64, c->comm, c->s_comm));
+    NCCL_OK(g_nccl.AllGather(d_cnt + R, d_cnt, 1, ncclInt64, c->comm, c->s_comm));
     CUDA_OK(cudaStreamSynchronize(c->s_comm));
     std::vector<int64_t> counts(R);
     CUDA_OK(cudaMemcpy(counts.data(), d_cnt, sizeof(int64_t) * R, cudaMemcpyDeviceToHost));
@@ -431,7 +523,7 @@ int exchange_singletons_nccl(Ctx *c)
     std::vector<int64_t> ids(mx, 0);
     for (size_t q = 0; q < c->singles.size(); q++) ids[q] = c->singles[q].first;
     CUDA_OK(cudaMemcpy(d_ids + mx * R, ids.data(), sizeof(int64_t) * mx, cudaMemcpyHostToDevice));
-    NCCL_OK(ncclAllGather(d_ids + mx * R, d_ids, mx, ncclInt64, c->comm, c->s_comm));
+    NCCL_OK(g_nccl.AllGather(d_ids + mx * R, d_ids, mx, ncclInt64, c->comm, c->s_comm));
     CUDA_OK(cudaStreamSynchronize(c->s_comm));
     std::vector<int64_t> padded(mx * R), all;
     CUDA_OK(cudaMemcpy(padded.data(), d_ids, sizeof(int64_t) * mx * R, cudaMemcpyDeviceToHost));
@@ -448,7 +540,7 @@ int require(Ctx *c, std::initializer_list<int> ids)
         "dxm1", "w3mn", "rxmn", "rymn", "rzmn", "sxmn", "symn", "szmn", "txmn", "tymn", "tzmn",
         "bmn", "hbm1", "ebm1", "unxm", "unym", "unzm", "aream", "Y_0", "Y_1", "Z_0", "Z_1", "hn",
         "en", "khn", "ken", "permittivity", "permeability", "pmlsigma", "pmlbn", "pmldn",
-        "kpmlbn", "kpmldn"};
+        "kpmlbn", "kpmldn", "xmn", "ymn", "zmn"};
     for (int id : ids)
         if (!c->have[id]) return fail("array '%s' has not been uploaded", names[id]);
     return 0;
@@ -580,13 +672,13 @@ int run_stage(Ctx *c, int rkstep /*1..5*/)
             a.u_in, c->ld, c->send_node, c->sendbuf, c->nhalo, c->inc_send_d, c->inc_amp_d,
             c->inc_phase_d, (int)c->inc_fp.size(), a.inc_wt);
         c->last_launches++;
-        NCCL_OK(ncclGroupStart());
+        NCCL_OK(g_nccl.GroupStart());
         for (auto &p : c->peers) {
             const size_t cnt = p.send_fp.size() * 6;
-            NCCL_OK(ncclSend(c->sendbuf + 6 * p.off, cnt, ncclDouble, p.rank, c->comm, c->s_comm));
-            NCCL_OK(ncclRecv(c->halo + 6 * p.off, cnt, ncclDouble, p.rank, c->comm, c->s_comm));
+            NCCL_OK(g_nccl.Send(c->sendbuf + 6 * p.off, cnt, ncclDouble, p.rank, c->comm, c->s_comm));
+            NCCL_OK(g_nccl.Recv(c->halo + 6 * p.off, cnt, ncclDouble, p.rank, c->comm, c->s_comm));
         }
-        NCCL_OK(ncclGroupEnd());
+        NCCL_OK(g_nccl.GroupEnd());
         CUDA_OK(cudaEventRecord(c->ev_halo, c->s_comm));
     }
     for (int q = 0; q < 4; q++)
@@ -676,7 +768,7 @@ int nekcem_b200_destroy(int handle)
     if (!c->host_only) {
         cudaSetDevice(c->d.device);
         cudaDeviceSynchronize();
-        if (c->has_comm) ncclCommDestroy(c->comm);
+        if (c->has_comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
         for (auto &p : c->dev) cudaFree(p);
         cudaFree(c->u[0]); cudaFree(c->u[1]); cudaFree(c->kf);
         cudaFree(c->hY); cudaFree(c->hZ); cudaFree(c->vmapP_d); cudaFree(c->elist_d);
@@ -791,7 +883,8 @@ int nekcem_b200_comm_unique_id(char id[128])
 {
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
     ncclUniqueId u;
-    NCCL_OK(ncclGetUniqueId(&u));
+    if (nccl_load()) return 1;
+    NCCL_OK(g_nccl.GetUniqueId(&u));
     memcpy(id, &u, 128);
     return 0;
 }
@@ -805,7 +898,8 @@ int nekcem_b200_comm_init(int handle, const char id[128])
     CUDA_OK(cudaSetDevice(c->d.device));
     ncclUniqueId u;
     memcpy(&u, id, 128);
-    NCCL_OK(ncclCommInitRank(&c->comm, c->d.nranks, u, c->d.rank));
+    if (nccl_load()) return 1;
+    NCCL_OK(g_nccl.CommInitRank(&c->comm, c->d.nranks, u, c->d.rank));
     c->has_comm = true;
     return 0;
 }
@@ -1196,6 +1290,44 @@ int nekcem_b200_error_sums(int handle, const double *exact_hn, const double *exa
         }
         sumsq[q] = s;
         linf[q] = m;
+    }
+    return 0;
+}
+
+int nekcem_b200_error_sums_mode(int handle, const int32_t kind[18], const double k[3],
+                                const double ph[3], const double amp[6], double sumsq[6],
+                                double linf[6])
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (!c->setup_done) return fail("nekcem_b200_setup has not completed");
+    if (!kind || !k || !ph || !amp || !sumsq || !linf) return fail("null argument");
+    if (require(c, {NKB_XMN, NKB_YMN})) return 1;
+    if (c->d.ldim == 3 && require(c, {NKB_ZMN})) return 1;
+    CUDA_OK(cudaSetDevice(c->d.device));
+    ModeSol m;
+    for (int q = 0; q < 18; q++) {
+        if (kind[q] < 0 || kind[q] > 2) return fail("mode kind must be 0 (one), 1 (sin) or 2 (cos)");
+        m.kind[q] = kind[q];
+    }
+    for (int q = 0; q < 3; q++) { m.k[q] = k[q]; m.ph[q] = ph[q]; }
+    for (int q = 0; q < 6; q++) m.amp[q] = amp[q];
+    const int nb = (int)std::min<int64_t>(c->red_blocks, (c->npts + 255) / 256);
+    error_mode_kernel<<<nb, 256, 0, c->s_compute>>>(c->u[c->cur], c->ld, m, c->dev[NKB_XMN],
+                                                    c->dev[NKB_YMN],
+                                                    c->d.ldim == 3 ? c->dev[NKB_ZMN] : nullptr,
+                                                    c->npts, c->dev[NKB_BMN], c->red_d);
+    std::vector<double> part(12 * nb);
+    CUDA_OK(cudaStreamSynchronize(c->s_compute));
+    CUDA_OK(cudaMemcpy(part.data(), c->red_d, sizeof(double) * 12 * nb, cudaMemcpyDeviceToHost));
+    for (int q = 0; q < 6; q++) {
+        double s = 0.0, mxv = 0.0;
+        for (int b = 0; b < nb; b++) {
+            s += part[b * 12 + q];
+            mxv = std::max(mxv, part[b * 12 + 6 + q]);
+        }
+        sumsq[q] = s;
+        linf[q] = mxv;
     }
     return 0;
 }

@@ -13,7 +13,7 @@ for spec in "$@"; do
   name="${spec%%=*}"; defs="${spec#*=}"
   (
     $NVCC $FLAGS $defs -Xptxas -v -c stage_slab.cu -o _obj/variants/$name.o 2> _obj/variants/$name.log
-    $NVCC $ARCH -shared -o ../lib/variants/$name.so _obj/nekcem_b200.o _obj/stage2d.o _obj/variants/$name.o _obj/fortran_abi.o -lnccl -lcudart
+    $NVCC $ARCH -shared -o ../lib/variants/$name.so _obj/nekcem_b200.o _obj/stage2d.o _obj/variants/$name.o _obj/fortran_abi.o -lcudart -ldl
     grep -E "Used|spill" _obj/variants/$name.log | paste - - | awk -v n=$name '{print n": "$0}' | sed 's/ptxas info    ://g' | head -4
   ) &
 done

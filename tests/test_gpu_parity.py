@@ -433,7 +433,7 @@ def test_geometry_replaced_after_setup_is_rescanned():
     elements it changed (the scan is redone lazily before the next stage)."""
     from oracle import cases
     from nekcem_b200.api import ARRAY_IDS
-    c = cases.case_boxper((2, 2, 3), 6, dt=-1e-3)
+    c = cases.case_boxper((3, 3, 3), 6, dt=-1e-3)
     noisy = {k: getattr(c, k).copy() for k in ("rxmn", "symn", "tzmn")}
     for k in ("rxmn", "rymn", "rzmn", "sxmn", "symn", "szmn", "txmn", "tymn", "tzmn"):
         v = getattr(c, k).reshape(c.nelt, c.nxyz)
@@ -447,4 +447,99 @@ def test_geometry_replaced_after_setup_is_rescanned():
     assert s.geometry_info()[0] == 0
     c.step(2); s.step(2)
     assert rel_l2(_fields(s), _fields(c)) <= TOL
+    s.close()
+
+
+def test_checkpoint_resume_full_state_bitwise():
+    """Checkpoint / resume through the host-sync seams (the reference's restart
+    writes HN,EN only, src/io.F:411-491, and loses kHN,kEN and the PML/ADE state): pull the whole
+    state after 3 steps -- fields, RK registers, PML B/D fields and their registers, the Drude
+    current and its register, time -- destroy the context, create a new one, push the state and
+    continue.  The continued run must equal an uninterrupted one bit for bit."""
+    from oracle import cases
+    c = cases.case_drude()          # 2D TE with PEC, PML, incident field and the Drude ADE
+    u = c.user
+
+    def make(jn, kjn):
+        return solver_from_refcase(c, incident=u.incident(c),
+                                   ade=("drude", jn, kjn, u.params, u.index))
+
+    a = make(u.jn.copy(), u.kjn.copy())
+    a.step(7)
+    want = _fields(a).copy()
+    ja, ka = a.get_ade()
+    a.close()
+
+    b = make(u.jn.copy(), u.kjn.copy())
+    b.step(3)
+    state = {k: b.get_array(k) for k in ("hn", "en", "khn", "ken", "pmlbn", "pmldn", "kpmlbn",
+                                        "kpmldn")}
+    jb, kb = b.get_ade()
+    t = b.time
+    b.close()
+
+    r = make(jb, kb)                # new context: geometry + the checkpointed ADE state
+    for k, v in state.items():
+        r.set_array(k, v)
+    r.set_time(t, c.dt)
+    r.step(4)
+    assert np.array_equal(_fields(r), want)
+    jr, kr = r.get_ade()
+    assert np.array_equal(jr, ja) and np.array_equal(kr, ka)
+    r.close()
+
+
+@pytest.mark.parametrize("which", ["3dboxper", "3dboxpec", "2dboxper-te", "2dboxper-tm"])
+def test_device_side_usersol_error_norms(which):
+    """usersol evaluated on the device.  The standing modes of the shipped
+    box tests as (kind, wavenumber, amplitude) tables; the L2 / Linf errors must equal those of
+    cem_error against the host usersol (to the round-off of device vs host sin/cos) and meet the
+    .usr tolerances."""
+    import math
+    from oracle import cases
+    name, _, mode = which.partition("-")
+    imode = {"te": 1, "tm": 2}.get(mode, 3)
+    c = {"3dboxper": cases.case_3dboxper, "3dboxpec": cases.case_3dboxpec,
+         "2dboxper": lambda: cases.case_2dboxper(imode)}[name]()
+    s = solver_from_refcase(c)
+    s.set_array("xmn", c.xm1); s.set_array("ymn", c.ym1)
+    if c.ldim == 3:
+        s.set_array("zmn", c.zm1)
+    s.step(10); c.step(10)
+    tt = s.time
+    ONE, SIN, COS = 0, 1, 2
+    if name == "3dboxper":          # 3dboxper.usr:64-80
+        om = math.sqrt(3.0); th, te = math.sin(om * tt) / om, math.cos(om * tt)
+        kind = [[COS, SIN, COS], [SIN, COS, COS], [SIN, SIN, SIN],
+                [ONE, ONE, ONE], [COS, SIN, SIN], [COS, COS, COS]]
+        amp = [2 * th, -th, th, 0.0, te, te]
+        k = [1.0, 1.0, 1.0]
+    elif name == "3dboxpec":        # 3dboxpec.usr:88-110
+        ww = math.pi
+        th = math.cos(ww * math.sqrt(3.0) * tt) / math.sqrt(6.0)
+        te = math.sin(ww * math.sqrt(3.0) * tt) / math.sqrt(2.0)
+        kind = [[SIN, COS, COS], [COS, SIN, COS], [COS, COS, SIN],
+                [COS, SIN, SIN], [SIN, COS, SIN], [ONE, ONE, ONE]]
+        amp = [-th, -th, 2 * th, -te, te, 0.0]
+        k = [ww, ww, ww]
+    else:                           # 2dboxper.usr usersol
+        om = math.sqrt(2.0)
+        k = [1.0, 1.0, 0.0]
+        if imode == 2:              # TM
+            th, te = math.sin(om * tt) / om, math.cos(om * tt)
+            kind = [[COS, SIN, ONE], [SIN, COS, ONE], [ONE, ONE, ONE],
+                    [ONE, ONE, ONE], [ONE, ONE, ONE], [COS, COS, ONE]]
+            amp = [th, -th, 0.0, 0.0, 0.0, te]
+        else:                       # TE
+            th, te = math.cos(om * tt), math.sin(om * tt) / om
+            kind = [[ONE, ONE, ONE], [ONE, ONE, ONE], [SIN, SIN, ONE],
+                    [SIN, COS, ONE], [COS, SIN, ONE], [ONE, ONE, ONE]]
+            amp = [0.0, 0.0, th, te, -te, 0.0]
+    l2d, linfd = s.cem_error_mode(kind, k, [0.0, 0.0, 0.0], amp)
+    shn, sen = c.usersol(c, tt)
+    l2h, linfh = s.cem_error(shn, sen)
+    assert np.allclose(l2d, l2h, rtol=1e-6, atol=1e-15)
+    assert np.allclose(linfd, linfh, rtol=1e-6, atol=1e-14)
+    assert np.all(l2d <= np.array(c.tol["l2"])) and np.all(linfd <= np.array(c.tol["linf"]))
+    assert l2d.max() > 1e-13
     s.close()
