@@ -28,6 +28,12 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# stdout carries exactly ONE JSON line: native libraries (NCCL prints "NCCL version ..." on
+# stdout when NCCL_DEBUG is set) and anything else that writes to fd 1 are sent to stderr
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+sys.stdout = sys.stderr
+
 METRIC = "GDOF-RK-stage/s (FP64)"
 UNIT = "Gnode-stage/s"
 
@@ -75,7 +81,7 @@ def _ref_worker(elems: int, nx1: int, steps: int, warmup: int, sync_dir: str, id
     t0 = time.perf_counter()
     r.step(steps)
     dt = time.perf_counter() - t0
-    print(json.dumps({"dt": dt, "npts": int(c.npts)}), flush=True)
+    print(json.dumps({"dt": dt, "npts": int(c.npts)}), file=_JSON_OUT, flush=True)
 
 
 def cpu_reference_rate(elems: int, nx1: int, steps: int, warmup: int):
@@ -140,7 +146,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------
@@ -379,7 +385,7 @@ def run_gpu(args):
                     "what": "per step: H2D(hn,en) from pinned host + nekcem_b200_step(1) + D2H(hn,en)"},
             "gpu_launches": int(launches),
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     slv.close()
     if world > 1:
         dist.destroy_process_group()
