@@ -15,7 +15,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 
-def _worker(rank, world, port, nel, nx1, q):
+def _worker(rank, world, port, nel, nx1, q, rotated=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from helpers import arrays_from_refcase
@@ -23,7 +23,9 @@ def _worker(rank, world, port, nel, nx1, q):
     from nekcem_b200.boxcase import gllnid_box
     from oracle import cases
 
-    ref = cases.case_boxper(nel, nx1)            # the whole mesh (same on every rank)
+    # the whole mesh (same on every rank); rotated: every element's local frame turned by one
+    # of the 24 proper rotations, so paired face lattices run in different directions
+    ref = cases.case_boxper_rotated(nel, nx1)[0] if rotated else cases.case_boxper(nel, nx1)
     rng = np.random.default_rng(7)
     ref.hn[:] = rng.standard_normal(ref.hn.size)  # arbitrary traces
     ref.en[:] = rng.standard_normal(ref.en.size)
@@ -80,12 +82,17 @@ def _worker(rank, world, port, nel, nx1, q):
     dist.destroy_process_group()
 
 
-def test_two_rank_exchange_plan_gloo():
+import pytest  # noqa: E402
+
+
+@pytest.mark.parametrize("rotated", [False, True])
+def test_two_rank_exchange_plan_gloo(rotated):
     nel, nx1, world = (3, 3, 6), 4, 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, world, port, nel, nx1, q)) for r in range(world)]
+    port = 29500 + (os.getpid() % 2000) + (7 if rotated else 0)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, nel, nx1, q, rotated))
+             for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in range(world)]
