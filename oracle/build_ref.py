@@ -44,7 +44,7 @@ UNITS = [
     ("src/nek5_mat1.F", ["chsign", "rzero", "rone", "copy", "addcol3", "addcol4", "subcol3",
                          "subcol4", "ascol5", "col2", "col3", "invcol1", "invcol3", "invers2",
                          "vdot2", "vdot3", "vcross", "unitvec", "rzero3", "cmult", "sub3",
-                         "izero", "vlmax", "vlmin", "glsc3", "glamax", "glmin"]),
+                         "izero", "vlmax", "vlmin", "glsc3", "glamax", "glmin", "glmax"]),
     # setup routines whose OUTPUT the path consumes: GLL nodes/weights and
     # derivative matrix, metric cofactors / Jacobian / mass, face areas and normals
     ("src/nek5_speclib.F", ["zwgll", "zwglj", "zwgljd", "jacg", "jacobf", "zwgjd", "endw1",
@@ -63,6 +63,14 @@ UNITS = [
     ("tests/3dboxpec/3dboxpec.usr", ["usersol"], "__3dboxpec"),
     ("tests/2dboxper/2dboxper.usr", ["usersol"], "__2dboxper"),
     ("tests/2dboxpec/2dboxpec.usr", ["usersol"], "__2dboxpec"),
+    # the other callbacks of the shipped cases that are plain real arithmetic (drude.usr /
+    # lorentz.usr evaluate their analytic solution in COMPLEX arithmetic: not translated)
+    ("tests/3dboxper/3dboxper.usr", ["usrdat2"], "__3dboxper"),
+    ("tests/3dboxpec/3dboxpec.usr", ["usrdat2"], "__3dboxpec"),
+    ("tests/3ddielectric/3ddielectric.usr", ["userinc", "usersol", "userini", "uservp",
+                                             "usrdat2"], "__3ddielectric"),
+    ("tests/3dboxpml/3dboxpml.usr", ["usersrc", "usrdat2"], "__3dboxpml"),
+    ("tests/drude/drude.usr", ["userinc", "usersrc"], "__drude"),
 ]
 # reference gather-scatter library, compiled unchanged (flags of bin/configurenek:132-139
 # without -DMPI: single process)

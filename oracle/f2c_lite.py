@@ -1099,6 +1099,10 @@ class Emitter:
             return [";"]
         if s == "return":
             return ["goto f_return;"]
+        if s == "exit":
+            return ["break;"]
+        if s == "cycle":
+            return ["continue;"]
         if s.startswith("stop"):
             return ["exit(1);"]
         if re.match(r"^(write|print|format|read|open|close|rewind)\b", s) and top_level_eq(s.split(")")[0] if "(" in s else s) < 0:

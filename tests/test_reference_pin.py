@@ -458,3 +458,106 @@ def test_pin_genxyz(which):
     if ldim == 3:
         assert np.array_equal(z, c.zm1)
     r.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# the shipped .usr files themselves (translated from /root/reference/tests/<case>/<case>.usr):
+# pins the numpy restatements of the user callbacks in oracle/cases.py
+# ---------------------------------------------------------------------------------------------
+def _usr(L, name, case):
+    return getattr(L, "%s__%s_" % (name, case))
+
+
+@pytest.mark.parametrize("case", ["3dboxper", "3dboxpec", "3ddielectric", "3dboxpml"])
+def test_pin_usrdat2_mesh_rescaling(case):
+    """usrdat2 of the .usr files: the affine rescaling of the mesh (glmin/glmax of the
+    coordinates, then the per-node formula) applied to the raw genxyz coordinates"""
+    from oracle import oracle as O
+    build = {"3dboxper": cases.case_3dboxper, "3dboxpec": cases.case_3dboxpec,
+             "3ddielectric": lambda: cases.case_3ddielectric(False),
+             "3dboxpml": lambda: cases.case_3dboxpml(nx1=5, nel=(4, 4, 4))}[case]
+    c = build()                                      # coordinates AFTER the oracle's usrdat2
+    raw = O.RefCase(c.mesh, c.nx1)                   # raw genxyz output
+    r = refrun.ReferenceRun(c)
+    for nm in ("xm1", "ym1", "zm1"):
+        r.put(nm, getattr(raw, nm))
+    _usr(r.L, "usrdat2", case)()
+    for nm in ("xm1", "ym1", "zm1"):
+        assert np.array_equal(r.view(nm)[:c.npts], getattr(c, nm)), nm
+    r.close()
+
+
+@pytest.mark.parametrize("twomat", [False, True])
+def test_pin_3ddielectric_with_the_shipped_usr(twomat):
+    """tests/3ddielectric driven by ITS OWN .usr: uservp (materials + the incident-face index),
+    userini -> usersol (initial fields incl. the PML decay factor, pmlbn/pmldn), userinc in every
+    stage.  Materials and the index must equal the oracle's restatement exactly; fields agree to
+    the round-off of libm vs numpy cos/exp (<= 1e-13 relative after 10 steps)."""
+    c = cases.case_3ddielectric(twomat)
+    r = refrun.ReferenceRun(c)
+    L = r.L
+    r.set_cbc(c.mesh.cbc)
+    for nm in ("xm1", "ym1", "zm1"):
+        r.put(nm, getattr(c, nm))
+    r.view("param")[69] = 1.0 if twomat else 0.0       # param(70)
+    # PML layout first (cem_maxwell_init order, src/cem_maxwell.F:164-175), all reference code
+    for a, b in (("rxmn", "rxm1"), ("rymn", "rym1"), ("rzmn", "rzm1"), ("sxmn", "sxm1"),
+                 ("symn", "sym1"), ("szmn", "szm1"), ("txmn", "txm1"), ("tymn", "tym1"),
+                 ("tzmn", "tzm1")):
+        r.put_opt(b, getattr(c, a))
+    faceary = np.zeros(c.nxzfl)
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+    L.pml_fill_faceary_(_dp(faceary), C.byref(C.c_int(c.pmlthick)))
+    L.pml_extent_and_tags_(_dp(r.view("pmlinner")), _dp(r.view("pmlouter")), ip(r.view("pmltag")),
+                           _dp(faceary))
+    one = C.c_int(1)
+    r.view("permittivity")[:] = 0.0
+    _usr(L, "uservp", "3ddielectric")(C.byref(one), C.byref(one), C.byref(one), C.byref(one))
+    assert np.array_equal(r.view("permittivity")[:c.npts], c.permittivity)
+    assert np.array_equal(r.view("permeability")[:c.npts], c.permeability)
+    ninc = int(r.get("ninc"))
+    assert ninc == c.user.incindex.size
+    assert np.array_equal(r.view("incindex")[:ninc], c.user.incindex + 1)
+    L.pml_calc_sigma_(_dp(r.view("pmlinner")), _dp(r.view("pmlouter")), ip(r.view("pmltag")),
+                      C.byref(C.c_double(c.pmlorder)), C.byref(C.c_double(c.pmlreferr)))
+    r.set("pmlorder", c.pmlorder); r.set("pmlreferr", c.pmlreferr)
+    # userini -> usersol: initial condition
+    n, n3 = c.npts, 3 * c.npts
+    hn, en = r.view("hn"), r.view("en")
+    hn[:] = 0.0; en[:] = 0.0
+    tt = C.c_double(0.0)
+    _usr(L, "userini", "3ddielectric")(C.byref(tt), _dp(hn[0:]), _dp(hn[n:]), _dp(hn[2 * n:]),
+                                      _dp(en[0:]), _dp(en[n:]), _dp(en[2 * n:]))
+    shn, sen = c.user.usersol(c, 0.0)
+    assert np.abs(hn[:n3] - shn).max() <= 2e-15 and np.abs(en[:n3] - sen).max() <= 2e-15
+    assert np.abs(r.view("pmldn")[:n3] - c.pmldn).max() <= 4e-15
+    # time stepping with the .usr's userinc as the callback
+    L.ref_set_user(0, C.cast(_usr(L, "userinc", "3ddielectric"), refrun.USERCB))
+    c.step(10); r.step(10)
+    num = np.sqrt(np.sum((c.hn - hn[:n3]) ** 2) + np.sum((c.en - en[:n3]) ** 2))
+    den = np.sqrt(np.sum(c.hn ** 2) + np.sum(c.en ** 2))
+    assert num / den <= 1e-13
+    # and the .usr's usersol at the end time: the reference's userchk tolerances hold
+    sol = [np.zeros(n) for _ in range(6)]
+    tt = C.c_double(c.time)
+    _usr(L, "usersol", "3ddielectric")(C.byref(tt), *[_dp(a) for a in sol])
+    mine_h, mine_e = c.user.usersol(c, c.time)
+    for k in range(3):
+        assert np.abs(sol[k] - c.comp(mine_h, k)).max() <= 2e-15
+        assert np.abs(sol[3 + k] - c.comp(mine_e, k)).max() <= 2e-15
+    r.close()
+
+
+def test_pin_3dboxpml_with_the_shipped_usersrc():
+    """tests/3dboxpml driven by its own usersrc (Gaussian dipole, 3dboxpml.usr:30-88)"""
+    c = cases.case_3dboxpml(nx1=6, nel=(5, 5, 5))
+    r = refrun.ReferenceRun(c)
+    for nm in ("xm1", "ym1", "zm1"):
+        r.put(nm, getattr(c, nm))
+    r.L.ref_set_user(1, C.cast(_usr(r.L, "usersrc", "3dboxpml"), refrun.USERCB))
+    c.step(15); r.step(15)
+    n3 = 3 * c.npts
+    num = np.sqrt(np.sum((c.hn - r.hn) ** 2) + np.sum((c.en - r.en) ** 2))
+    den = np.sqrt(np.sum(c.hn ** 2) + np.sum(c.en ** 2))
+    assert den > 1e-8 and num / den <= 1e-13
+    r.close()
