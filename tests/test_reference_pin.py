@@ -561,3 +561,32 @@ def test_pin_3dboxpml_with_the_shipped_usersrc():
     den = np.sqrt(np.sum(c.hn ** 2) + np.sum(c.en ** 2))
     assert den > 1e-8 and num / den <= 1e-13
     r.close()
+
+
+def test_pin_drude_with_the_shipped_userinc_and_usersrc():
+    """tests/drude driven by its own userinc (plane-wave injection) and usersrc (which calls the
+    reference's cem_maxwell_drude on the arrays of the .usr's COMMON /userdrude/).  The analytic
+    solution of this case is evaluated in COMPLEX arithmetic by the .usr and is not translated;
+    the initial state and the material tables come from the oracle's restatement."""
+    c = cases.case_drude()
+    u = c.user
+    r = refrun.ReferenceRun(c)
+    L = r.L
+    r.put("ym1", c.ym1)
+    n = c.npts
+    # COMMON /userparam/ and /userincvars/ (drude.usr:20-30), /userdrude/ (:53-56)
+    r.set("omega", u.omega); r.set("k1", u.k1); r.set("eta1", u.eta1)
+    r.put("incindex", u.incindex + 1); r.set("ninc", u.incindex.size)
+    r.put("jn", u.jn); r.put("kjn", u.kjn)
+    r.put("drudeparams", u.params)
+    r.put("drudeindex", u.index + 1); r.set("ndrude", u.index.size)
+    L.ref_set_user(0, C.cast(_usr(L, "userinc", "drude"), refrun.USERCB))
+    L.ref_set_user(1, C.cast(_usr(L, "usersrc", "drude"), refrun.USERCB))
+    c.step(40); r.step(40)
+    num = np.sqrt(np.sum((c.hn - r.hn) ** 2) + np.sum((c.en - r.en) ** 2))
+    den = np.sqrt(np.sum(c.hn ** 2) + np.sum(c.en ** 2))
+    assert num / den <= 1e-13
+    j = r.view("jn")[:3 * n]
+    assert np.abs(j).max() > 1e-3
+    assert np.sqrt(np.sum((j - u.jn) ** 2)) / np.sqrt(np.sum(u.jn ** 2)) <= 1e-13
+    r.close()
