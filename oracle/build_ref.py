@@ -63,14 +63,16 @@ UNITS = [
     ("tests/3dboxpec/3dboxpec.usr", ["usersol"], "__3dboxpec"),
     ("tests/2dboxper/2dboxper.usr", ["usersol"], "__2dboxper"),
     ("tests/2dboxpec/2dboxpec.usr", ["usersol"], "__2dboxpec"),
-    # the other callbacks of the shipped cases that are plain real arithmetic (drude.usr /
-    # lorentz.usr evaluate their analytic solution in COMPLEX arithmetic: not translated)
+    # the other callbacks of the shipped cases (drude.usr / lorentz.usr evaluate their analytic
+    # solution in COMPLEX arithmetic: C99 double _Complex, compiled with -fcx-fortran-rules)
     ("tests/3dboxper/3dboxper.usr", ["usrdat2"], "__3dboxper"),
     ("tests/3dboxpec/3dboxpec.usr", ["usrdat2"], "__3dboxpec"),
     ("tests/3ddielectric/3ddielectric.usr", ["userinc", "usersol", "userini", "uservp",
                                              "usrdat2"], "__3ddielectric"),
     ("tests/3dboxpml/3dboxpml.usr", ["usersrc", "usrdat2"], "__3dboxpml"),
-    ("tests/drude/drude.usr", ["userinc", "usersrc"], "__drude"),
+    ("tests/drude/drude.usr", ["userinc", "usersrc", "usersol", "userini", "uservp"], "__drude"),
+    ("tests/lorentz/lorentz.usr", ["userinc", "usersrc", "usersol", "userini", "uservp"],
+     "__lorentz"),
 ]
 # reference gather-scatter library, compiled unchanged (flags of bin/configurenek:132-139
 # without -DMPI: single process)
@@ -116,8 +118,8 @@ def build(force: bool = False, verbose: bool = False) -> str | None:
     gen = os.path.join(OUT, "ref_gen.c")
     with open(gen, "w") as f:
         f.write(ctext)
-    cmd = (["gcc", "-O3", "-std=gnu11", "-ffp-contract=off", "-fPIC", "-shared", "-w",
-            "-I" + os.path.join(REF, "src/jl")] + JL_FLAGS +
+    cmd = (["gcc", "-O3", "-std=gnu11", "-ffp-contract=off", "-fcx-fortran-rules", "-fPIC",
+            "-shared", "-w", "-I" + os.path.join(REF, "src/jl")] + JL_FLAGS +
            ["-o", LIB, gen, os.path.join(HERE, "ref_harness.c")] +
            [os.path.join(REF, "src/jl", f) for f in JL] + ["-lm"])
     if verbose:
@@ -141,8 +143,8 @@ def build_dropin(inc, verbose=False):
     gen = os.path.join(OUT, "ref_dropin_gen.c")
     with open(gen, "w") as f:
         f.write(ctext)
-    cmd = (["gcc", "-O3", "-std=gnu11", "-ffp-contract=off", "-fPIC", "-shared", "-w",
-            "-I" + os.path.join(REF, "src/jl")] + JL_FLAGS +
+    cmd = (["gcc", "-O3", "-std=gnu11", "-ffp-contract=off", "-fcx-fortran-rules", "-fPIC",
+            "-shared", "-w", "-I" + os.path.join(REF, "src/jl")] + JL_FLAGS +
            ["-o", LIB_DROPIN, gen, os.path.join(HERE, "ref_harness.c")] +
            [os.path.join(REF, "src/jl", f) for f in JL] +
            ["-L" + PRODUCT_LIB_DIR, "-lnekcem_b200",

@@ -284,6 +284,10 @@ class Parser:
             return ("logical", 1 if v == ".true." else 0)
         if k == "op" and v == "(":
             e = self.expr()
+            if self.accept("op", ","):          # (re, im): complex constant
+                im = self.expr()
+                self.expect("op", ")")
+                return ("cplx", e, im)
             self.expect("op", ")")
             return ("paren", e)
         if k == "op" and v in "+-":
@@ -404,18 +408,22 @@ class Sym:
         self.data_unsupported = False
         self.init_list = None
         self.kind8 = False     # integer*8
+        self.gname = name      # name of the C global (COMMON variables)
 
     def ctype(self):
         if self.ftype == "integer" and self.kind8:
             return "long long"
-        return {"real": "double", "integer": "int", "logical": "int", "character": "char"}[self.ftype]
+        return {"real": "double", "integer": "int", "logical": "int", "character": "char",
+                "complex": "double _Complex"}[self.ftype]
 
 
 INTRINSICS = {"sqrt", "abs", "sin", "cos", "tan", "exp", "log", "log10", "atan", "atan2", "asin",
               "acos", "sinh", "cosh", "tanh", "max", "min", "mod", "real", "dble", "int", "nint",
               "float", "sign", "iand", "ior", "dsqrt", "dabs", "dsin", "dcos", "dexp", "dlog",
               "datan", "datan2", "dmax1", "dmin1", "amax1", "amin1", "max0", "min0", "iabs",
-              "modulo", "ishft", "ifix", "dfloat", "sngl", "aint", "anint", "floor", "ceiling"}
+              "modulo", "ishft", "ifix", "dfloat", "sngl", "aint", "anint", "floor", "ceiling",
+              "cexp", "csqrt", "clog", "cmplx", "dcmplx", "conjg", "aimag", "dimag", "imag",
+              "dreal", "cabs"}
 
 TYPE_RE = re.compile(r"^(real|integer|logical|character|double\s*precision|complex)\s*(\*\s*(\d+|\(\s*\*\s*\)))?\s*(.*)$")
 
@@ -428,6 +436,7 @@ class Unit:
         self.body = []         # (label, stmt) executable statements
         self.decl_order = []   # parameter names in order of definition
         self.common_blocks = {}
+        self.suffix = ""
 
     def sym(self, name):
         if name not in self.syms:
@@ -499,6 +508,7 @@ class Translator:
                 if wanted is None or cur.name in wanted:
                     cur.fname = cur.name          # Fortran name (function result variable)
                     cur.rename = {}
+                    cur.suffix = suffix
                     key = cur.name + suffix
                     self.units[key] = cur
                     self.order.append(key)
@@ -639,6 +649,10 @@ class Translator:
                             if d:
                                 sy = self.parse_declarator(u, d, kind="common", block=blk)
                                 sy.kind, sy.block = "common", blk
+                                if not from_inc and u.suffix:
+                                    # a COMMON of this .usr file: other .usr files reuse the
+                                    # block names with different layouts
+                                    sy.gname = sy.name + u.suffix
                                 names.append(sy.name)
                         u.common_blocks.setdefault(blk, []).extend(names)
                     continue
@@ -689,14 +703,20 @@ class Emitter:
             return "char"
         if k == "paren":
             return self.typ(u, e[1])
+        if k == "cplx":
+            return "double _Complex"
         if k == "un":
             return "int" if e[1] == "!" else self.typ(u, e[2])
         if k == "pow":
+            if "double _Complex" in (self.typ(u, e[1]), self.typ(u, e[2])):
+                return "double _Complex"
             return self.typ(u, e[1]) if self.typ(u, e[2]) == "int" else "double"
         if k == "bin":
             if e[1] in ("==", "!=", "<", "<=", ">", ">=", "&&", "||"):
                 return "int"
             a, b = self.typ(u, e[2]), self.typ(u, e[3])
+            if "double _Complex" in (a, b):
+                return "double _Complex"
             return "double" if "double" in (a, b) else ("long long" if "long long" in (a, b) else "int")
         if k == "var":
             sy = self.lookup(u, e[1])
@@ -710,12 +730,19 @@ class Emitter:
                 if name in ("int", "nint", "iand", "ior", "max0", "min0", "iabs", "ishft", "ifix",
                             "floor", "ceiling"):
                     return "int"
+                ts = [self.typ(u, a) for a in e[2]]
+                if name in ("cexp", "csqrt", "cmplx", "dcmplx", "conjg", "clog", "ccos", "csin"):
+                    return "double _Complex"
+                if name in ("exp", "sqrt", "log", "sin", "cos") and "double _Complex" in ts:
+                    return "double _Complex"
                 if name in ("max", "min", "mod", "abs", "sign", "modulo"):
-                    ts = [self.typ(u, a) for a in e[2]]
+                    if "double _Complex" in ts:
+                        return "double"
                     return "double" if "double" in ts else "int"
                 return "double"
             ft = (sy.ftype if sy and sy.ftype else implicit_type(name))
-            return {"real": "double", "integer": "int", "logical": "int"}.get(ft, "double")
+            return {"real": "double", "integer": "int", "logical": "int",
+                    "complex": "double _Complex"}.get(ft, "double")
         raise F2CError("typ: " + str(e))
 
     def lookup(self, u, name):
@@ -737,6 +764,7 @@ class Emitter:
             return "(*%s)" % self.vname(name)
         if sy.kind == "common":
             self.note_global(u, sy)
+            return self.vname(sy.gname)
         if sy.kind == "param":
             self.used_params.add(name)
         if u.kind == "function" and name == u.name:
@@ -744,9 +772,9 @@ class Emitter:
         return self.vname(name)
 
     def note_global(self, u, sy):
-        g = self.used_globals.get(sy.name)
+        g = self.used_globals.get(sy.gname)
         if g is None:
-            self.used_globals[sy.name] = (sy, u)
+            self.used_globals[sy.gname] = (sy, u)
             # dims may reference parameters
             if sy.dims:
                 for lo, hi in sy.dims:
@@ -823,6 +851,7 @@ class Emitter:
     def base(self, u, sy):
         if sy.kind == "common":
             self.note_global(u, sy)
+            return self.vname(sy.gname)
         return self.vname(sy.name)
 
     def ex(self, u, e):
@@ -846,10 +875,14 @@ class Emitter:
             return '"%s"' % e[1].replace("\\", "\\\\").replace('"', '\\"')
         if k == "paren":
             return "(%s)" % self.ex(u, e[1])
+        if k == "cplx":
+            return "CMPLX(%s,%s)" % (self.ex(u, e[1]), self.ex(u, e[2]))
         if k == "un":
             return "(%s%s)" % (e[1], self.ex(u, e[2]))
         if k == "pow":
             b, x = e[1], e[2]
+            if "double _Complex" in (self.typ(u, b), self.typ(u, x)):
+                return "cpow(%s,%s)" % (self.ex(u, b), self.ex(u, x))
             if self.typ(u, x) == "int":
                 if self.typ(u, b) == "int":
                     return "f_ipow(%s,%s)" % (self.ex(u, b), self.ex(u, x))
@@ -859,7 +892,18 @@ class Emitter:
             if e[1] in ("==", "!=") and "char" in (self.typ(u, e[2]), self.typ(u, e[3])):
                 (pa, la), (pb, lb) = self.chref(u, e[2]), self.chref(u, e[3])
                 return "(f_chcmp(%s,%d,%s,%d)%s0)" % (pa, la, pb, lb, e[1])
-            return "(%s%s%s)" % (self.ex(u, e[2]), e[1], self.ex(u, e[3]))
+            la, lb = self.ex(u, e[2]), self.ex(u, e[3])
+            ta, tb = self.typ(u, e[2]), self.typ(u, e[3])
+            if e[1] in ("+", "-", "*", "/") and (ta == "double _Complex") != (tb == "double _Complex"):
+                # Fortran converts the real operand to COMPLEX (x, 0.0) first and then applies the
+                # complex operation; C's mixed real/complex arithmetic skips the imaginary part of
+                # the real operand, which changes signed zeros (1.0 - (4.0,+0.0) is (-3.0,+0.0) in
+                # Fortran but (-3.0,-0.0) in C: the other side of csqrt's branch cut)
+                if ta != "double _Complex":
+                    la = "CMPLX((double)(%s),0.0)" % la
+                else:
+                    lb = "CMPLX((double)(%s),0.0)" % lb
+            return "(%s%s%s)" % (la, e[1], lb)
         if k == "var":
             sy = self.lookup(u, e[1])
             if sy.dims is not None:
@@ -891,6 +935,7 @@ class Emitter:
                 raise F2CError("character operand expected: %s in %s" % (e[1], u.name))
             if sy.kind == "common":
                 self.note_global(u, sy)
+                return self.vname(sy.gname), sy.charlen
             return self.vname(e[1]), sy.charlen
         if e[0] == "call":
             sy = u.syms.get(e[1])
@@ -903,6 +948,23 @@ class Emitter:
         a = [self.ex(u, x) for x in args]
         ts = [self.typ(u, x) for x in args]
         isd = "double" in ts
+        isc = "double _Complex" in ts
+        if name in ("cexp",) or (name == "exp" and isc):
+            return "cexp(%s)" % a[0]
+        if name in ("csqrt",) or (name == "sqrt" and isc):
+            return "csqrt(%s)" % a[0]
+        if name in ("clog",) or (name == "log" and isc):
+            return "clog(%s)" % a[0]
+        if name in ("cmplx", "dcmplx"):
+            return "CMPLX(%s,%s)" % (a[0], a[1] if len(a) > 1 else "0.0")
+        if name == "conjg":
+            return "conj(%s)" % a[0]
+        if name in ("aimag", "dimag", "imag"):
+            return "cimag(%s)" % a[0]
+        if isc and name in ("real", "dble", "dreal"):
+            return "creal(%s)" % a[0]
+        if isc and name in ("abs", "cabs"):
+            return "cabs(%s)" % a[0]
         one = {"sqrt": "sqrt", "dsqrt": "sqrt", "sin": "sin", "dsin": "sin", "cos": "cos", "dcos": "cos",
                "tan": "tan", "exp": "exp", "dexp": "exp", "log": "log", "dlog": "log", "log10": "log10",
                "atan": "atan", "datan": "atan", "asin": "asin", "acos": "acos", "sinh": "sinh",
@@ -1267,7 +1329,8 @@ class Emitter:
         for name, val, u in pnames:
             out.append("    if (!strcmp(name, \"%s\")) { *isint = 1; *count = 1; return &%s; }" % (name, self.vname(name)))
         for name, (sy, u) in sorted(self.used_globals.items()):
-            isint = 0 if sy.ftype == "real" else (2 if sy.ftype == "character" else (3 if sy.kind8 else 1))
+            isint = 0 if sy.ftype == "real" else (2 if sy.ftype == "character" else (
+                4 if sy.ftype == "complex" else (3 if sy.kind8 else 1)))
             if sy.ftype == "character":
                 n = "*".join("(long)(%s)" % self.extent(u, sy, d) for d in range(len(sy.dims))) if sy.dims else "1"
                 out.append("    if (!strcmp(name, \"%s\")) { *isint = 2; *count = (%s)*%d; return %s; }" %
@@ -1288,6 +1351,7 @@ class Emitter:
 
 
 PRELUDE = r"""/* GENERATED by oracle/f2c_lite.py from the reference's Fortran sources -- do not commit */
+#include <complex.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>

@@ -153,6 +153,9 @@ class ReferenceRun:
         isint = kind == 1
         if kind == 3:
             return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_longlong)), shape=(cnt,))
+        if kind == 4:   # complex (double _Complex)
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_double)),
+                                         shape=(2 * cnt,)).view(np.complex128)
         t = C.c_int if isint else C.c_double
         return np.ctypeslib.as_array(C.cast(p, C.POINTER(t)), shape=(cnt,))
 

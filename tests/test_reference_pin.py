@@ -515,9 +515,9 @@ def test_pin_3ddielectric_with_the_shipped_usr(twomat):
     _usr(L, "uservp", "3ddielectric")(C.byref(one), C.byref(one), C.byref(one), C.byref(one))
     assert np.array_equal(r.view("permittivity")[:c.npts], c.permittivity)
     assert np.array_equal(r.view("permeability")[:c.npts], c.permeability)
-    ninc = int(r.get("ninc"))
+    ninc = int(r.get("ninc__3ddielectric"))
     assert ninc == c.user.incindex.size
-    assert np.array_equal(r.view("incindex")[:ninc], c.user.incindex + 1)
+    assert np.array_equal(r.view("incindex__3ddielectric")[:ninc], c.user.incindex + 1)
     L.pml_calc_sigma_(_dp(r.view("pmlinner")), _dp(r.view("pmlouter")), ip(r.view("pmltag")),
                       C.byref(C.c_double(c.pmlorder)), C.byref(C.c_double(c.pmlreferr)))
     r.set("pmlorder", c.pmlorder); r.set("pmlreferr", c.pmlreferr)
@@ -575,18 +575,92 @@ def test_pin_drude_with_the_shipped_userinc_and_usersrc():
     r.put("ym1", c.ym1)
     n = c.npts
     # COMMON /userparam/ and /userincvars/ (drude.usr:20-30), /userdrude/ (:53-56)
-    r.set("omega", u.omega); r.set("k1", u.k1); r.set("eta1", u.eta1)
-    r.put("incindex", u.incindex + 1); r.set("ninc", u.incindex.size)
-    r.put("jn", u.jn); r.put("kjn", u.kjn)
-    r.put("drudeparams", u.params)
-    r.put("drudeindex", u.index + 1); r.set("ndrude", u.index.size)
+    # (the .usr's own COMMON blocks get per-file globals: <name>__drude)
+    r.set("omega__drude", u.omega); r.set("k1__drude", u.k1); r.set("eta1__drude", u.eta1)
+    r.put("incindex__drude", u.incindex + 1); r.set("ninc__drude", u.incindex.size)
+    r.put("jn__drude", u.jn); r.put("kjn__drude", u.kjn)
+    r.put("drudeparams__drude", u.params)
+    r.put("drudeindex__drude", u.index + 1); r.set("ndrude__drude", u.index.size)
     L.ref_set_user(0, C.cast(_usr(L, "userinc", "drude"), refrun.USERCB))
     L.ref_set_user(1, C.cast(_usr(L, "usersrc", "drude"), refrun.USERCB))
     c.step(40); r.step(40)
     num = np.sqrt(np.sum((c.hn - r.hn) ** 2) + np.sum((c.en - r.en) ** 2))
     den = np.sqrt(np.sum(c.hn ** 2) + np.sum(c.en ** 2))
     assert num / den <= 1e-13
-    j = r.view("jn")[:3 * n]
+    j = r.view("jn__drude")[:3 * n]
     assert np.abs(j).max() > 1e-3
     assert np.sqrt(np.sum((j - u.jn) ** 2)) / np.sqrt(np.sum(u.jn ** 2)) <= 1e-13
+    r.close()
+
+
+@pytest.mark.parametrize("kind", ["drude", "lorentz"])
+def test_pin_dispersive_case_with_its_whole_usr(kind):
+    """tests/drude and tests/lorentz driven entirely by their own .usr (complex arithmetic incl.
+    the csqrt branch choices, translated to C99 double _Complex): uservp (materials, ADE
+    parameter table, node list, incident-face index), userini -> usersol (initial fields, PML
+    fields, initial currents), userinc + usersrc in every stage, usersol at the end.  The integer
+    tables must equal the oracle's restatement exactly, the real ones to round-off."""
+    c = cases.case_drude() if kind == "drude" else cases.case_lorentz()
+    u = c.user
+    sfx = "__" + kind
+    r = refrun.ReferenceRun(c)
+    L = r.L
+    r.put("ym1", c.ym1); r.put("xm1", c.xm1)
+    # PML description the .usr's usersol reads (src/PML)
+    r.put("pmltag", c.pmltag); r.put("pmlinner", c.pmlinner); r.put("pmlouter", c.pmlouter)
+    r.set("pmlorder", c.pmlorder); r.set("pmlreferr", c.pmlreferr)
+    n, n3 = c.npts, 3 * c.npts
+    one = C.c_int(1)
+    r.view("permittivity")[:] = 0.0
+    _usr(L, "uservp", kind)(C.byref(one), C.byref(one), C.byref(one), C.byref(one))
+    assert np.array_equal(r.view("permittivity")[:n], c.permittivity)
+    assert np.array_equal(r.view("permeability")[:n], c.permeability)
+    idx_name, n_name, par_name = (("drudeindex", "ndrude", "drudeparams") if kind == "drude"
+                                  else ("lorentzindex", "nlorentz", "lorentzparams"))
+    nade = int(r.get(n_name + sfx))
+    assert nade == u.index.size
+    assert np.array_equal(r.view(idx_name + sfx)[:nade], u.index + 1)
+    assert np.array_equal(r.view(par_name + sfx)[:u.params.size], u.params)
+    ninc = int(r.get("ninc" + sfx))
+    assert ninc == u.incindex.size and np.array_equal(r.view("incindex" + sfx)[:ninc], u.incindex + 1)
+    # the complex material constants: same branch of the square roots
+    assert abs(r.view("eta2" + sfx)[0] - u.eta2) <= 1e-15 * abs(u.eta2)
+    assert abs(r.view("k2" + sfx)[0] - u.k2) <= 1e-15 * abs(u.k2)
+    assert abs(r.view("tran" + sfx)[0] - u.tran) <= 1e-15 * abs(u.tran)
+    # userini -> usersol
+    hn, en = r.view("hn"), r.view("en")
+    c0 = cases.case_drude() if kind == "drude" else cases.case_lorentz()   # pristine t=0 state
+    hn[:] = 0.0; en[:] = 0.0
+    tt = C.c_double(0.0)
+    _usr(L, "userini", kind)(C.byref(tt), _dp(hn[0:]), _dp(hn[n:]), _dp(hn[2 * n:]),
+                             _dp(en[0:]), _dp(en[n:]), _dp(en[2 * n:]))
+    scale = max(np.abs(c0.hn).max(), np.abs(c0.en).max())
+    assert np.abs(hn[:n3] - c0.hn).max() <= 1e-14 * scale
+    assert np.abs(en[:n3] - c0.en).max() <= 1e-14 * scale
+    j0 = r.view("jn" + sfx)[:c0.user.jn.size]
+    assert np.abs(j0 - c0.user.jn).max() <= 1e-13 * np.abs(c0.user.jn).max()
+    assert np.abs(r.view("pmldn")[:n3] - c0.pmldn).max() <= 1e-14 * scale
+    # time stepping with the .usr's userinc and usersrc
+    L.ref_set_user(0, C.cast(_usr(L, "userinc", kind), refrun.USERCB))
+    L.ref_set_user(1, C.cast(_usr(L, "usersrc", kind), refrun.USERCB))
+    c.step(40); r.step(40)
+    num = np.sqrt(np.sum((c.hn - hn[:n3]) ** 2) + np.sum((c.en - en[:n3]) ** 2))
+    den = np.sqrt(np.sum(c.hn ** 2) + np.sum(c.en ** 2))
+    assert num / den <= 1e-12
+    # the .usr's usersol at the end time agrees with the restatement; userchk tolerances hold
+    sol = [np.zeros(n) for _ in range(6)]
+    tt = C.c_double(c.time)
+    _usr(L, "usersol", kind)(C.byref(tt), *[_dp(a) for a in sol])
+    mh, me = u.usersol(c, c.time)
+    for k in range(3):
+        assert np.abs(sol[k] - c.comp(mh, k)).max() <= 1e-14 * scale
+        assert np.abs(sol[3 + k] - c.comp(me, k)).max() <= 1e-14 * scale
+    r.set("volvm1", c.volvm1)
+    err = np.zeros(n)
+    nn = C.c_int(n)
+    for k in (2, 3, 4):                                  # hz, ex, ey (drude.usr userchk)
+        fld = np.ascontiguousarray(c.comp(c.hn if k < 3 else c.en, k % 3))
+        l2, linf = C.c_double(), C.c_double()
+        L.cem_error_(_dp(fld), _dp(sol[k]), _dp(err), C.byref(nn), C.byref(l2), C.byref(linf))
+        assert l2.value <= c.tol["l2"][k] and linf.value <= c.tol["linf"][k]
     r.close()
