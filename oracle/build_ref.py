@@ -33,7 +33,9 @@ UNITS = [
         "cem_maxwell_restrict_to_face", "cem_maxwell_flux", "cem_maxwell_flux2d",
         "cem_maxwell_flux3d", "cem_maxwell_flux_pec", "cem_maxwell_add_flux_to_res",
         "cem_maxwell_invqmass", "rk_maxwell_ab", "cem_maxwell_drude", "cem_maxwell_lorentz",
-        "cem_maxwell_materials", "cem_maxwell_pec_init"]),
+        "cem_maxwell_materials", "cem_maxwell_pec_init",
+        # graphene sheets: surface-current ADEs called from the .usr's userfsrc (8f rank 1/4)
+        "cem_3d_graphene_current", "cem_te_graphene_current", "cem_tm_graphene_current"]),
     ("src/cem_maxwell_pml.F", ["pml_step", "pml_faces", "march_faces", "pml_fill_faceary",
                                "dir_local_to_global", "pml_extent_and_tags", "pml_calc_sigma"]),
     ("src/cem_common.F", ["rk_c", "rk4_upd", "rk_storage", "cem_set_fc_ptr", "cem_error"]),
@@ -73,6 +75,10 @@ UNITS = [
     ("tests/drude/drude.usr", ["userinc", "usersrc", "usersol", "userini", "uservp"], "__drude"),
     ("tests/lorentz/lorentz.usr", ["userinc", "usersrc", "usersol", "userini", "uservp"],
      "__lorentz"),
+    ("tests/3dgraphene/3dgraphene.usr", ["userinc", "userfsrc", "usersol", "userini", "uservp",
+                                         "usrdat2"], "__3dgraphene"),
+    ("tests/2dgraphene/2dgraphene.usr", ["userinc", "userfsrc", "usersol", "userini", "uservp",
+                                         "usrdat2"], "__2dgraphene"),
 ]
 # reference gather-scatter library, compiled unchanged (flags of bin/configurenek:132-139
 # without -DMPI: single process)

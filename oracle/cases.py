@@ -561,6 +561,240 @@ def case_lorentz(nx1=9, nel=(4, 32), thick=6):
 
 
 # ------------------------------------------------------------------------------------
+# tests/3dgraphene, tests/2dgraphene : plane wave(s) onto a flat graphene sheet at y = 0; the
+# sheet is a surface current advanced by face-point ADEs inside userfsrc
+# ------------------------------------------------------------------------------------
+class _Graphene:
+    """tests/3dgraphene/3dgraphene.usr and tests/2dgraphene/2dgraphene.usr (uservp, usrdat2,
+    userinc, userini, usersol, userfsrc).  imode: 3 = 3D (TE and TM waves superimposed),
+    1 = 2D TE, 2 = 2D TM."""
+
+    # graphene parameters (3dgraphene.usr:326-337): Drude term + two critical-point terms
+    PARAMS = (0.000e+00, 1.499e+00, -2.599e-03, 4.632e+05, 1.090e+03, -1.391e+00, -3.125e+02,
+              -1.049e-03, 4.271e+05, 2.742e+02, -7.769e-02, 4.268e+02)
+
+    def __init__(self, imode: int):
+        self.imode = imode
+        self.omega = om = 5.0
+        self.eps1 = self.eps2 = self.mu1 = self.mu2 = 1.0
+        (a_d, b_d, b_cp1, a_211, a_221, b_11, b_21, b_cp2, a_212, a_222, b_12,
+         b_22) = self.PARAMS
+        CI = 1j
+        csigma_d = b_d / (a_d - CI * om)
+        csigma_cp1 = (CI / om) * ((a_211 * b_11 + CI * om * b_21)
+                                  / (om ** 2 - a_211 + CI * om * a_221) + b_11) - b_cp1
+        csigma_cp2 = (CI / om) * ((a_212 * b_12 + CI * om * b_22)
+                                  / (om ** 2 - a_212 + CI * om * a_222) + b_12) - b_cp2
+        self.sigmagraph = sg = csigma_d + csigma_cp1 + csigma_cp2
+        z1 = math.sqrt(self.mu1 / self.eps1)
+        z2 = math.sqrt(self.mu2 / self.eps2)
+        self.z1 = z1
+        self.reflte = (z1 - z2 + sg * z1 * z2) / (z1 + z2 + sg * z1 * z2)
+        self.trante = 2 * z1 / (z1 + z2 + sg * z1 * z2)
+        self.refltm = (z2 - z1 - z1 * z2 * sg) / (z1 + z2 + z1 * z2 * sg)
+        self.trantm = 2 * z2 / (z1 + z2 + z1 * z2 * sg)
+        self.te = imode in (3, 1)  # which of the two polarisations are present
+        self.tm = imode in (3, 2)
+
+    def usrdat2(self, case):
+        arrs = (case.xm1, case.ym1, case.zm1) if case.ldim == 3 else (case.xm1, case.ym1)
+        for arr, s in zip(arrs, (5.0, 10.0, 5.0)):
+            mn, mx = arr.min(), arr.max()
+            arr[:] = s * (arr - mn) / (mx - mn) - (s / 2.0)
+
+    def _mid(self, case):
+        h = case.nx1 // 2 - 1
+        n = case.nx1
+        return h + n * h + (n * n * h if case.ldim == 3 else 0)
+
+    def uservp(self, case):
+        ym = case.ym1.reshape(case.nelt, case.nxyz)
+        upper = ym[:, self._mid(case)] > 0
+        self.upper = upper
+        case.permittivity[:] = np.repeat(np.where(upper, self.eps1, self.eps2), case.nxyz)
+        case.permeability[:] = np.repeat(np.where(upper, self.mu1, self.mu2), case.nxyz)
+        inc, gr = [], []
+        for e in range(case.nelt):
+            markinc = True  # 2D: set once per element (2dgraphene.usr:397-398)
+            for f in range(case.nfaces):
+                base = e * case.nxzf * case.nfaces + case.nxzf * f
+                js = np.arange(base, base + case.nxzf)
+                onsheet = not np.any(np.abs(case.ym1[case.cemface[js]]) > 1e-8)
+                if upper[e]:
+                    if case.ldim == 3:
+                        markinc = True  # 3D: reset per face (3dgraphene.usr:370)
+                    if not onsheet:
+                        markinc = False
+                    if markinc:
+                        inc.extend(js.tolist())
+                if onsheet:
+                    gr.extend(js.tolist())
+        self.incindex = np.array(inc, dtype=np.int64)
+        self.graphindex = np.array(gr, dtype=np.int32)  # 0-based face points
+        nf = case.nxzfl
+        self.graphparams = np.zeros(12 * nf)
+        for q, v in enumerate(self.PARAMS):
+            self.graphparams[q * nf + self.graphindex] = v
+        self.fjn = np.zeros(18 * nf); self.kfjn = np.zeros(18 * nf); self.resfjn = np.zeros(18 * nf)
+
+    def _inc_amp(self, eta):
+        """amplitudes of userinc per component (hx,hy,hz,ex,ey,ez) for a unit uinc"""
+        amp = np.zeros((6,) + np.shape(eta))
+        if self.te:
+            amp[2] = 1.0; amp[3] = eta
+        if self.tm:
+            amp[5] = 1.0; amp[0] = -1.0 / eta
+        return amp
+
+    def userinc(self, case):
+        j = self.incindex
+        k = case.cemface[j]
+        eps = case.permittivity[k]; mu = case.permeability[k]
+        eta = np.sqrt(mu / eps)
+        ky = self.omega * np.sqrt(mu * eps)
+        yy = case.ym1[k]
+
+        def cb(tt, fhx, fhy, fhz, fex, fey, fez):
+            uinc = np.cos(-ky * yy - self.omega * tt)
+            if self.te:
+                fhz[j] = fhz[j] + uinc
+                fex[j] = fex[j] + eta * uinc
+            if self.tm:
+                fez[j] = fez[j] + uinc
+                fhx[j] = fhx[j] - uinc / eta
+
+        return cb
+
+    def incident(self, case):
+        """the same userinc as arguments of MaxwellB200.set_incident"""
+        j = self.incindex
+        k = case.cemface[j]
+        eps = case.permittivity[k]; mu = case.permeability[k]
+        eta = np.sqrt(mu / eps)
+        ky = self.omega * np.sqrt(mu * eps)
+        return j, self._inc_amp(eta), -ky * case.ym1[k], self.omega
+
+    def usersol(self, case, tt):
+        n = case.npts
+        eps = case.permittivity; mu = case.permeability
+        eta = np.sqrt(mu / eps)
+        ky = self.omega * np.sqrt(eps * mu)
+        yy = case.ym1
+        upper = np.repeat(self.upper, case.nxyz)
+        inpml = np.repeat(case.pmltag != 0, case.nxyz)
+        order, referr = case.pmlorder, case.pmlreferr
+        d = case.pmlouter[3] - case.pmlinner[3]
+        smax = -(order + 1) * math.log(referr) / (2 * eta * d)
+        with np.errstate(invalid="ignore"):
+            fu = (smax * d / (order + 1)) * ((yy - case.pmlinner[3]) / d) ** (order + 1)
+        d2 = case.pmlinner[2] - case.pmlouter[2]
+        smax2 = -(order + 1) * math.log(referr) / (2 * eta * d2)
+        with np.errstate(invalid="ignore"):
+            fl = (smax2 * d2 / (order + 1)) * ((case.pmlinner[2] - yy) / d2) ** (order + 1)
+        pmlfac = np.where(inpml, np.where(upper, fu, fl), 0.0)
+        uu_u = np.exp(1j * (ky * yy - self.omega * tt) - eta * pmlfac)
+        uu_l = np.exp(1j * (-ky * yy - self.omega * tt) - eta * pmlfac)
+        shn = np.zeros(3 * n); sen = np.zeros(3 * n)
+        if self.te:
+            r, t = self.reflte, self.trante
+            shn[2 * n:] = np.where(upper, (r * uu_u).real, (t * uu_l).real)                # hz
+            sen[0:n] = np.where(upper, -(r * eta * uu_u).real, (t * eta * uu_l).real)      # ex
+        if self.tm:
+            r, t = self.refltm, self.trantm
+            sen[2 * n:] = np.where(upper, (r * uu_u).real, (t * uu_l).real)                # ez
+            shn[0:n] = np.where(upper, (r * uu_u / eta).real, -(t * uu_l / eta).real)      # hx
+        return shn, sen
+
+    def userini(self, case):
+        n = case.npts
+        shn, sen = self.usersol(case, 0.0)
+        case.hn[:] = shn; case.en[:] = sen
+        for k in range(3):
+            case.pmlbn[k * n:(k + 1) * n] = case.permeability * shn[k * n:(k + 1) * n]
+            case.pmldn[k * n:(k + 1) * n] = case.permittivity * sen[k * n:(k + 1) * n]
+        # currents: 1/2 of the parallel part of the complex E field at the interface
+        enpar = [0.5 * self.z1 * (1.0 - self.reflte) if self.te else 0.0, 0.0,
+                 0.5 * (1.0 + self.refltm) if self.tm else 0.0]
+        nf = case.nxzfl
+        j = self.graphindex
+        P = lambda q: self.graphparams[q * nf + j]
+        om = self.omega
+        CI = 1j
+
+        def put(c, q, val):  # fjn(j, c+1, q+1)
+            self.fjn[(c + 3 * q) * nf + j] = val
+
+        fac_d = P(1) / (P(0) - CI * om)
+        fac_14 = (P(3) * P(5) + CI * om * P(6)) / (om ** 2 - P(3) + CI * om * P(4))
+        fac_13 = (CI / om) * (fac_14 + P(5))
+        fac_16 = (P(8) * P(10) + CI * om * P(11)) / (om ** 2 - P(8) + CI * om * P(9))
+        fac_15 = (CI / om) * (fac_16 + P(10))
+        for c in range(3):
+            put(c, 1, (fac_d * enpar[c]).real)
+            put(c, 3, (fac_14 * enpar[c]).real)
+            put(c, 2, (fac_13 * enpar[c]).real)
+            put(c, 5, (fac_16 * enpar[c]).real)
+            put(c, 4, (fac_15 * enpar[c]).real)
+
+    def userfsrc(self, case):
+        """userfsrc of the .usr: advance the sheet currents, then srcfh(c) -= fjn(j,c,1)"""
+        import ctypes as C
+        j = self.graphindex
+        nf = case.nxzfl
+        comps = (0, 1, 2) if self.imode == 3 else ((0, 1) if self.imode == 1 else (2,))
+
+        def cb(tt, srcfhx, srcfhy, srcfhz, srcfex, srcfey, srcfez):
+            case.L.ora_cem_graphene_current(C.byref(case.s), O.dp(self.fjn), O.dp(self.kfjn),
+                                            O.dp(self.resfjn), O.dp(self.graphparams),
+                                            O.dp(case.yconduc), O.ip(self.graphindex),
+                                            int(j.size))
+            src = (srcfhx, srcfhy, srcfhz)
+            for c in comps:
+                src[c][j] = src[c][j] - self.fjn[c * nf + j]
+
+        return cb
+
+
+def _case_graphene(imode, nx1, nel, box, param, dt):
+    ldim = 3 if imode == 3 else 2
+    bcs = ("P  ", "P  ", "PML", "PML", "P  ", "P  ")[:2 * ldim]
+    mesh = O.box_mesh(nel, (box,) * ldim, bcs)
+    u = _Graphene(imode)
+    c = O.RefCase(mesh, nx1, imode=None if ldim == 3 else imode, upwind=True,
+                  usrdat2=u.usrdat2, uservp=u.uservp, param=param)
+    c.user = u
+    c.set_dt(dt)
+    c.usersol = lambda case, tt: u.usersol(case, tt)
+    u.userini(c)
+    c.set_callback("userinc", u.userinc(c))
+    c.set_callback("userfsrc", u.userfsrc(c))
+    c.nsteps = 1000
+    return c
+
+
+def case_3dgraphene(nx1=9, nel=(4, 12, 4)):
+    """tests/3dgraphene (.box 4x12x4 on [-1,1]^3 rescaled to 5x10x5, BC P,P,PML,PML,P,P; N=8;
+    dt=5e-3; 1000 steps; PML thick 2, order 3, referr 1e-10).  Tolerances 5e-4 / 5e-3 on
+    hx,hz,ex,ez and 1e-14 / 5e-12 on hy,ey (3dgraphene.usr userchk)."""
+    c = _case_graphene(3, nx1, nel, (-1.0, 1.0), {77: 2, 78: 3.0, 79: 1e-10}, -0.005)
+    c.tol = dict(l2=[5e-4, 1e-14, 5e-4, 5e-4, 1e-14, 5e-4],
+                 linf=[5e-3, 5e-12, 5e-3, 5e-3, 5e-12, 5e-3])
+    return c
+
+
+def case_2dgraphene(imode=1, nx1=9, nel=(4, 32)):
+    """tests/2dgraphene (.box 4x32 on [-1500,1500]^2 rescaled to 5x10, BC P,P,PML,PML; N=8;
+    param(12)=+0.2 -> CFL dt; 1000 steps; PML thick 6, order 3, referr 1e-15).  TE: 1e-7 / 5e-6 on
+    hz, ex and 1e-14 / 5e-13 on ey; TM: the same on hx, ez / hy (2dgraphene.usr userchk)."""
+    c = _case_graphene(imode, nx1, nel, (-1500.0, 1500.0), {77: 6, 78: 3.0, 79: 1e-15}, 0.2)
+    if imode == 1:
+        c.tol = dict(l2=[0, 0, 1e-7, 1e-7, 1e-14, 0], linf=[0, 0, 5e-6, 5e-6, 5e-13, 0])
+    else:
+        c.tol = dict(l2=[1e-7, 1e-14, 0, 0, 0, 1e-7], linf=[5e-6, 5e-13, 0, 0, 0, 5e-6])
+    return c
+
+
+# ------------------------------------------------------------------------------------
 # rotated elements: the same physical mesh with every element's local (r,s,t) frame turned by
 # one of the 24 proper rotations -- neighbouring face lattices then run in different directions,
 # which is what unstructured meshes (tests/cylwave, graphene) look like to the face pairing

@@ -1239,6 +1239,70 @@ ORA_API void ora_cem_maxwell_lorentz(ora_state *s, double *jn, double *kjn, doub
         ora_rk4_upd(jn + q * np, kjn + q * np, resjn + q * np, cb, ca, s->dt, s->npts);
 }
 
+/* cem_3d_graphene_current / cem_te_graphene_current / cem_tm_graphene_current
+ * src/cem_maxwell.F:2827-2931, 2933-3022, 3024-3093 (which one: s->imode, as the shipped
+ * userfsrc of tests/3dgraphene and tests/2dgraphene selects it).  fjn,kfjn,resfjn: (nxzfl,3,6);
+ * params: (nxzfl,12); gindex: 0-based face points; yconduc: own-side conductance restricted to
+ * the faces (src/cem_maxwell.F:285, COMMON /EMWAVE/).  Called from the user's userfsrc like the
+ * reference: slot 1 of fjn is the algebraic total surface current the caller then subtracts from
+ * its -(n x H) face source. */
+ORA_API void ora_cem_graphene_current(ora_state *s, double *fjn, double *kfjn, double *resfjn,
+                                      const double *params, const double *yconduc,
+                                      const int *gindex, int n)
+{
+    size_t nf = s->nxzfl;
+    const double *unx = s->unxm, *uny = s->unym, *unz = s->unzm;
+#define FJ(a, c, q) ((a)[(size_t)j + nf * ((c) + 3 * (q))]) /* (j, c+1, q+1) */
+#define PAR(q) (params[(size_t)j + nf * (q)])
+    const int c0 = s->imode == 2 ? 2 : 0, c1 = s->imode == 1 ? 2 : 3; /* active components */
+#pragma omp parallel for
+    for (int i = 0; i < n; i++) {
+        int j = gindex[i];
+        double a_d = PAR(0), b_d = PAR(1), b_cp1 = PAR(2), a_211 = PAR(3), a_221 = PAR(4),
+               b_11 = PAR(5), b_21 = PAR(6), b_cp2 = PAR(7), a_212 = PAR(8), a_222 = PAR(9),
+               b_12 = PAR(10), b_22 = PAR(11);
+        double nH[3] = {0, 0, 0}, nEn[3] = {0, 0, 0};
+        if (s->imode == 3) {
+            nH[0] = -uny[j] * FHN(2)[j] + unz[j] * FHN(1)[j];
+            nH[1] = unx[j] * FHN(2)[j] - unz[j] * FHN(0)[j];
+            nH[2] = -unx[j] * FHN(1)[j] + uny[j] * FHN(0)[j];
+            double ndotE = unx[j] * FEN(0)[j] + uny[j] * FEN(1)[j] + unz[j] * FEN(2)[j];
+            nEn[0] = FEN(0)[j] - unx[j] * ndotE;
+            nEn[1] = FEN(1)[j] - uny[j] * ndotE;
+            nEn[2] = FEN(2)[j] - unz[j] * ndotE;
+        } else if (s->imode == 1) { /* TE :2969-2976 */
+            nH[0] = -uny[j] * FHN(2)[j];
+            nH[1] = unx[j] * FHN(2)[j];
+            nEn[0] = (uny[j] * uny[j]) * FEN(0)[j] - unx[j] * uny[j] * FEN(1)[j];
+            nEn[1] = (unx[j] * unx[j]) * FEN(1)[j] - unx[j] * uny[j] * FEN(0)[j];
+        } else { /* TM :3061-3065: n x (E x n) = E */
+            nH[2] = -unx[j] * FHN(1)[j] + uny[j] * FHN(0)[j];
+            nEn[2] = FEN(2)[j];
+        }
+        double Yfac = 0.5 / s->Y_0[j];
+        double cpfac = b_cp1 + b_cp2;
+        double jnfac = 1.0 - cpfac * Yfac;
+        for (int c = c0; c < c1; c++) {
+            double tmp = Yfac * (nH[c] + yconduc[j] * nEn[c]);
+            FJ(fjn, c, 0) = (FJ(fjn, c, 1) + FJ(fjn, c, 2) + FJ(fjn, c, 4) - cpfac * tmp) / jnfac;
+            double f = tmp - Yfac * FJ(fjn, c, 0);
+            FJ(resfjn, c, 1) = -a_d * FJ(fjn, c, 1) + b_d * f;
+            FJ(resfjn, c, 2) = FJ(fjn, c, 3) + b_11 * f;
+            FJ(resfjn, c, 3) = -a_211 * FJ(fjn, c, 2) - a_221 * FJ(fjn, c, 3) + b_21 * f;
+            FJ(resfjn, c, 4) = FJ(fjn, c, 5) + b_12 * f;
+            FJ(resfjn, c, 5) = -a_212 * FJ(fjn, c, 4) - a_222 * FJ(fjn, c, 5) + b_22 * f;
+        }
+    }
+#undef FJ
+#undef PAR
+    double ca = s->rk4a[s->rkstep - 1], cb = s->rk4b[s->rkstep - 1];
+    for (int q = 1; q < 6; q++)
+        for (int c = c0; c < c1; c++) {
+            size_t o = nf * (c + 3 * q);
+            ora_rk4_upd(fjn + o, kfjn + o, resfjn + o, cb, ca, s->dt, s->nxzfl);
+        }
+}
+
 /* cem_maxwell_op src/cem_maxwell.F:484-508 */
 ORA_API void ora_cem_maxwell_op(ora_state *s)
 {

@@ -103,6 +103,7 @@ def lib():
         L.ora_rk4_upd.argtypes = [c_dp, c_dp, c_dp, C.c_double, C.c_double, C.c_double, C.c_int]
         L.ora_cem_maxwell_drude.argtypes = [sp, c_dp, c_dp, c_dp, c_dp, c_ip, C.c_int]
         L.ora_cem_maxwell_lorentz.argtypes = [sp, c_dp, c_dp, c_dp, c_dp, c_ip, C.c_int]
+        L.ora_cem_graphene_current.argtypes = [sp, c_dp, c_dp, c_dp, c_dp, c_dp, c_ip, C.c_int]
         L.ora_cem_error.argtypes = [c_dp, c_dp, c_dp, C.c_int, c_dp, C.c_double, c_dp, c_dp]
         L.ora_get_dxmin.argtypes = [C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp]
         L.ora_get_dxmin.restype = C.c_double
@@ -560,6 +561,7 @@ class RefCase:
         Z_0 = 0.5 * Z_0
         Y_0 = 0.5 * Y_0
         self.Y_0, self.Y_1, self.Z_0, self.Z_1 = Y_0, Y_1, Z_0, Z_1
+        self.yconduc = yconduc  # COMMON /EMWAVE/ yconduc: read by the graphene currents
 
     # -- PML setup -----------------------------------------------------------------------
     def _march_faces(self, faceary):

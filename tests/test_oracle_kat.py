@@ -100,3 +100,25 @@ def test_kat_lorentz():
     _check(c, list(range(1, 11)) + list(range(100, 401, 100)), 400)
     n = c.npts
     assert np.max(np.abs(c.user.jn[3 * n:4 * n])) > 1e-3  # the polarisation variable too
+
+
+@pytest.mark.parametrize("imode", [1, 2])
+def test_kat_2dgraphene(imode):
+    """tests/2dgraphene TE (param(4)=1) and TM (=2): 4x32 elements, N=8, CFL 0.2, PML in +-y,
+    plane wave onto a graphene sheet at y=0 whose surface current (Drude + two critical-point
+    terms) is advanced per face point by userfsrc -> cem_te/tm_graphene_current; 1e-7 / 5e-6 on
+    the two wave components and 1e-14 / 5e-13 on the zero one, userchk at steps 1..10 and every
+    100 (2dgraphene.usr userchk).  All 1000 steps."""
+    c = cases.case_2dgraphene(imode)
+    assert c.nelt == 128 and c.user.graphindex.size == 8 * 9 and c.user.incindex.size == 4 * 9
+    _check(c, list(range(1, 11)) + list(range(100, 1001, 100)), 1000)
+    assert np.max(np.abs(c.user.fjn)) > 1e-2  # the sheet carries current
+
+
+def test_kat_3dgraphene():
+    """tests/3dgraphene: 4x12x4 elements, N=8, dt=5e-3, TE and TM waves superimposed; 5e-4 / 5e-3
+    on hx,hz,ex,ez and 1e-14 / 5e-12 on hy,ey (3dgraphene.usr:483-495), iocomm = 50.  300 of the
+    1000 steps (the error is periodic; the full run was checked once: max L2 1.8e-4, hy 6.5e-15)."""
+    c = cases.case_3dgraphene()
+    assert c.nelt == 192 and c.user.graphindex.size == 32 * 81 and c.user.incindex.size == 16 * 81
+    _check(c, list(range(1, 11)) + list(range(50, 301, 50)), 300)

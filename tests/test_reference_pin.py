@@ -664,3 +664,139 @@ def test_pin_dispersive_case_with_its_whole_usr(kind):
         L.cem_error_(_dp(fld), _dp(sol[k]), _dp(err), C.byref(nn), C.byref(l2), C.byref(linf))
         assert l2.value <= c.tol["l2"][k] and linf.value <= c.tol["linf"][k]
     r.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# graphene sheets (SURVEY.md 8f rank 1 userfsrc / rank 4 surface-current ADEs):
+# cem_3d/te/tm_graphene_current (src/cem_maxwell.F:2827-3093) and the .usr files that call them
+# ---------------------------------------------------------------------------------------------
+def _graphene_case(which, small=True):
+    if which == "3dgraphene":
+        return cases.case_3dgraphene(nel=(3, 12, 3) if small else (4, 12, 4))
+    return cases.case_2dgraphene(1 if which.endswith("te") else 2)
+
+
+_GRAPHENE = ["3dgraphene", "2dgraphene-te", "2dgraphene-tm"]
+
+
+@pytest.mark.parametrize("which", _GRAPHENE)
+def test_pin_graphene_current(which):
+    """the oracle's restatement of the three graphene-current routines equals the translated
+    reference bit for bit: fields, RK registers, PML state, and the sheet currents fjn/kfjn;
+    userfsrc is a test-side callback calling the reference's routine on its own arrays"""
+    c = _graphene_case(which)
+    u = c.user
+    r = refrun.ReferenceRun(c)
+    r.put("yconduc", c.yconduc)
+    r.set_callback("userinc", u.userinc(c))
+    fjn, kfjn, resfjn = u.fjn.copy(), u.kfjn.copy(), u.resfjn.copy()
+    params = u.graphparams.copy()
+    gidx = (u.graphindex + 1).astype(np.int32)
+    n = C.c_int(gidx.size)
+    fn = {3: r.L.cem_3d_graphene_current_, 1: r.L.cem_te_graphene_current_,
+          2: r.L.cem_tm_graphene_current_}[c.imode]
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    nf = c.nxzfl
+    comps = {3: (0, 1, 2), 1: (0, 1), 2: (2,)}[c.imode]
+    j = u.graphindex
+
+    def userfsrc(tt, shx, shy, shz, sex, sey, sez):  # 3dgraphene.usr:236-266
+        fn(dp(fjn), dp(kfjn), dp(resfjn), dp(params), gidx.ctypes.data_as(C.POINTER(C.c_int)),
+           C.byref(n))
+        src = (shx, shy, shz)
+        for q in comps:
+            src[q][j] = src[q][j] - fjn[q * nf + j]
+
+    r.set_callback("userfsrc", userfsrc)
+    c.step(20); r.step(20)
+    _assert_same(c, r)
+    assert np.array_equal(u.fjn, fjn) and np.array_equal(u.kfjn, kfjn)
+    assert np.abs(fjn).max() > 1e-3 and np.abs(kfjn).max() > 0
+    r.close()
+
+
+@pytest.mark.parametrize("which", _GRAPHENE)
+def test_pin_graphene_case_with_its_whole_usr(which):
+    """tests/3dgraphene and tests/2dgraphene (TE, TM) driven entirely by their own .usr: usrdat2,
+    uservp (materials, complex sheet conductivity, reflection / transmission coefficients,
+    incident-face and graphene-face index, parameter table), userini -> usersol (fields, PML
+    fields, initial sheet currents), userinc + userfsrc in every stage, usersol at the end and
+    the userchk tolerances evaluated by the reference's cem_error."""
+    c = _graphene_case(which)
+    u = c.user
+    kind = which.split("-")[0]
+    sfx = "__" + kind
+    r = refrun.ReferenceRun(c)
+    L = r.L
+    r.put("xm1", c.xm1); r.put("ym1", c.ym1)
+    if c.ldim == 3:
+        r.put("zm1", c.zm1)
+    r.put("yconduc", c.yconduc)
+    r.put("pmltag", c.pmltag); r.put("pmlinner", c.pmlinner); r.put("pmlouter", c.pmlouter)
+    r.set("pmlorder", c.pmlorder); r.set("pmlreferr", c.pmlreferr)
+    try:
+        r.set("if3d", int(c.ldim == 3))
+    except KeyError:
+        pass
+    n, n3, nf = c.npts, 3 * c.npts, c.nxzfl
+    one = C.c_int(1)
+    r.view("permittivity")[:] = 0.0
+    _usr(L, "uservp", kind)(C.byref(one), C.byref(one), C.byref(one), C.byref(one))
+    assert np.array_equal(r.view("permittivity")[:n], c.permittivity)
+    assert np.array_equal(r.view("permeability")[:n], c.permeability)
+    ng = int(r.get("ngraph" + sfx))
+    assert ng == u.graphindex.size
+    assert np.array_equal(r.view("graphindex" + sfx)[:ng], u.graphindex + 1)
+    assert np.array_equal(r.view("graphparams" + sfx)[:12 * nf], u.graphparams)
+    ninc = int(r.get("ninc" + sfx))
+    assert ninc == u.incindex.size and np.array_equal(r.view("incindex" + sfx)[:ninc], u.incindex + 1)
+    assert abs(r.view("sigmagraph" + sfx)[0] - u.sigmagraph) <= 4e-16 * abs(u.sigmagraph)
+    if kind == "3dgraphene":
+        coefs = (("reflte", u.reflte), ("trante", u.trante), ("refltm", u.refltm), ("trantm", u.trantm))
+    else:
+        coefs = ((("refl", u.reflte), ("tran", u.trante)) if c.imode == 1
+                 else (("refl", u.refltm), ("tran", u.trantm)))
+    for name, val in coefs:
+        assert abs(r.view(name + sfx)[0] - val) <= 4e-16 * abs(val), name
+    # userini -> usersol
+    hn, en = r.view("hn"), r.view("en")
+    c0 = _graphene_case(which)  # pristine t=0 state
+    hn[:] = 0.0; en[:] = 0.0
+    tt = C.c_double(0.0)
+    _usr(L, "userini", kind)(C.byref(tt), _dp(hn[0:]), _dp(hn[n:]), _dp(hn[2 * n:]),
+                             _dp(en[0:]), _dp(en[n:]), _dp(en[2 * n:]))
+    scale = max(np.abs(c0.hn).max(), np.abs(c0.en).max())
+    assert np.abs(hn[:n3] - c0.hn).max() <= 1e-14 * scale
+    assert np.abs(en[:n3] - c0.en).max() <= 1e-14 * scale
+    f0 = r.view("fjn" + sfx)[:18 * nf]
+    assert np.abs(f0 - c0.user.fjn).max() <= 1e-13 * np.abs(c0.user.fjn).max()
+    assert np.abs(r.view("pmldn")[:n3] - c0.pmldn).max() <= 1e-14 * scale
+    assert np.abs(r.view("pmlbn")[:n3] - c0.pmlbn).max() <= 1e-14 * scale
+    # time stepping with the .usr's userinc and userfsrc
+    L.ref_set_user(0, C.cast(_usr(L, "userinc", kind), refrun.USERCB))
+    L.ref_set_user(2, C.cast(_usr(L, "userfsrc", kind), refrun.USERCB))
+    c.step(40); r.step(40)
+    num = np.sqrt(np.sum((c.hn - hn[:n3]) ** 2) + np.sum((c.en - en[:n3]) ** 2))
+    den = np.sqrt(np.sum(c.hn ** 2) + np.sum(c.en ** 2))
+    assert num / den <= 1e-12
+    fj = r.view("fjn" + sfx)[:18 * nf]
+    assert np.sqrt(np.sum((fj - u.fjn) ** 2)) <= 1e-12 * np.sqrt(np.sum(u.fjn ** 2))
+    # the .usr's usersol at the end time agrees with the restatement; userchk tolerances hold
+    sol = [np.zeros(n) for _ in range(6)]
+    tt = C.c_double(c.time)
+    _usr(L, "usersol", kind)(C.byref(tt), *[_dp(a) for a in sol])
+    mh, me = u.usersol(c, c.time)
+    for k in range(3):
+        assert np.abs(sol[k] - c.comp(mh, k)).max() <= 1e-14 * scale
+        assert np.abs(sol[3 + k] - c.comp(me, k)).max() <= 1e-14 * scale
+    r.set("volvm1", c.volvm1)
+    err = np.zeros(n)
+    nn = C.c_int(n)
+    for k in range(6):
+        if c.tol["l2"][k] == 0:
+            continue
+        fld = np.ascontiguousarray(c.comp(c.hn if k < 3 else c.en, k % 3))
+        l2, linf = C.c_double(), C.c_double()
+        L.cem_error_(_dp(fld), _dp(sol[k]), _dp(err), C.byref(nn), C.byref(l2), C.byref(linf))
+        assert l2.value <= c.tol["l2"][k] and linf.value <= c.tol["linf"][k], (k, l2.value, linf.value)
+    r.close()
