@@ -26,7 +26,7 @@ module nekcem_b200
        NKB_HN = 22, NKB_EN = 23, NKB_KHN = 24, NKB_KEN = 25,                      &
        NKB_PERMITTIVITY = 26, NKB_PERMEABILITY = 27, NKB_PMLSIGMA = 28,           &
        NKB_PMLBN = 29, NKB_PMLDN = 30, NKB_KPMLBN = 31, NKB_KPMLDN = 32,           &
-       NKB_XMN = 33, NKB_YMN = 34, NKB_ZMN = 35
+       NKB_XMN = 33, NKB_YMN = 34, NKB_ZMN = 35, NKB_YCONDUC = 36
 
   type, bind(C) :: nekcem_b200_desc
      integer(c_int32_t) :: abi_version, ldim, nx1, nelt, imode, ifupwind, ifpec, ifpml
@@ -171,6 +171,22 @@ module nekcem_b200
        import :: c_int, c_double
        integer(c_int), value :: handle
        real(c_double), intent(out) :: jn(*), kjn(*)
+     end function
+     !> Graphene sheets (replaces the per-stage cem_3d/te/tm_graphene_current calls of the .usr
+     !> userfsrc and its srcfh -= fjn(:,:,1), src/cem_maxwell.F:2827-3093).  yconduc may be
+     !> c_null_ptr-like absent in C; from Fortran pass COMMON /EMWAVE/ yconduc.
+     integer(c_int) function nekcem_b200_set_graphene(handle, fjn, kfjn, params, yconduc, &
+          gindex, n) bind(C, name='nekcem_b200_set_graphene')
+       import :: c_int, c_double
+       integer(c_int), value :: handle, n
+       real(c_double), intent(in) :: fjn(*), kfjn(*), params(*), yconduc(*)
+       integer(c_int), intent(in) :: gindex(*)
+     end function
+     integer(c_int) function nekcem_b200_get_graphene(handle, fjn, kfjn) &
+          bind(C, name='nekcem_b200_get_graphene')
+       import :: c_int, c_double
+       integer(c_int), value :: handle
+       real(c_double), intent(inout) :: fjn(*), kfjn(*)
      end function
      integer(c_int) function nekcem_b200_algorithmic_bytes(handle, bytes_per_stage) &
           bind(C, name='nekcem_b200_algorithmic_bytes')

@@ -57,6 +57,8 @@ enum nekcem_b200_array {
     NKB_PMLBN, NKB_PMLDN, NKB_KPMLBN, NKB_KPMLDN, /* (npts,3) src/PML:14-28              */
     NKB_XMN, NKB_YMN, NKB_ZMN, /* xmn,ymn,zmn(npts) node coordinates, src/GEOM:30-33; only needed
                                   by nekcem_b200_error_sums_mode                             */
+    NKB_YCONDUC,       /* yconduc(nxzfl) own-side conductance on the faces, src/EMWAVE,
+                          cem_maxwell.F:285; only needed by graphene sheets                  */
     NKB_ARRAY_COUNT
 };
 
@@ -157,6 +159,24 @@ int nekcem_b200_set_drude(int handle, const double *jn, const double *kjn, const
 int nekcem_b200_set_lorentz(int handle, const double *jn, const double *kjn, const double *params,
                             const int32_t *lindex, int32_t n);
 int nekcem_b200_get_ade(int handle, double *jn, double *kjn);
+
+/* Graphene sheets (SURVEY.md 8f rank 1 `userfsrc`, rank 4 surface-current ADEs).  Replace the
+ * per-stage calls `cem_3d_graphene_current / cem_te_graphene_current / cem_tm_graphene_current
+ * (fjn,kfjn,resfjn,params,gindex,n)` (src/cem_maxwell.F:2827-2931, 2933-3022, 3024-3093; which
+ * one follows from desc.imode) that the reference's .usr files make from `userfsrc`
+ * (tests/3dgraphene/3dgraphene.usr:236-266, tests/2dgraphene/2dgraphene.usr:249-290), together
+ * with that userfsrc's `srcfh(c)(j) -= fjn(j,c,1)`: the sheet currents live on the device, are
+ * advanced once per RK stage from the stage-start face values (after userinc), and the total
+ * current is subtracted from -(n x H) on both sides of the face before the flux is formed.
+ * fjn,kfjn: (nxzfl,3,6) (NULL = zeros); params: (nxzfl,12); yconduc: (nxzfl) COMMON /EMWAVE/
+ * yconduc, or NULL to use the uploaded NKB_YCONDUC; gindex: the user's 1-based face-point list,
+ * n entries; n = 0 removes the sheets.  Call before nekcem_b200_setup.  A sheet must not lie on
+ * an inter-rank face (setup fails).  get_graphene writes the listed face points of fjn / kfjn
+ * (the `!$ACC UPDATE HOST` seam); other entries are left untouched. */
+int nekcem_b200_set_graphene(int handle, const double *fjn, const double *kfjn,
+                             const double *params, const double *yconduc, const int32_t *gindex,
+                             int32_t n);
+int nekcem_b200_get_graphene(int handle, double *fjn, double *kfjn);
 
 /* The hot path.  Replaces `cem_maxwell_op_rk` (src/cem_maxwell.F:327-345): nsteps time
  * steps of 5 x {rk_c; cem_maxwell_op; rk_maxwell_ab}; advances the context's time by

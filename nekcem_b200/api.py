@@ -30,7 +30,7 @@ ARRAY_IDS = {name: i for i, name in enumerate([
     "dxm1", "w3mn", "rxmn", "rymn", "rzmn", "sxmn", "symn", "szmn", "txmn", "tymn", "tzmn",
     "bmn", "hbm1", "ebm1", "unxm", "unym", "unzm", "aream", "Y_0", "Y_1", "Z_0", "Z_1",
     "hn", "en", "khn", "ken", "permittivity", "permeability", "pmlsigma", "pmlbn", "pmldn",
-    "kpmlbn", "kpmldn", "xmn", "ymn", "zmn"])}
+    "kpmlbn", "kpmldn", "xmn", "ymn", "zmn", "yconduc"])}
 
 GEOMETRY_ARRAYS = ["dxm1", "w3mn", "rxmn", "rymn", "rzmn", "sxmn", "symn", "szmn", "txmn",
                    "tymn", "tzmn", "bmn", "hbm1", "ebm1", "unxm", "unym", "unzm", "aream",
@@ -85,6 +85,8 @@ def lib():
         L.nekcem_b200_set_drude.argtypes = [C.c_int, c_dp, c_dp, c_dp, c_i32p, C.c_int32]
         L.nekcem_b200_set_lorentz.argtypes = [C.c_int, c_dp, c_dp, c_dp, c_i32p, C.c_int32]
         L.nekcem_b200_get_ade.argtypes = [C.c_int, c_dp, c_dp]
+        L.nekcem_b200_set_graphene.argtypes = [C.c_int, c_dp, c_dp, c_dp, c_dp, c_i32p, C.c_int32]
+        L.nekcem_b200_get_graphene.argtypes = [C.c_int, c_dp, c_dp]
         L.nekcem_b200_set_option.argtypes = [C.c_int, C.c_char_p, C.c_int]
         L.nekcem_b200_error_sums_mode.argtypes = [C.c_int, C.POINTER(C.c_int32), c_dp, c_dp, c_dp,
                                                   c_dp, c_dp]
@@ -161,7 +163,7 @@ class MaxwellB200:
             n = self.nx1 * self.nx1
         elif name == "w3mn":
             n = self.nxyz
-        elif name in ("unxm", "unym", "unzm", "aream", "Y_0", "Y_1", "Z_0", "Z_1"):
+        elif name in ("unxm", "unym", "unzm", "aream", "Y_0", "Y_1", "Z_0", "Z_1", "yconduc"):
             n = self.nxzfl
         elif name in ("hn", "en", "khn", "ken", "pmlsigma", "pmlbn", "pmldn", "kpmlbn",
                       "kpmldn"):
@@ -307,6 +309,45 @@ class MaxwellB200:
         jn = np.zeros(self._ade_ncomp * self.npts); kjn = np.zeros_like(jn)
         _chk(self.L.nekcem_b200_get_ade(self.h, _dp(jn), _dp(kjn)))
         return jn, kjn
+
+    def cem_graphene_current(self, fjn, kfjn, params, yconduc, gindex0):
+        """Registers the graphene sheets that the reference's userfsrc advances every stage
+        through ``cem_3d_graphene_current / cem_te_graphene_current / cem_tm_graphene_current
+        (fjn,kfjn,resfjn,params,gindex,n)`` (src/cem_maxwell.F:2827-3093; the variant follows
+        from imode) and whose total current it subtracts from its -(n x H) face source
+        (tests/3dgraphene/3dgraphene.usr:236-266).  fjn,kfjn (nxzfl,3,6) or None, params
+        (nxzfl,12), yconduc (nxzfl) = COMMON /EMWAVE/ yconduc (or None when the array "yconduc"
+        was uploaded), gindex0 0-based face points.  Call before setup()."""
+        idx = np.ascontiguousarray(np.asarray(gindex0, dtype=np.int64) + 1, dtype=np.int32)
+        nf = self.nxzfl
+        par = np.ascontiguousarray(params, dtype=np.float64).reshape(-1)
+        if par.size != 12 * nf:
+            raise NekcemB200Error(f"graphene params: {par.size} values, expected {12 * nf}")
+        ptr = []
+        for a in (fjn, kfjn):
+            if a is None:
+                ptr.append(None)
+            else:
+                a = np.ascontiguousarray(a, dtype=np.float64).reshape(-1)
+                if a.size != 18 * nf:
+                    raise NekcemB200Error(f"graphene state: {a.size} values, expected {18 * nf}")
+                ptr.append(a)
+        yc = None
+        if yconduc is not None:
+            yc = np.ascontiguousarray(yconduc, dtype=np.float64).reshape(-1)
+            if yc.size != nf:
+                raise NekcemB200Error(f"yconduc: {yc.size} values, expected {nf}")
+        _chk(self.L.nekcem_b200_set_graphene(
+            self.h, None if ptr[0] is None else _dp(ptr[0]),
+            None if ptr[1] is None else _dp(ptr[1]), _dp(par), None if yc is None else _dp(yc),
+            idx.ctypes.data_as(c_i32p), idx.size))
+
+    def get_graphene(self):
+        """(fjn, kfjn) as (nxzfl,3,6) flat arrays: the listed face points downloaded from the
+        device, zeros elsewhere."""
+        fjn = np.zeros(18 * self.nxzfl); kfjn = np.zeros_like(fjn)
+        _chk(self.L.nekcem_b200_get_graphene(self.h, _dp(fjn), _dp(kfjn)))
+        return fjn, kfjn
 
     def set_option(self, name: str, value: int):
         _chk(self.L.nekcem_b200_set_option(self.h, name.encode(), int(value)))

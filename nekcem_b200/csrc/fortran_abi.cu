@@ -147,11 +147,13 @@ NKB_EXPORT void nekcem_b200_get_ade_(const int *h, double *jn, double *kjn)
 // is not needed here.
 static int g_bound_handle = -1;
 static int g_ade_registered = 0;
+static int g_graphene_registered_for = -1;
 
 NKB_EXPORT void nekcem_b200_bind_(const int *h)
 {
     g_bound_handle = *h;
     g_ade_registered = 0;
+    g_graphene_registered_for = -1;
 }
 
 NKB_EXPORT void cem_maxwell_drude_(const double *jn, const double *kjn, double *resjn,
@@ -179,4 +181,59 @@ NKB_EXPORT void cem_maxwell_lorentz_(const double *jn, const double *kjn, double
     check(nekcem_b200_set_lorentz(g_bound_handle, jn, kjn, params, lindex, *n),
           "cem_maxwell_lorentz");
     g_ade_registered = 1;
+}
+
+// ---- graphene sheets --------------------------------------------------------------------
+NKB_EXPORT void nekcem_b200_set_graphene_(const int *h, const double *fjn, const double *kfjn,
+                                          const double *params, const double *yconduc,
+                                          const int *gindex, const int *n)
+{
+    check(nekcem_b200_set_graphene(*h, fjn, kfjn, params, yconduc, gindex, *n),
+          "nekcem_b200_set_graphene");
+}
+
+NKB_EXPORT void nekcem_b200_get_graphene_(const int *h, double *fjn, double *kfjn)
+{
+    check(nekcem_b200_get_graphene(*h, fjn, kfjn), "nekcem_b200_get_graphene");
+}
+
+// Drop-in twins of the reference's graphene-current entry points, same names and argument lists
+// (src/cem_maxwell.F:2827, 2933, 3024).  The reference's .usr calls them from `userfsrc` in
+// every stage and then subtracts fjn(:,:,1) from its face source; here the FIRST call (made by
+// the shim's b200_update_device through the user's own userfsrc) registers the user's COMMON
+// arrays with the bound context -- yconduc comes from the uploaded NKB_YCONDUC -- and the
+// currents then advance on the device inside nekcem_b200_step; later calls are no-ops.  Which of
+// the three routines the .usr picked must agree with the context's imode (checked by the C ABI
+// only through the component set it advances).  resfjn is scratch in the reference.
+static void graphene_twin(const char *name, const double *fjn, const double *kfjn,
+                          const double *params, const int *gindex, const int *n)
+{
+    if (g_bound_handle < 0) {
+        fprintf(stderr, "nekcem_b200: %s called before nekcem_b200_bind\n", name);
+        exit(1);
+    }
+    if (g_graphene_registered_for == g_bound_handle) return;
+    check(nekcem_b200_set_graphene(g_bound_handle, fjn, kfjn, params, nullptr, gindex, *n), name);
+    g_graphene_registered_for = g_bound_handle;
+}
+
+NKB_EXPORT void cem_3d_graphene_current_(const double *fjn, const double *kfjn, double *resfjn,
+                                         const double *params, const int *gindex, const int *n)
+{
+    (void)resfjn;
+    graphene_twin("cem_3d_graphene_current", fjn, kfjn, params, gindex, n);
+}
+
+NKB_EXPORT void cem_te_graphene_current_(const double *fjn, const double *kfjn, double *resfjn,
+                                         const double *params, const int *gindex, const int *n)
+{
+    (void)resfjn;
+    graphene_twin("cem_te_graphene_current", fjn, kfjn, params, gindex, n);
+}
+
+NKB_EXPORT void cem_tm_graphene_current_(const double *fjn, const double *kfjn, double *resfjn,
+                                         const double *params, const int *gindex, const int *n)
+{
+    (void)resfjn;
+    graphene_twin("cem_tm_graphene_current", fjn, kfjn, params, gindex, n);
 }

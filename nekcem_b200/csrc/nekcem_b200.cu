@@ -25,6 +25,7 @@
 
 #include "../../include/nekcem_b200.h"
 #include "stage_args.h"
+#include "stage_graphene.h"
 
 namespace nkb {
 int launch_stage_slab(const StageArgs &a, const double *Dhost, int nx1, bool aux, bool cm, void *stream);
@@ -171,6 +172,14 @@ struct Ctx {
     unsigned char *ade_mask = nullptr;
     unsigned char *elflag_d = nullptr; // per element: bit 0 PML, bit 1 ADE, bit 2 constant metrics
     std::vector<char> ade_el; // per element: contains ADE nodes
+    // graphene sheets (userfsrc hook): compact per-face-point state, index q = position in the
+    // user's graphindex list.  Host staging until setup, then device-resident.
+    std::vector<int32_t> g_fp;              // 0-based face points
+    std::vector<double> g_fj_h, g_kj_h, g_par_h, g_yc_h; // [18][ng], [18][ng], [12][ng], [ng]
+    bool g_yc_given = false;
+    bool g_dev_current = false; // the device copy of the sheet state is newer than the staging
+    int *g_fp_d = nullptr, *g_node_d = nullptr, *fs_own_d = nullptr, *fs_nbr_d = nullptr;
+    double *g_fj = nullptr, *g_kj = nullptr, *g_par = nullptr, *g_yc = nullptr;
     // redundancy found in the geometry at setup (exact, bitwise): elements whose nine cofactors
     // do not vary over the element read them once per element; identical hbm1/ebm1 share one array
     bool opt_const_metrics = true;
@@ -202,7 +211,7 @@ int64_t array_count(const Ctx *c, int which)
     case NKB_PERMITTIVITY: case NKB_PERMEABILITY: case NKB_XMN: case NKB_YMN: case NKB_ZMN:
         return c->npts;
     case NKB_UNXM: case NKB_UNYM: case NKB_UNZM: case NKB_AREAM:
-    case NKB_Y_0: case NKB_Y_1: case NKB_Z_0: case NKB_Z_1:
+    case NKB_Y_0: case NKB_Y_1: case NKB_Z_0: case NKB_Z_1: case NKB_YCONDUC:
         return c->nxzfl;
     case NKB_HN: case NKB_EN: case NKB_KHN: case NKB_KEN:
     case NKB_PMLSIGMA: case NKB_PMLBN: case NKB_PMLDN: case NKB_KPMLBN: case NKB_KPMLDN:
@@ -306,6 +315,63 @@ __global__ void pack_kernel(const double *u, long long ld, const int *send_node,
         if (qi >= 0) v += inc_amp[c * inc_n + qi] * cos(inc_phase[qi] - inc_wt);
     }
     sendbuf[t] = v;
+}
+
+// Graphene sheets: one thread per face point of the user's graphindex list advances the surface
+// current ADEs of that point by one RK stage (stage_graphene.h) from the stage-start fields,
+// exactly where the reference's userfsrc runs (own-side face values after userinc, before the
+// face sum).  Slot m = 0 of fj then holds fjn(j,:,1), which the stage kernels subtract from
+// -(n x H) on both sides of the face.
+struct GrapheneArgs {
+    const double *u;
+    long long ld;
+    int ng, imode;
+    const int *fp, *node;
+    const double *unx, *uny, *unz, *hY, *yc, *par;
+    double *fj, *kj;
+    const int *inc_own;
+    const double *inc_amp, *inc_phase;
+    int inc_n;
+    double inc_wt, ca, cb, dt;
+};
+__global__ void graphene_kernel(GrapheneArgs g)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= g.ng) return;
+    const int j = g.fp[q];
+    const long long nd = g.node[q];
+    double H[3], E[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        H[c] = g.u[c * g.ld + nd];
+        E[c] = g.u[(3 + c) * g.ld + nd];
+    }
+    if (g.inc_own != nullptr) { // userinc precedes the flux (src/cem_maxwell.F:498)
+        const int qi = g.inc_own[j];
+        if (qi >= 0) {
+            const double ui = cos(g.inc_phase[qi] - g.inc_wt);
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                H[c] += g.inc_amp[c * g.inc_n + qi] * ui;
+                E[c] += g.inc_amp[(3 + c) * g.inc_n + qi] * ui;
+            }
+        }
+    }
+    const double n[3] = {g.unx[j], g.uny[j], g.unz ? g.unz[j] : 0.0};
+    double par[12], fj[18], kj[18];
+#pragma unroll
+    for (int m = 0; m < 12; m++) par[m] = g.par[(long long)m * g.ng + q];
+#pragma unroll
+    for (int m = 0; m < 18; m++) {
+        fj[m] = g.fj[(long long)m * g.ng + q];
+        kj[m] = g.kj[(long long)m * g.ng + q];
+    }
+    nkb::graphene_point(g.imode, H, E, n, g.hY[j], g.yc[q], par, fj, kj, g.ca, g.cb, g.dt);
+#pragma unroll
+    for (int m = 0; m < 18; m++) {
+        g.fj[(long long)m * g.ng + q] = fj[m];
+        g.kj[(long long)m * g.ng + q] = kj[m];
+    }
 }
 
 // cem_error partial sums (src/cem_common.F:1335-1355): per block, per component
@@ -479,6 +545,12 @@ int build_lists(Ctx *c, std::vector<int32_t> &lists)
     if (c->ade_kind)
         for (int e = 0; e < c->d.nelt; e++)
             if (c->ade_el[e]) is_pml[e] = 1;
+    // elements holding a graphene face point, or paired with one, take the AUX instantiation
+    // (the only one that carries the face-source code)
+    for (int32_t fp : c->g_fp) {
+        is_pml[fp / nfp] = 1;
+        if (c->pairfp[fp] >= 0) is_pml[c->pairfp[fp] / nfp] = 1;
+    }
     const bool have_flags = (int)c->elflag_h.size() == c->d.nelt;
     std::vector<int32_t> L[8];
     for (int e = 0; e < c->d.nelt; e++) {
@@ -645,6 +717,26 @@ int run_stage(Ctx *c, int rkstep /*1..5*/)
     a.inc_amp = c->inc_amp_d; a.inc_phase = c->inc_phase_d;
     a.inc_n = (int)c->inc_fp.size();
     a.inc_wt = c->inc_omega * rktime;
+    a.fs_own = c->fs_own_d; a.fs_nbr = c->fs_nbr_d;
+    a.fs_val = c->g_fj; // slot m = 0: fjn(:,1:3,1)
+    a.fs_n = (int)c->g_fp.size();
+    if (!c->g_fp.empty()) {
+        // userfsrc -> cem_*_graphene_current: needs only stage-start data, so it runs first on
+        // the compute stream; every stage launch of this stage is ordered after it
+        GrapheneArgs g{};
+        g.u = a.u_in; g.ld = c->ld;
+        g.ng = a.fs_n; g.imode = c->d.imode;
+        g.fp = c->g_fp_d; g.node = c->g_node_d;
+        g.unx = a.unx; g.uny = a.uny; g.unz = c->d.ldim == 3 ? a.unz : nullptr;
+        g.hY = c->hY; g.yc = c->g_yc; g.par = c->g_par;
+        g.fj = c->g_fj; g.kj = c->g_kj;
+        g.inc_own = c->inc_own_d; g.inc_amp = c->inc_amp_d; g.inc_phase = c->inc_phase_d;
+        g.inc_n = a.inc_n; g.inc_wt = a.inc_wt;
+        g.ca = a.ca; g.cb = a.cb; g.dt = a.dt;
+        graphene_kernel<<<(unsigned)((g.ng + 127) / 128), 128, 0, c->s_compute>>>(g);
+        CUDA_OK(cudaGetLastError());
+        c->last_launches++;
+    }
 
     auto launch_list = [&](int q) -> int {
         if (c->list_n[q] == 0) return 0;
@@ -688,6 +780,68 @@ int run_stage(Ctx *c, int rkstep /*1..5*/)
         if (launch_list(q)) return 1;
     CUDA_OK(cudaEventRecord(c->ev_stage, c->s_compute));
     c->cur ^= 1;
+    return 0;
+}
+
+// Graphene state: host staging -> device (called from nekcem_b200_setup, after the face plan)
+int upload_graphene(Ctx *c)
+{
+    if (c->g_dev_current && c->g_fj && !c->g_fp.empty()) {
+        // setup re-run after time steps (e.g. geometry replaced): keep the advanced state
+        const size_t ng0 = c->g_fp.size();
+        CUDA_OK(cudaMemcpy(c->g_fj_h.data(), c->g_fj, sizeof(double) * 18 * ng0, cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(c->g_kj_h.data(), c->g_kj, sizeof(double) * 18 * ng0, cudaMemcpyDeviceToHost));
+    }
+    c->g_dev_current = false;
+    cudaFree(c->g_fp_d); cudaFree(c->g_node_d); cudaFree(c->fs_own_d); cudaFree(c->fs_nbr_d);
+    cudaFree(c->g_fj); cudaFree(c->g_kj); cudaFree(c->g_par); cudaFree(c->g_yc);
+    c->g_fp_d = c->g_node_d = c->fs_own_d = c->fs_nbr_d = nullptr;
+    c->g_fj = c->g_kj = c->g_par = c->g_yc = nullptr;
+    const size_t ng = c->g_fp.size();
+    if (ng == 0) return 0;
+    const int nfp = c->nxzf * c->nfaces;
+    std::vector<int32_t> own(c->nxzfl, -1), nbr(c->nxzfl, -1), node(ng);
+    for (size_t q = 0; q < ng; q++) {
+        const int64_t fp = c->g_fp[q], e = fp / nfp;
+        const int f = (int)(fp - e * nfp);
+        if (own[fp] >= 0) return fail("graphene index lists face point %lld twice", (long long)fp + 1);
+        if (c->vmapP[fp] <= -3)
+            return fail("graphene face point %lld lies on an inter-rank face: sheets must not "
+                        "coincide with partition boundaries in this version", (long long)fp + 1);
+        own[fp] = (int32_t)q;
+        node[q] = (int32_t)(e * c->nxyz + face_node(c->n, f / c->nxzf, f % c->nxzf));
+    }
+    for (int64_t j = 0; j < c->nxzfl; j++)
+        if (c->pairfp[j] >= 0) nbr[j] = own[c->pairfp[j]];
+    if (!c->g_yc_given) {
+        // yconduc from the reference's COMMON /EMWAVE/ (src/cem_maxwell.F:285), uploaded as
+        // NKB_YCONDUC by the host code
+        if (!c->have[NKB_YCONDUC])
+            return fail("graphene sheets need yconduc: pass it to nekcem_b200_set_graphene or "
+                        "upload NKB_YCONDUC");
+        std::vector<double> yc(c->nxzfl);
+        CUDA_OK(cudaMemcpy(yc.data(), c->dev[NKB_YCONDUC], sizeof(double) * c->nxzfl,
+                           cudaMemcpyDeviceToHost));
+        c->g_yc_h.resize(ng);
+        for (size_t q = 0; q < ng; q++) c->g_yc_h[q] = yc[c->g_fp[q]];
+    }
+    CUDA_OK(cudaMalloc(&c->g_fp_d, sizeof(int) * ng));
+    CUDA_OK(cudaMalloc(&c->g_node_d, sizeof(int) * ng));
+    CUDA_OK(cudaMalloc(&c->fs_own_d, sizeof(int) * c->nxzfl));
+    CUDA_OK(cudaMalloc(&c->fs_nbr_d, sizeof(int) * c->nxzfl));
+    CUDA_OK(cudaMalloc(&c->g_fj, sizeof(double) * 18 * ng));
+    CUDA_OK(cudaMalloc(&c->g_kj, sizeof(double) * 18 * ng));
+    CUDA_OK(cudaMalloc(&c->g_par, sizeof(double) * 12 * ng));
+    CUDA_OK(cudaMalloc(&c->g_yc, sizeof(double) * ng));
+    CUDA_OK(cudaMemcpy(c->g_fp_d, c->g_fp.data(), sizeof(int) * ng, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(c->g_node_d, node.data(), sizeof(int) * ng, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(c->fs_own_d, own.data(), sizeof(int) * c->nxzfl, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(c->fs_nbr_d, nbr.data(), sizeof(int) * c->nxzfl, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(c->g_fj, c->g_fj_h.data(), sizeof(double) * 18 * ng, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(c->g_kj, c->g_kj_h.data(), sizeof(double) * 18 * ng, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(c->g_par, c->g_par_h.data(), sizeof(double) * 12 * ng, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(c->g_yc, c->g_yc_h.data(), sizeof(double) * ng, cudaMemcpyHostToDevice));
+    c->g_dev_current = true;
     return 0;
 }
 
@@ -777,6 +931,8 @@ int nekcem_b200_destroy(int handle)
         cudaFree(c->ade_j); cudaFree(c->ade_k); cudaFree(c->ade_par); cudaFree(c->ade_mask);
         cudaFree(c->inc_own_d); cudaFree(c->inc_nbr_d); cudaFree(c->inc_send_d);
         cudaFree(c->inc_amp_d); cudaFree(c->inc_phase_d);
+        cudaFree(c->g_fp_d); cudaFree(c->g_node_d); cudaFree(c->fs_own_d); cudaFree(c->fs_nbr_d);
+        cudaFree(c->g_fj); cudaFree(c->g_kj); cudaFree(c->g_par); cudaFree(c->g_yc);
         cudaEventDestroy(c->ev_stage); cudaEventDestroy(c->ev_halo);
         cudaEventDestroy(c->ev_t0); cudaEventDestroy(c->ev_t1);
         cudaStreamDestroy(c->s_compute); cudaStreamDestroy(c->s_comm);
@@ -1050,6 +1206,7 @@ int nekcem_b200_setup(int handle)
             CUDA_OK(cudaMemcpy(c->inc_send_d, snd.data(), sizeof(int) * c->nhalo, cudaMemcpyHostToDevice));
         }
     }
+    if (upload_graphene(c)) return 1;
     if (!c->red_d) {
         c->red_blocks = 1024;
         CUDA_OK(cudaMalloc(&c->red_d, sizeof(double) * 12 * c->red_blocks));
@@ -1162,6 +1319,68 @@ int nekcem_b200_get_ade(int handle, double *jn, double *kjn)
     const size_t bj = sizeof(double) * (c->ade_kind == 1 ? 3 : 6) * c->npts;
     if (jn) CUDA_OK(cudaMemcpy(jn, c->ade_j, bj, cudaMemcpyDeviceToHost));
     if (kjn) CUDA_OK(cudaMemcpy(kjn, c->ade_k, bj, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int nekcem_b200_set_graphene(int handle, const double *fjn, const double *kfjn,
+                             const double *params, const double *yconduc, const int32_t *gindex,
+                             int32_t n)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (n < 0 || (n > 0 && (!gindex || !params))) return fail("bad graphene arguments");
+    if (!c->host_only) {
+        CUDA_OK(cudaSetDevice(c->d.device));
+        CUDA_OK(cudaStreamSynchronize(c->s_compute));
+    }
+    c->g_fp.clear();
+    c->setup_done = false;
+    c->g_dev_current = false;
+    const size_t ng = (size_t)n;
+    const int64_t nf = c->nxzfl;
+    for (int q = 0; q < n; q++) {
+        if (gindex[q] < 1 || gindex[q] > nf)
+            return fail("graphene index(%d)=%d out of range 1..%lld", q + 1, gindex[q], (long long)nf);
+        c->g_fp.push_back(gindex[q] - 1);
+    }
+    // (nxzfl,3,6) / (nxzfl,12) user arrays -> compact [m][q]
+    c->g_fj_h.assign(18 * ng, 0.0);
+    c->g_kj_h.assign(18 * ng, 0.0);
+    c->g_par_h.assign(12 * ng, 0.0);
+    c->g_yc_h.assign(ng, 0.0);
+    c->g_yc_given = yconduc != nullptr;
+    for (size_t q = 0; q < ng; q++) {
+        const int64_t j = c->g_fp[q];
+        for (int m = 0; m < 18; m++) {
+            if (fjn) c->g_fj_h[m * ng + q] = fjn[j + nf * m];
+            if (kfjn) c->g_kj_h[m * ng + q] = kfjn[j + nf * m];
+        }
+        for (int m = 0; m < 12; m++) c->g_par_h[m * ng + q] = params[j + nf * m];
+        if (yconduc) c->g_yc_h[q] = yconduc[j];
+    }
+    return 0;
+}
+
+int nekcem_b200_get_graphene(int handle, double *fjn, double *kfjn)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (c->g_fp.empty()) return fail("no graphene state has been set");
+    const size_t ng = c->g_fp.size();
+    const int64_t nf = c->nxzfl;
+    if (c->g_fj && c->g_dev_current) { // device state is current once setup has run
+        CUDA_OK(cudaSetDevice(c->d.device));
+        CUDA_OK(cudaStreamSynchronize(c->s_compute));
+        CUDA_OK(cudaMemcpy(c->g_fj_h.data(), c->g_fj, sizeof(double) * 18 * ng, cudaMemcpyDeviceToHost));
+        CUDA_OK(cudaMemcpy(c->g_kj_h.data(), c->g_kj, sizeof(double) * 18 * ng, cudaMemcpyDeviceToHost));
+    }
+    for (size_t q = 0; q < ng; q++) {
+        const int64_t j = c->g_fp[q];
+        for (int m = 0; m < 18; m++) {
+            if (fjn) fjn[j + nf * m] = c->g_fj_h[m * ng + q];
+            if (kfjn) kfjn[j + nf * m] = c->g_kj_h[m * ng + q];
+        }
+    }
     return 0;
 }
 

@@ -103,9 +103,28 @@ __global__ void __launch_bounds__(Cfg2<N>::NT)
         }
         // own side (:825-828 TM, :880-883 TE): f0 = -ny*z, f1 = nx*z, f2 = -nx*B + ny*A
         double f0 = -uny * oc, f1 = unx * oc, f2 = -unx * ob + uny * oa;
+        // userfsrc hook (:850-851 TM, :887-888 TE): graphene sheet current subtracted from the
+        // -(n x H) slots -- f2 in TM (component 3), f0,f1 in TE (components 1,2)
+        int gqn = -1;
+        if (AUX) {
+            if (a.fs_own != nullptr) {
+                const int gqo = a.fs_own[jf];
+                gqn = a.fs_nbr[jf];
+                if (gqo >= 0) {
+                    if (tm) f2 = f2 - a.fs_val[2 * a.fs_n + gqo];
+                    else { f0 = f0 - a.fs_val[gqo]; f1 = f1 - a.fs_val[a.fs_n + gqo]; }
+                }
+            }
+        }
         if (vp >= 0 || vp <= -3) {
             // neighbour's contribution with n+ = -n- (the gs_op_fields sum)
             f0 = f0 + uny * pc; f1 = f1 - unx * pc; f2 = f2 - (-unx * pb + uny * pa);
+            if (AUX) {
+                if (gqn >= 0) {
+                    if (tm) f2 = f2 - a.fs_val[2 * a.fs_n + gqn];
+                    else { f0 = f0 - a.fs_val[gqn]; f1 = f1 - a.fs_val[a.fs_n + gqn]; }
+                }
+            }
         } else if (vp == -1) { // PEC / PML outer face (cem_maxwell_flux_pec :1407-1421)
             if (tm) { f0 = 2.0 * f0; f1 = 2.0 * f1; f2 = 0.0; }
             else { f0 = 0.0; f1 = 0.0; f2 = 2.0 * f2; }

@@ -49,6 +49,12 @@ struct StageArgs {
     const double *src_prof;
     int src_comp;
     double src_tfac;
+    // face sources of graphene sheets (userfsrc hook, AUX launches only): slot of the own / the
+    // neighbour's face point in the graphene list (-1: none); fs_val[c*fs_n + q] = fjn(j,c,1) of
+    // this stage, written by graphene_kernel before the stage kernel starts
+    const int *fs_own, *fs_nbr;
+    const double *fs_val;
+    int fs_n;
 };
 
 } // namespace nkb

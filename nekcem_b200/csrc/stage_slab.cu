@@ -586,6 +586,18 @@ __global__ void __launch_bounds__(Slab<N, KS>::NT, CM ? Slab<N, KS>::MINB_CM : S
             double s3 = -uny * Hz + unz * Hy;
             double s4 = -unz * Hx + unx * Hz;
             double s5 = -unx * Hy + uny * Hx;
+            int gqn = -1;
+            if constexpr (PML) { // userfsrc hook (:958): graphene sheet current, own side
+                if (a.fs_own != nullptr && valid) {
+                    const int gqo = a.fs_own[jf];
+                    gqn = a.fs_nbr[jf];
+                    if (gqo >= 0) {
+                        s3 = s3 - a.fs_val[gqo];
+                        s4 = s4 - a.fs_val[a.fs_n + gqo];
+                        s5 = s5 - a.fs_val[2 * a.fs_n + gqo];
+                    }
+                }
+            }
             if (vp >= 0 || vp <= -3) {
                 // neighbour's (-n+ x E+) with n+ = -n-  (the gs_op_fields sum of :962)
                 s0 = s0 - (-uny * pEz + unz * pEy);
@@ -594,6 +606,13 @@ __global__ void __launch_bounds__(Slab<N, KS>::NT, CM ? Slab<N, KS>::MINB_CM : S
                 s3 = s3 - (-uny * pHz + unz * pHy);
                 s4 = s4 - (-unz * pHx + unx * pHz);
                 s5 = s5 - (-unx * pHy + uny * pHx);
+                if constexpr (PML) { // the neighbour's face source arrives through the same sum
+                    if (gqn >= 0) {
+                        s3 = s3 - a.fs_val[gqn];
+                        s4 = s4 - a.fs_val[a.fs_n + gqn];
+                        s5 = s5 - a.fs_val[2 * a.fs_n + gqn];
+                    }
+                }
             } else if (vp == -1) { // 'PEC' / 'PML' outer face: cem_maxwell_flux_pec :1397-1405
                 s0 = 2.0 * s0; s1 = 2.0 * s1; s2 = 2.0 * s2;
                 s3 = 0.0; s4 = 0.0; s5 = 0.0;

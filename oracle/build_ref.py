@@ -89,8 +89,9 @@ DEFINES = ("MPI", "MPIIO", "MAXWELL", "NOTIMER")
 
 # Drop-in variant: the same translated reference + THIS REPO'S fixed-form shim
 # (fortran/cem_maxwell_b200_f77.F, translated by the same tool) linked against the product
-# library.  cem_maxwell_drude / cem_maxwell_lorentz are left out so that the .usr's calls
-# resolve to the library's twins, exactly as a -DB200 build of the reference would link.
+# library.  cem_maxwell_drude / cem_maxwell_lorentz and the three graphene-current routines are
+# left out so that the .usr's calls resolve to the library's twins, exactly as a -DB200 build of
+# the reference would link.
 LIB_DROPIN = os.path.join(OUT, "libnekcem_ref_dropin.so")
 REPO = os.path.dirname(HERE)
 SHIM = (os.path.join(REPO, "fortran", "cem_maxwell_b200_f77.F"),
@@ -142,7 +143,9 @@ def build_dropin(inc, verbose=False):
         return None
     units = []
     for u in UNITS:
-        names = [n for n in u[1] if n not in ("cem_maxwell_drude", "cem_maxwell_lorentz")]
+        names = [n for n in u[1] if n not in (
+            "cem_maxwell_drude", "cem_maxwell_lorentz", "cem_3d_graphene_current",
+            "cem_te_graphene_current", "cem_tm_graphene_current")]
         units.append((os.path.join(REF, u[0]), names) + tuple(u[2:]))
     units.append(SHIM)
     ctext, em = f2c_lite.translate(units, inc + [os.path.join(REPO, "fortran")], DEFINES)

@@ -28,7 +28,10 @@ def test_library_exports_every_declared_symbol():
               "nekcem_b200_error_sums_mode_",
               "nekcem_b200_comm_unique_id_", "nekcem_b200_comm_init_",
               "nekcem_b200_set_drude_", "nekcem_b200_set_lorentz_", "nekcem_b200_get_ade_",
-              "nekcem_b200_bind_", "cem_maxwell_drude_", "cem_maxwell_lorentz_"):
+              "nekcem_b200_bind_", "cem_maxwell_drude_", "cem_maxwell_lorentz_",
+              "nekcem_b200_set_graphene_", "nekcem_b200_get_graphene_",
+              "cem_3d_graphene_current_", "cem_te_graphene_current_",
+              "cem_tm_graphene_current_"):
         assert hasattr(L, n), f"Fortran twin {n} missing"
 
 
@@ -131,4 +134,28 @@ def test_host_plan_2d_box():
         d = np.abs(arr[own] - arr[vm])
         d = np.minimum(d, np.abs(d - 2 * np.pi))
         assert d.max() < 1e-12
+    s.close()
+
+
+def test_graphene_registration_host_side():
+    """set_graphene / get_graphene in a host-only context: the (nxzfl,3,6) user arrays are packed
+    into the library's per-sheet-point layout and come back at the listed face points only;
+    bad indices fail loudly."""
+    from oracle import cases
+    c = cases.case_2dgraphene(1, nx1=4, nel=(3, 6))
+    u = c.user
+    s = MaxwellB200(2, 4, c.nelt, imode=1, device=-1)
+    s.set_faces(c.glo_num, c.cempec[:c.ncempec])
+    rng = np.random.default_rng(3)
+    fjn = rng.standard_normal(18 * c.nxzfl); kfjn = rng.standard_normal(18 * c.nxzfl)
+    s.cem_graphene_current(fjn, kfjn, u.graphparams, c.yconduc, u.graphindex)
+    f2, k2 = s.get_graphene()
+    mask = np.zeros(c.nxzfl, dtype=bool); mask[u.graphindex] = True
+    m18 = np.tile(mask, 18)
+    assert np.array_equal(f2[m18], fjn[m18]) and np.array_equal(k2[m18], kfjn[m18])
+    assert not f2[~m18].any() and not k2[~m18].any()
+    with pytest.raises(NekcemB200Error, match="out of range"):
+        s.cem_graphene_current(None, None, u.graphparams, c.yconduc, [c.nxzfl])
+    with pytest.raises(NekcemB200Error, match="expected"):
+        s.cem_graphene_current(None, None, u.graphparams[:5], c.yconduc, u.graphindex)
     s.close()

@@ -1,0 +1,184 @@
+"""Graphene sheets on the GPU (SURVEY.md 8f rank 1 `userfsrc`, rank 4 surface-current ADEs):
+graphene_kernel + the face-source hook of the AUX stage kernels against the oracle, which is
+pinned bit for bit to the reference's cem_3d/te/tm_graphene_current and to the shipped
+tests/3dgraphene, tests/2dgraphene .usr files (tests/test_reference_pin.py).  The arithmetic of
+the per-point update is additionally checked on the CPU (tests/test_graphene_point.py).
+This file sorts after the other GPU suites on purpose: it was written after the round's GPU
+budget was spent and is the first thing to confirm on hardware."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import rel_l2, solver_from_refcase
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12
+
+
+def _fields(obj):
+    return np.concatenate([obj.hn, obj.en])
+
+
+def _solver(c, gindex=None, incident=True):
+    u = c.user
+    from nekcem_b200 import MaxwellB200
+    from helpers import arrays_from_refcase
+    s = MaxwellB200(c.ldim, c.nx1, c.nelt, imode=c.imode, upwind=True, ifpec=c.ifpec,
+                    ifpml=c.ifpml, device=0)
+    s.cem_maxwell_init(arrays_from_refcase(c))
+    if incident:
+        s.set_incident(*u.incident(c))
+    s.cem_graphene_current(u.fjn, u.kfjn, u.graphparams, c.yconduc,
+                           u.graphindex if gindex is None else gindex)
+    s.setup()
+    s.set_time(c.s.time, c.s.dt)
+    return s
+
+
+def _sheet_state(c, s):
+    """(gpu, oracle) sheet currents and RK registers restricted to the listed face points"""
+    u = c.user
+    nf = c.nxzfl
+    m = np.zeros(nf, dtype=bool); m[u.graphindex] = True
+    m18 = np.tile(m, 18)
+    fj, kj = s.get_graphene()
+    return (fj[m18], u.fjn[m18]), (kj[m18], u.kfjn[m18])
+
+
+@pytest.mark.parametrize("imode", [1, 2])
+def test_kat_2dgraphene_on_gpu(imode):
+    """tests/2dgraphene TE / TM as shipped (4x32 elements, N=8, CFL 0.2, PML, plane-wave
+    injection, graphene sheet at y=0): parity with the oracle for fields, sheet currents, their RK
+    registers and the PML fields, and the .usr tolerances at steps 1..10, 100, 200."""
+    from oracle import cases
+    c = cases.case_2dgraphene(imode)
+    s = _solver(c)
+    done = 0
+    for target in list(range(1, 11)) + [100, 200]:
+        s.step(target - done); c.step(target - done)
+        done = target
+        shn, sen = c.usersol(c, s.time)
+        l2, linf = s.cem_error(shn, sen)
+        assert np.all(l2 <= np.array(c.tol["l2"]) + 1e-300), (target, l2)
+        assert np.all(linf <= np.array(c.tol["linf"]) + 1e-300), (target, linf)
+    assert rel_l2(_fields(s), _fields(c)) <= TOL
+    (fg, fo), (kg, ko) = _sheet_state(c, s)
+    assert np.abs(fo).max() > 1e-2
+    assert rel_l2(fg, fo) <= TOL and rel_l2(kg, ko) <= TOL
+    assert rel_l2(s.get_array("pmlbn"), c.pmlbn) <= TOL
+    assert rel_l2(s.get_array("pmldn"), c.pmldn) <= TOL
+    s.close()
+
+
+def test_3dgraphene_parity_and_tolerances():
+    """tests/3dgraphene (3x12x3 of its 4x12x4 elements in x,z; N=8, dt=5e-3; TE and TM waves
+    superimposed): parity after 20 steps, the .usr tolerances at steps 1..10, 50."""
+    from oracle import cases
+    c = cases.case_3dgraphene(nel=(3, 12, 3))
+    s = _solver(c)
+    done = 0
+    for target in list(range(1, 11)) + [20]:
+        s.step(target - done); c.step(target - done)
+        done = target
+        shn, sen = c.usersol(c, s.time)
+        l2, linf = s.cem_error(shn, sen)
+        assert np.all(l2 <= np.array(c.tol["l2"])), (target, l2)
+        assert np.all(linf <= np.array(c.tol["linf"])), (target, linf)
+    assert rel_l2(_fields(s), _fields(c)) <= TOL
+    (fg, fo), (kg, ko) = _sheet_state(c, s)
+    assert rel_l2(fg, fo) <= TOL and rel_l2(kg, ko) <= TOL
+    s.step(30)
+    shn, sen = c.usersol(c, s.time)
+    l2, linf = s.cem_error(shn, sen)
+    assert np.all(l2 <= np.array(c.tol["l2"])) and np.all(linf <= np.array(c.tol["linf"]))
+    s.close()
+
+
+@pytest.mark.parametrize("which", ["3d", "te"])
+def test_graphene_stage_by_stage(which):
+    """every RK stage of the first two steps separately: fields and the sheet state"""
+    from oracle import cases
+    c = cases.case_3dgraphene(nx1=6, nel=(3, 6, 3)) if which == "3d" else cases.case_2dgraphene(
+        1, nx1=7, nel=(3, 8))
+    s = _solver(c)
+    for step in range(2):
+        for rk in range(1, 6):
+            s.stage(rk); c.stage(rk)
+            assert rel_l2(_fields(s), _fields(c)) <= TOL, (step, rk)
+            (fg, fo), (kg, ko) = _sheet_state(c, s)
+            assert rel_l2(fg, fo) <= TOL and rel_l2(kg, ko) <= TOL, (step, rk)
+        t = c.s.time + c.s.dt
+        c.s.time = t
+        s.set_time(t, c.s.dt)
+    s.close()
+
+
+def test_graphene_listed_on_one_side_only():
+    """a user list that names only the upper side of the sheet: the lower side still receives
+    the current through the face sum (the neighbour slot of the hook), exactly like gs_op_fields"""
+    from oracle import cases
+    c = cases.case_3dgraphene(nx1=5, nel=(3, 6, 3))
+    u = c.user
+    nfp = c.nxzf * c.nfaces
+    upper = u.upper[u.graphindex // nfp]
+    one = u.graphindex[upper].copy()
+    assert 0 < one.size < u.graphindex.size
+    # oracle side: restrict the list (parameters of unlisted points are never read)
+    u.graphindex = one
+    c.set_callback("userfsrc", u.userfsrc(c))
+    s = _solver(c, gindex=one)
+    s.step(6); c.step(6)
+    assert rel_l2(_fields(s), _fields(c)) <= TOL
+    (fg, fo), (kg, ko) = _sheet_state(c, s)
+    assert rel_l2(fg, fo) <= TOL and rel_l2(kg, ko) <= TOL
+    s.close()
+
+
+def test_dropin_graphene_through_the_users_userfsrc():
+    """tests/2dgraphene TE through the Fortran shim: the .usr's userfsrc calls
+    cem_te_graphene_current(fjn,kfjn,resfjn,params,gindex,n) (2dgraphene.usr:267-269).  In the
+    drop-in build that name resolves to the library's twin: the first call (made by
+    b200_update_device through the user's own userfsrc) registers the user's arrays, yconduc
+    comes from COMMON /EMWAVE/ via b200_copy_all_in, and the currents then advance on the device.
+    Reference side: the oracle (bit-identical to the translated reference on this case).
+    userinc is left out on both sides (the shim has no device-side registration for it)."""
+    from oracle import cases, refrun
+    if not refrun.available("dropin"):
+        pytest.skip("oracle/_ref/libnekcem_ref_dropin.so did not travel with the tree")
+    nsteps = 20
+    c = cases.case_2dgraphene(1)
+    c.set_callback("userinc", lambda tt, *a: None)
+    c.step(nsteps)
+
+    c2 = cases.case_2dgraphene(1)
+    u = c2.user
+    drop = refrun.lib("dropin")
+    gidx = (u.graphindex + 1).astype(np.int32)
+    n = C.c_int(gidx.size)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    fjn, kfjn, resfjn, par = u.fjn.copy(), u.kfjn.copy(), u.resfjn.copy(), u.graphparams.copy()
+
+    def userfsrc(tt, *src):
+        drop.cem_te_graphene_current_(dp(fjn), dp(kfjn), dp(resfjn), dp(par),
+                                      gidx.ctypes.data_as(C.POINTER(C.c_int)), C.byref(n))
+
+    r = refrun.ReferenceRun(c2, kind="dropin")
+    r.put("yconduc", c2.yconduc)
+    r.set_callback("userfsrc", userfsrc)
+    r.L.b200_copy_all_in_()
+    r.L.b200_update_device_()
+    for _ in range(nsteps):
+        r.L.b200_op_rk_()
+        r.set("time", r.get("time") + r.get("dt"))
+    r.L.b200_update_host_()
+    n3 = 3 * c.npts
+    got = np.concatenate([r.view("hn")[:n3], r.view("en")[:n3]])
+    h = C.c_int(int(r.get("b200_handle")))
+    drop.nekcem_b200_get_graphene_(C.byref(h), dp(fjn), dp(kfjn))
+    r.L.b200_copy_all_out_()
+    r.close()
+    assert rel_l2(got, np.concatenate([c.hn, c.en])) <= TOL
+    assert np.abs(c.user.fjn).max() > 1e-3
+    assert rel_l2(fjn, c.user.fjn) <= TOL and rel_l2(kfjn, c.user.kfjn) <= TOL
