@@ -3,8 +3,7 @@ graphene_kernel + the face-source hook of the AUX stage kernels against the orac
 pinned bit for bit to the reference's cem_3d/te/tm_graphene_current and to the shipped
 tests/3dgraphene, tests/2dgraphene .usr files (tests/test_reference_pin.py).  The arithmetic of
 the per-point update is additionally checked on the CPU (tests/test_graphene_point.py).
-This file sorts after the other GPU suites on purpose: it was written after the round's GPU
-budget was spent and is the first thing to confirm on hardware."""
+Green on B200 (round 1, last GPU minutes of the round)."""
 import ctypes as C
 
 import numpy as np
@@ -15,6 +14,12 @@ from helpers import rel_l2, solver_from_refcase
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-12
+# RK registers of the sheet ODEs: kfjn = ca*kfjn + dt*res, where the critical-point residuals
+# res = -a_21*j - a_22*j' + b_2*f (a_21 ~ 4.6e5) are differences of terms 1e3..1e4 times larger
+# than the result.  The device contracts a*b+c to FMA, the oracle does not, so the last-bit
+# differences of those terms show up magnified in k (measured 4e-12 on B200) while the currents
+# fjn -- what enters the flux -- and the fields agree to ~3e-15.
+KTOL = 1e-10
 
 
 def _fields(obj):
@@ -66,7 +71,7 @@ def test_kat_2dgraphene_on_gpu(imode):
     assert rel_l2(_fields(s), _fields(c)) <= TOL
     (fg, fo), (kg, ko) = _sheet_state(c, s)
     assert np.abs(fo).max() > 1e-2
-    assert rel_l2(fg, fo) <= TOL and rel_l2(kg, ko) <= TOL
+    assert rel_l2(fg, fo) <= TOL and rel_l2(kg, ko) <= KTOL
     assert rel_l2(s.get_array("pmlbn"), c.pmlbn) <= TOL
     assert rel_l2(s.get_array("pmldn"), c.pmldn) <= TOL
     s.close()
@@ -88,7 +93,7 @@ def test_3dgraphene_parity_and_tolerances():
         assert np.all(linf <= np.array(c.tol["linf"])), (target, linf)
     assert rel_l2(_fields(s), _fields(c)) <= TOL
     (fg, fo), (kg, ko) = _sheet_state(c, s)
-    assert rel_l2(fg, fo) <= TOL and rel_l2(kg, ko) <= TOL
+    assert rel_l2(fg, fo) <= TOL and rel_l2(kg, ko) <= KTOL
     s.step(30)
     shn, sen = c.usersol(c, s.time)
     l2, linf = s.cem_error(shn, sen)
@@ -100,15 +105,17 @@ def test_3dgraphene_parity_and_tolerances():
 def test_graphene_stage_by_stage(which):
     """every RK stage of the first two steps separately: fields and the sheet state"""
     from oracle import cases
+    # fixed dt = 4e-3 in 2D: the CFL step of a coarse mesh would leave the stability region of
+    # the stiff sheet ODEs (see oracle/cases.py: case_2dgraphene)
     c = cases.case_3dgraphene(nx1=6, nel=(3, 6, 3)) if which == "3d" else cases.case_2dgraphene(
-        1, nx1=7, nel=(3, 8))
+        1, nx1=7, nel=(3, 16), dt=-4e-3)
     s = _solver(c)
     for step in range(2):
         for rk in range(1, 6):
             s.stage(rk); c.stage(rk)
             assert rel_l2(_fields(s), _fields(c)) <= TOL, (step, rk)
             (fg, fo), (kg, ko) = _sheet_state(c, s)
-            assert rel_l2(fg, fo) <= TOL and rel_l2(kg, ko) <= TOL, (step, rk)
+            assert rel_l2(fg, fo) <= TOL and rel_l2(kg, ko) <= KTOL, (step, rk)
         t = c.s.time + c.s.dt
         c.s.time = t
         s.set_time(t, c.s.dt)
@@ -132,7 +139,7 @@ def test_graphene_listed_on_one_side_only():
     s.step(6); c.step(6)
     assert rel_l2(_fields(s), _fields(c)) <= TOL
     (fg, fo), (kg, ko) = _sheet_state(c, s)
-    assert rel_l2(fg, fo) <= TOL and rel_l2(kg, ko) <= TOL
+    assert rel_l2(fg, fo) <= TOL and rel_l2(kg, ko) <= KTOL
     s.close()
 
 
@@ -181,4 +188,4 @@ def test_dropin_graphene_through_the_users_userfsrc():
     r.close()
     assert rel_l2(got, np.concatenate([c.hn, c.en])) <= TOL
     assert np.abs(c.user.fjn).max() > 1e-3
-    assert rel_l2(fjn, c.user.fjn) <= TOL and rel_l2(kfjn, c.user.kfjn) <= TOL
+    assert rel_l2(fjn, c.user.fjn) <= TOL and rel_l2(kfjn, c.user.kfjn) <= KTOL
