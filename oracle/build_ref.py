@@ -75,6 +75,9 @@ UNITS = [
     ("tests/drude/drude.usr", ["userinc", "usersrc", "usersol", "userini", "uservp"], "__drude"),
     ("tests/lorentz/lorentz.usr", ["userinc", "usersrc", "usersol", "userini", "uservp"],
      "__lorentz"),
+    ("tests/2ddielectric/2ddielectric.usr", ["userinc", "usersol", "userini", "uservp",
+                                             "usrdat2"], "__2ddielectric"),
+    ("tests/2dboxpml/2dboxpml.usr", ["usersrc", "usrdat2"], "__2dboxpml"),
     ("tests/3dgraphene/3dgraphene.usr", ["userinc", "userfsrc", "usersol", "userini", "uservp",
                                          "usrdat2"], "__3dgraphene"),
     ("tests/2dgraphene/2dgraphene.usr", ["userinc", "userfsrc", "usersol", "userini", "uservp",

@@ -269,6 +269,128 @@ def case_3ddielectric(twomat=False, nx1=9, nel=(4, 8, 4)):
     return c
 
 
+class _Dielectric2D(_Dielectric):
+    """tests/2ddielectric/2ddielectric.usr: the same interface problem in 2D, one polarisation
+    per run (TE: hz, ex; TM: ez, hx), omega = 5."""
+
+    def __init__(self, imode: int, twomat: bool):
+        super().__init__(twomat)
+        self.imode = imode
+        self.omega = 5.0
+        z1 = math.sqrt(self.mu1 / self.eps1)
+        z2 = math.sqrt(self.mu2 / self.eps2)
+        if imode == 1:   # 2ddielectric.usr:241-243
+            self.refl, self.tran = (z1 - z2) / (z1 + z2), 2 * z1 / (z1 + z2)
+        else:            # :244-246
+            self.refl, self.tran = (z2 - z1) / (z1 + z2), 2 * z2 / (z1 + z2)
+        self.reflte = self.refltm = self.trante = self.trantm = None  # 3D names: unused
+
+    def usrdat2(self, case):
+        for arr, s in zip((case.xm1, case.ym1), (5.0, 10.0)):
+            mn, mx = arr.min(), arr.max()
+            arr[:] = s * (arr - mn) / (mx - mn) - (s / 2.0)
+
+    def _mid(self, case):
+        h = case.nx1 // 2 - 1
+        return h + case.nx1 * h
+
+    def _amp(self, eta):
+        amp = np.zeros((6,) + np.shape(eta))
+        if self.imode == 1:
+            amp[2] = 1.0; amp[3] = eta
+        else:
+            amp[5] = 1.0; amp[0] = -1.0 / eta
+        return amp
+
+    def userinc(self, case):
+        j = self.incindex
+        k = case.cemface[j]
+        eps = case.permittivity[k]; mu = case.permeability[k]
+        eta = np.sqrt(mu / eps)
+        ky = self.omega * np.sqrt(mu * eps)
+        yy = case.ym1[k]
+
+        def cb(tt, fhx, fhy, fhz, fex, fey, fez):
+            uinc = np.cos(-ky * yy - self.omega * tt)
+            if self.imode == 1:
+                fhz[j] = fhz[j] + uinc
+                fex[j] = fex[j] + eta * uinc
+            else:
+                fez[j] = fez[j] + uinc
+                fhx[j] = fhx[j] - uinc / eta
+
+        return cb
+
+    def incident(self, case):
+        """the same userinc as arguments of MaxwellB200.set_incident"""
+        j = self.incindex
+        k = case.cemface[j]
+        eps = case.permittivity[k]; mu = case.permeability[k]
+        eta = np.sqrt(mu / eps)
+        ky = self.omega * np.sqrt(mu * eps)
+        return j, self._amp(eta), -ky * case.ym1[k], self.omega
+
+    def usersol(self, case, tt):
+        n = case.npts
+        eps = case.permittivity; mu = case.permeability
+        eta = np.sqrt(mu / eps)
+        ky = self.omega * np.sqrt(eps * mu)
+        yy = case.ym1
+        upper = np.repeat(self.upper, case.nxyz)
+        inpml = np.repeat(case.pmltag != 0, case.nxyz)
+        order, referr = case.pmlorder, case.pmlreferr
+        d = case.pmlouter[3] - case.pmlinner[3]
+        smax = -(order + 1) * math.log(referr) / (2 * eta * d)
+        with np.errstate(invalid="ignore"):
+            fu = (smax * d / (order + 1)) * ((yy - case.pmlinner[3]) / d) ** (order + 1)
+        d2 = case.pmlinner[2] - case.pmlouter[2]
+        smax2 = -(order + 1) * math.log(referr) / (2 * eta * d2)
+        with np.errstate(invalid="ignore"):
+            fl = (smax2 * d2 / (order + 1)) * ((case.pmlinner[2] - yy) / d2) ** (order + 1)
+        pmlfac = np.where(inpml, np.where(upper, fu, fl), 0.0)
+        uu_u = self.refl * np.exp(-eta * pmlfac) * np.cos(ky * yy - self.omega * tt)
+        uu_l = self.tran * np.exp(-eta * pmlfac) * np.cos(-ky * yy - self.omega * tt)
+        shn = np.zeros(3 * n); sen = np.zeros(3 * n)
+        if self.imode == 1:
+            shn[2 * n:] = np.where(upper, uu_u, uu_l)                # hz
+            sen[0:n] = np.where(upper, -eta * uu_u, eta * uu_l)      # ex
+        else:
+            sen[2 * n:] = np.where(upper, uu_u, uu_l)                # ez
+            shn[0:n] = np.where(upper, uu_u / eta, -uu_l / eta)      # hx
+        return shn, sen
+
+
+def case_2ddielectric(imode=1, twomat=False, nx1=9, nel=(4, 32)):
+    """tests/2ddielectric (.box 4x32, BC P,P,PML,PML; N=8; dt=5e-3; 1000 steps; param(70)=1 ->
+    two materials; PML thick 10, order 3, referr 1e-30).  Tolerances (2ddielectric.usr userchk):
+    one material 5e-8 / 1e-6 (TM Linf 5e-6), two materials 5e-7 / 5e-6; zero component
+    ~1e-14 / 1e-12."""
+    mesh = O.box_mesh(nel, ((-1500.0, 1500.0),) * 2, ("P  ", "P  ", "PML", "PML"))
+    u = _Dielectric2D(imode, twomat)
+    c = O.RefCase(mesh, nx1, imode=imode, upwind=True, usrdat2=u.usrdat2, uservp=u.uservp,
+                  param={77: 10, 78: 3.0, 79: 1e-30, 70: 1 if twomat else 0})
+    c.user = u
+    c.set_dt(-0.005)
+    c.usersol = lambda case, tt: u.usersol(case, tt)
+    shn, sen = u.usersol(c, 0.0)
+    c.hn[:] = shn; c.en[:] = sen
+    n = c.npts
+    for k in range(3):  # userini
+        c.pmlbn[k * n:(k + 1) * n] = c.permeability * shn[k * n:(k + 1) * n]
+        c.pmldn[k * n:(k + 1) * n] = c.permittivity * sen[k * n:(k + 1) * n]
+    c.set_callback("userinc", u.userinc(c))
+    if twomat:
+        w, z, wi, zi = 5e-7, 5e-15 if imode == 1 else 1e-14, 5e-6, 5e-13
+    else:
+        w, z, wi, zi = 5e-8, 1e-14, 1e-6 if imode == 1 else 5e-6, 1e-12
+    if imode == 1:   # hz, ex wave; ey zero
+        c.tol = dict(l2=[0, 0, w, w, z, 0], linf=[0, 0, wi, wi, zi, 0])
+    else:            # hx, ez wave; hy zero
+        c.tol = dict(l2=[w, z, 0, 0, 0, w], linf=[wi, zi, 0, 0, 0, wi])
+    c.nsteps = 1000
+    return c
+
+
 # ------------------------------------------------------------------------------------
 # tests/3dboxpml : Gaussian-pulsed dipole in an all-PML box (stability check only)
 # ------------------------------------------------------------------------------------
@@ -309,6 +431,48 @@ def case_3dboxpml(nx1=9, nel=(6, 6, 6)):
     c.usersol = lambda case, tt: (np.zeros(3 * case.npts), np.zeros(3 * case.npts))
     c.tol = dict(l2=[1.0] * 6, linf=[1.0] * 6)
     c.nsteps = 2000
+    return c
+
+
+def usersrc_2dboxpml(case):
+    """tests/2dboxpml/2dboxpml.usr usersrc: 2D Gaussian source, srchz (TE) or srcez (TM)
+    -= i0*norm*exp(-r^2/(2 w^2)) * sin(-omega t) * bm1 with norm = 1/(2 pi w^2)."""
+    omega, width, i0 = 2.0, 0.1, 1.0
+    norm = 1.0 / (8 * math.atan(1.0) * width ** 2)
+    xfac = -0.5 * ((case.xm1 - 0.0) / width) ** 2
+    yfac = -0.5 * ((case.ym1 - 0.0) / width) ** 2
+    g = i0 * norm * np.exp(xfac + yfac)
+    te = case.imode == 1
+
+    def cb(tt, shx, shy, shz, sex, sey, sez):
+        tfac = math.sin(-omega * tt)
+        tgt = shz if te else sez
+        tgt[:] = tgt - g * (tfac * case.bmn)
+
+    cb.profile = g
+    cb.omega = omega
+    cb.comp = 2 if te else 5
+    return cb
+
+
+def case_2dboxpml(imode=1, nx1=9, nel=(8, 8)):
+    """tests/2dboxpml (.box 8x8, all PML, thick 2, order 3, referr 1e-8, CFL 0.1; zero initial
+    fields; usrdat2 maps onto [-1,1]^2; 4000 steps).  userchk only bounds |fields| <= 1."""
+    mesh = O.box_mesh(nel, ((-1500.0, 1500.0),) * 2, ("PML",) * 4)
+
+    def usrdat2(case):
+        for arr in (case.xm1, case.ym1):
+            mn, mx = arr.min(), arr.max()
+            arr[:] = 2.0 * (arr - mn) / (mx - mn) - 2.0 / 2.0
+
+    c = O.RefCase(mesh, nx1, imode=imode, upwind=True, usrdat2=usrdat2,
+                  param={77: 2, 78: 3.0, 79: 1e-8})
+    c.set_dt(0.1)
+    c.usersrc_fn = usersrc_2dboxpml(c)
+    c.set_callback("usersrc", c.usersrc_fn)
+    c.usersol = lambda case, tt: (np.zeros(3 * case.npts), np.zeros(3 * case.npts))
+    c.tol = dict(l2=[1.0] * 6, linf=[1.0] * 6)
+    c.nsteps = 4000
     return c
 
 

@@ -122,3 +122,27 @@ def test_kat_3dgraphene():
     c = cases.case_3dgraphene()
     assert c.nelt == 192 and c.user.graphindex.size == 32 * 81 and c.user.incindex.size == 16 * 81
     _check(c, list(range(1, 11)) + list(range(50, 301, 50)), 300)
+
+
+@pytest.mark.parametrize("imode", [1, 2])
+@pytest.mark.parametrize("twomat", [False, True])
+def test_kat_2ddielectric(imode, twomat):
+    """tests/2ddielectric TE/TM with one and two materials: 4x32 elements, N=8, dt=5e-3, PML
+    thick 10 in +-y, plane-wave injection through userinc; tolerances of the .usr's userchk
+    (5e-8 / 1e-6 one material, 5e-7 / 5e-6 two; ~1e-14 on the zero component) at steps 1..10 and
+    every 100 of all 1000 steps."""
+    c = cases.case_2ddielectric(imode, twomat)
+    assert c.nelt == 128 and c.maxpml == 80 and c.user.incindex.size == 4 * 9
+    _check(c, list(range(1, 11)) + list(range(100, 1001, 100)), 1000)
+
+
+@pytest.mark.parametrize("imode", [1, 2])
+def test_kat_2dboxpml_stability(imode):
+    """tests/2dboxpml TE/TM: all-PML 8x8 box (thick 2) with a Gaussian source; userchk only
+    requires the fields to stay below 1.0.  800 of the 4000 steps at CFL 0.1."""
+    c = cases.case_2dboxpml(imode)
+    assert c.maxpml == 64 - 16
+    c.step(800)
+    assert np.all(np.isfinite(c.hn)) and np.all(np.isfinite(c.en))
+    assert np.max(np.abs(c.en)) < 1.0 and np.max(np.abs(c.hn)) < 1.0
+    assert np.max(np.abs(c.en)) > 1e-3  # the source did radiate

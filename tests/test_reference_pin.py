@@ -800,3 +800,101 @@ def test_pin_graphene_case_with_its_whole_usr(which):
         L.cem_error_(_dp(fld), _dp(sol[k]), _dp(err), C.byref(nn), C.byref(l2), C.byref(linf))
         assert l2.value <= c.tol["l2"][k] and linf.value <= c.tol["linf"][k], (k, l2.value, linf.value)
     r.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# the remaining 2D Maxwell configurations of the reference's test suite
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("imode", [1, 2])
+@pytest.mark.parametrize("twomat", [False, True])
+def test_pin_2ddielectric_with_its_whole_usr(imode, twomat):
+    """tests/2ddielectric (TE/TM x one/two materials) driven by its own .usr: usrdat2, uservp
+    (materials from param(70), reflection/transmission coefficient of the mode, incident-face
+    index), userini -> usersol (fields incl. the PML decay factor, pmlbn/pmldn), userinc in every
+    stage, usersol at the end and the userchk tolerances evaluated by the reference's cem_error."""
+    from oracle import oracle as O
+    c = cases.case_2ddielectric(imode, twomat)
+    u = c.user
+    sfx = "__2ddielectric"
+    r = refrun.ReferenceRun(c)
+    L = r.L
+    raw = O.RefCase(c.mesh, c.nx1, imode=imode)
+    r.put("xm1", raw.xm1); r.put("ym1", raw.ym1)
+    _usr(L, "usrdat2", "2ddielectric")()
+    assert np.array_equal(r.view("xm1")[:c.npts], c.xm1)
+    assert np.array_equal(r.view("ym1")[:c.npts], c.ym1)
+    r.view("param")[69] = 1.0 if twomat else 0.0       # param(70)
+    r.put("pmltag", c.pmltag); r.put("pmlinner", c.pmlinner); r.put("pmlouter", c.pmlouter)
+    r.set("pmlorder", c.pmlorder); r.set("pmlreferr", c.pmlreferr)
+    n, n3 = c.npts, 3 * c.npts
+    one = C.c_int(1)
+    r.view("permittivity")[:] = 0.0
+    _usr(L, "uservp", "2ddielectric")(C.byref(one), C.byref(one), C.byref(one), C.byref(one))
+    assert np.array_equal(r.view("permittivity")[:n], c.permittivity)
+    assert np.array_equal(r.view("permeability")[:n], c.permeability)
+    ninc = int(r.get("ninc" + sfx))
+    assert ninc == u.incindex.size and np.array_equal(r.view("incindex" + sfx)[:ninc], u.incindex + 1)
+    assert r.get("refl" + sfx) == u.refl and r.get("tran" + sfx) == u.tran
+    hn, en = r.view("hn"), r.view("en")
+    hn[:] = 0.0; en[:] = 0.0
+    tt = C.c_double(0.0)
+    _usr(L, "userini", "2ddielectric")(C.byref(tt), _dp(hn[0:]), _dp(hn[n:]), _dp(hn[2 * n:]),
+                                      _dp(en[0:]), _dp(en[n:]), _dp(en[2 * n:]))
+    assert np.abs(hn[:n3] - c.hn).max() <= 4e-15 and np.abs(en[:n3] - c.en).max() <= 4e-15
+    assert np.abs(r.view("pmldn")[:n3] - c.pmldn).max() <= 8e-15
+    assert np.abs(r.view("pmlbn")[:n3] - c.pmlbn).max() <= 8e-15
+    L.ref_set_user(0, C.cast(_usr(L, "userinc", "2ddielectric"), refrun.USERCB))
+    c.step(40); r.step(40)
+    num = np.sqrt(np.sum((c.hn - hn[:n3]) ** 2) + np.sum((c.en - en[:n3]) ** 2))
+    den = np.sqrt(np.sum(c.hn ** 2) + np.sum(c.en ** 2))
+    assert num / den <= 1e-12
+    sol = [np.zeros(n) for _ in range(6)]
+    tt = C.c_double(c.time)
+    _usr(L, "usersol", "2ddielectric")(C.byref(tt), *[_dp(a) for a in sol])
+    mh, me = u.usersol(c, c.time)
+    for k in range(3):
+        assert np.abs(sol[k] - c.comp(mh, k)).max() <= 4e-15
+        assert np.abs(sol[3 + k] - c.comp(me, k)).max() <= 4e-15
+    r.set("volvm1", c.volvm1)
+    err = np.zeros(n)
+    nn = C.c_int(n)
+    for k in range(6):
+        if c.tol["l2"][k] == 0:
+            continue
+        fld = np.ascontiguousarray(c.comp(c.hn if k < 3 else c.en, k % 3))
+        l2, linf = C.c_double(), C.c_double()
+        L.cem_error_(_dp(fld), _dp(sol[k]), _dp(err), C.byref(nn), C.byref(l2), C.byref(linf))
+        assert l2.value <= c.tol["l2"][k] and linf.value <= c.tol["linf"][k], (k, l2.value, linf.value)
+    r.close()
+
+
+@pytest.mark.parametrize("imode", [1, 2])
+def test_pin_2dboxpml_with_the_shipped_usr(imode):
+    """tests/2dboxpml TE / TM driven by its own usrdat2 and usersrc (2D Gaussian source into hz
+    or ez): bit-level PML state is covered by _assert_same on the oracle-side callback run, the
+    .usr-driven run agrees to the round-off of libm vs numpy exp/sin"""
+    from oracle import oracle as O
+    c = cases.case_2dboxpml(imode, nx1=7, nel=(6, 6))
+    r = refrun.ReferenceRun(c)
+    raw = O.RefCase(c.mesh, c.nx1, imode=imode)
+    r.put("xm1", raw.xm1); r.put("ym1", raw.ym1)
+    _usr(r.L, "usrdat2", "2dboxpml")()
+    assert np.array_equal(r.view("xm1")[:c.npts], c.xm1)
+    assert np.array_equal(r.view("ym1")[:c.npts], c.ym1)
+    r.L.ref_set_user(1, C.cast(_usr(r.L, "usersrc", "2dboxpml"), refrun.USERCB))
+    c.step(30); r.step(30)
+    n3 = 3 * c.npts
+    num = np.sqrt(np.sum((c.hn - r.hn) ** 2) + np.sum((c.en - r.en) ** 2))
+    den = np.sqrt(np.sum(c.hn ** 2) + np.sum(c.en ** 2))
+    assert den > 1e-8 and num / den <= 1e-13
+    for name in ("pmlbn", "pmldn"):
+        a, b = getattr(c, name), r.view(name)[:n3]
+        assert np.abs(a - b).max() <= 1e-13 * max(np.abs(a).max(), 1e-300), name
+    r.close()
+    # the same case with the oracle's own callback on both sides: bit for bit
+    c = cases.case_2dboxpml(imode, nx1=7, nel=(6, 6))
+    r = refrun.ReferenceRun(c)
+    r.set_callback("usersrc", c.usersrc_fn)
+    c.step(30); r.step(30)
+    _assert_same(c, r)
+    r.close()
