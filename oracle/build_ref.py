@@ -46,7 +46,8 @@ UNITS = [
     ("src/nek5_mat1.F", ["chsign", "rzero", "rone", "copy", "addcol3", "addcol4", "subcol3",
                          "subcol4", "ascol5", "col2", "col3", "invcol1", "invcol3", "invers2",
                          "vdot2", "vdot3", "vcross", "unitvec", "rzero3", "cmult", "sub3",
-                         "izero", "vlmax", "vlmin", "glsc3", "glamax", "glmin", "glmax"]),
+                         "izero", "vlmax", "vlmin", "glsc3", "glamax", "glmin", "glmax",
+                         "addtnsr", "mod1"]),
     # setup routines whose OUTPUT the path consumes: GLL nodes/weights and
     # derivative matrix, metric cofactors / Jacobian / mass, face areas and normals
     ("src/nek5_speclib.F", ["zwgll", "zwglj", "zwgljd", "jacg", "jacobf", "zwgjd", "endw1",
@@ -54,9 +55,9 @@ UNITS = [
     ("src/nek5_coef.F", ["xyzrst", "glmapm1", "chkjac", "geodat1", "setarea", "area2", "area3",
                          "setwgtr", "set_unr"]),
     ("src/nek5_subs2.F", ["facexv", "setaxdy", "setaxw1"]),
-    # node coordinates from the element vertices (straight-sided elements; the curved-side
-    # generators sphsrf / gensrf / arcsrf are outside the configs of the path)
-    ("src/nek5_genxyz.F", ["genxyz", "setzgml"]),
+    # node coordinates from the element vertices, incl. circular-arc sides (tests/cylwave); the
+    # other curved-side generators sphsrf / gensrf are outside the configs of the path
+    ("src/nek5_genxyz.F", ["genxyz", "setzgml", "arcsrf"]),
     # setup routines that define the face numbering the path relies on
     ("src/nek5_connect11.F", ["initds", "dsset"]),
     # the analytic solutions the reference's own tests check against: the
@@ -75,6 +76,8 @@ UNITS = [
     ("tests/drude/drude.usr", ["userinc", "usersrc", "usersol", "userini", "uservp"], "__drude"),
     ("tests/lorentz/lorentz.usr", ["userinc", "usersrc", "usersol", "userini", "uservp"],
      "__lorentz"),
+    ("tests/cylwave/cylwave.usr", ["usrdat", "usrdat2"], "__cylwave"),
+    ("src/cem_common.F", ["geom_xyradius"]),
     ("tests/2ddielectric/2ddielectric.usr", ["userinc", "usersol", "userini", "uservp",
                                              "usrdat2"], "__2ddielectric"),
     ("tests/2dboxpml/2dboxpml.usr", ["usersrc", "usrdat2"], "__2dboxpml"),

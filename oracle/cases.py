@@ -18,8 +18,10 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests",
 
 def _load_mesh(name):
     d = np.load(os.path.join(GOLDEN, name))
+    extra = dict(ccurve=d["ccurve"], curve=d["curve"]) if "ccurve" in d.files else {}
     return O.mesh_from_arrays(int(d["ndim"]), d["xc"], d["yc"], d["zc"],
-                              [[str(c) for c in row] for row in d["cbc"]], d["vertex"]), d["part"]
+                              [[str(c) for c in row] for row in d["cbc"]], d["vertex"],
+                              **extra), d["part"]
 
 
 def _rescale(case, lo, hi):
@@ -721,6 +723,86 @@ def case_lorentz(nx1=9, nel=(4, 32), thick=6):
     (lorentz.usr:373-387)."""
     c = _case_dispersive("lorentz", nx1, nel, thick)
     c.tol = dict(l2=[0, 0, 5e-6, 5e-6, 5e-10, 0], linf=[0, 0, 5e-5, 5e-5, 5e-10, 0])
+    return c
+
+
+# ------------------------------------------------------------------------------------
+# tests/cylwave : TM_01 mode of a circular PEC waveguide, periodic along z -- an unstructured
+# mesh of 5 x 10 hexahedra whose outer sides are circular arcs (curved, non-affine elements)
+# ------------------------------------------------------------------------------------
+BSSLJ_RT_0_1 = 2.4048255576957729   # bsrt(0,1): first zero of J_0 (src/cem_bessel.F:870)
+
+
+def geom_xyradius(mesh):
+    """src/cem_common.F:817-843: largest radius of the element corners in the x-y plane"""
+    return math.sqrt(float(np.max(mesh.xc * mesh.xc + mesh.yc * mesh.yc)))
+
+
+def usrdat_cylwave(mesh):
+    """cylwave.usr usrdat: corners within 1e-4 (squared) of the outer radius, rounded to one
+    decimal, are projected onto it"""
+    radius = geom_xyradius(mesh)
+    radius = int(10 * radius + 0.1) / 10.0
+    e1 = radius * radius - 1e-4
+    rr = mesh.xc * mesh.xc + mesh.yc * mesh.yc
+    outer = rr > e1
+    rn = np.where(outer, radius / np.sqrt(np.where(outer, rr, 1.0)), 1.0)
+    mesh.xc[:] = np.where(outer, rn * mesh.xc, mesh.xc)
+    mesh.yc[:] = np.where(outer, rn * mesh.yc, mesh.yc)
+
+
+def usrdat2_cylwave(case):
+    """cylwave.usr usrdat2: the z extent becomes 2 pi xmax"""
+    pi = 4.0 * math.atan(1.0)
+    zmin, zmax = case.zm1.min(), case.zm1.max()
+    sz = 2 * pi * case.xm1.max() / (zmax - zmin)
+    case.zm1[:] = sz * (case.zm1 - zmin)
+
+
+def usersol_cylwave(case, tt):
+    """cylwave.usr usersol (de Wolf, Essentials of Electromagnetics for Engineering, 19.7): TM
+    mode m = 0, first root, one wavelength along z.  J_0 and J_0' = -J_1 from scipy (the
+    reference evaluates them with Cody's RJBESL, src/cem_bessel.F; not translated)."""
+    from scipy import special
+    n = case.npts
+    pi = 4.0 * math.atan(1.0)
+    radius = case.cyl_radius
+    xx, yy, zz = case.xm1, case.ym1, case.zm1
+    zsize = zz.max() - zz.min()
+    kz = 2 * pi * 1.0 / zsize
+    rho = np.sqrt(xx ** 2 + yy ** 2)
+    phi = np.arctan2(yy, xx)
+    bigk = BSSLJ_RT_0_1 / radius
+    omega = math.sqrt(kz ** 2 + bigk ** 2)
+    allfac = np.exp(-1j * kz * zz) * np.exp(1j * omega * tt)
+    j0 = special.j0(bigk * rho)
+    j0p = -special.j1(bigk * rho)
+    ezz = (allfac * j0).real
+    erho = (allfac * (-1j) * kz / bigk * j0p).real
+    hphi = (allfac * (-1j) * omega * 1.0 / bigk * j0p).real
+    shn = np.zeros(3 * n); sen = np.zeros(3 * n)
+    shn[0:n] = -np.sin(phi) * hphi
+    shn[n:2 * n] = np.cos(phi) * hphi
+    sen[0:n] = np.cos(phi) * erho
+    sen[n:2 * n] = np.sin(phi) * erho
+    sen[2 * n:] = ezz
+    return shn, sen
+
+
+def case_cylwave(nx1=12):
+    """tests/cylwave (50 elements from the reference's .rea/.map, 80 circular-arc sides, PEC wall,
+    periodic in z; N=11; param(12)=+0.25 -> CFL dt; 1000 steps).  Tolerances 5e-9 / 5e-8 on all
+    six components (cylwave.usr userchk)."""
+    mesh, _ = _load_mesh("cylwave_mesh.npz")
+    usrdat_cylwave(mesh)
+    c = O.RefCase(mesh, nx1, upwind=True, usrdat2=usrdat2_cylwave)
+    c.cyl_radius = geom_xyradius(mesh)
+    c.set_dt(0.25)
+    c.usersol = usersol_cylwave
+    shn, sen = usersol_cylwave(c, 0.0)
+    c.hn[:] = shn; c.en[:] = sen
+    c.tol = dict(l2=[5e-9] * 6, linf=[5e-8] * 6)
+    c.nsteps = 1000
     return c
 
 

@@ -678,6 +678,9 @@ class Translator:
         if u.kind == "function" and u.ftype is None:
             r = u.syms.get(u.name)
             u.ftype = r.ftype if r else implicit_type(u.name)
+        if u.kind == "function" and u.name not in u.syms:
+            # `real function f()` under implicit none: the header types the result variable
+            u.sym(u.name).ftype = u.ftype
 
 
 # ------------------------------------------------------------------ emission

@@ -156,7 +156,10 @@ class Mesh:
     (preprocessor order 1..6 = -y,+x,+y,-x,-z,+z), global vertex ids (symmetric order
     l = i + 2j + 4k) and, for box meshes, the box shape."""
 
-    def __init__(self, ldim, xc, yc, zc, cbc, vertex, nelbox=None):
+    def __init__(self, ldim, xc, yc, zc, cbc, vertex, nelbox=None, ccurve=None, curve=None):
+        # curved sides (src/INPUT: CCURVE(12,lelt), CURVE(6,12,lelt)): ccurve[e][edge] is the
+        # 1-char flag (' ' straight, 'C' circular arc of radius curve[e,edge,0]); None = none
+        self.ccurve, self.curve = ccurve, curve
         self.ldim = ldim
         self.xc, self.yc, self.zc = xc, yc, zc
         self.cbc = cbc  # list[nelt][2*ldim] of 3-char strings
@@ -254,11 +257,13 @@ def box_mesh(nel, lo_hi, bcs, gain=(1.0, 1.0, 1.0)) -> Mesh:
     return Mesh(ldim, xc, yc, zc, cbc, vertex, nelbox=(nelx, nely, nelz))
 
 
-def mesh_from_arrays(ldim, xc, yc, zc, cbc, vertex) -> Mesh:
+def mesh_from_arrays(ldim, xc, yc, zc, cbc, vertex, ccurve=None, curve=None) -> Mesh:
     return Mesh(ldim, np.ascontiguousarray(xc, dtype=np.float64),
                 np.ascontiguousarray(yc, dtype=np.float64),
                 np.ascontiguousarray(zc, dtype=np.float64),
-                [list(r) for r in cbc], np.ascontiguousarray(vertex, dtype=np.int64))
+                [list(r) for r in cbc], np.ascontiguousarray(vertex, dtype=np.int64),
+                ccurve=None if ccurve is None else [[str(c) for c in r] for r in ccurve],
+                curve=None if curve is None else np.ascontiguousarray(curve, dtype=np.float64))
 
 
 # ----------------------------------------------------------------------------------
@@ -373,6 +378,9 @@ class RefCase:
         L.ora_genxyz(ldim, nx1, nelt, dp(self.zgm1), dp(np.ascontiguousarray(mesh.xc)),
                      dp(np.ascontiguousarray(mesh.yc)), dp(np.ascontiguousarray(mesh.zc)),
                      dp(self.xm1), dp(self.ym1), dp(self.zm1))
+        # curved sides: the ARCSRF loop of GENXYZ (src/nek5_genxyz.F:669-674)
+        if mesh.ccurve is not None:
+            self._arcsrf()
         # usrdat2 (user rescale) then geom_reset
         if usrdat2 is not None:
             usrdat2(self)
@@ -471,6 +479,65 @@ class RefCase:
         self._cbs = {}
 
     # -- helpers ---------------------------------------------------------------------
+    def _arcsrf(self):
+        """ARCSRF (src/nek5_genxyz.F:2-108, non-axisymmetric branch) for every edge flagged 'C',
+        in GENXYZ's order (elements, then ISID = 1..8): the edge between preprocessor corners
+        ISID and ISID+1 becomes a circular arc of radius CURVE(1,ISID,IE); the deviation from
+        the straight edge is blended into the element with the linear hat functions (ADDTNSR,
+        src/nek5_mat1.F:1003-1019).  libm sin/cos/atan2 point by point (math.*), so that the
+        coordinates equal the reference's bit for bit."""
+        import math
+        mesh, n, ldim = self.mesh, self.nx1, self.ldim
+        nz = n if ldim == 3 else 1
+        z = self.zgm1
+        h = [(1.0 - z) * 0.5, (1.0 + z) * 0.5]                 # H(.,d,1), H(.,d,2), d = 1,2
+        h3 = h if ldim == 3 else [np.ones(nz), np.ones(nz)]     # H(.,3,.)
+        eface1 = (3, 2, 4, 1)
+        for e in range(self.nelt):
+            sl = slice(e * self.nxyz, (e + 1) * self.nxyz)
+            X = self.xm1[sl].reshape(nz, n, n)                  # [iz, iy, ix]
+            Y = self.ym1[sl].reshape(nz, n, n)
+            for isid in range(1, 9):
+                if mesh.ccurve[e][isid - 1] != "C":
+                    continue
+                nxt = {4: 1, 8: 5}.get(isid, isid + 1)
+                pt1x, pt1y = float(mesh.xc[e, isid - 1]), float(mesh.yc[e, isid - 1])
+                pt2x, pt2y = float(mesh.xc[e, nxt - 1]), float(mesh.yc[e, nxt - 1])
+                radius = float(mesh.curve[e, isid - 1, 0])
+                gap = math.sqrt((pt1x - pt2x) ** 2 + (pt1y - pt2y) ** 2)
+                if abs(2.0 * radius) <= gap * 1.00001:
+                    raise ValueError("arcsrf: radius too small for side %d of element %d" % (isid, e + 1))
+                xs = pt2y - pt1y
+                ys = pt1x - pt2x
+                xys = math.sqrt(xs ** 2 + ys ** 2)
+                dtheta = abs(math.asin(0.5 * gap / radius))
+                pt12x = (pt1x + pt2x) / 2.0
+                pt12y = (pt1y + pt2y) / 2.0
+                xcenn = pt12x - xs / xys * radius * math.cos(dtheta)
+                ycenn = pt12y - ys / xys * radius * math.cos(dtheta)
+                theta0 = math.atan2(pt12y - ycenn, pt12x - xcenn)
+                isid1 = (isid - 1) % 4 + 1                       # MOD1(ISID,4)
+                xcrv = np.zeros(n); ycrv = np.zeros(n)
+                for ix in range(n):
+                    ixt = n - 1 - ix if isid1 > 2 else ix
+                    r = float(z[ix])
+                    if radius < 0.0:
+                        r = -r
+                    xcrv[ixt] = (xcenn + abs(radius) * math.cos(theta0 + r * dtheta)
+                                 - (float(h[0][ix]) * pt1x + float(h[1][ix]) * pt2x))
+                    ycrv[ixt] = (ycenn + abs(radius) * math.sin(theta0 + r * dtheta)
+                                 - (float(h[0][ix]) * pt1y + float(h[1][ix]) * pt2y))
+                f = eface1[isid1 - 1]
+                hz = h3[(isid - 1) // 4]
+                if f <= 2:   # x-face: S(ix,iy,iz) += (crv(iy)*H3(iz)) * H(ix,1,f)
+                    for S, crv in ((X, xcrv), (Y, ycrv)):
+                        hh = crv[None, :] * hz[:, None]          # [iz, iy]
+                        S += hh[:, :, None] * h[f - 1][None, None, :]
+                else:        # y-face: S += (H(iy,2,f-2)*H3(iz)) * crv(ix)
+                    for S, crv in ((X, xcrv), (Y, ycrv)):
+                        hh = h[f - 3][None, :] * hz[:, None]
+                        S += hh[:, :, None] * crv[None, None, :]
+
     def comp(self, arr, c):
         n = arr.size // 3
         return arr[c * n:(c + 1) * n]

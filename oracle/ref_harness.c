@@ -52,4 +52,3 @@ EXPORT void bcast_(void *buf, int *len) { (void)buf; (void)len; }
 /* curved-side generators (src/nek5_genxyz.F): no case of the path has curved sides */
 EXPORT void sphsrf_(void) { fprintf(stderr, "sphsrf is outside the path\n"); exit(1); }
 EXPORT void gensrf_(void) { fprintf(stderr, "gensrf is outside the path\n"); exit(1); }
-EXPORT void arcsrf_(void) { fprintf(stderr, "arcsrf is outside the path\n"); exit(1); }

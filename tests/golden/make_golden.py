@@ -92,9 +92,26 @@ def read_rea_mesh(path):
     return ndim, xc, yc, zc, cbc
 
 
-def save(name, ndim, xc, yc, zc, cbc, part, vertex):
+def read_rea_curves(path, nel):
+    """"***** CURVED SIDE DATA *****" block of a .rea (src/nek5_connect2.F rdcurve, nelgt < 1000:
+    format (I3,I3,5G14.6,1X,A1)): per curved side IEDGE, IEL, CURVE(1:5), CCURVE.  Returns
+    ccurve[nel][12] (1-char flags, ' ' = straight) and curve[nel,12,5]."""
+    lines = open(path).read().splitlines()
+    i = next(k for k, l in enumerate(lines) if "CURVED SIDE DATA" in l)
+    ncurve = int(lines[i + 1].split()[0])
+    ccurve = [[" "] * 12 for _ in range(nel)]
+    curve = np.zeros((nel, 12, 5))
+    for q in range(ncurve):
+        t = lines[i + 2 + q].split()
+        edge, e = int(t[0]), int(t[1])
+        curve[e - 1, edge - 1] = [float(v) for v in t[2:7]]
+        ccurve[e - 1][edge - 1] = t[7]
+    return ccurve, curve
+
+
+def save(name, ndim, xc, yc, zc, cbc, part, vertex, **extra):
     np.savez_compressed(os.path.join(OUT, name), ndim=ndim, xc=xc, yc=yc, zc=zc,
-                        cbc=np.array(cbc), part=part, vertex=vertex)
+                        cbc=np.array(cbc), part=part, vertex=vertex, **extra)
     print(name, "nel", xc.shape[0], "bcs", sorted(set(np.array(cbc).ravel())))
 
 
@@ -105,3 +122,9 @@ if __name__ == "__main__":
     nd, xc, yc, zc, cbc = read_rea_mesh(f"{REF}/3dboxpec/3dboxpec.rea")
     part, vert = read_map(f"{REF}/3dboxpec/3dboxpec.map", 2 ** nd)
     save("3dboxpec_mesh.npz", nd, xc, yc, zc, cbc, part, vert)
+    # tests/cylwave: 50 hexahedra (5 layers of 10) in a cylinder of radius 4, circular-arc sides
+    nd, xc, yc, zc, cbc = read_rea_mesh(f"{REF}/cylwave/cylwave.rea")
+    part, vert = read_map(f"{REF}/cylwave/cylwave.map", 2 ** nd)
+    ccurve, curve = read_rea_curves(f"{REF}/cylwave/cylwave.rea", xc.shape[0])
+    save("cylwave_mesh.npz", nd, xc, yc, zc, cbc, part, vert, ccurve=np.array(ccurve),
+         curve=curve)

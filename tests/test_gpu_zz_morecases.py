@@ -1,6 +1,7 @@
-"""The remaining 2D Maxwell configurations of the reference's test suite on the GPU:
+"""The remaining Maxwell configurations of the reference's test suite on the GPU:
 tests/2ddielectric (TE/TM x one/two materials: PML + incident hook in the 2D kernel) and
-tests/2dboxpml (TE/TM: all-PML box + the volume-source hook on hz / ez)."""
+tests/2dboxpml (TE/TM: all-PML box + the volume-source hook on hz / ez), tests/cylwave (curved
+unstructured mesh)."""
 import numpy as np
 import pytest
 
@@ -52,4 +53,25 @@ def test_2dboxpml_with_gaussian_source(imode):
     assert rel_l2(s.get_array("pmlbn"), c.pmlbn) <= TOL
     assert rel_l2(s.get_array("pmldn"), c.pmldn) <= TOL
     assert np.abs(_fields(s)).max() < 1.0
+    s.close()
+
+
+def test_kat_cylwave_on_gpu():
+    """tests/cylwave as shipped (the reference's unstructured 50-element mesh with circular-arc
+    sides, N=11, PEC wall, periodic in z): truly curved elements through the general-metric path
+    (the setup scan must find no constant-metric element), parity with the oracle after 100 steps
+    and the .usr tolerances 5e-9 / 5e-8 at steps 1..10 and 100."""
+    from oracle import cases
+    c = cases.case_cylwave()
+    s = solver_from_refcase(c)
+    ncm, _ = s.geometry_info()
+    assert ncm == 0
+    done = 0
+    for target in list(range(1, 11)) + [100]:
+        s.step(target - done); c.step(target - done)
+        done = target
+        shn, sen = c.usersol(c, s.time)
+        l2, linf = s.cem_error(shn, sen)
+        assert np.all(l2 <= 5e-9) and np.all(linf <= 5e-8), (target, l2, linf)
+    assert rel_l2(_fields(s), _fields(c)) <= TOL
     s.close()

@@ -146,3 +146,15 @@ def test_kat_2dboxpml_stability(imode):
     assert np.all(np.isfinite(c.hn)) and np.all(np.isfinite(c.en))
     assert np.max(np.abs(c.en)) < 1.0 and np.max(np.abs(c.hn)) < 1.0
     assert np.max(np.abs(c.en)) > 1e-3  # the source did radiate
+
+
+def test_kat_cylwave():
+    """tests/cylwave: TM_01 mode of a circular PEC waveguide on the reference's own unstructured
+    mesh (50 hexahedra from cylwave.rea/.map, 80 circular-arc sides generated by the restated
+    ARCSRF), N=11, CFL 0.25, periodic in z; 5e-9 / 5e-8 on all six components at steps 1..10 and
+    every 100 (cylwave.usr userchk).  300 of the 1000 steps."""
+    c = cases.case_cylwave()
+    assert c.nelt == 50 and c.nx1 == 12 and c.ifpec and c.ncempec == 40 * 144
+    # curved elements: the quadrature reproduces the cylinder's volume pi r^2 L
+    assert abs(c.volvm1 - np.pi * c.cyl_radius ** 2 * c.zm1.max()) < 1e-11 * c.volvm1
+    _check(c, list(range(1, 11)) + [100, 200, 300], 300)

@@ -222,6 +222,8 @@ def _geometry_case(which):
         return cases.case_3ddielectric(True)
     if which == "drude2d":
         return cases.case_drude()
+    if which == "cylwave":
+        return cases.case_cylwave(nx1=8)
     # sheared, non-affine 3D elements (curved-metric terms all non-zero)
     mesh = O.box_mesh((2, 2, 2), ((0.0, 1.0),) * 3, ("P  ",) * 6)
 
@@ -234,7 +236,7 @@ def _geometry_case(which):
     return O.RefCase(mesh, 6, usrdat2=warp)
 
 
-@pytest.mark.parametrize("which", ["3dboxper", "3ddielectric", "drude2d", "warped"])
+@pytest.mark.parametrize("which", ["3dboxper", "3ddielectric", "drude2d", "warped", "cylwave"])
 def test_pin_geometry(which):
     """GLMAPM1 (XYZRST + cofactors + Jacobian), GEODAT1 (mass bm1 = jac*w3m1) and SETAREA
     (AREA2/AREA3 + UNITVEC): src/nek5_coef.F:555-636, 637-785, 877-925, 992-1237, run on
@@ -279,12 +281,12 @@ def _dp(a):
     return a.ctypes.data_as(C.POINTER(C.c_double))
 
 
-@pytest.mark.parametrize("which", ["3dboxpec", "3ddielectric", "drude2d"])
+@pytest.mark.parametrize("which", ["3dboxpec", "3ddielectric", "drude2d", "cylwave"])
 def test_pin_materials_and_pec_list(which):
     """cem_maxwell_materials (impedances Y_0,Y_1,Z_0,Z_1 via the reference's gs_op, PEC
     doubling, src/cem_maxwell.F:262-325) and cem_maxwell_pec_init (:1338-1366)"""
     c = {"3dboxpec": cases.case_3dboxpec, "3ddielectric": lambda: cases.case_3ddielectric(True),
-         "drude2d": cases.case_drude}[which]()
+         "drude2d": cases.case_drude, "cylwave": lambda: cases.case_cylwave(nx1=6)}[which]()
     r = refrun.ReferenceRun(c)
     r.set_cbc(c.mesh.cbc)
     for name in ("y_0", "y_1", "z_0", "z_1"):
@@ -897,4 +899,81 @@ def test_pin_2dboxpml_with_the_shipped_usr(imode):
     r.set_callback("usersrc", c.usersrc_fn)
     c.step(30); r.step(30)
     _assert_same(c, r)
+    r.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# tests/cylwave: unstructured mesh with circular-arc sides (curved, non-affine elements)
+# ---------------------------------------------------------------------------------------------
+def _put_corners(r, mesh, nelt):
+    for name, arr in (("xc", mesh.xc), ("yc", mesh.yc), ("zc", mesh.zc)):
+        v = r.view(name).reshape(-1)
+        v[:] = 0.0
+        v[:8 * nelt] = arr.reshape(-1)
+
+
+def test_pin_cylwave_mesh_generation():
+    """the whole chain from the reference's .rea corner coordinates to the GLL nodes of the
+    curved elements, all reference code: usrdat of cylwave.usr (corners projected onto the
+    radius found by geom_xyradius, src/cem_common.F:817-843), GENXYZ + ARCSRF
+    (src/nek5_genxyz.F:2-108, 562-680) for the 80 sides flagged 'C', usrdat2 (z rescaled to
+    2 pi xmax).  Bit for bit."""
+    raw, _ = cases._load_mesh("cylwave_mesh.npz")       # corners exactly as in cylwave.rea
+    c = cases.case_cylwave(nx1=8)
+    mesh = c.mesh                                       # corners after the oracle's usrdat
+    assert np.abs(mesh.xc - raw.xc).max() > 1e-7        # usrdat did move the outer corners
+    r = refrun.ReferenceRun(c)
+    _put_corners(r, raw, c.nelt)
+    _usr(r.L, "usrdat", "cylwave")()
+    assert np.array_equal(r.view("xc").reshape(-1)[:8 * c.nelt], mesh.xc.reshape(-1))
+    assert np.array_equal(r.view("yc").reshape(-1)[:8 * c.nelt], mesh.yc.reshape(-1))
+    r.L.geom_xyradius_.restype = C.c_double
+    assert r.L.geom_xyradius_() == c.cyl_radius
+    # CCURVE(12,lelt) character*1, CURVE(6,12,lelt)
+    cc = r.view_char("ccurve")
+    cc[:] = ord(" ")
+    cv = r.view("curve")
+    cv[:] = 0.0
+    for e in range(c.nelt):
+        for k in range(12):
+            cc[k + 12 * e] = ord(mesh.ccurve[e][k])
+            cv[6 * (k + 12 * e):6 * (k + 12 * e) + 5] = mesh.curve[e, k]
+    n = c.nx1
+    r.put("zgm1", np.concatenate([c.zgm1, c.zgm1, c.zgm1]))
+    for k in ("ifgmsh3", "ifaxis"):
+        try:
+            r.set(k, 0)
+        except KeyError:
+            pass
+    r.L.initds_()
+    x, y, z = r.view("xm1"), r.view("ym1"), r.view("zm1")
+    r.L.genxyz_(_dp(x), _dp(y), _dp(z), C.byref(C.c_int(n)), C.byref(C.c_int(n)),
+                C.byref(C.c_int(n)))
+    # nodes of the curved sides lie on the cylinder
+    rad = np.sqrt(x[:c.npts] ** 2 + y[:c.npts] ** 2)
+    assert abs(rad.max() - c.cyl_radius) < 1e-14 * c.cyl_radius
+    _usr(r.L, "usrdat2", "cylwave")()
+    assert np.array_equal(x[:c.npts], c.xm1) and np.array_equal(y[:c.npts], c.ym1)
+    assert np.array_equal(z[:c.npts], c.zm1)
+    r.close()
+
+
+def test_pin_cylwave_time_stepping():
+    """tests/cylwave at N=11 as shipped (50 curved elements, PEC wall, periodic in z, CFL 0.25):
+    10 steps, fields and RK registers bit for bit; the analytic TM_01 mode stays within the
+    userchk tolerances (5e-9 / 5e-8) evaluated by the reference's cem_error"""
+    c, r = _pair(cases.case_cylwave())
+    c.step(10); r.step(10)
+    _assert_same(c, r)
+    r.set("volvm1", c.volvm1)
+    shn, sen = c.usersol(c, c.time)
+    n = c.npts
+    err = np.zeros(n)
+    nn = C.c_int(n)
+    for k in range(6):
+        fld = np.ascontiguousarray(r.view("hn" if k < 3 else "en")[(k % 3) * n:(k % 3 + 1) * n])
+        sol = np.ascontiguousarray(c.comp(shn if k < 3 else sen, k % 3))
+        l2, linf = C.c_double(), C.c_double()
+        r.L.cem_error_(_dp(fld), _dp(sol), _dp(err), C.byref(nn), C.byref(l2), C.byref(linf))
+        assert l2.value <= 5e-9 and linf.value <= 5e-8, (k, l2.value, linf.value)
     r.close()
