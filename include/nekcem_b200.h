@@ -205,6 +205,38 @@ int nekcem_b200_error_sums_mode(int handle, const int32_t kind[18], const double
                                 const double ph[3], const double amp[6], double sumsq[6],
                                 double linf[6]);
 
+/* The same for the plane-wave solutions of the layered-media tests (usersol of
+ * tests/3ddielectric/3ddielectric.usr:83-151, 2ddielectric.usr, drude.usr, lorentz.usr,
+ * 3dgraphene.usr:148-222, 2dgraphene.usr): two regions of elements (region[e] = 0 / 1, e.g.
+ * upper / lower half space), in each a wave travelling along y with a complex wavenumber and
+ * complex per-component amplitudes, damped inside PML elements (inpml[e] != 0) by the graded
+ * profile the .usr files use:
+ *   exact_c = Re( amp[r][c] * exp( i*(k[r]*y - omega*time) - pml_eta[r]*pmlfac ) ),
+ *   pmlfac  = pml_smax[r]*pml_d[r]/(pml_order+1) * (pml_sign[r]*(y - pml_y0[r])/pml_d[r])^(pml_order+1)
+ * c = 0..2 H, 3..5 E.  The caller folds reflection / transmission coefficients, impedances and
+ * the direction of travel into amp and k.  Needs NKB_YMN uploaded. */
+typedef struct nekcem_b200_planewave {
+    double omega;
+    double k_re[2], k_im[2];
+    double amp_re[2][6], amp_im[2][6];
+    double pml_eta[2], pml_smax[2], pml_d[2], pml_y0[2], pml_sign[2];
+    double pml_order;
+} nekcem_b200_planewave;
+int nekcem_b200_error_sums_planewave(int handle, const nekcem_b200_planewave *wave,
+                                     const unsigned char *region, const unsigned char *inpml,
+                                     double time, double sumsq[6], double linf[6]);
+
+/* Output hand-off (the `!$ACC UPDATE HOST(HN,EN)` seam of cem_out,
+ * src/io.F:193-195): the payload of one VTK "VECTORS" block exactly as the reference's writer
+ * assembles it on the host -- vtk_nonswap_field interleaves the three components per node
+ * (src/io_dumpvtk.F:858-878; call site src/io.F:207-208), writefield4 casts each value to float,
+ * writefield4_double keeps double, both byte-swap to big-endian (src/io_co.c:443-456, 511-524).
+ * which: 0 = EN ("VECTORS" block of vtkout1), 1 = HN (vtkout2); as_double: 0 = float32 (param(87)
+ * != 0), 1 = float64.  out receives 3*npts values of 4 or 8 bytes, ready for
+ * MPI_File_write_at_all; interleave, cast and swap run on the device, so a float dump moves
+ * 12 B/node over PCIe instead of 48 and the host touches no node. */
+int nekcem_b200_vtk_payload(int handle, int which, int as_double, void *out);
+
 /* Device-time of the last nekcem_b200_step call in milliseconds (CUDA events on the
  * compute stream) and the number of kernels it launched. */
 int nekcem_b200_last_step_ms(int handle, float *ms, int64_t *launches);

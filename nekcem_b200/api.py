@@ -42,6 +42,15 @@ class NekcemB200Error(RuntimeError):
     pass
 
 
+class PlaneWave(C.Structure):
+    """nekcem_b200_planewave (include/nekcem_b200.h)"""
+    _fields_ = [("omega", C.c_double), ("k_re", C.c_double * 2), ("k_im", C.c_double * 2),
+                ("amp_re", (C.c_double * 6) * 2), ("amp_im", (C.c_double * 6) * 2),
+                ("pml_eta", C.c_double * 2), ("pml_smax", C.c_double * 2),
+                ("pml_d", C.c_double * 2), ("pml_y0", C.c_double * 2),
+                ("pml_sign", C.c_double * 2), ("pml_order", C.c_double)]
+
+
 class Desc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "abi_version", "ldim", "nx1", "nelt", "imode", "ifupwind", "ifpec", "ifpml", "device",
@@ -90,6 +99,10 @@ def lib():
         L.nekcem_b200_set_option.argtypes = [C.c_int, C.c_char_p, C.c_int]
         L.nekcem_b200_error_sums_mode.argtypes = [C.c_int, C.POINTER(C.c_int32), c_dp, c_dp, c_dp,
                                                   c_dp, c_dp]
+        L.nekcem_b200_error_sums_planewave.argtypes = [C.c_int, C.POINTER(PlaneWave),
+                                                       C.POINTER(C.c_ubyte), C.POINTER(C.c_ubyte),
+                                                       C.c_double, c_dp, c_dp]
+        L.nekcem_b200_vtk_payload.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.nekcem_b200_geometry_info.argtypes = [C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
         L.nekcem_b200_set_time.argtypes = [C.c_int, C.c_double, C.c_double]
         L.nekcem_b200_get_time.argtypes = [C.c_int, c_dp]
@@ -349,6 +362,16 @@ class MaxwellB200:
         _chk(self.L.nekcem_b200_get_graphene(self.h, _dp(fjn), _dp(kfjn)))
         return fjn, kfjn
 
+    def vtk_payload(self, which: str, as_double: bool = False) -> bytes:
+        """The byte payload of the VTK "VECTORS" block cem_out writes for EN ('en') or HN ('hn'):
+        per node three values, cast to float32 unless as_double, big-endian
+        (vtk_nonswap_field + writefield4[_double], src/io_dumpvtk.F:858-878, src/io_co.c:414-536),
+        assembled on the device."""
+        w = {"en": 0, "hn": 1}[which]
+        buf = np.empty(3 * self.npts * (8 if as_double else 4), dtype=np.uint8)
+        _chk(self.L.nekcem_b200_vtk_payload(self.h, w, int(as_double), buf.ctypes.data_as(C.c_void_p)))
+        return buf.tobytes()
+
     def set_option(self, name: str, value: int):
         _chk(self.L.nekcem_b200_set_option(self.h, name.encode(), int(value)))
 
@@ -411,6 +434,36 @@ class MaxwellB200:
         s, m = np.zeros(6), np.zeros(6)
         _chk(self.L.nekcem_b200_error_sums_mode(self.h, kd.ctypes.data_as(C.POINTER(C.c_int32)),
                                                 _dp(kk), _dp(pp), _dp(aa), _dp(s), _dp(m)))
+        if reduce is not None:
+            s, m = reduce(s, m)
+        vol = self.volvm1 if volvm1 is None else volvm1
+        l2 = s / vol
+        l2 = np.where(l2 > 0, np.sqrt(np.maximum(l2, 0)), l2)
+        return l2, m
+
+    def cem_error_planewave(self, omega, k, amp, region, inpml, pml, time, volvm1=None,
+                            reduce=None):
+        """cem_error against the plane-wave solution of the layered-media tests evaluated on the
+        device (device-side usersol): in region r (region[e] in {0,1}),
+        exact_c = Re(amp[r][c] * exp(i (k[r] y - omega t) - eta_r pmlfac)); k (2,) and amp (2,6)
+        complex; pml = dict(eta, smax, d, y0, sign: (2,) each; order) describes the graded decay
+        inside elements with inpml[e] != 0.  Needs 'ymn' uploaded."""
+        w = PlaneWave()
+        w.omega = float(omega)
+        k = np.asarray(k, dtype=np.complex128); amp = np.asarray(amp, dtype=np.complex128)
+        for r in range(2):
+            w.k_re[r], w.k_im[r] = float(k[r].real), float(k[r].imag)
+            for c in range(6):
+                w.amp_re[r][c], w.amp_im[r][c] = float(amp[r, c].real), float(amp[r, c].imag)
+            for name in ("eta", "smax", "d", "y0", "sign"):
+                getattr(w, "pml_" + name)[r] = float(pml[name][r])
+        w.pml_order = float(pml["order"])
+        reg = np.ascontiguousarray(region, dtype=np.uint8); pm = np.ascontiguousarray(inpml, dtype=np.uint8)
+        assert reg.size == self.nelt and pm.size == self.nelt
+        s, m = np.zeros(6), np.zeros(6)
+        _chk(self.L.nekcem_b200_error_sums_planewave(
+            self.h, C.byref(w), reg.ctypes.data_as(C.POINTER(C.c_ubyte)),
+            pm.ctypes.data_as(C.POINTER(C.c_ubyte)), float(time), _dp(s), _dp(m)))
         if reduce is not None:
             s, m = reduce(s, m)
         vol = self.volvm1 if volvm1 is None else volvm1

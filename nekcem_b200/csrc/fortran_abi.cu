@@ -6,6 +6,7 @@
 // twins serve fixed-form F77 call sites that cannot use BIND(C).
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "../../include/nekcem_b200.h"
 
@@ -120,6 +121,33 @@ NKB_EXPORT void nekcem_b200_error_sums_mode_(const int *h, const int *kind, cons
 {
     check(nekcem_b200_error_sums_mode(*h, kind, k, ph, amp, sumsq, linf),
           "nekcem_b200_error_sums_mode");
+}
+
+NKB_EXPORT void nekcem_b200_vtk_payload_(const int *h, const int *which, const int *as_double,
+                                         void *out)
+{
+    check(nekcem_b200_vtk_payload(*h, *which, *as_double, out), "nekcem_b200_vtk_payload");
+}
+
+// wave: the 40 reals of nekcem_b200_planewave in declaration order (omega, k_re(2), k_im(2),
+// amp_re(6,2), amp_im(6,2), pml_eta(2), pml_smax(2), pml_d(2), pml_y0(2), pml_sign(2), pml_order);
+// region, inpml: INTEGER arrays of nelt entries (Fortran has no 1-byte integer in F77)
+NKB_EXPORT void nekcem_b200_error_sums_planewave_(const int *h, const double *wave,
+                                                  const int *region, const int *inpml,
+                                                  const int *nelt, const double *time,
+                                                  double *sumsq, double *linf)
+{
+    static_assert(sizeof(nekcem_b200_planewave) == 40 * sizeof(double), "planewave layout");
+    nekcem_b200_planewave w;
+    memcpy(&w, wave, sizeof w);
+    unsigned char *f = (unsigned char *)malloc(2 * (size_t)(*nelt > 0 ? *nelt : 1));
+    for (int e = 0; e < *nelt; e++) {
+        f[e] = region[e] ? 1 : 0;
+        f[*nelt + e] = inpml[e] ? 1 : 0;
+    }
+    int rc = nekcem_b200_error_sums_planewave(*h, &w, f, f + *nelt, *time, sumsq, linf);
+    free(f);
+    check(rc, "nekcem_b200_error_sums_planewave");
 }
 
 NKB_EXPORT void nekcem_b200_set_drude_(const int *h, const double *jn, const double *kjn,

@@ -449,6 +449,81 @@ __global__ void error_mode_kernel(const double *u, long long ld, ModeSol m, cons
     }
 }
 
+// Output hand-off (cem_out): the payload of one VTK "VECTORS" block exactly as the reference's
+// writer assembles it on the host -- vtk_nonswap_field interleaves the three components per node
+// (src/io_dumpvtk.F:858-878), writefield4 / writefield4_double cast each value to float (or keep
+// double) and byte-swap it to big-endian (src/io_co.c:443-456, 511-524, src/io_util.c:99-146).
+// One thread per (node, component); 4- or 8-byte stores are coalesced along the output.
+template <typename OUT>
+__global__ void vtk_payload_kernel(const double *u, long long ld, long long npts, OUT *out)
+{
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= 3 * npts) return;
+    const long long i = t / 3;
+    const int c = (int)(t - 3 * i);
+    const double v = u[c * ld + i];
+    if constexpr (sizeof(OUT) == 4) {
+        const unsigned int b = __float_as_uint(__double2float_rn(v));
+        out[t] = __byte_perm(b, 0, 0x0123);
+    } else {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+        const unsigned int lo = (unsigned int)b, hi = (unsigned int)(b >> 32);
+        out[t] = ((unsigned long long)__byte_perm(lo, 0, 0x0123) << 32) | __byte_perm(hi, 0, 0x0123);
+    }
+}
+
+// cem_error against a plane wave in two half spaces with a graded PML decay (device-side usersol
+// of the layered-media tests): exact_c = Re( amp[r][c] * exp(i (k_r y - omega t) - eta_r pmlfac) )
+__global__ void error_planewave_kernel(const double *u, long long ld, nekcem_b200_planewave w,
+                                       double wt, const unsigned char *region,
+                                       const unsigned char *inpml, int nxyz, const double *y,
+                                       long long npts, const double *bm,
+                                       double *part /* [blocks][12] */)
+{
+    __shared__ double ssum[256], smax[256];
+    double sum[6] = {0, 0, 0, 0, 0, 0}, mx[6] = {0, 0, 0, 0, 0, 0};
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npts;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long e = i / nxyz;
+        const int r = region[e] ? 1 : 0;
+        const double yy = y[i];
+        double pmlfac = 0.0;
+        if (inpml[e]) {
+            const double d = w.pml_d[r];
+            pmlfac = (w.pml_smax[r] * d / (w.pml_order + 1.0)) *
+                     pow(w.pml_sign[r] * (yy - w.pml_y0[r]) / d, w.pml_order + 1.0);
+        }
+        const double th = w.k_re[r] * yy - wt;
+        const double mag = exp(-w.k_im[r] * yy - w.pml_eta[r] * pmlfac);
+        const double cr = mag * cos(th), ci = mag * sin(th);
+        const double b = bm[i];
+#pragma unroll
+        for (int c = 0; c < 6; c++) {
+            const double ex = w.amp_re[r][c] * cr - w.amp_im[r][c] * ci;
+            const double err = ex - u[c * ld + i];
+            sum[c] += err * b * err;
+            mx[c] = fmax(mx[c], fabs(err));
+        }
+    }
+    for (int c = 0; c < 6; c++) {
+        ssum[threadIdx.x] = sum[c];
+        smax[threadIdx.x] = mx[c];
+        __syncthreads();
+        for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+            if (threadIdx.x < s) {
+                ssum[threadIdx.x] += ssum[threadIdx.x + s];
+                smax[threadIdx.x] = fmax(smax[threadIdx.x], smax[threadIdx.x + s]);
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            part[blockIdx.x * 12 + c] = ssum[0];
+            part[blockIdx.x * 12 + 6 + c] = smax[0];
+        }
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------------------------------
 // host planning
 // ---------------------------------------------------------------------------------------
@@ -1548,6 +1623,70 @@ int nekcem_b200_error_sums_mode(int handle, const int32_t kind[18], const double
         sumsq[q] = s;
         linf[q] = mxv;
     }
+    return 0;
+}
+
+int nekcem_b200_error_sums_planewave(int handle, const nekcem_b200_planewave *wave,
+                                     const unsigned char *region, const unsigned char *inpml,
+                                     double time, double sumsq[6], double linf[6])
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (!c->setup_done) return fail("nekcem_b200_setup has not completed");
+    if (!wave || !region || !inpml || !sumsq || !linf) return fail("null argument");
+    if (require(c, {NKB_YMN})) return 1;
+    for (int r = 0; r < 2; r++)
+        if (!(wave->pml_d[r] != 0.0)) return fail("planewave: pml_d[%d] must be non-zero", r);
+    CUDA_OK(cudaSetDevice(c->d.device));
+    unsigned char *flags = nullptr;
+    CUDA_OK(cudaMalloc(&flags, 2 * (size_t)c->d.nelt));
+    CUDA_OK(cudaMemcpy(flags, region, c->d.nelt, cudaMemcpyHostToDevice));
+    CUDA_OK(cudaMemcpy(flags + c->d.nelt, inpml, c->d.nelt, cudaMemcpyHostToDevice));
+    const int nb = (int)std::min<int64_t>(c->red_blocks, (c->npts + 255) / 256);
+    error_planewave_kernel<<<nb, 256, 0, c->s_compute>>>(
+        c->u[c->cur], c->ld, *wave, wave->omega * time, flags, flags + c->d.nelt, c->nxyz,
+        c->dev[NKB_YMN], c->npts, c->dev[NKB_BMN], c->red_d);
+    std::vector<double> part(12 * nb);
+    cudaError_t e1 = cudaStreamSynchronize(c->s_compute);
+    cudaFree(flags);
+    CUDA_OK(e1);
+    CUDA_OK(cudaMemcpy(part.data(), c->red_d, sizeof(double) * 12 * nb, cudaMemcpyDeviceToHost));
+    for (int q = 0; q < 6; q++) {
+        double s = 0.0, mxv = 0.0;
+        for (int b = 0; b < nb; b++) {
+            s += part[b * 12 + q];
+            mxv = std::max(mxv, part[b * 12 + 6 + q]);
+        }
+        sumsq[q] = s;
+        linf[q] = mxv;
+    }
+    return 0;
+}
+
+int nekcem_b200_vtk_payload(int handle, int which, int as_double, void *out)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (c->host_only) return fail("host-only planning context: no device arrays");
+    if (which != 0 && which != 1) return fail("vtk_payload: which must be 0 (EN) or 1 (HN)");
+    if (!out) return fail("null output pointer");
+    CUDA_OK(cudaSetDevice(c->d.device));
+    const size_t esz = as_double ? 8 : 4, bytes = esz * 3 * (size_t)c->npts;
+    void *buf = nullptr;
+    CUDA_OK(cudaMalloc(&buf, bytes));
+    const double *base = c->u[c->cur] + (which == 0 ? 3 : 0) * c->ld;
+    const long long tot = 3 * (long long)c->npts;
+    const unsigned grid = (unsigned)((tot + 255) / 256);
+    if (as_double)
+        vtk_payload_kernel<unsigned long long><<<grid, 256, 0, c->s_compute>>>(
+            base, c->ld, c->npts, (unsigned long long *)buf);
+    else
+        vtk_payload_kernel<unsigned int><<<grid, 256, 0, c->s_compute>>>(base, c->ld, c->npts,
+                                                                         (unsigned int *)buf);
+    cudaError_t e1 = cudaStreamSynchronize(c->s_compute);
+    if (e1 == cudaSuccess) e1 = cudaMemcpy(out, buf, bytes, cudaMemcpyDeviceToHost);
+    cudaFree(buf);
+    CUDA_OK(e1);
     return 0;
 }
 

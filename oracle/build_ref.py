@@ -76,6 +76,8 @@ UNITS = [
     ("tests/drude/drude.usr", ["userinc", "usersrc", "usersol", "userini", "uservp"], "__drude"),
     ("tests/lorentz/lorentz.usr", ["userinc", "usersrc", "usersol", "userini", "uservp"],
      "__lorentz"),
+    # output hand-off: the per-node interleave of cem_out (src/io.F:207-210)
+    ("src/io_dumpvtk.F", ["vtk_nonswap_field"]),
     ("tests/cylwave/cylwave.usr", ["usrdat", "usrdat2"], "__cylwave"),
     ("src/cem_common.F", ["geom_xyradius"]),
     ("tests/2ddielectric/2ddielectric.usr", ["userinc", "usersol", "userini", "uservp",
@@ -134,7 +136,9 @@ def build(force: bool = False, verbose: bool = False) -> str | None:
     cmd = (["gcc", "-O3", "-std=gnu11", "-ffp-contract=off", "-fcx-fortran-rules", "-fPIC",
             "-shared", "-w", "-I" + os.path.join(REF, "src/jl")] + JL_FLAGS +
            ["-o", LIB, gen, os.path.join(HERE, "ref_harness.c")] +
-           [os.path.join(REF, "src/jl", f) for f in JL] + ["-lm"])
+           [os.path.join(REF, "src/jl", f) for f in JL] +
+           # byte-order helpers of the reference's VTK writer (swap_float_byte, ...), unchanged
+           [os.path.join(REF, "src", "io_util.c"), "-I" + os.path.join(REF, "src")] + ["-lm"])
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)

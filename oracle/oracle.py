@@ -538,6 +538,15 @@ class RefCase:
                         hh = h[f - 3][None, :] * hz[:, None]
                         S += hh[:, :, None] * crv[None, None, :]
 
+    def vtk_payload(self, which: str, as_double: bool = False) -> bytes:
+        """payload of the VTK "VECTORS" block cem_out writes for EN ('en') / HN ('hn'):
+        vtk_nonswap_field (src/io_dumpvtk.F:858-878) interleaves the components per node,
+        writefield4 / writefield4_double (src/io_co.c:443-456, 511-524) cast to float / keep
+        double and swap to big-endian"""
+        a = (self.en if which == "en" else self.hn).reshape(3, self.npts)
+        inter = np.ascontiguousarray(a.T)                       # (npts, 3): x,y,z per node
+        return inter.astype(">f8" if as_double else ">f4").tobytes()
+
     def comp(self, arr, c):
         n = arr.size // 3
         return arr[c * n:(c + 1) * n]

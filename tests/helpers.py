@@ -105,3 +105,70 @@ def restrict_to_elems(c, elems, facepts=None, nodes=None):
     j = np.asarray(nodes, dtype=np.int64)
     keep = loc[j // c.nxyz] >= 0
     return keep, loc[j[keep] // c.nxyz] * c.nxyz + j[keep] % c.nxyz
+
+
+def planewave_args(c):
+    """Arguments of MaxwellB200.cem_error_planewave for the layered-media cases of
+    oracle/cases.py (3ddielectric, 2ddielectric, drude, lorentz, 3dgraphene, 2dgraphene): the
+    `usersol` of their .usr files restated as two half-space plane waves with complex amplitudes
+    and wavenumbers plus the graded PML decay.  Region 0 = upper half space, 1 = lower."""
+    import math
+    u = c.user
+    kind = type(u).__name__
+    region = (~u.upper).astype(np.uint8)
+    inpml = (c.pmltag != 0).astype(np.uint8)
+    order, referr = c.pmlorder, c.pmlreferr
+    amp = np.zeros((2, 6), dtype=np.complex128)
+    if kind == "_Dispersive":
+        eta = [u.eta1, u.eta2]
+        k = [u.k1, -u.k2]
+        amp[0, 2], amp[0, 3] = u.refl, -u.eta1 * u.refl
+        amp[1, 2], amp[1, 3] = u.tran, u.eta2 * u.tran
+        eta_pml = [u.eta1, 0.0]
+    else:
+        e1, e2 = math.sqrt(u.mu1 / u.eps1), math.sqrt(u.mu2 / u.eps2)
+        eta = [e1, e2]
+        k = [u.omega * math.sqrt(u.mu1 * u.eps1), -u.omega * math.sqrt(u.mu2 * u.eps2)]
+        imode = getattr(u, "imode", 3)
+        if kind == "_Dielectric2D":
+            te = (u.refl, u.tran) if imode == 1 else None
+            tm = (u.refl, u.tran) if imode == 2 else None
+        else:
+            te = (u.reflte, u.trante) if imode in (3, 1) else None
+            tm = (u.refltm, u.trantm) if imode in (3, 2) else None
+        if te:
+            amp[0, 2], amp[0, 3] = te[0], -e1 * te[0]
+            amp[1, 2], amp[1, 3] = te[1], e2 * te[1]
+        if tm:
+            amp[0, 5], amp[0, 0] = tm[0], tm[0] / e1
+            amp[1, 5], amp[1, 0] = tm[1], -tm[1] / e2
+        eta_pml = eta
+    d_u = c.pmlouter[3] - c.pmlinner[3]
+    d_l = c.pmlinner[2] - c.pmlouter[2]
+    pml = dict(order=order, eta=[0.0, 0.0], smax=[0.0, 0.0], d=[1.0, 1.0], y0=[0.0, 0.0],
+               sign=[1.0, -1.0])
+    for r, (d, y0) in enumerate(((d_u, c.pmlinner[3]), (d_l, c.pmlinner[2]))):
+        if d > 0 and eta_pml[r] != 0.0:
+            pml["eta"][r] = eta_pml[r]
+            pml["smax"][r] = -(order + 1) * math.log(referr) / (2 * eta_pml[r] * d)
+            pml["d"][r] = d
+            pml["y0"][r] = y0
+    return dict(omega=u.omega, k=k, amp=amp, region=region, inpml=inpml, pml=pml)
+
+
+def planewave_numpy(c, args, tt):
+    """the same formula in numpy (what the device kernel evaluates), for CPU checks of
+    planewave_args against the cases' own usersol"""
+    n = c.npts
+    r = np.repeat(args["region"].astype(int), c.nxyz)
+    pm = np.repeat(args["inpml"] != 0, c.nxyz)
+    y = c.ym1
+    p = args["pml"]
+    g = lambda key: np.asarray(p[key], dtype=float)[r]
+    with np.errstate(invalid="ignore"):
+        fac = (g("smax") * g("d") / (p["order"] + 1)) * (g("sign") * (y - g("y0")) / g("d")) ** (p["order"] + 1)
+    fac = np.where(pm, fac, 0.0)
+    k = np.asarray(args["k"], dtype=complex)[r]
+    uu = np.exp(1j * (k * y - args["omega"] * tt) - g("eta") * fac)
+    out = [(args["amp"][r, cc] * uu).real for cc in range(6)]
+    return np.concatenate(out[:3]), np.concatenate(out[3:])

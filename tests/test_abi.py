@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
               "nekcem_b200_get_array_", "nekcem_b200_set_faces_", "nekcem_b200_set_pml_",
               "nekcem_b200_setup_", "nekcem_b200_set_time_", "nekcem_b200_set_incident_",
               "nekcem_b200_set_volume_source_", "nekcem_b200_error_sums_",
-              "nekcem_b200_error_sums_mode_",
+              "nekcem_b200_error_sums_mode_", "nekcem_b200_error_sums_planewave_",
               "nekcem_b200_comm_unique_id_", "nekcem_b200_comm_init_",
               "nekcem_b200_set_drude_", "nekcem_b200_set_lorentz_", "nekcem_b200_get_ade_",
               "nekcem_b200_bind_", "cem_maxwell_drude_", "cem_maxwell_lorentz_",

@@ -75,3 +75,70 @@ def test_kat_cylwave_on_gpu():
         assert np.all(l2 <= 5e-9) and np.all(linf <= 5e-8), (target, l2, linf)
     assert rel_l2(_fields(s), _fields(c)) <= TOL
     s.close()
+
+
+@pytest.mark.parametrize("which", ["3ddielectric-2mat", "2ddielectric-tm", "drude", "lorentz",
+                                   "3dgraphene", "2dgraphene-te"])
+def test_device_side_usersol_planewave(which):
+    """usersol of the layered-media tests evaluated on the device
+    (nekcem_b200_error_sums_planewave: two half-space plane waves with complex amplitudes and
+    wavenumbers + the graded PML decay).  The L2 / Linf errors must equal those of cem_error
+    against the host usersol (to the round-off of device vs host exp/sin/cos/pow) and meet the
+    .usr tolerances; no exact-solution array crosses PCIe."""
+    from helpers import planewave_args
+    from oracle import cases
+    import test_gpu_zgraphene as G
+    mk = {"3ddielectric-2mat": lambda: cases.case_3ddielectric(True),
+          "2ddielectric-tm": lambda: cases.case_2ddielectric(2, True),
+          "drude": cases.case_drude, "lorentz": cases.case_lorentz,
+          "3dgraphene": lambda: cases.case_3dgraphene(nel=(3, 12, 3)),
+          "2dgraphene-te": lambda: cases.case_2dgraphene(1)}[which]
+    c = mk()
+    u = c.user
+    if "graphene" in which:
+        s = G._solver(c)
+    elif which in ("drude", "lorentz"):
+        s = solver_from_refcase(c, incident=u.incident(c),
+                                ade=(which, u.jn, u.kjn, u.params, u.index))
+    elif which.startswith("3d"):
+        from helpers import incident_3ddielectric
+        s = solver_from_refcase(c, incident=incident_3ddielectric(c))
+    else:
+        s = solver_from_refcase(c, incident=u.incident(c))
+    s.set_array("ymn", c.ym1)
+    s.step(10)
+    tt = s.time
+    a = planewave_args(c)
+    l2d, linfd = s.cem_error_planewave(a["omega"], a["k"], a["amp"], a["region"], a["inpml"],
+                                       a["pml"], tt)
+    shn, sen = c.usersol(c, tt)
+    l2h, linfh = s.cem_error(shn, sen)
+    assert np.abs(l2h).max() > 1e-12                      # a real truncation error is visible
+    assert np.allclose(l2d, l2h, rtol=1e-6, atol=1e-15), (l2d, l2h)
+    assert np.allclose(linfd, linfh, rtol=1e-6, atol=1e-14), (linfd, linfh)
+    assert np.all(l2d <= np.array(c.tol["l2"]) + 1e-300)
+    assert np.all(linfd <= np.array(c.tol["linf"]) + 1e-300)
+    s.close()
+
+
+@pytest.mark.parametrize("case", ["3d", "2d-te"])
+def test_vtk_payload_assembled_on_device(case):
+    """Output hand-off: the VTK "VECTORS" payload of EN and HN -- per node
+    three values, cast to float32 (or kept as float64), big-endian -- assembled on the device must
+    be byte-identical to the oracle's restatement of vtk_nonswap_field + writefield4[_double],
+    which is pinned to the reference's own pieces (tests/test_reference_pin.py)."""
+    from oracle import cases
+    c = cases.case_boxper((3, 3, 3), 5) if case == "3d" else cases.case_2dboxper(1, nx1=6)
+    s = solver_from_refcase(c)
+    s.step(3)
+    # the oracle restates the byte format; feed it the GPU's own fields so that the comparison
+    # is about the payload, bit for bit, not about the time stepping
+    c.hn[:] = s.hn; c.en[:] = s.en
+    for which in ("en", "hn"):
+        for dbl in (False, True):
+            got = s.vtk_payload(which, as_double=dbl)
+            want = c.vtk_payload(which, as_double=dbl)
+            assert len(got) == 3 * c.npts * (8 if dbl else 4)
+            assert got == want, (which, dbl)
+    assert np.abs(c.en).max() > 1e-3
+    s.close()

@@ -113,3 +113,30 @@ def test_rotated_element_frames_leave_the_solution_unchanged():
     n = c0.npts
     for a, b in ((c1.hn, c0.hn), (c1.en, c0.en)):
         assert np.abs(a.reshape(3, n)[:, m] - b.reshape(3, n)).max() < 1e-13
+
+
+@pytest.mark.parametrize("which", ["3ddielectric", "2ddielectric-te", "2ddielectric-tm", "drude",
+                                   "lorentz", "3dgraphene", "2dgraphene-te", "2dgraphene-tm"])
+def test_planewave_parameters_reproduce_usersol(which):
+    """tests/helpers.py: planewave_args (the arguments of the device-side plane-wave usersol,
+    nekcem_b200_error_sums_planewave) evaluated with numpy reproduces the usersol of every
+    layered-media case -- i.e. the two-half-space parameterisation is exact, PML decay, complex
+    wavenumber of the Drude metal and complex graphene coefficients included."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from helpers import planewave_args, planewave_numpy
+    from oracle import cases
+    mk = {"3ddielectric": lambda: cases.case_3ddielectric(True),
+          "2ddielectric-te": lambda: cases.case_2ddielectric(1, True),
+          "2ddielectric-tm": lambda: cases.case_2ddielectric(2, False),
+          "drude": cases.case_drude, "lorentz": cases.case_lorentz,
+          "3dgraphene": lambda: cases.case_3dgraphene(nel=(3, 12, 3)),
+          "2dgraphene-te": lambda: cases.case_2dgraphene(1),
+          "2dgraphene-tm": lambda: cases.case_2dgraphene(2)}[which]
+    c = mk()
+    a = planewave_args(c)
+    for tt in (0.0, 0.37, 2.5):
+        sh, se = c.usersol(c, tt)
+        ph, pe = planewave_numpy(c, a, tt)
+        assert np.abs(sh).max() > 0.5
+        assert np.abs(sh - ph).max() <= 1e-15 and np.abs(se - pe).max() <= 1e-15

@@ -977,3 +977,35 @@ def test_pin_cylwave_time_stepping():
         r.L.cem_error_(_dp(fld), _dp(sol), _dp(err), C.byref(nn), C.byref(l2), C.byref(linf))
         assert l2.value <= 5e-9 and linf.value <= 5e-8, (k, l2.value, linf.value)
     r.close()
+
+
+def test_pin_vtk_payload_against_the_references_writer_pieces():
+    """Output hand-off: the oracle's VTK "VECTORS" payload equals what the reference assembles --
+    its own vtk_nonswap_field (translated, src/io_dumpvtk.F:858-878) followed by the cast and
+    byte swap of writefield4 / writefield4_double (src/io_co.c:443-456, 511-524) done with the
+    reference's own swap_float_byte / swap_double_byte (src/io_util.c, compiled unchanged; the
+    five-line loop around them needs MPI-IO and is restated here)."""
+    c = cases.case_boxper((2, 2, 2), 4)
+    c.step(2)
+    r = refrun.ReferenceRun(c)
+    L = r.L
+    n = c.npts
+    L.adjust_endian()
+    for which in ("en", "hn"):
+        f = getattr(c, which)
+        out = np.zeros(3 * n)
+        comps = [np.ascontiguousarray(f[k * n:(k + 1) * n]) for k in range(3)]
+        L.vtk_nonswap_field_(_dp(comps[0]), _dp(comps[1]), _dp(comps[2]), _dp(out))
+        # writefield4: (float) cast + swap_float_byte per value
+        fl = out.astype(np.float32)
+        fp = fl.ctypes.data_as(C.POINTER(C.c_float))
+        for i in range(fl.size):
+            L.swap_float_byte(C.byref(C.c_float.from_address(C.addressof(fp.contents) + 4 * i)))
+        assert fl.tobytes() == c.vtk_payload(which, as_double=False)
+        db = out.copy()
+        dpp = db.ctypes.data_as(C.POINTER(C.c_double))
+        for i in range(db.size):
+            L.swap_double_byte(C.byref(C.c_double.from_address(C.addressof(dpp.contents) + 8 * i)))
+        assert db.tobytes() == c.vtk_payload(which, as_double=True)
+    assert np.abs(c.en).max() > 1e-3
+    r.close()
