@@ -170,8 +170,9 @@ int nekcem_b200_get_ade(int handle, double *jn, double *kjn);
  * current is subtracted from -(n x H) on both sides of the face before the flux is formed.
  * fjn,kfjn: (nxzfl,3,6) (NULL = zeros); params: (nxzfl,12); yconduc: (nxzfl) COMMON /EMWAVE/
  * yconduc, or NULL to use the uploaded NKB_YCONDUC; gindex: the user's 1-based face-point list,
- * n entries; n = 0 removes the sheets.  Call before nekcem_b200_setup.  A sheet must not lie on
- * an inter-rank face (setup fails).  get_graphene writes the listed face points of fjn / kfjn
+ * n entries; n = 0 removes the sheets.  Call before nekcem_b200_setup.  A sheet may lie on an
+ * inter-rank face: its (tangential) current then travels folded into the packed H trace,
+ * H' = H - n x f, so that the peer's n x H' reproduces the face sum.  get_graphene writes the listed face points of fjn / kfjn
  * (the `!$ACC UPDATE HOST` seam); other entries are left untouched. */
 int nekcem_b200_set_graphene(int handle, const double *fjn, const double *kfjn,
                              const double *params, const double *yconduc, const int32_t *gindex,
@@ -187,6 +188,22 @@ int nekcem_b200_step(int handle, int nsteps);
 /* One RK stage (rkstep = 1..5) for stage-level parity tests. */
 int nekcem_b200_stage(int handle, int rkstep);
 int nekcem_b200_synchronize(int handle);
+
+/* Transport-independent stage (option "external_exchange" = 1; no communicator needed): the
+ * caller performs the inter-rank face exchange that replaces gs_op_fields between ranks
+ * (src/cem_maxwell.F:962) itself -- MPI from the Fortran host, or a device copy between two
+ * contexts of one process.  stage_pack advances the graphene sheet currents and packs the
+ * stage-start traces of the inter-rank faces into the send buffer (synchronised on return);
+ * halo_buffers returns the DEVICE pointers of peer ipeer's send / receive slices (6 doubles per
+ * shared face point, ordered by global face id on both sides) and their length in doubles;
+ * stage_compute then runs the fused stage on all elements.  halo_exchange_local copies, for two
+ * contexts of this process on one device, src's slice for dst's rank into dst's halo -- the
+ * single-GPU stand-in for the NCCL exchange used by the tests. */
+int nekcem_b200_stage_pack(int handle, int rkstep);
+int nekcem_b200_stage_compute(int handle, int rkstep);
+int nekcem_b200_halo_buffers(int handle, int32_t ipeer, double **send, double **recv,
+                             int64_t *count);
+int nekcem_b200_halo_exchange_local(int dst_handle, int src_handle);
 
 /* cem_error (src/cem_common.F:1335-1355) on device: l2[c] = sqrt(sum(err*bm*err)/vol),
  * linf[c] = max|err| for the six components against exact (npts,3)+(npts,3) host arrays.
@@ -241,7 +258,8 @@ int nekcem_b200_vtk_payload(int handle, int which, int as_double, void *out);
  * compute stream) and the number of kernels it launched. */
 int nekcem_b200_last_step_ms(int handle, float *ms, int64_t *launches);
 
-/* Performance tunables (no effect on results).  "pf_dist": reserved (accepted, ignored).
+/* Options.  "external_exchange": see nekcem_b200_stage_pack.  Performance tunables (no effect on
+ * results): "pf_dist": reserved (accepted, ignored).
  * "const_metrics" (default 1): exploit exact, bitwise redundancy found in the geometry at setup
  * -- elements whose nine cofactors rxmn..tzmn (src/GEOM:30-45) hold one value each over the
  * whole element read them once per element instead of once per node, and bitwise identical

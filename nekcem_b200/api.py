@@ -109,6 +109,11 @@ def lib():
         L.nekcem_b200_step.argtypes = [C.c_int, C.c_int]
         L.nekcem_b200_stage.argtypes = [C.c_int, C.c_int]
         L.nekcem_b200_synchronize.argtypes = [C.c_int]
+        L.nekcem_b200_stage_pack.argtypes = [C.c_int, C.c_int]
+        L.nekcem_b200_stage_compute.argtypes = [C.c_int, C.c_int]
+        L.nekcem_b200_halo_exchange_local.argtypes = [C.c_int, C.c_int]
+        L.nekcem_b200_halo_buffers.argtypes = [C.c_int, C.c_int32, C.POINTER(C.c_void_p),
+                                               C.POINTER(C.c_void_p), c_i64p]
         L.nekcem_b200_error_sums.argtypes = [C.c_int, c_dp, c_dp, c_dp, c_dp]
         L.nekcem_b200_last_step_ms.argtypes = [C.c_int, C.POINTER(C.c_float), c_i64p]
         L.nekcem_b200_algorithmic_bytes.argtypes = [C.c_int, c_dp]
@@ -395,6 +400,19 @@ class MaxwellB200:
 
     def stage(self, rkstep: int):
         _chk(self.L.nekcem_b200_stage(self.h, rkstep))
+
+    def stage_pack(self, rkstep: int):
+        """first half of a stage with option external_exchange: sheet currents + send buffer"""
+        _chk(self.L.nekcem_b200_stage_pack(self.h, rkstep))
+
+    def stage_compute(self, rkstep: int):
+        """second half: the fused stage on all elements, halo as filled by the caller"""
+        _chk(self.L.nekcem_b200_stage_compute(self.h, rkstep))
+
+    def halo_from(self, other: "MaxwellB200"):
+        """device copy of ``other``'s send slice for this rank into this context's halo (both
+        contexts in this process, same GPU): the tests' stand-in for the NCCL exchange"""
+        _chk(self.L.nekcem_b200_halo_exchange_local(self.h, other.h))
 
     def synchronize(self):
         _chk(self.L.nekcem_b200_synchronize(self.h))

@@ -178,6 +178,11 @@ struct Ctx {
     std::vector<double> g_fj_h, g_kj_h, g_par_h, g_yc_h; // [18][ng], [18][ng], [12][ng], [ng]
     bool g_yc_given = false;
     bool g_dev_current = false; // the device copy of the sheet state is newer than the staging
+    int *g_send_d = nullptr, *send_fp_d = nullptr; // per halo entry: sheet slot (-1: none), face point
+    cudaEvent_t ev_sheet = nullptr;
+    // transport-independent stepping (nekcem_b200_stage_pack / stage_compute): the caller moves
+    // sendbuf -> the peers' halo itself; no communicator needed
+    bool opt_external_exchange = false;
     int *g_fp_d = nullptr, *g_node_d = nullptr, *fs_own_d = nullptr, *fs_nbr_d = nullptr;
     double *g_fj = nullptr, *g_kj = nullptr, *g_par = nullptr, *g_yc = nullptr;
     // redundancy found in the geometry at setup (exact, bitwise): elements whose nine cofactors
@@ -303,7 +308,9 @@ __global__ void arrays_differ_kernel(const double *a, const double *b, long long
 // reference's gs_op_fields sum would give it)
 __global__ void pack_kernel(const double *u, long long ld, const int *send_node, double *sendbuf,
                             long long nsend, const int *inc_send, const double *inc_amp,
-                            const double *inc_phase, int inc_n, double inc_wt)
+                            const double *inc_phase, int inc_n, double inc_wt,
+                            const int *g_send, const int *send_fp, const double *fs_val, int fs_n,
+                            const double *unx, const double *uny, const double *unz)
 {
     long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (t >= nsend * 6) return;
@@ -313,6 +320,20 @@ __global__ void pack_kernel(const double *u, long long ld, const int *send_node,
     if (inc_send != nullptr) {
         const int qi = inc_send[q];
         if (qi >= 0) v += inc_amp[c * inc_n + qi] * cos(inc_phase[qi] - inc_wt);
+    }
+    if (g_send != nullptr && c < 3) {
+        // graphene sheet on an inter-rank face: the peer must see -(n+ x H+) - f+ in its face sum
+        // (userfsrc precedes gs_op_fields, src/cem_maxwell.F:958-962).  It forms the sum from the
+        // received trace as n x H (n = -n+), so the tangential sheet current f+ travels folded
+        // into the H trace: H' = H+ - n+ x f+, because n x (n x f) = -f for tangential f.
+        const int gq = g_send[q];
+        if (gq >= 0) {
+            const int jf = send_fp[q];
+            const double nx = unx[jf], ny = uny[jf], nz = unz ? unz[jf] : 0.0;
+            const double fx = fs_val[gq], fy = fs_val[fs_n + gq], fz = fs_val[2 * fs_n + gq];
+            const double d = c == 0 ? ny * fz - nz * fy : (c == 1 ? nz * fx - nx * fz : nx * fy - ny * fx);
+            v -= d;
+        }
     }
     sendbuf[t] = v;
 }
@@ -752,7 +773,9 @@ int scan_geometry(Ctx *c)
     return 0;
 }
 
-int run_stage(Ctx *c, int rkstep /*1..5*/)
+// phase 0: the whole stage (NCCL exchange between ranks); phase 1: sheet currents + pack of the
+// send buffer only; phase 2: the element launches only (halo filled by the caller)
+int run_stage(Ctx *c, int rkstep /*1..5*/, int phase = 0)
 {
     if (!c->geom_scanned && scan_geometry(c)) return 1;
     nkb::StageArgs a{};
@@ -795,7 +818,7 @@ int run_stage(Ctx *c, int rkstep /*1..5*/)
     a.fs_own = c->fs_own_d; a.fs_nbr = c->fs_nbr_d;
     a.fs_val = c->g_fj; // slot m = 0: fjn(:,1:3,1)
     a.fs_n = (int)c->g_fp.size();
-    if (!c->g_fp.empty()) {
+    if (!c->g_fp.empty() && phase != 2) {
         // userfsrc -> cem_*_graphene_current: needs only stage-start data, so it runs first on
         // the compute stream; every stage launch of this stage is ordered after it
         GrapheneArgs g{};
@@ -811,6 +834,7 @@ int run_stage(Ctx *c, int rkstep /*1..5*/)
         graphene_kernel<<<(unsigned)((g.ng + 127) / 128), 128, 0, c->s_compute>>>(g);
         CUDA_OK(cudaGetLastError());
         c->last_launches++;
+        if (c->g_send_d) CUDA_OK(cudaEventRecord(c->ev_sheet, c->s_compute));
     }
 
     auto launch_list = [&](int q) -> int {
@@ -830,15 +854,27 @@ int run_stage(Ctx *c, int rkstep /*1..5*/)
     };
 
     const bool exchange = !c->peers.empty();
-    if (exchange) {
+    if (exchange && phase == 0 && c->opt_external_exchange)
+        return fail("external_exchange is set: drive the stages with nekcem_b200_stage_pack / "
+                    "nekcem_b200_stage_compute");
+    if (exchange && phase != 2) {
         // side stream: pack stage-start traces, grouped send/recv (replaces gs_op_fields
         // between ranks, src/cem_maxwell.F:962); overlaps the interior-element launches
         CUDA_OK(cudaStreamWaitEvent(c->s_comm, c->ev_stage, 0));
+        if (c->g_send_d) CUDA_OK(cudaStreamWaitEvent(c->s_comm, c->ev_sheet, 0));
         const long long tot = c->nhalo * 6;
         pack_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c->s_comm>>>(
             a.u_in, c->ld, c->send_node, c->sendbuf, c->nhalo, c->inc_send_d, c->inc_amp_d,
-            c->inc_phase_d, (int)c->inc_fp.size(), a.inc_wt);
+            c->inc_phase_d, (int)c->inc_fp.size(), a.inc_wt, c->g_send_d, c->send_fp_d, c->g_fj,
+            a.fs_n, a.unx, a.uny, c->d.ldim == 3 ? a.unz : nullptr);
         c->last_launches++;
+    }
+    if (phase == 1) {
+        CUDA_OK(cudaStreamSynchronize(c->s_compute));
+        CUDA_OK(cudaStreamSynchronize(c->s_comm));
+        return 0;
+    }
+    if (exchange && phase == 0) {
         NCCL_OK(g_nccl.GroupStart());
         for (auto &p : c->peers) {
             const size_t cnt = p.send_fp.size() * 6;
@@ -850,7 +886,7 @@ int run_stage(Ctx *c, int rkstep /*1..5*/)
     }
     for (int q = 0; q < 4; q++)
         if (launch_list(q)) return 1;
-    if (exchange) CUDA_OK(cudaStreamWaitEvent(c->s_compute, c->ev_halo, 0));
+    if (exchange && phase == 0) CUDA_OK(cudaStreamWaitEvent(c->s_compute, c->ev_halo, 0));
     for (int q = 4; q < 8; q++)
         if (launch_list(q)) return 1;
     CUDA_OK(cudaEventRecord(c->ev_stage, c->s_compute));
@@ -870,8 +906,10 @@ int upload_graphene(Ctx *c)
     c->g_dev_current = false;
     cudaFree(c->g_fp_d); cudaFree(c->g_node_d); cudaFree(c->fs_own_d); cudaFree(c->fs_nbr_d);
     cudaFree(c->g_fj); cudaFree(c->g_kj); cudaFree(c->g_par); cudaFree(c->g_yc);
+    cudaFree(c->g_send_d); cudaFree(c->send_fp_d);
     c->g_fp_d = c->g_node_d = c->fs_own_d = c->fs_nbr_d = nullptr;
     c->g_fj = c->g_kj = c->g_par = c->g_yc = nullptr;
+    c->g_send_d = c->send_fp_d = nullptr;
     const size_t ng = c->g_fp.size();
     if (ng == 0) return 0;
     const int nfp = c->nxzf * c->nfaces;
@@ -880,9 +918,6 @@ int upload_graphene(Ctx *c)
         const int64_t fp = c->g_fp[q], e = fp / nfp;
         const int f = (int)(fp - e * nfp);
         if (own[fp] >= 0) return fail("graphene index lists face point %lld twice", (long long)fp + 1);
-        if (c->vmapP[fp] <= -3)
-            return fail("graphene face point %lld lies on an inter-rank face: sheets must not "
-                        "coincide with partition boundaries in this version", (long long)fp + 1);
         own[fp] = (int32_t)q;
         node[q] = (int32_t)(e * c->nxyz + face_node(c->n, f / c->nxzf, f % c->nxzf));
     }
@@ -916,6 +951,23 @@ int upload_graphene(Ctx *c)
     CUDA_OK(cudaMemcpy(c->g_kj, c->g_kj_h.data(), sizeof(double) * 18 * ng, cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(c->g_par, c->g_par_h.data(), sizeof(double) * 12 * ng, cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(c->g_yc, c->g_yc_h.data(), sizeof(double) * ng, cudaMemcpyHostToDevice));
+    if (c->nhalo > 0) {
+        // sheet points on inter-rank faces: their current is folded into the packed H trace
+        std::vector<int32_t> gs(c->nhalo, -1), sfp(c->nhalo, 0);
+        bool any = false;
+        for (auto &p : c->peers)
+            for (size_t q = 0; q < p.send_fp.size(); q++) {
+                gs[p.off + q] = own[p.send_fp[q]];
+                sfp[p.off + q] = (int32_t)p.send_fp[q];
+                any = any || gs[p.off + q] >= 0;
+            }
+        if (any) {
+            CUDA_OK(cudaMalloc(&c->g_send_d, sizeof(int) * c->nhalo));
+            CUDA_OK(cudaMalloc(&c->send_fp_d, sizeof(int) * c->nhalo));
+            CUDA_OK(cudaMemcpy(c->g_send_d, gs.data(), sizeof(int) * c->nhalo, cudaMemcpyHostToDevice));
+            CUDA_OK(cudaMemcpy(c->send_fp_d, sfp.data(), sizeof(int) * c->nhalo, cudaMemcpyHostToDevice));
+        }
+    }
     c->g_dev_current = true;
     return 0;
 }
@@ -975,6 +1027,7 @@ int nekcem_b200_create(const nekcem_b200_desc *desc, int *handle)
         CUDA_OK(cudaStreamCreateWithFlags(&c->s_comm, cudaStreamNonBlocking));
         CUDA_OK(cudaEventCreateWithFlags(&c->ev_stage, cudaEventDisableTiming));
         CUDA_OK(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
+        CUDA_OK(cudaEventCreateWithFlags(&c->ev_sheet, cudaEventDisableTiming));
         CUDA_OK(cudaEventCreate(&c->ev_t0));
         CUDA_OK(cudaEventCreate(&c->ev_t1));
         for (int q = 0; q < 2; q++) {
@@ -1008,6 +1061,8 @@ int nekcem_b200_destroy(int handle)
         cudaFree(c->inc_amp_d); cudaFree(c->inc_phase_d);
         cudaFree(c->g_fp_d); cudaFree(c->g_node_d); cudaFree(c->fs_own_d); cudaFree(c->fs_nbr_d);
         cudaFree(c->g_fj); cudaFree(c->g_kj); cudaFree(c->g_par); cudaFree(c->g_yc);
+        cudaFree(c->g_send_d); cudaFree(c->send_fp_d);
+        cudaEventDestroy(c->ev_sheet);
         cudaEventDestroy(c->ev_stage); cudaEventDestroy(c->ev_halo);
         cudaEventDestroy(c->ev_t0); cudaEventDestroy(c->ev_t1);
         cudaStreamDestroy(c->s_compute); cudaStreamDestroy(c->s_comm);
@@ -1240,7 +1295,8 @@ int nekcem_b200_setup(int handle)
         if (scan_geometry(c)) return 1;
     }
     if (c->nhalo > 0) {
-        if (!c->has_comm) return fail("inter-rank faces exist but no communicator was initialised");
+        if (!c->has_comm && !c->opt_external_exchange)
+            return fail("inter-rank faces exist but no communicator was initialised");
         const int nfp = c->nxzf * c->nfaces;
         std::vector<int> send_node(c->nhalo);
         for (auto &p : c->peers)
@@ -1475,6 +1531,12 @@ int nekcem_b200_set_option(int handle, const char *name, int value)
         c->geom_scanned = false;
         return 0;
     }
+    if (strcmp(name, "external_exchange") == 0) {
+        // 1: the caller performs the inter-rank halo exchange itself between
+        // nekcem_b200_stage_pack and nekcem_b200_stage_compute (any transport); no communicator
+        c->opt_external_exchange = value != 0;
+        return 0;
+    }
     return fail("unknown option '%s'", name);
 }
 
@@ -1516,6 +1578,59 @@ int nekcem_b200_stage(int handle, int rkstep)
     if (rkstep < 1 || rkstep > 5) return fail("rkstep %d out of range 1..5", rkstep);
     CUDA_OK(cudaSetDevice(c->d.device));
     return run_stage(c, rkstep);
+}
+
+int nekcem_b200_stage_pack(int handle, int rkstep)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (!c->setup_done) return fail("nekcem_b200_setup has not completed");
+    if (rkstep < 1 || rkstep > 5) return fail("rkstep %d out of range 1..5", rkstep);
+    CUDA_OK(cudaSetDevice(c->d.device));
+    return run_stage(c, rkstep, 1);
+}
+
+int nekcem_b200_stage_compute(int handle, int rkstep)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (!c->setup_done) return fail("nekcem_b200_setup has not completed");
+    if (rkstep < 1 || rkstep > 5) return fail("rkstep %d out of range 1..5", rkstep);
+    CUDA_OK(cudaSetDevice(c->d.device));
+    return run_stage(c, rkstep, 2);
+}
+
+int nekcem_b200_halo_buffers(int handle, int32_t ipeer, double **send, double **recv,
+                             int64_t *count)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (!c->setup_done) return fail("nekcem_b200_setup has not completed");
+    if (ipeer < 0 || ipeer >= (int)c->peers.size()) return fail("peer index %d out of range", ipeer);
+    const Peer &p = c->peers[ipeer];
+    if (send) *send = c->sendbuf + 6 * p.off;
+    if (recv) *recv = c->halo + 6 * p.off;
+    if (count) *count = 6 * (int64_t)p.send_fp.size();
+    return 0;
+}
+
+int nekcem_b200_halo_exchange_local(int dst_handle, int src_handle)
+{
+    Ctx *d = get(dst_handle), *sx = get(src_handle);
+    if (!d || !sx) return 1;
+    if (!d->setup_done || !sx->setup_done) return fail("nekcem_b200_setup has not completed");
+    if (d->d.device != sx->d.device) return fail("halo_exchange_local: contexts on different devices");
+    const Peer *ps = nullptr, *pd = nullptr;
+    for (auto &p : sx->peers) if (p.rank == d->d.rank) ps = &p;
+    for (auto &p : d->peers) if (p.rank == sx->d.rank) pd = &p;
+    if (!ps && !pd) return 0; // the two ranks share no face
+    if (!ps || !pd || ps->send_fp.size() != pd->send_fp.size())
+        return fail("halo_exchange_local: ranks %d and %d disagree about their shared faces",
+                    sx->d.rank, d->d.rank);
+    CUDA_OK(cudaSetDevice(d->d.device));
+    CUDA_OK(cudaMemcpy(d->halo + 6 * pd->off, sx->sendbuf + 6 * ps->off,
+                       sizeof(double) * 6 * ps->send_fp.size(), cudaMemcpyDeviceToDevice));
+    return 0;
 }
 
 int nekcem_b200_step(int handle, int nsteps)
