@@ -179,8 +179,17 @@ int nekcem_b200_set_graphene(int handle, const double *fjn, const double *kfjn,
                              int32_t n);
 int nekcem_b200_get_graphene(int handle, double *fjn, double *kfjn);
 
+/* Optional modal filter (`if (iffilter) call q_filter(0.01)` at the end of
+ * cem_maxwell_op_rk, src/cem_maxwell.F:342; param(18) = 1).  intv: the nx1 x nx1 matrix the
+ * reference's own build_new_filter(intv,zgm1,nx1,ncut,wght,nid) returns (src/nek5_filter.F:171-249;
+ * q_filter uses ncut = 2, wght = 0.01), column-major; NULL switches the filter off.  Once set,
+ * every time step of nekcem_b200_step ends with filterq (src/nek5_filter.F:92-144) on ex,ey,ez,
+ * hx,hy,hz on the device.  apply_filter runs it once (for callers that drive single stages). */
+int nekcem_b200_set_filter(int handle, const double *intv);
+int nekcem_b200_apply_filter(int handle);
+
 /* The hot path.  Replaces `cem_maxwell_op_rk` (src/cem_maxwell.F:327-345): nsteps time
- * steps of 5 x {rk_c; cem_maxwell_op; rk_maxwell_ab}; advances the context's time by
+ * steps of 5 x {rk_c; cem_maxwell_op; rk_maxwell_ab} (+ q_filter when a filter is set); advances the context's time by
  * nsteps*dt like time_advancing_pde (src/cem_drive.F:618-654). */
 int nekcem_b200_set_time(int handle, double time, double dt);
 int nekcem_b200_get_time(int handle, double *time);

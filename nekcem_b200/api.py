@@ -102,6 +102,8 @@ def lib():
         L.nekcem_b200_error_sums_planewave.argtypes = [C.c_int, C.POINTER(PlaneWave),
                                                        C.POINTER(C.c_ubyte), C.POINTER(C.c_ubyte),
                                                        C.c_double, c_dp, c_dp]
+        L.nekcem_b200_set_filter.argtypes = [C.c_int, c_dp]
+        L.nekcem_b200_apply_filter.argtypes = [C.c_int]
         L.nekcem_b200_vtk_payload.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.nekcem_b200_geometry_info.argtypes = [C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
         L.nekcem_b200_set_time.argtypes = [C.c_int, C.c_double, C.c_double]
@@ -366,6 +368,20 @@ class MaxwellB200:
         fjn = np.zeros(18 * self.nxzfl); kfjn = np.zeros_like(fjn)
         _chk(self.L.nekcem_b200_get_graphene(self.h, _dp(fjn), _dp(kfjn)))
         return fjn, kfjn
+
+    def set_filter(self, intv):
+        """param(18) = 1: every time step ends with q_filter (src/nek5_filter.F:2-144); intv is
+        the nx1 x nx1 matrix of the reference's build_new_filter, column-major (None: off)"""
+        if intv is None:
+            _chk(self.L.nekcem_b200_set_filter(self.h, None))
+            return
+        f = np.ascontiguousarray(intv, dtype=np.float64).reshape(-1)
+        if f.size != self.nx1 * self.nx1:
+            raise NekcemB200Error(f"filter matrix: {f.size} values, expected {self.nx1 ** 2}")
+        _chk(self.L.nekcem_b200_set_filter(self.h, _dp(f)))
+
+    def apply_filter(self):
+        _chk(self.L.nekcem_b200_apply_filter(self.h))
 
     def vtk_payload(self, which: str, as_double: bool = False) -> bytes:
         """The byte payload of the VTK "VECTORS" block cem_out writes for EN ('en') or HN ('hn'):

@@ -123,6 +123,11 @@ NKB_EXPORT void nekcem_b200_error_sums_mode_(const int *h, const int *kind, cons
           "nekcem_b200_error_sums_mode");
 }
 
+NKB_EXPORT void nekcem_b200_set_filter_(const int *h, const double *intv)
+{
+    check(nekcem_b200_set_filter(*h, intv), "nekcem_b200_set_filter");
+}
+
 NKB_EXPORT void nekcem_b200_vtk_payload_(const int *h, const int *which, const int *as_double,
                                          void *out)
 {

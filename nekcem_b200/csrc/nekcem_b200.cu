@@ -180,6 +180,8 @@ struct Ctx {
     bool g_dev_current = false; // the device copy of the sheet state is newer than the staging
     int *g_send_d = nullptr, *send_fp_d = nullptr; // per halo entry: sheet slot (-1: none), face point
     cudaEvent_t ev_sheet = nullptr;
+    // optional modal filter at the end of every time step (q_filter, param(18) = 1)
+    double *filter_d = nullptr;
     // transport-independent stepping (nekcem_b200_stage_pack / stage_compute): the caller moves
     // sendbuf -> the peers' halo itself; no communicator needed
     bool opt_external_exchange = false;
@@ -467,6 +469,50 @@ __global__ void error_mode_kernel(const double *u, long long ld, ModeSol m, cons
             part[blockIdx.x * 12 + 6 + c] = smax[0];
         }
         __syncthreads();
+    }
+}
+
+// q_filter / filterq (src/nek5_filter.F:2-144): v <- (F (x) F (x) F) v for one component of one
+// element per CTA; the three contractions in the order of the reference's mxm calls (r, then s,
+// then t; contracted index ascending), ping-ponging between two shared-memory copies of the
+// element.  F: the n x n matrix of build_new_filter, column-major.  2D: two contractions.
+__global__ void filter_kernel(double *u, long long ld, const double *F, int n, int nz, int nxyz)
+{
+    extern __shared__ double fsm[];
+    double *A = fsm, *B = fsm + nxyz, *Fs = fsm + 2 * nxyz;
+    const int e = blockIdx.x, c = blockIdx.y;
+    double *v = u + (long long)c * ld + (long long)e * nxyz;
+    for (int q = threadIdx.x; q < n * n; q += blockDim.x) Fs[q] = F[q];
+    for (int q = threadIdx.x; q < nxyz; q += blockDim.x) A[q] = v[q];
+    __syncthreads();
+    const int n2 = n * n;
+    // r: B(i,j,k) = sum_m F(i,m) A(m,j,k)
+    for (int q = threadIdx.x; q < nxyz; q += blockDim.x) {
+        const int i = q % n, jk = q / n;
+        double sum = Fs[i] * A[n * jk];
+        for (int m = 1; m < n; m++) sum = sum + Fs[i + n * m] * A[m + n * jk];
+        B[q] = sum;
+    }
+    __syncthreads();
+    // s: A(i,j,k) = sum_m B(i,m,k) F(j,m)
+    for (int q = threadIdx.x; q < nxyz; q += blockDim.x) {
+        const int i = q % n, j = (q / n) % n, k = q / n2;
+        const double *b = B + n2 * k;
+        double sum = b[i] * Fs[j];
+        for (int m = 1; m < n; m++) sum = sum + b[i + n * m] * Fs[j + n * m];
+        A[q] = sum;
+    }
+    __syncthreads();
+    if (nz > 1) {
+        // t: v(i,j,k) = sum_m A(i,j,m) F(k,m)
+        for (int q = threadIdx.x; q < nxyz; q += blockDim.x) {
+            const int ij = q % n2, k = q / n2;
+            double sum = A[ij] * Fs[k];
+            for (int m = 1; m < n; m++) sum = sum + A[ij + n2 * m] * Fs[k + n * m];
+            v[q] = sum;
+        }
+    } else {
+        for (int q = threadIdx.x; q < nxyz; q += blockDim.x) v[q] = A[q];
     }
 }
 
@@ -972,6 +1018,37 @@ int upload_graphene(Ctx *c)
     return 0;
 }
 
+// `if (iffilter) call q_filter(0.01)` at the end of cem_maxwell_op_rk (src/cem_maxwell.F:342):
+// all six components of the current fields, in place
+int apply_filter(Ctx *c)
+{
+    if (!c->filter_d) return 0;
+    const int n = c->n, nz = c->d.ldim == 3 ? n : 1;
+    const size_t smem = sizeof(double) * (2 * (size_t)c->nxyz + (size_t)n * n);
+    static bool configured = false;
+    if (!configured) {
+        CUDA_OK(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(sizeof(double) * (2 * 4096 + 256))));
+        configured = true;
+    }
+    const int nt = c->nxyz >= 256 ? 256 : ((c->nxyz + 31) / 32) * 32;
+    filter_kernel<<<dim3((unsigned)c->d.nelt, 6), nt, smem, c->s_compute>>>(
+        c->u[c->cur], c->ld, c->filter_d, n, nz, c->nxyz);
+    CUDA_OK(cudaGetLastError());
+    c->last_launches++;
+    if (c->d.ldim == 2) {
+        // the 2D stage kernels never write the three inactive components, so both ping-pong
+        // buffers must hold the same (now filtered) values of them
+        const bool tm = c->d.imode == 2;
+        const int inact[3] = {tm ? 2 : 0, tm ? 3 : 1, tm ? 4 : 5};
+        for (int q = 0; q < 3; q++)
+            CUDA_OK(cudaMemcpyAsync(c->u[c->cur ^ 1] + inact[q] * c->ld,
+                                    c->u[c->cur] + inact[q] * c->ld, sizeof(double) * c->npts,
+                                    cudaMemcpyDeviceToDevice, c->s_compute));
+    }
+    return 0;
+}
+
 } // namespace
 
 // =========================================================================================
@@ -1062,6 +1139,7 @@ int nekcem_b200_destroy(int handle)
         cudaFree(c->g_fp_d); cudaFree(c->g_node_d); cudaFree(c->fs_own_d); cudaFree(c->fs_nbr_d);
         cudaFree(c->g_fj); cudaFree(c->g_kj); cudaFree(c->g_par); cudaFree(c->g_yc);
         cudaFree(c->g_send_d); cudaFree(c->send_fp_d);
+        cudaFree(c->filter_d);
         cudaEventDestroy(c->ev_sheet);
         cudaEventDestroy(c->ev_stage); cudaEventDestroy(c->ev_halo);
         cudaEventDestroy(c->ev_t0); cudaEventDestroy(c->ev_t1);
@@ -1515,6 +1593,34 @@ int nekcem_b200_get_graphene(int handle, double *fjn, double *kfjn)
     return 0;
 }
 
+int nekcem_b200_set_filter(int handle, const double *intv)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (c->host_only) return fail("host-only planning context");
+    CUDA_OK(cudaSetDevice(c->d.device));
+    CUDA_OK(cudaStreamSynchronize(c->s_compute));
+    if (!intv) {
+        cudaFree(c->filter_d);
+        c->filter_d = nullptr;
+        return 0;
+    }
+    const size_t bytes = sizeof(double) * (size_t)c->n * c->n;
+    if (!c->filter_d) CUDA_OK(cudaMalloc(&c->filter_d, bytes));
+    CUDA_OK(cudaMemcpy(c->filter_d, intv, bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int nekcem_b200_apply_filter(int handle)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (!c->setup_done) return fail("nekcem_b200_setup has not completed");
+    if (!c->filter_d) return fail("no filter matrix has been set");
+    CUDA_OK(cudaSetDevice(c->d.device));
+    return apply_filter(c);
+}
+
 int nekcem_b200_set_option(int handle, const char *name, int value)
 {
     Ctx *c = get(handle);
@@ -1645,6 +1751,7 @@ int nekcem_b200_step(int handle, int nsteps)
     for (int s = 0; s < nsteps; s++) {
         for (int rk = 1; rk <= 5; rk++)
             if (run_stage(c, rk)) return 1;
+        if (apply_filter(c)) return 1;
         c->time = c->time + c->dt;
     }
     CUDA_OK(cudaEventRecord(c->ev_t1, c->s_compute));

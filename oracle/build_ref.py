@@ -76,6 +76,12 @@ UNITS = [
     ("tests/drude/drude.usr", ["userinc", "usersrc", "usersol", "userini", "uservp"], "__drude"),
     ("tests/lorentz/lorentz.usr", ["userinc", "usersrc", "usersol", "userini", "uservp"],
      "__lorentz"),
+    # the optional modal filter at the end of a time step (src/cem_maxwell.F:342, param(18) = 1):
+    # its two workers.  q_filter itself (six filterq calls around a SAVEd matrix, which the
+    # translator cannot keep across calls for run-time array sizes) is driven by the tests
+    ("src/nek5_filter.F", ["filterq", "build_new_filter"]),
+    ("src/nek5_grad.F", ["legendre_poly"]),
+    ("src/nek5_mat1.F", ["ident", "transpose", "gaujordf", "vlamax"]),
     # output hand-off: the per-node interleave of cem_out (src/io.F:207-210)
     ("src/io_dumpvtk.F", ["vtk_nonswap_field"]),
     ("tests/cylwave/cylwave.usr", ["usrdat", "usrdat2"], "__cylwave"),

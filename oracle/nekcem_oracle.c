@@ -1362,6 +1362,73 @@ ORA_API void ora_advance(ora_state *s, int nsteps)
     }
 }
 
+/* filterq src/nek5_filter.F:92-144 applied to one field v(nxyz,nelt) with the n x n filter matrix f
+ * (column-major, as build_new_filter returns it): v <- (F (x) F (x) F) v, every contraction in the
+ * order of the reference's mxm calls (sum over the contracted index ascending). */
+static void filterq_field(double *v, const double *f, int n, int nz, int nelt)
+{
+    int nxyz = n * n * nz;
+#pragma omp parallel
+    {
+        double *w1 = (double *)malloc(sizeof(double) * nxyz);
+        double *w2 = (double *)malloc(sizeof(double) * nxyz);
+#pragma omp for
+        for (int e = 0; e < nelt; e++) {
+            double *ve = v + (size_t)nxyz * e;
+            if (nz > 1) {
+                /* w1 = F * v  (n x n)(n x n^2) */
+                for (int jk = 0; jk < n * n; jk++)
+                    for (int i = 0; i < n; i++) {
+                        double sum = f[i] * ve[n * jk];
+                        for (int m = 1; m < n; m++) sum = sum + f[i + n * m] * ve[m + n * jk];
+                        w1[i + n * jk] = sum;
+                    }
+                /* per k: w2(:,:,k) = w1(:,:,k) * F^T */
+                for (int k = 0; k < n; k++)
+                    for (int j = 0; j < n; j++)
+                        for (int i = 0; i < n; i++) {
+                            const double *a = w1 + n * n * k;
+                            double sum = a[i] * f[j];
+                            for (int m = 1; m < n; m++) sum = sum + a[i + n * m] * f[j + n * m];
+                            w2[i + n * j + n * n * k] = sum;
+                        }
+                /* w1 = w2 (n^2 x n) * F^T */
+                for (int k = 0; k < n; k++)
+                    for (int ij = 0; ij < n * n; ij++) {
+                        double sum = w2[ij] * f[k];
+                        for (int m = 1; m < n; m++) sum = sum + w2[ij + n * n * m] * f[k + n * m];
+                        w1[ij + n * n * k] = sum;
+                    }
+            } else {
+                /* w2 = F * v ; w1 = w2 * F^T */
+                for (int j = 0; j < n; j++)
+                    for (int i = 0; i < n; i++) {
+                        double sum = f[i] * ve[n * j];
+                        for (int m = 1; m < n; m++) sum = sum + f[i + n * m] * ve[m + n * j];
+                        w2[i + n * j] = sum;
+                    }
+                for (int j = 0; j < n; j++)
+                    for (int i = 0; i < n; i++) {
+                        double sum = w2[i] * f[j];
+                        for (int m = 1; m < n; m++) sum = sum + w2[i + n * m] * f[j + n * m];
+                        w1[i + n * j] = sum;
+                    }
+            }
+            for (int i = 0; i < nxyz; i++) ve[i] = w1[i];
+        }
+        free(w1);
+        free(w2);
+    }
+}
+
+/* q_filter src/nek5_filter.F:2-90 (MAXWELL branch): the six field components, E first */
+ORA_API void ora_q_filter(ora_state *s, const double *intv)
+{
+    int nz = s->ldim == 3 ? s->nx1 : 1;
+    for (int c = 0; c < 3; c++) filterq_field(EN(c), intv, s->nx1, nz, s->nelt);
+    for (int c = 0; c < 3; c++) filterq_field(HN(c), intv, s->nx1, nz, s->nelt);
+}
+
 /* cem_error src/cem_common.F:1335-1355: l2 = sqrt(sum(err*bm1*err)/volvm1), linf = max|err| */
 ORA_API void ora_cem_error(const double *u, const double *exact, double *error, int n,
                            const double *bm1, double volvm1, double *l2, double *linf)

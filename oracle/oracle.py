@@ -103,6 +103,7 @@ def lib():
         L.ora_rk4_upd.argtypes = [c_dp, c_dp, c_dp, C.c_double, C.c_double, C.c_double, C.c_int]
         L.ora_cem_maxwell_drude.argtypes = [sp, c_dp, c_dp, c_dp, c_dp, c_ip, C.c_int]
         L.ora_cem_maxwell_lorentz.argtypes = [sp, c_dp, c_dp, c_dp, c_dp, c_ip, C.c_int]
+        L.ora_q_filter.argtypes = [sp, c_dp]
         L.ora_cem_graphene_current.argtypes = [sp, c_dp, c_dp, c_dp, c_dp, c_dp, c_ip, C.c_int]
         L.ora_cem_error.argtypes = [c_dp, c_dp, c_dp, C.c_int, c_dp, C.c_double, c_dp, c_dp]
         L.ora_get_dxmin.argtypes = [C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_dp]
@@ -346,6 +347,36 @@ def face_glo_num(mesh: Mesh, nx1: int) -> np.ndarray:
 
 # ----------------------------------------------------------------------------------
 # The reference case: COMMON-block arrays + step driver
+def build_new_filter(zpts: np.ndarray, kut: int, wght: float) -> np.ndarray:
+    """build_new_filter src/nek5_filter.F:171-249: the 1D modal filter F = V D V^-1 in the basis
+    phi_1 = L_0, phi_2 = L_1, phi_k = L_{k-1} - L_{k-3}, with transfer function d_k = 1 below
+    k0 = nx - kut and 1 - wght (k-k0)^2 / kut^2 above (quadratic roll-off of the top kut modes).
+    Column-major n x n, flat.  numpy's solve in place of the reference's Gauss-Jordan inverse
+    (setup; agreement ~1e-14, tests/test_reference_pin.py) -- in the drop-in the matrix comes
+    from the host's own build_new_filter."""
+    nx = zpts.size
+    n = nx - 1
+    pht = np.zeros((nx, nx))  # pht[k, j] = phi_k(z_j)
+    for j, z in enumerate(zpts):
+        L = np.zeros(nx + 1)
+        L[0] = 1.0
+        L[1] = z
+        for k in range(2, n + 1):  # legendre_poly src/nek5_grad.F:272-289
+            L[k] = ((2 * k - 1) * z * L[k - 1] - (k - 1) * L[k - 2]) / k
+        pht[0, j] = L[0]
+        pht[1, j] = L[1]
+        for k in range(2, nx):
+            pht[k, j] = L[k] - L[k - 2]
+    phi = pht.T.copy()        # phi[j, k] = phi_k(z_j): V
+    diag = np.eye(nx)
+    k0 = nx - kut
+    for k in range(k0 + 1, nx + 1):
+        amp = wght * (k - k0) * (k - k0) / (kut * kut)
+        diag[k - 1, k - 1] = 1.0 - amp
+    intv = phi @ (diag @ np.linalg.inv(phi))
+    return np.ascontiguousarray(intv.T).reshape(-1)  # column-major flat
+
+
 # ----------------------------------------------------------------------------------
 class RefCase:
     """Restates cem_init/cem_solve setup for the Maxwell RK path (src/cem_drive.F:17-190,
@@ -585,7 +616,17 @@ class RefCase:
         return self.s.dt
 
     def step(self, nsteps: int = 1):
-        self.L.ora_advance(C.byref(self.s), nsteps)
+        if getattr(self, "filter", None) is None:
+            self.L.ora_advance(C.byref(self.s), nsteps)
+            return
+        for _ in range(nsteps):  # cem_maxwell_op_rk: `if (iffilter) call q_filter(0.01)` (:342)
+            self.L.ora_advance(C.byref(self.s), 1)
+            self.L.ora_q_filter(C.byref(self.s), dp(self.filter))
+
+    def set_filter(self, wght: float = 0.01, ncut: int = 2):
+        """param(18) = 1: iffilter (src/cem_param.F:71); q_filter builds its matrix once with
+        ncut = 2 and the weight cem_maxwell_op_rk passes (0.01)"""
+        self.filter = build_new_filter(self.zgm1, ncut, wght)
 
     def stage(self, rkstep: int):
         """One RK stage (rk_c; cem_maxwell_op; rk_maxwell_ab), 1-based rkstep."""

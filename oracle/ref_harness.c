@@ -40,7 +40,7 @@ EXPORT void measure_comm_(double *t0) { (void)t0; }
 /* src/nek5_acc_dummy.F: .false. without OpenACC */
 EXPORT int acc_nek_present_(double *a, int *n) { (void)a; (void)n; return 0; }
 EXPORT void exitt_(int *rc) { fprintf(stderr, "reference called exitt(%d)\n", rc ? *rc : 0); exit(1); }
-EXPORT void q_filter_(double *w) { (void)w; fprintf(stderr, "q_filter is outside the path\n"); exit(1); }
+EXPORT void q_filter_(double *w) { (void)w; fprintf(stderr, "q_filter: drive filterq from the test (see build_ref.py)\n"); exit(1); }
 /* dealiased curl (src/cem_maxwell.F:1541-1729): ifdealias is off in every case of the path */
 EXPORT void maxwell_wght_dcurl_(void) { fprintf(stderr, "maxwell_wght_dcurl is outside the path\n"); exit(1); }
 /* global integer sum over ranks (src/nek5_mat1.F): one process here */

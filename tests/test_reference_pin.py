@@ -1009,3 +1009,57 @@ def test_pin_vtk_payload_against_the_references_writer_pieces():
         assert db.tobytes() == c.vtk_payload(which, as_double=True)
     assert np.abs(c.en).max() > 1e-3
     r.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# the optional modal filter of cem_maxwell_op_rk (`if (iffilter) call q_filter(0.01)`, :342)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [4, 8, 9, 12, 16])
+def test_pin_filter_matrix(n):
+    """build_new_filter (src/nek5_filter.F:171-249, Gauss-Jordan inverse of the modal basis):
+    the oracle's numpy restatement agrees to round-off; rows sum to 1 (constants pass)"""
+    from oracle import oracle as O
+    c = cases.case_boxper((3, 3, 3), n)
+    r = refrun.ReferenceRun(c)
+    intv = np.zeros(n * n)
+    z = np.ascontiguousarray(c.zgm1)
+    r.L.build_new_filter_(_dp(intv), _dp(z), C.byref(C.c_int(n)), C.byref(C.c_int(2)),
+                          C.byref(C.c_double(0.01)), C.byref(C.c_int(1)))
+    mine = O.build_new_filter(c.zgm1, 2, 0.01)
+    assert np.abs(intv - mine).max() <= 2e-13
+    assert np.abs(intv.reshape(n, n).T.sum(axis=1) - 1.0).max() <= 1e-13
+    assert np.abs(intv.reshape(n, n).T - np.eye(n)).max() > 1e-4   # it does filter
+    r.close()
+
+
+@pytest.mark.parametrize("which", ["3d", "2d-te"])
+def test_pin_filtered_time_stepping(which):
+    """param(18) = 1: every time step ends with q_filter(0.01) = filterq on ex,ey,ez,hx,hy,hz
+    (src/nek5_filter.F:68-74, 92-144).  Reference side: its own cem_maxwell_op_rk followed by its
+    own filterq on the six components with the matrix from its own build_new_filter; the oracle
+    uses the same matrix.  Fields and RK registers bit for bit after 6 filtered steps."""
+    c = cases.case_boxper((3, 3, 3), 7, dt=-2e-3) if which == "3d" else cases.case_2dboxper(1, nx1=8)
+    r = refrun.ReferenceRun(c)
+    n, nz = c.nx1, (c.nx1 if c.ldim == 3 else 1)
+    intv = np.zeros(n * n)
+    z = np.ascontiguousarray(c.zgm1)
+    r.L.build_new_filter_(_dp(intv), _dp(z), C.byref(C.c_int(n)), C.byref(C.c_int(2)),
+                          C.byref(C.c_double(0.01)), C.byref(C.c_int(1)))
+    c.filter = intv.copy()                         # the reference's own matrix on both sides
+    w1 = np.zeros(c.nxyz * c.nelt); w2 = np.zeros(c.nxyz); ft = np.zeros(n * n)
+    if3d, dmax = C.c_int(int(c.ldim == 3)), C.c_double()
+    N = c.npts
+    for _ in range(6):
+        c.step(1)
+        r.step(1)
+        for name in ("en", "hn"):                  # q_filter's order: E first
+            v = r.view(name)
+            for k in range(3):
+                r.L.filterq_(_dp(v[k * N:]), _dp(intv), C.byref(C.c_int(n)), C.byref(C.c_int(nz)),
+                             _dp(w1), _dp(w2), _dp(ft), C.byref(if3d), C.byref(dmax))
+    _assert_same(c, r)
+    # and the filter is not a no-op on this run
+    c0 = cases.case_boxper((3, 3, 3), 7, dt=-2e-3) if which == "3d" else cases.case_2dboxper(1, nx1=8)
+    c0.step(6)
+    assert np.abs(c0.en - c.en).max() > 1e-9
+    r.close()
