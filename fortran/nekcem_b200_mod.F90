@@ -188,6 +188,38 @@ module nekcem_b200
        integer(c_int), value :: handle
        real(c_double), intent(inout) :: fjn(*), kfjn(*)
      end function
+     !> RK tables of COMMON /RKCOEF/ as rk_storage left them (src/cem_common.F:78-114)
+     integer(c_int) function nekcem_b200_set_rk_coefficients(handle, a, b, c) &
+          bind(C, name='nekcem_b200_set_rk_coefficients')
+       import :: c_int, c_double
+       integer(c_int), value :: handle
+       real(c_double), intent(in) :: a(5), b(5), c(6)
+     end function
+     !> modal filter at the end of every step (q_filter, src/nek5_filter.F); intv from build_new_filter
+     integer(c_int) function nekcem_b200_set_filter(handle, intv) &
+          bind(C, name='nekcem_b200_set_filter')
+       import :: c_int, c_double
+       integer(c_int), value :: handle
+       real(c_double), intent(in) :: intv(*)
+     end function
+     !> big-endian "VECTORS" payload of cem_out for EN (which=0) / HN (1), float32 or float64
+     integer(c_int) function nekcem_b200_vtk_payload(handle, which, as_double, out) &
+          bind(C, name='nekcem_b200_vtk_payload')
+       import :: c_int, c_ptr
+       integer(c_int), value :: handle, which, as_double
+       type(c_ptr), value :: out
+     end function
+     !> the two halves of a stage around a caller-provided halo exchange (option external_exchange)
+     integer(c_int) function nekcem_b200_stage_pack(handle, rkstep) &
+          bind(C, name='nekcem_b200_stage_pack')
+       import :: c_int
+       integer(c_int), value :: handle, rkstep
+     end function
+     integer(c_int) function nekcem_b200_stage_compute(handle, rkstep) &
+          bind(C, name='nekcem_b200_stage_compute')
+       import :: c_int
+       integer(c_int), value :: handle, rkstep
+     end function
      integer(c_int) function nekcem_b200_algorithmic_bytes(handle, bytes_per_stage) &
           bind(C, name='nekcem_b200_algorithmic_bytes')
        import :: c_int, c_double

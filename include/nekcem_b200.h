@@ -179,6 +179,16 @@ int nekcem_b200_set_graphene(int handle, const double *fjn, const double *kfjn,
                              int32_t n);
 int nekcem_b200_get_graphene(int handle, double *fjn, double *kfjn);
 
+/* RK tables of COMMON /RKCOEF/ (src/RK5): rk4a(5), rk4b(5), rk4c(6).  A new context holds the
+ * LSRK(5,4) values of rk_storage's ifrk45 branch (src/cem_common.F:86-104); the shim uploads the
+ * host's own arrays after rk_storage so that the device uses bit-identical coefficients, and so
+ * that param(17) = 22 behaves as it does in the reference: rk_storage fills only rk4a(1:2),
+ * rk4b(1:2) (:106-110), cem_maxwell_op_rk still runs five stages (src/cem_maxwell.F:336-340),
+ * of which the last three then leave the fields unchanged (b = 0) and rktime = time (c = 0). */
+int nekcem_b200_set_rk_coefficients(int handle, const double a[5], const double b[5],
+                                    const double c[6]);
+int nekcem_b200_get_rk_coefficients(int handle, double a[5], double b[5], double c[6]);
+
 /* Optional modal filter (`if (iffilter) call q_filter(0.01)` at the end of
  * cem_maxwell_op_rk, src/cem_maxwell.F:342; param(18) = 1).  intv: the nx1 x nx1 matrix the
  * reference's own build_new_filter(intv,zgm1,nx1,ncut,wght,nid) returns (src/nek5_filter.F:171-249;

@@ -102,6 +102,8 @@ def lib():
         L.nekcem_b200_error_sums_planewave.argtypes = [C.c_int, C.POINTER(PlaneWave),
                                                        C.POINTER(C.c_ubyte), C.POINTER(C.c_ubyte),
                                                        C.c_double, c_dp, c_dp]
+        L.nekcem_b200_set_rk_coefficients.argtypes = [C.c_int, c_dp, c_dp, c_dp]
+        L.nekcem_b200_get_rk_coefficients.argtypes = [C.c_int, c_dp, c_dp, c_dp]
         L.nekcem_b200_set_filter.argtypes = [C.c_int, c_dp]
         L.nekcem_b200_apply_filter.argtypes = [C.c_int]
         L.nekcem_b200_vtk_payload.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
@@ -368,6 +370,17 @@ class MaxwellB200:
         fjn = np.zeros(18 * self.nxzfl); kfjn = np.zeros_like(fjn)
         _chk(self.L.nekcem_b200_get_graphene(self.h, _dp(fjn), _dp(kfjn)))
         return fjn, kfjn
+
+    def set_rk_coefficients(self, a, b, c):
+        """COMMON /RKCOEF/ rk4a(5), rk4b(5), rk4c(6) as rk_storage left them (src/cem_common.F:78-114)"""
+        a, b, c = (np.ascontiguousarray(x, dtype=np.float64) for x in (a, b, c))
+        assert a.size == 5 and b.size == 5 and c.size == 6
+        _chk(self.L.nekcem_b200_set_rk_coefficients(self.h, _dp(a), _dp(b), _dp(c)))
+
+    def get_rk_coefficients(self):
+        a, b, c = np.zeros(5), np.zeros(5), np.zeros(6)
+        _chk(self.L.nekcem_b200_get_rk_coefficients(self.h, _dp(a), _dp(b), _dp(c)))
+        return a, b, c
 
     def set_filter(self, intv):
         """param(18) = 1: every time step ends with q_filter (src/nek5_filter.F:2-144); intv is

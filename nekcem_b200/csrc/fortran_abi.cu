@@ -123,6 +123,12 @@ NKB_EXPORT void nekcem_b200_error_sums_mode_(const int *h, const int *kind, cons
           "nekcem_b200_error_sums_mode");
 }
 
+NKB_EXPORT void nekcem_b200_set_rk_coefficients_(const int *h, const double *a, const double *b,
+                                                 const double *c)
+{
+    check(nekcem_b200_set_rk_coefficients(*h, a, b, c), "nekcem_b200_set_rk_coefficients");
+}
+
 NKB_EXPORT void nekcem_b200_set_filter_(const int *h, const double *intv)
 {
     check(nekcem_b200_set_filter(*h, intv), "nekcem_b200_set_filter");

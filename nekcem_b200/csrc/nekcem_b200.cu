@@ -1593,6 +1593,27 @@ int nekcem_b200_get_graphene(int handle, double *fjn, double *kfjn)
     return 0;
 }
 
+int nekcem_b200_set_rk_coefficients(int handle, const double a[5], const double b[5],
+                                    const double cc[6])
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (!a || !b || !cc) return fail("null argument");
+    for (int q = 0; q < 5; q++) { c->rk4a[q] = a[q]; c->rk4b[q] = b[q]; }
+    for (int q = 0; q < 6; q++) c->rk4c[q] = cc[q];
+    return 0;
+}
+
+int nekcem_b200_get_rk_coefficients(int handle, double a[5], double b[5], double cc[6])
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (!a || !b || !cc) return fail("null argument");
+    for (int q = 0; q < 5; q++) { a[q] = c->rk4a[q]; b[q] = c->rk4b[q]; }
+    for (int q = 0; q < 6; q++) cc[q] = c->rk4c[q];
+    return 0;
+}
+
 int nekcem_b200_set_filter(int handle, const double *intv)
 {
     Ctx *c = get(handle);

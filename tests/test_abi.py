@@ -30,6 +30,8 @@ def test_library_exports_every_declared_symbol():
               "nekcem_b200_set_drude_", "nekcem_b200_set_lorentz_", "nekcem_b200_get_ade_",
               "nekcem_b200_bind_", "cem_maxwell_drude_", "cem_maxwell_lorentz_",
               "nekcem_b200_set_graphene_", "nekcem_b200_get_graphene_",
+              "nekcem_b200_set_filter_", "nekcem_b200_set_rk_coefficients_",
+              "nekcem_b200_vtk_payload_",
               "cem_3d_graphene_current_", "cem_te_graphene_current_",
               "cem_tm_graphene_current_"):
         assert hasattr(L, n), f"Fortran twin {n} missing"
@@ -158,4 +160,33 @@ def test_graphene_registration_host_side():
         s.cem_graphene_current(None, None, u.graphparams, c.yconduc, [c.nxzfl])
     with pytest.raises(NekcemB200Error, match="expected"):
         s.cem_graphene_current(None, None, u.graphparams[:5], c.yconduc, u.graphindex)
+    s.close()
+
+
+def test_rk_tables_default_and_upload():
+    """a new context holds rk_storage's LSRK(5,4) tables (src/cem_common.F:86-104), equal to the
+    oracle's and -- through the Fortran twin, with the translated reference's COMMON /RKCOEF/ as
+    the argument -- to the reference's; param(17) = 22 tables can be uploaded"""
+    from oracle import cases
+    c = cases.case_boxper((3, 3, 3), 4)
+    s = MaxwellB200(3, 4, c.nelt, device=-1)
+    a, b, cc = s.get_rk_coefficients()
+    assert np.array_equal(a, np.array(c.s.rk4a)) and np.array_equal(b, np.array(c.s.rk4b))
+    assert np.array_equal(cc, np.array(c.s.rk4c))
+    from oracle import refrun
+    if refrun.available():
+        r = refrun.ReferenceRun(c)
+        L = lib()
+        dp = lambda v: v.ctypes.data_as(C.POINTER(C.c_double))
+        s.set_rk_coefficients(np.zeros(5), np.zeros(5), np.zeros(6))
+        h = C.c_int(s.h)
+        L.nekcem_b200_set_rk_coefficients_(C.byref(h), dp(r.view("rk4a")), dp(r.view("rk4b")),
+                                           dp(r.view("rk4c")))
+        a2, b2, c2 = s.get_rk_coefficients()
+        assert np.array_equal(a2, a) and np.array_equal(b2, b) and np.array_equal(c2, cc)
+        r.close()
+    # rk_storage, ifrk22 branch (:106-110): only the first two entries are set
+    s.set_rk_coefficients([0.0, -1.0, 0, 0, 0], [1.0, 0.5, 0, 0, 0], np.zeros(6))
+    a3, b3, c3 = s.get_rk_coefficients()
+    assert a3[1] == -1.0 and b3[1] == 0.5 and not c3.any()
     s.close()
