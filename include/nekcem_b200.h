@@ -91,6 +91,18 @@ int nekcem_b200_set_array(int handle, int which, const double *host, int64_t cou
  * src/io.F:193-195). */
 int nekcem_b200_get_array(int handle, int which, double *host, int64_t count);
 
+/* Fortran leading dimensions.  The reference dimensions its arrays by SIZE with lelt >= nelt
+ * (lelt = lelg/lpmin + 3, tests/3dboxper/SIZE:15), so a vector field is hn(lpts1,3) with
+ * lpts1 = lx1*ly1*lz1*lelt >= npts (src/EMWAVE:5-16, src/PML), a .usr's ADE arrays are jn(lpts,3),
+ * params(lpts,2) and its graphene arrays fjn(lxzfl,3,6), params(lxzfl,12).  set_array_ld /
+ * get_array_ld transfer the three components of an (ld,3) array (ids NKB_HN .. NKB_KEN,
+ * NKB_PMLSIGMA .. NKB_KPMLDN; one-component arrays: same as set_array on their first entries);
+ * set_leading_dims declares lpts and lxzfl for the arrays that set_drude / set_lorentz / get_ade
+ * and set_graphene / get_graphene receive (default: npts, nxzfl -- compact arrays). */
+int nekcem_b200_set_leading_dims(int handle, int64_t lpts, int64_t lxzfl);
+int nekcem_b200_set_array_ld(int handle, int which, const double *host, int64_t ld);
+int nekcem_b200_get_array_ld(int handle, int which, double *host, int64_t ld);
+
 /* Face connectivity.  glo_num are the face-point global ids the reference hands to
  * `gs_setup(gsh_face,glo_num,ntot,nekcomm,np)` (src/nek5_connect11.F:2217-2223,
  * src/jl/gs.c:1898-1907): two face points are paired iff they carry the same non-zero id.

@@ -102,6 +102,9 @@ def lib():
         L.nekcem_b200_error_sums_planewave.argtypes = [C.c_int, C.POINTER(PlaneWave),
                                                        C.POINTER(C.c_ubyte), C.POINTER(C.c_ubyte),
                                                        C.c_double, c_dp, c_dp]
+        L.nekcem_b200_set_leading_dims.argtypes = [C.c_int, C.c_int64, C.c_int64]
+        L.nekcem_b200_set_array_ld.argtypes = [C.c_int, C.c_int, c_dp, C.c_int64]
+        L.nekcem_b200_get_array_ld.argtypes = [C.c_int, C.c_int, c_dp, C.c_int64]
         L.nekcem_b200_set_rk_coefficients.argtypes = [C.c_int, c_dp, c_dp, c_dp]
         L.nekcem_b200_get_rk_coefficients.argtypes = [C.c_int, c_dp, c_dp, c_dp]
         L.nekcem_b200_set_filter.argtypes = [C.c_int, c_dp]

@@ -47,6 +47,24 @@ NKB_EXPORT void nekcem_b200_get_array_(const int *h, const int *which, double *h
     check(nekcem_b200_get_array(*h, *which, host, *count), "nekcem_b200_get_array");
 }
 
+NKB_EXPORT void nekcem_b200_set_leading_dims_(const int *h, const long long *lpts,
+                                              const long long *lxzfl)
+{
+    check(nekcem_b200_set_leading_dims(*h, *lpts, *lxzfl), "nekcem_b200_set_leading_dims");
+}
+
+NKB_EXPORT void nekcem_b200_set_array_ld_(const int *h, const int *which, const double *host,
+                                          const long long *ld)
+{
+    check(nekcem_b200_set_array_ld(*h, *which, host, *ld), "nekcem_b200_set_array_ld");
+}
+
+NKB_EXPORT void nekcem_b200_get_array_ld_(const int *h, const int *which, double *host,
+                                          const long long *ld)
+{
+    check(nekcem_b200_get_array_ld(*h, *which, host, *ld), "nekcem_b200_get_array_ld");
+}
+
 NKB_EXPORT void nekcem_b200_set_faces_(const int *h, const long long *glo_num,
                                        const long long *nxzfl, const int *cempec,
                                        const int *ncempec)
@@ -121,6 +139,22 @@ NKB_EXPORT void nekcem_b200_error_sums_mode_(const int *h, const int *kind, cons
 {
     check(nekcem_b200_error_sums_mode(*h, kind, k, ph, amp, sumsq, linf),
           "nekcem_b200_error_sums_mode");
+}
+
+// The two host-sync seams under the names SURVEY.md 8b gives them: `!$ACC UPDATE HOST(hn,en)`
+// (tests/3dboxper/3dboxper.usr:199, src/io.F:193-195) and `!$ACC UPDATE DEVICE(...)` after
+// userini (tests/drude/drude.usr:94).  hn, en: the (lpts1,3) COMMON arrays, ld = lpts1.
+NKB_EXPORT void nekcem_b200_sync_host_(const int *h, double *hn, double *en, const long long *ld)
+{
+    check(nekcem_b200_get_array_ld(*h, NKB_HN, hn, *ld), "nekcem_b200_sync_host");
+    check(nekcem_b200_get_array_ld(*h, NKB_EN, en, *ld), "nekcem_b200_sync_host");
+}
+
+NKB_EXPORT void nekcem_b200_sync_device_(const int *h, const double *hn, const double *en,
+                                         const long long *ld)
+{
+    check(nekcem_b200_set_array_ld(*h, NKB_HN, hn, *ld), "nekcem_b200_sync_device");
+    check(nekcem_b200_set_array_ld(*h, NKB_EN, en, *ld), "nekcem_b200_sync_device");
 }
 
 NKB_EXPORT void nekcem_b200_set_rk_coefficients_(const int *h, const double *a, const double *b,

@@ -180,6 +180,9 @@ struct Ctx {
     bool g_dev_current = false; // the device copy of the sheet state is newer than the staging
     int *g_send_d = nullptr, *send_fp_d = nullptr; // per halo entry: sheet slot (-1: none), face point
     cudaEvent_t ev_sheet = nullptr;
+    // leading dimensions of the caller's multi-component Fortran arrays: (lpts,k) for the ADE
+    // arrays of a .usr, (lxzfl,3,6) / (lxzfl,12) for its graphene arrays (SIZE: lelt >= nelt)
+    int64_t ld_pts = 0, ld_fac = 0; // 0: npts / nxzfl
     // optional modal filter at the end of every time step (q_filter, param(18) = 1)
     double *filter_d = nullptr;
     // transport-independent stepping (nekcem_b200_stage_pack / stage_compute): the caller moves
@@ -1496,11 +1499,18 @@ static int set_ade(int handle, int kind, const double *jn, const double *kjn, co
     CUDA_OK(cudaMalloc(&c->ade_k, bj));
     CUDA_OK(cudaMalloc(&c->ade_par, bp));
     CUDA_OK(cudaMalloc(&c->ade_mask, c->npts));
-    if (jn) CUDA_OK(cudaMemcpy(c->ade_j, jn, bj, cudaMemcpyHostToDevice));
+    const int64_t lp = c->ld_pts ? c->ld_pts : c->npts; // the user's (lpts,k) arrays
+    auto h2d = [&](double *dst, const double *src, int ncomp) -> cudaError_t {
+        if (lp == c->npts)
+            return cudaMemcpy(dst, src, sizeof(double) * ncomp * c->npts, cudaMemcpyHostToDevice);
+        return cudaMemcpy2D(dst, sizeof(double) * c->npts, src, sizeof(double) * lp,
+                            sizeof(double) * c->npts, ncomp, cudaMemcpyHostToDevice);
+    };
+    if (jn) CUDA_OK(h2d(c->ade_j, jn, nj));
     else CUDA_OK(cudaMemset(c->ade_j, 0, bj));
-    if (kjn) CUDA_OK(cudaMemcpy(c->ade_k, kjn, bj, cudaMemcpyHostToDevice));
+    if (kjn) CUDA_OK(h2d(c->ade_k, kjn, nj));
     else CUDA_OK(cudaMemset(c->ade_k, 0, bj));
-    CUDA_OK(cudaMemcpy(c->ade_par, params, bp, cudaMemcpyHostToDevice));
+    CUDA_OK(h2d(c->ade_par, params, np));
     CUDA_OK(cudaMemcpy(c->ade_mask, mask.data(), c->npts, cudaMemcpyHostToDevice));
     c->ade_kind = kind;
     return 0;
@@ -1525,9 +1535,16 @@ int nekcem_b200_get_ade(int handle, double *jn, double *kjn)
     if (!c->ade_kind) return fail("no Drude/Lorentz state has been set");
     CUDA_OK(cudaSetDevice(c->d.device));
     CUDA_OK(cudaStreamSynchronize(c->s_compute));
-    const size_t bj = sizeof(double) * (c->ade_kind == 1 ? 3 : 6) * c->npts;
-    if (jn) CUDA_OK(cudaMemcpy(jn, c->ade_j, bj, cudaMemcpyDeviceToHost));
-    if (kjn) CUDA_OK(cudaMemcpy(kjn, c->ade_k, bj, cudaMemcpyDeviceToHost));
+    const int nj = c->ade_kind == 1 ? 3 : 6;
+    const int64_t lp = c->ld_pts ? c->ld_pts : c->npts;
+    auto d2h = [&](double *dst, const double *src) -> cudaError_t {
+        if (lp == c->npts)
+            return cudaMemcpy(dst, src, sizeof(double) * nj * c->npts, cudaMemcpyDeviceToHost);
+        return cudaMemcpy2D(dst, sizeof(double) * lp, src, sizeof(double) * c->npts,
+                            sizeof(double) * c->npts, nj, cudaMemcpyDeviceToHost);
+    };
+    if (jn) CUDA_OK(d2h(jn, c->ade_j));
+    if (kjn) CUDA_OK(d2h(kjn, c->ade_k));
     return 0;
 }
 
@@ -1546,10 +1563,11 @@ int nekcem_b200_set_graphene(int handle, const double *fjn, const double *kfjn,
     c->setup_done = false;
     c->g_dev_current = false;
     const size_t ng = (size_t)n;
-    const int64_t nf = c->nxzfl;
+    const int64_t nfp = c->nxzfl;                       // valid face points
+    const int64_t nf = c->ld_fac ? c->ld_fac : nfp;     // leading dimension of the user's arrays
     for (int q = 0; q < n; q++) {
-        if (gindex[q] < 1 || gindex[q] > nf)
-            return fail("graphene index(%d)=%d out of range 1..%lld", q + 1, gindex[q], (long long)nf);
+        if (gindex[q] < 1 || gindex[q] > nfp)
+            return fail("graphene index(%d)=%d out of range 1..%lld", q + 1, gindex[q], (long long)nfp);
         c->g_fp.push_back(gindex[q] - 1);
     }
     // (nxzfl,3,6) / (nxzfl,12) user arrays -> compact [m][q]
@@ -1576,7 +1594,7 @@ int nekcem_b200_get_graphene(int handle, double *fjn, double *kfjn)
     if (!c) return 1;
     if (c->g_fp.empty()) return fail("no graphene state has been set");
     const size_t ng = c->g_fp.size();
-    const int64_t nf = c->nxzfl;
+    const int64_t nf = c->ld_fac ? c->ld_fac : c->nxzfl;
     if (c->g_fj && c->g_dev_current) { // device state is current once setup has run
         CUDA_OK(cudaSetDevice(c->d.device));
         CUDA_OK(cudaStreamSynchronize(c->s_compute));
@@ -1590,6 +1608,49 @@ int nekcem_b200_get_graphene(int handle, double *fjn, double *kfjn)
             if (kfjn) kfjn[j + nf * m] = c->g_kj_h[m * ng + q];
         }
     }
+    return 0;
+}
+
+int nekcem_b200_set_leading_dims(int handle, int64_t lpts, int64_t lxzfl)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (lpts < c->npts || lxzfl < c->nxzfl)
+        return fail("leading dimensions (%lld, %lld) smaller than npts, nxzfl (%lld, %lld)",
+                    (long long)lpts, (long long)lxzfl, (long long)c->npts, (long long)c->nxzfl);
+    c->ld_pts = lpts;
+    c->ld_fac = lxzfl;
+    return 0;
+}
+
+int nekcem_b200_set_array_ld(int handle, int which, const double *host, int64_t ld)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (which < 0 || which >= NKB_ARRAY_COUNT) return fail("bad array id %d", which);
+    if (!host) return fail("null host pointer");
+    const int64_t cnt = array_count(c, which);
+    if (cnt != 3 * c->npts || ld == c->npts) return nekcem_b200_set_array(handle, which, host, cnt);
+    if (ld < c->npts) return fail("leading dimension %lld smaller than npts %lld", (long long)ld, (long long)c->npts);
+    std::vector<double> tmp(3 * (size_t)c->npts);
+    for (int q = 0; q < 3; q++)
+        memcpy(tmp.data() + q * c->npts, host + q * ld, sizeof(double) * c->npts);
+    return nekcem_b200_set_array(handle, which, tmp.data(), cnt);
+}
+
+int nekcem_b200_get_array_ld(int handle, int which, double *host, int64_t ld)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (which < 0 || which >= NKB_ARRAY_COUNT) return fail("bad array id %d", which);
+    if (!host) return fail("null host pointer");
+    const int64_t cnt = array_count(c, which);
+    if (cnt != 3 * c->npts || ld == c->npts) return nekcem_b200_get_array(handle, which, host, cnt);
+    if (ld < c->npts) return fail("leading dimension %lld smaller than npts %lld", (long long)ld, (long long)c->npts);
+    std::vector<double> tmp(3 * (size_t)c->npts);
+    if (nekcem_b200_get_array(handle, which, tmp.data(), cnt)) return 1;
+    for (int q = 0; q < 3; q++)
+        memcpy(host + q * ld, tmp.data() + q * c->npts, sizeof(double) * c->npts);
     return 0;
 }
 

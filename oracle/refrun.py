@@ -55,20 +55,26 @@ def lib(kind: str = "base"):
 class ReferenceRun:
     """One process-wide instance at a time (the reference's state is global COMMON storage)."""
 
-    def __init__(self, case, kind: str = "base"):
+    def __init__(self, case, kind: str = "base", pad_elems: int = 0):
+        """pad_elems > 0 dimensions the COMMON arrays for lelt = nelt + pad_elems elements, as a
+        real SIZE file does (lelt = lelg/lpmin + 3, tests/3dboxper/SIZE:15): vector fields then
+        have the leading dimension lpts1 > npts, which put() / field() honour."""
         L = lib(kind)
         self.L, self.case = L, case
+        self.pad_elems = pad_elems
         ldim, nx1, nelt = case.ldim, case.nx1, case.nelt
         # SIZE: parameter (ldim, lxi, lelg ...) of this case; lelt = nelt exactly so that the
         # (lpts1,3) arrays have the oracle's layout (the reference pads lelt by 3 unused
         # elements, tests/3dboxper/SIZE:15)
+        lelt = nelt + pad_elems
         for k, v in (("ldim", ldim), ("lxi", nx1 - 1), ("lelg", nelt), ("lpmin", 1),
-                     ("lelv", nelt), ("lelt", nelt), ("lpts10", case.npts),
-                     ("lxzfl10", case.nxzfl)):
+                     ("lelv", lelt), ("lelt", lelt), ("lpts10", case.nxyz * lelt),
+                     ("lxzfl10", case.nxzf * case.nfaces * lelt)):
             L.ref_set_param(k.encode(), v)
         L.ref_alloc()
         npts, nxzfl = case.npts, case.nxzfl
-        assert self.get("lpts1") == npts and self.get("lxzfl1") == nxzfl
+        self.lpts1 = int(self.get("lpts1"))
+        assert self.lpts1 == case.nxyz * lelt and self.get("lxzfl1") == case.nxzf * case.nfaces * lelt
         nz1 = nx1 if ldim == 3 else 1
         # /DIMN/ (src/cem_drive.F:697-707)
         for k, v in (("nelt", nelt), ("nelv", nelt), ("nx1", nx1), ("ny1", nx1), ("nz1", nz1),
@@ -169,7 +175,17 @@ class ReferenceRun:
         v = self.view(name)
         a = np.asarray(arr).reshape(-1)
         assert a.size <= v.size, (name, a.size, v.size)
+        npts = self.case.npts
+        if self.pad_elems and a.size == 3 * npts and v.size == 3 * self.lpts1:
+            for k in range(3):           # (lpts1,3) Fortran array <- compact (npts,3)
+                v[k * self.lpts1:k * self.lpts1 + npts] = a[k * npts:(k + 1) * npts]
+            return
         v[:a.size] = a
+
+    def field(self, name):
+        """compact (npts,3) copy of an (lpts1,3) COMMON array"""
+        v, npts = self.view(name), self.case.npts
+        return np.concatenate([v[k * self.lpts1:k * self.lpts1 + npts] for k in range(3)])
 
     def view_char(self, name):
         p, kind, cnt = self._sym_kind(name)

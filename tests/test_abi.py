@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
               "nekcem_b200_bind_", "cem_maxwell_drude_", "cem_maxwell_lorentz_",
               "nekcem_b200_set_graphene_", "nekcem_b200_get_graphene_",
               "nekcem_b200_set_filter_", "nekcem_b200_set_rk_coefficients_",
-              "nekcem_b200_vtk_payload_",
+              "nekcem_b200_vtk_payload_", "nekcem_b200_sync_host_", "nekcem_b200_sync_device_",
               "cem_3d_graphene_current_", "cem_te_graphene_current_",
               "cem_tm_graphene_current_"):
         assert hasattr(L, n), f"Fortran twin {n} missing"
@@ -189,4 +189,38 @@ def test_rk_tables_default_and_upload():
     s.set_rk_coefficients([0.0, -1.0, 0, 0, 0], [1.0, 0.5, 0, 0, 0], np.zeros(6))
     a3, b3, c3 = s.get_rk_coefficients()
     assert a3[1] == -1.0 and b3[1] == 0.5 and not c3.any()
+    s.close()
+
+
+def test_leading_dimensions_of_fortran_arrays_host_side():
+    """SIZE pads lelt, so a .usr's graphene arrays are fjn(lxzfl,3,6), params(lxzfl,12) with
+    lxzfl > nxzfl: after nekcem_b200_set_leading_dims the library reads and writes them with that
+    leading dimension (host-only context: the packing is host code)."""
+    from oracle import cases
+    c = cases.case_2dgraphene(1, nx1=4, nel=(3, 6))
+    u = c.user
+    nf = c.nxzfl
+    lf, lp = nf + 3 * c.nxzf * c.nfaces, c.npts + 3 * c.nxyz     # three padding elements
+    s = MaxwellB200(2, 4, c.nelt, imode=1, device=-1)
+    s.set_faces(c.glo_num, c.cempec[:c.ncempec])
+    L = lib()
+    assert L.nekcem_b200_set_leading_dims(s.h, c.npts - 1, nf) != 0      # too small: refused
+    assert b"smaller" in L.nekcem_b200_last_error()
+    assert L.nekcem_b200_set_leading_dims(s.h, lp, lf) == 0
+    rng = np.random.default_rng(5)
+    pad = lambda a, m: np.concatenate([np.concatenate([a[k * nf:(k + 1) * nf], np.full(lf - nf, np.nan)])
+                                       for k in range(m)])
+    fjn = rng.standard_normal(18 * nf); kfjn = rng.standard_normal(18 * nf)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    fp, kp, pp = pad(fjn, 18), pad(kfjn, 18), pad(u.graphparams, 12)
+    gi = (u.graphindex + 1).astype(np.int32)
+    yc = np.ascontiguousarray(c.yconduc)
+    assert L.nekcem_b200_set_graphene(s.h, dp(fp), dp(kp), dp(pp), dp(yc),
+                                      gi.ctypes.data_as(C.POINTER(C.c_int32)), gi.size) == 0
+    fo = np.zeros(18 * lf); ko = np.zeros(18 * lf)
+    assert L.nekcem_b200_get_graphene(s.h, dp(fo), dp(ko)) == 0
+    for m in range(18):
+        assert np.array_equal(fo[m * lf + u.graphindex], fjn[m * nf + u.graphindex])
+        assert np.array_equal(ko[m * lf + u.graphindex], kfjn[m * nf + u.graphindex])
+    assert not np.isnan(fo).any()                  # the padding (NaN on input) was never read
     s.close()

@@ -1063,3 +1063,20 @@ def test_pin_filtered_time_stepping(which):
     c0.step(6)
     assert np.abs(c0.en - c.en).max() > 1e-9
     r.close()
+
+
+def test_pin_padded_size_layout():
+    """A real SIZE file dimensions the arrays for lelt = lelg/lpmin + 3 > nelt elements
+    (tests/3dboxper/SIZE:15), so hn(lpts1,3) etc. have a leading dimension larger than npts.
+    The translated reference run with that layout (3 padding elements) equals the oracle run
+    bit for bit -- this pins ReferenceRun's padded placement, which the drop-in test of the
+    shim's leading-dimension handling (tests/test_gpu_zz_padded_size.py) relies on."""
+    c = cases.case_3ddielectric(True, nx1=5, nel=(3, 6, 3))
+    c.set_callback("userinc", lambda tt, *a: None)
+    r = refrun.ReferenceRun(c, pad_elems=3)
+    assert r.lpts1 == c.nxyz * (c.nelt + 3)
+    c.step(5); r.step(5)
+    for name in ("hn", "en", "khn", "ken", "pmlbn", "pmldn"):
+        assert np.array_equal(r.field(name), getattr(c, name)), name
+    assert np.abs(c.hn).max() > 1e-3
+    r.close()
