@@ -12,13 +12,21 @@
 
 #define NKB_EXPORT extern "C" __attribute__((visibility("default")))
 
+// NEKCEM_B200_TWIN_NO_EXIT (test aid, set by tests/conftest.py): report the error and return
+// instead of exiting, so that an in-process test runner survives and the test fails on its own
+// comparison.  Without it: print and exit(1), the reference's behaviour.
+static int g_twin_errors = 0;
 static void check(int rc, const char *what)
 {
     if (rc != 0) {
         fprintf(stderr, "nekcem_b200: %s failed: %s\n", what, nekcem_b200_last_error());
-        exit(1);
+        g_twin_errors++;
+        if (getenv("NEKCEM_B200_TWIN_NO_EXIT") == nullptr) exit(1);
     }
 }
+
+// number of errors the twins have reported so far (only ever non-zero with the test aid above)
+NKB_EXPORT int nekcem_b200_twin_errors(void) { return g_twin_errors; }
 
 NKB_EXPORT void nekcem_b200_create_(const int *ldim, const int *nx1, const int *nelt,
                                     const int *imode, const int *ifupwind, const int *ifpec,
@@ -30,7 +38,9 @@ NKB_EXPORT void nekcem_b200_create_(const int *ldim, const int *nx1, const int *
     d.ldim = *ldim; d.nx1 = *nx1; d.nelt = *nelt; d.imode = *imode;
     d.ifupwind = *ifupwind; d.ifpec = *ifpec; d.ifpml = *ifpml;
     d.device = *device; d.strict = 0; d.rank = *rank; d.nranks = *nranks;
-    check(nekcem_b200_create(&d, handle), "nekcem_b200_create");
+    const int rc = nekcem_b200_create(&d, handle);
+    if (rc != 0) *handle = -1;
+    check(rc, "nekcem_b200_create");
 }
 
 NKB_EXPORT void nekcem_b200_destroy_(const int *h) { check(nekcem_b200_destroy(*h), "destroy"); }
@@ -235,7 +245,9 @@ NKB_EXPORT void cem_maxwell_drude_(const double *jn, const double *kjn, double *
     (void)resjn;
     if (g_bound_handle < 0) {
         fprintf(stderr, "nekcem_b200: cem_maxwell_drude called before nekcem_b200_bind\n");
-        exit(1);
+        g_twin_errors++;
+        if (getenv("NEKCEM_B200_TWIN_NO_EXIT") == nullptr) exit(1);
+        return;
     }
     if (g_ade_registered) return;
     check(nekcem_b200_set_drude(g_bound_handle, jn, kjn, params, dindex, *n), "cem_maxwell_drude");
@@ -248,7 +260,9 @@ NKB_EXPORT void cem_maxwell_lorentz_(const double *jn, const double *kjn, double
     (void)resjn;
     if (g_bound_handle < 0) {
         fprintf(stderr, "nekcem_b200: cem_maxwell_lorentz called before nekcem_b200_bind\n");
-        exit(1);
+        g_twin_errors++;
+        if (getenv("NEKCEM_B200_TWIN_NO_EXIT") == nullptr) exit(1);
+        return;
     }
     if (g_ade_registered) return;
     check(nekcem_b200_set_lorentz(g_bound_handle, jn, kjn, params, lindex, *n),
@@ -283,7 +297,9 @@ static void graphene_twin(const char *name, const double *fjn, const double *kfj
 {
     if (g_bound_handle < 0) {
         fprintf(stderr, "nekcem_b200: %s called before nekcem_b200_bind\n", name);
-        exit(1);
+        g_twin_errors++;
+        if (getenv("NEKCEM_B200_TWIN_NO_EXIT") == nullptr) exit(1);
+        return;
     }
     if (g_graphene_registered_for == g_bound_handle) return;
     check(nekcem_b200_set_graphene(g_bound_handle, fjn, kfjn, params, nullptr, gindex, *n), name);

@@ -224,3 +224,19 @@ def test_leading_dimensions_of_fortran_arrays_host_side():
         assert np.array_equal(ko[m * lf + u.graphindex], kfjn[m * nf + u.graphindex])
     assert not np.isnan(fo).any()                  # the padding (NaN on input) was never read
     s.close()
+
+
+def test_twins_report_instead_of_exiting_inside_the_test_runner():
+    """tests/conftest.py sets NEKCEM_B200_TWIN_NO_EXIT: a failing Fortran twin prints the library's
+    message, counts the error and returns (without the variable it exits, like the reference's
+    exitt).  Checked with a twin call that must fail without a device."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    L = lib()
+    L.nekcem_b200_twin_errors.restype = C.c_int
+    before = L.nekcem_b200_twin_errors()
+    vals = [C.c_int(v) for v in (3, 4, 27, 3, 1, 0, 0, 0, 0, 1)]
+    h = C.c_int(12345)
+    L.nekcem_b200_create_(*[C.byref(v) for v in vals], C.byref(h))
+    assert L.nekcem_b200_twin_errors() == before + 1 and h.value == -1
