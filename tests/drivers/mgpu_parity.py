@@ -8,7 +8,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from helpers import arrays_from_refcase, rel_l2, restrict_to_elems  # noqa: E402
 from nekcem_b200 import MaxwellB200, comm_unique_id  # noqa: E402

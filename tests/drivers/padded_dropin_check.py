@@ -1,14 +1,14 @@
 """Drop-in checks with a padded SIZE layout (lelt = nelt + 3), run in a process of their own by
 tests/test_gpu_zz_padded_size.py: the Fortran twins exit(1) on any library error -- the reference's
 error behaviour -- which must not take the test runner down with it.
-Usage: python scripts/padded_dropin_check.py pml|drude      (exit code 0 = parity within 1e-12)"""
+Usage: python tests/drivers/padded_dropin_check.py pml|drude      (exit code 0 = parity within 1e-12)"""
 import ctypes as C
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from helpers import rel_l2  # noqa: E402
 

@@ -18,6 +18,6 @@ def test_two_gpu_parity(case):
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", "29611",
-           os.path.join(ROOT, "scripts", "mgpu_parity.py"), case]
+           os.path.join(ROOT, "tests", "drivers", "mgpu_parity.py"), case]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr

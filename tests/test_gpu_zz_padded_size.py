@@ -25,8 +25,8 @@ def test_dropin_padded_size(which):
     """pml: 3ddielectric geometry with PML (pmlsigma, pmlbn, pmldn are (lpts1,3) too); drude:
     tests/drude with jn(lpts,3), params(lpts,2) dimensioned by the padded SIZE and registered
     through the .usr's usersrc -> cem_maxwell_drude twin.  Run in a process of its own
-    (scripts/padded_dropin_check.py): the twins exit(1) on a library error."""
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "padded_dropin_check.py"), which],
+    (tests/drivers/padded_dropin_check.py): the twins exit(1) on a library error."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "drivers", "padded_dropin_check.py"), which],
                        capture_output=True, text=True, timeout=600)
     if r.returncode == 77:
         pytest.skip(r.stdout.strip())
