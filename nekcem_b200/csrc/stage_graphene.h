@@ -25,12 +25,16 @@ namespace nkb {
 // Yfac = 0.5/Y_0(j); yc = yconduc(j).  imode 3: all components; 1 (TE): components 0,1 from
 // (Hz; Ex,Ey); 2 (TM): component 2 from (Hx,Hy; Ez).  ca, cb, dt: rk4_upd (src/cem_common.F:18-76)
 // with ca = rk4a(rkstep), cb = rk4b(rkstep).
-NKB_HD void graphene_point(int imode, const double H[3], const double E[3], const double n[3],
-                           double Yfac, double yc, const double par[12], double fj[18],
-                           double kj[18], double ca, double cb, double dt)
+// IMODE is a template parameter so that the component range is a compile-time constant: the
+// loops unroll and fj, kj, par stay in registers on the device (no local memory).
+template <int IMODE>
+NKB_HD void graphene_point_t(const double H[3], const double E[3], const double n[3], double Yfac,
+                             double yc, const double par[12], double fj[18], double kj[18],
+                             double ca, double cb, double dt)
 {
     double nH[3] = {0.0, 0.0, 0.0}, nEn[3] = {0.0, 0.0, 0.0};
-    int c0 = 0, c1 = 3;
+    constexpr int imode = IMODE;
+    constexpr int c0 = IMODE == 2 ? 2 : 0, c1 = IMODE == 1 ? 2 : 3;
     if (imode == 3) { // :2862-2871
         nH[0] = -n[1] * H[2] + n[2] * H[1];
         nH[1] = n[0] * H[2] - n[2] * H[0];
@@ -44,17 +48,18 @@ NKB_HD void graphene_point(int imode, const double H[3], const double E[3], cons
         nH[1] = n[0] * H[2];
         nEn[0] = (n[1] * n[1]) * E[0] - (n[0] * n[1]) * E[1];
         nEn[1] = (n[0] * n[0]) * E[1] - (n[0] * n[1]) * E[0];
-        c1 = 2;
     } else { // TM :3061-3065: n x (E x n) = E
         nH[2] = -n[0] * H[1] + n[1] * H[0];
         nEn[2] = E[2];
-        c0 = 2;
     }
     const double a_d = par[0], b_d = par[1], b_cp1 = par[2], a_211 = par[3], a_221 = par[4],
                  b_11 = par[5], b_21 = par[6], b_cp2 = par[7], a_212 = par[8], a_222 = par[9],
                  b_12 = par[10], b_22 = par[11];
     const double cpfac = b_cp1 + b_cp2;
     const double jnfac = 1.0 - cpfac * Yfac;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
     for (int c = c0; c < c1; c++) {
         const double tmp = Yfac * (nH[c] + yc * nEn[c]);
         const double j1 = fj[c + 3], j2 = fj[c + 6], j3 = fj[c + 9], j4 = fj[c + 12],
@@ -74,6 +79,15 @@ NKB_HD void graphene_point(int imode, const double H[3], const double E[3], cons
         t = ca * kj[c + 12] + dt * r4; kj[c + 12] = t; fj[c + 12] = j4 + cb * t;
         t = ca * kj[c + 15] + dt * r5; kj[c + 15] = t; fj[c + 15] = j5 + cb * t;
     }
+}
+
+NKB_HD void graphene_point(int imode, const double H[3], const double E[3], const double n[3],
+                           double Yfac, double yc, const double par[12], double fj[18],
+                           double kj[18], double ca, double cb, double dt)
+{
+    if (imode == 3) graphene_point_t<3>(H, E, n, Yfac, yc, par, fj, kj, ca, cb, dt);
+    else if (imode == 1) graphene_point_t<1>(H, E, n, Yfac, yc, par, fj, kj, ca, cb, dt);
+    else graphene_point_t<2>(H, E, n, Yfac, yc, par, fj, kj, ca, cb, dt);
 }
 
 } // namespace nkb
