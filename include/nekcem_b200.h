@@ -220,6 +220,14 @@ int nekcem_b200_step(int handle, int nsteps);
 int nekcem_b200_stage(int handle, int rkstep);
 int nekcem_b200_synchronize(int handle);
 
+/* The right-hand side alone.  Replaces `call cem_maxwell_op` (src/cem_maxwell.F:484-508) for the
+ * callers other than the RK loop -- the exponential and eigenvalue drivers apply it as an operator
+ * (amult, src/cem_maxwell.F:2310-2365: fields in, reshn/resen out; cem_maxwell_op_exp :2158-2242,
+ * cem_maxwell_op_eig :1970-1984).  One fused stage with (rk4a, rk4b, dt) = (0, 0, 1) at
+ * rktime: afterwards NKB_KHN / NKB_KEN hold reshn / resen (after invqmass), the PML and ADE
+ * registers hold their residuals, the fields are unchanged. */
+int nekcem_b200_apply_rhs(int handle, double rktime);
+
 /* Transport-independent stage (option "external_exchange" = 1; no communicator needed): the
  * caller performs the inter-rank face exchange that replaces gs_op_fields between ranks
  * (src/cem_maxwell.F:962) itself -- MPI from the Fortran host, or a device copy between two

@@ -116,6 +116,7 @@ def lib():
         L.nekcem_b200_step.argtypes = [C.c_int, C.c_int]
         L.nekcem_b200_stage.argtypes = [C.c_int, C.c_int]
         L.nekcem_b200_synchronize.argtypes = [C.c_int]
+        L.nekcem_b200_apply_rhs.argtypes = [C.c_int, C.c_double]
         L.nekcem_b200_stage_pack.argtypes = [C.c_int, C.c_int]
         L.nekcem_b200_stage_compute.argtypes = [C.c_int, C.c_int]
         L.nekcem_b200_halo_exchange_local.argtypes = [C.c_int, C.c_int]
@@ -432,6 +433,13 @@ class MaxwellB200:
 
     def stage(self, rkstep: int):
         _chk(self.L.nekcem_b200_stage(self.h, rkstep))
+
+    def cem_maxwell_op(self, rktime: float):
+        """``cem_maxwell_op`` (src/cem_maxwell.F:484-508) as an operator, the way ``amult``
+        (:2310-2365) uses it: returns (reshn, resen) after invqmass for the fields on the device;
+        the fields themselves are unchanged."""
+        _chk(self.L.nekcem_b200_apply_rhs(self.h, float(rktime)))
+        return self.get_array("khn"), self.get_array("ken")
 
     def stage_pack(self, rkstep: int):
         """first half of a stage with option external_exchange: sheet currents + send buffer"""

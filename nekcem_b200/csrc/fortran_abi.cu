@@ -167,6 +167,11 @@ NKB_EXPORT void nekcem_b200_sync_device_(const int *h, const double *hn, const d
     check(nekcem_b200_set_array_ld(*h, NKB_EN, en, *ld), "nekcem_b200_sync_device");
 }
 
+NKB_EXPORT void nekcem_b200_apply_rhs_(const int *h, const double *rktime)
+{
+    check(nekcem_b200_apply_rhs(*h, *rktime), "nekcem_b200_apply_rhs");
+}
+
 NKB_EXPORT void nekcem_b200_set_rk_coefficients_(const int *h, const double *a, const double *b,
                                                  const double *c)
 {

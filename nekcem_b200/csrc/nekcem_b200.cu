@@ -1768,6 +1768,22 @@ int nekcem_b200_stage(int handle, int rkstep)
     return run_stage(c, rkstep);
 }
 
+int nekcem_b200_apply_rhs(int handle, double rktime)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (!c->setup_done) return fail("nekcem_b200_setup has not completed");
+    CUDA_OK(cudaSetDevice(c->d.device));
+    // one fused stage with (a, b, dt) = (0, 0, 1): k <- res (after invqmass), fields unchanged
+    const double t0 = c->time, dt0 = c->dt, a0 = c->rk4a[0], b0 = c->rk4b[0], c0 = c->rk4c[0];
+    c->time = rktime; c->dt = 1.0;
+    c->rk4a[0] = 0.0; c->rk4b[0] = 0.0; c->rk4c[0] = 0.0;
+    const int rc = run_stage(c, 1);
+    c->time = t0; c->dt = dt0;
+    c->rk4a[0] = a0; c->rk4b[0] = b0; c->rk4c[0] = c0;
+    return rc;
+}
+
 int nekcem_b200_stage_pack(int handle, int rkstep)
 {
     Ctx *c = get(handle);
