@@ -105,3 +105,75 @@ def test_two_rank_exchange_plan_gloo(rotated):
         # z-slabs of 3 layers, periodic in z: both slab faces are remote: 2*3*3 faces * 16 pts
         assert nhalo == 2 * 9 * 16 and nremote == nhalo
         assert ni == 9 and nb == 18
+
+
+def _worker_2d_sheet(rank, world, port, q):
+    """tests/2dgraphene cut along the sheet (rows 0-15 / 16-31), as the reference's partition of
+    this mesh does at np = 2: 2D face numbering across ranks, and the registration of a sheet
+    whose every point lies on an inter-rank face (host side of nekcem_b200_set_graphene)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from helpers import arrays_from_refcase, restrict_to_elems
+    from nekcem_b200 import MaxwellB200
+    from oracle import cases
+
+    ref = cases.case_2dgraphene(1)
+    u = ref.user
+    row = np.arange(ref.nelt) // 4
+    elems = np.nonzero((row >= 16) == (rank == 1))[0]
+    A = arrays_from_refcase(ref, elems)
+    s = MaxwellB200(2, ref.nx1, elems.size, imode=1, ifpml=True, device=-1, rank=rank, nranks=world)
+    s.set_faces(A["glo_num"], A["cempec"])
+    nf, nfp = ref.nxzfl, ref.nxzf * ref.nfaces
+    fac = (elems[:, None] * nfp + np.arange(nfp)[None, :]).reshape(-1)
+    keep, gl = restrict_to_elems(ref, elems, facepts=u.graphindex)
+    take = lambda a, m: np.ascontiguousarray(a.reshape(m, nf)[:, fac]).reshape(-1)
+    s.cem_graphene_current(take(u.fjn, 18), take(u.kfjn, 18), take(u.graphparams, 12),
+                           np.ascontiguousarray(ref.yconduc[fac]), gl)
+    ids = s.face_singletons()
+    cnt = torch.tensor([ids.size], dtype=torch.int64)
+    cnts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(cnts, cnt)
+    counts = np.array([int(c.item()) for c in cnts])
+    mx = int(counts.max())
+    pad = torch.zeros(mx, dtype=torch.int64)
+    pad[:ids.size] = torch.from_numpy(ids)
+    allp = [torch.zeros(mx, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(allp, pad)
+    all_ids = np.concatenate([allp[r].numpy()[:counts[r]] for r in range(world)])
+    s.face_remote(counts, all_ids)
+    vm, peers, nhalo, ni, nb = s.plan()
+    # the peer's send list pairs point by point with ours: exchange the y coordinate of the send
+    # points (must all be 0: the sheet) and the x coordinate (must agree pairwise)
+    cf = ref.cemface[fac]                                   # global volume node per local face pt
+    fps = peers[0][1]
+    send = torch.from_numpy(np.ascontiguousarray(np.stack([ref.xm1[cf[fps]], ref.ym1[cf[fps]]], 1)))
+    recv = torch.zeros_like(send)
+    reqs = [dist.isend(send, peers[0][0]), dist.irecv(recv, peers[0][0])]
+    for r in reqs:
+        r.wait()
+    ok = (np.abs(send[:, 1].numpy()).max() < 1e-12 and np.abs(recv[:, 1].numpy()).max() < 1e-12
+          and np.abs(send[:, 0].numpy() - recv[:, 0].numpy()).max() < 1e-12)
+    on_halo = int(np.sum(vm[gl] <= -3))
+    q.put((rank, bool(ok), len(peers), int(nhalo), ni, nb, on_halo, int(gl.size)))
+    s.close()
+    dist.destroy_process_group()
+
+
+def test_two_rank_2d_sheet_on_the_partition_boundary_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + 23
+    procs = [ctx.Process(target=_worker_2d_sheet, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok, npeers, nhalo, ni, nb, on_halo, ng in sorted(res):
+        assert ok, f"rank {rank}: send lists of the two ranks do not pair point by point"
+        assert npeers == 1 and nhalo == 4 * 9        # one row of 4 element faces, 9 points each
+        assert ni == 60 and nb == 4
+        assert ng == 36 and on_halo == 36            # the whole sheet of this rank is remote
