@@ -240,3 +240,19 @@ def test_twins_report_instead_of_exiting_inside_the_test_runner():
     h = C.c_int(12345)
     L.nekcem_b200_create_(*[C.byref(v) for v in vals], C.byref(h))
     assert L.nekcem_b200_twin_errors() == before + 1 and h.value == -1
+
+
+def test_empty_registrations_are_accepted_and_remove_the_hook():
+    """n = 0 for the incident list and the graphene list (a rank that owns none of the faces
+    still makes the call, like the reference's loops over ninc = 0 / ngraph = 0)"""
+    b = BoxCase((3, 3, 3), 4)
+    s = MaxwellB200(3, 4, b.nelt, device=-1)
+    s.set_faces(b.array("glo_num"), b.array("cempec"))
+    s.set_incident(np.zeros(0, dtype=np.int64), np.zeros((6, 0)), np.zeros(0), 2.0)
+    L = lib()
+    z = np.zeros(1)
+    dp = z.ctypes.data_as(C.POINTER(C.c_double))
+    assert L.nekcem_b200_set_graphene(s.h, None, None, None, None, None, 0) == 0
+    assert L.nekcem_b200_get_graphene(s.h, dp, dp) != 0
+    assert b"no graphene state" in L.nekcem_b200_last_error()
+    s.close()
