@@ -118,6 +118,7 @@ struct Ctx {
     int n = 0, nxyz = 0, nxzf = 0, nfaces = 0;
     int64_t npts = 0, nxzfl = 0, ld = 0;
     bool host_only = false;
+    std::vector<double> host_copy[NKB_ARRAY_COUNT]; // host-only contexts: what was uploaded
     bool setup_done = false;
     // device arrays mirroring COMMON blocks (nullptr when not set)
     double *dev[NKB_ARRAY_COUNT] = {};
@@ -1088,7 +1089,11 @@ int nekcem_b200_create(const nekcem_b200_desc *desc, int *handle)
     c->nxzfl = (int64_t)c->nxzf * c->nfaces * desc->nelt;
     if (c->npts > 2147483647LL - 64) return fail("npts exceeds 32-bit node indexing");
     c->ld = ((c->npts + 31) / 32) * 32;
-    c->host_only = desc->device < 0;
+    // device < 0: host-only planning context (face pairing, exchange plan, registration checks; it
+    // keeps host copies of uploaded arrays so that the upload path can be inspected, and refuses
+    // every compute call).  NEKCEM_B200_HOST_ONLY in the environment forces it whatever the
+    // caller asked for -- a test aid for driving the Fortran shim on a machine without a GPU.
+    c->host_only = desc->device < 0 || getenv("NEKCEM_B200_HOST_ONLY") != nullptr;
     rk_storage(c.get());
     if (!c->host_only) {
         int ndev = 0;
@@ -1161,7 +1166,12 @@ int nekcem_b200_set_array(int handle, int which, const double *host, int64_t cou
     const int64_t want = array_count(c, which);
     if (count != want)
         return fail("array id %d: count %lld, expected %lld", which, (long long)count, (long long)want);
-    if (c->host_only) return fail("host-only planning context: no device arrays");
+    if (c->host_only) {
+        c->host_copy[which].assign(host, host + count);
+        c->have[which] = true;
+        if (which == NKB_DXM1) c->D_host.assign(host, host + count);
+        return 0;
+    }
     CUDA_OK(cudaSetDevice(c->d.device));
     CUDA_OK(cudaStreamSynchronize(c->s_compute));
     if (which == NKB_HN || which == NKB_EN || which == NKB_KHN || which == NKB_KEN) {
@@ -1202,7 +1212,11 @@ int nekcem_b200_get_array(int handle, int which, double *host, int64_t count)
     const int64_t want = array_count(c, which);
     if (count != want)
         return fail("array id %d: count %lld, expected %lld", which, (long long)count, (long long)want);
-    if (c->host_only) return fail("host-only planning context: no device arrays");
+    if (c->host_only) {
+        if ((int64_t)c->host_copy[which].size() != count) return fail("array id %d was never set", which);
+        memcpy(host, c->host_copy[which].data(), sizeof(double) * count);
+        return 0;
+    }
     CUDA_OK(cudaSetDevice(c->d.device));
     CUDA_OK(cudaStreamSynchronize(c->s_compute));
     if (which == NKB_HN || which == NKB_EN || which == NKB_KHN || which == NKB_KEN) {

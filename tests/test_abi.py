@@ -54,8 +54,15 @@ def test_bad_arguments_fail_loudly():
     with pytest.raises(NekcemB200Error, match="imode"):
         MaxwellB200(3, 8, 8, imode=1, device=-1)
     s = MaxwellB200(3, 4, 27, device=-1)
+    # a host-only context keeps what is uploaded (so that the upload path can be inspected) and
+    # refuses every compute call
+    v = np.arange(s.npts, dtype=np.float64)
+    s.set_array("rxmn", v)
+    assert np.array_equal(s.get_array("rxmn"), v)
+    with pytest.raises(NekcemB200Error, match="never set"):
+        s.get_array("rymn")
     with pytest.raises(NekcemB200Error, match="host-only"):
-        s.set_array("rxmn", np.zeros(s.npts))
+        s.set_volume_source(5, np.zeros(s.npts), 1.0, 1.0, 0.0)
     with pytest.raises(NekcemB200Error, match="set_faces has not been called"):
         s.setup()
     with pytest.raises(NekcemB200Error, match="nxzfl"):
@@ -256,3 +263,51 @@ def test_empty_registrations_are_accepted_and_remove_the_hook():
     assert L.nekcem_b200_get_graphene(s.h, dp, dp) != 0
     assert b"no graphene state" in L.nekcem_b200_last_error()
     s.close()
+
+
+def test_shim_with_a_padded_size_layout_on_the_host():
+    """The Fortran shim driven on the CPU (NEKCEM_B200_HOST_ONLY: the library keeps host copies
+    and refuses to compute) with lelt = nelt + 3 as a real SIZE file has it: what
+    b200_copy_all_in / b200_update_device hand to the library must be the compact arrays of the
+    case -- i.e. the (lpts1,3) leading dimension is honoured for pmlsigma, pmlbn, pmldn, HN, EN
+    and the RK registers --, the RK tables are the host's, and b200_update_host writes the
+    fields back into the padded COMMON arrays without touching the padding."""
+    from oracle import cases, refrun
+    if not refrun.available("dropin"):
+        pytest.skip("oracle/_ref/libnekcem_ref_dropin.so is not built")
+    # nx1 >= 6: the face ids live in COMMON /c_is1/ glo_num(lx1*ly1*lz1*lelv), which holds
+    # 6*nx1^2*nelt of them only from nx1 = 6 on (SURVEY.md 8b)
+    c = cases.case_3ddielectric(True, nx1=6, nel=(3, 6, 3))
+    c.khn[:] = np.linspace(0.0, 1.0, c.khn.size)          # non-trivial RK registers
+    os.environ["NEKCEM_B200_HOST_ONLY"] = "1"
+    try:
+        r = refrun.ReferenceRun(c, kind="dropin", pad_elems=3)
+        assert r.lpts1 == c.nxyz * (c.nelt + 3)
+        L = lib()
+        r.L.b200_copy_all_in_()                            # setup is refused: reported, not fatal
+        r.L.b200_update_device_()
+        h = int(r.get("b200_handle"))
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        for name in ("pmlsigma", "pmlbn", "pmldn", "hn", "en", "khn", "ken"):
+            got = np.zeros(3 * c.npts)
+            assert L.nekcem_b200_get_array(h, ARRAY_IDS[name], dp(got), got.size) == 0, name
+            assert np.array_equal(got, getattr(c, name)), name
+        for name in ("rxmn", "bmn", "hbm1"):
+            got = np.zeros(c.npts)
+            assert L.nekcem_b200_get_array(h, ARRAY_IDS[name], dp(got), got.size) == 0
+            assert np.array_equal(got, getattr(c, name)), name
+        got = np.zeros(c.nxzfl)
+        assert L.nekcem_b200_get_array(h, ARRAY_IDS["yconduc"], dp(got), got.size) == 0
+        a, b, cc = np.zeros(5), np.zeros(5), np.zeros(6)
+        assert L.nekcem_b200_get_rk_coefficients(h, dp(a), dp(b), dp(cc)) == 0
+        assert np.array_equal(a, np.array(c.s.rk4a)) and np.array_equal(cc, np.array(c.s.rk4c))
+        # the way back: poison the COMMON arrays, let the shim fetch the fields
+        for k in ("hn", "en"):
+            r.view(k)[:] = -7.0
+        r.L.b200_update_host_()
+        assert np.array_equal(r.field("hn"), c.hn) and np.array_equal(r.field("en"), c.en)
+        assert np.all(r.view("hn")[c.npts:r.lpts1] == -7.0)     # padding untouched
+        L.nekcem_b200_destroy(h)
+        r.close()
+    finally:
+        del os.environ["NEKCEM_B200_HOST_ONLY"]
