@@ -311,3 +311,50 @@ def test_shim_with_a_padded_size_layout_on_the_host():
         r.close()
     finally:
         del os.environ["NEKCEM_B200_HOST_ONLY"]
+
+
+def test_shim_registers_graphene_through_the_users_userfsrc_on_the_host():
+    """b200_update_device calls the user's userfsrc once on scratch arrays; its
+    cem_te_graphene_current call lands in the library twin, which registers the user's arrays
+    (here in a host-only context, padded SIZE layout: fjn(lxzfl,3,6) with lxzfl > nxzfl).  The
+    twin must not advance or modify the user's arrays."""
+    from oracle import cases, refrun
+    if not refrun.available("dropin"):
+        pytest.skip("oracle/_ref/libnekcem_ref_dropin.so is not built")
+    c = cases.case_2dgraphene(1)
+    u = c.user
+    os.environ["NEKCEM_B200_HOST_ONLY"] = "1"
+    try:
+        r = refrun.ReferenceRun(c, kind="dropin", pad_elems=3)
+        drop, L = refrun.lib("dropin"), lib()
+        nf, lf = c.nxzfl, int(r.get("lxzfl"))
+        assert lf > nf
+        pad = lambda a, m: np.concatenate([np.concatenate([a[k * nf:(k + 1) * nf], np.zeros(lf - nf)])
+                                           for k in range(m)])
+        fjn, kfjn, resfjn, par = pad(u.fjn, 18), pad(u.kfjn, 18), pad(u.resfjn, 18), pad(u.graphparams, 12)
+        f0 = fjn.copy()
+        gidx = (u.graphindex + 1).astype(np.int32)
+        n = C.c_int(gidx.size)
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        calls = []
+
+        def userfsrc(tt, *src):
+            calls.append(tt)
+            drop.cem_te_graphene_current_(dp(fjn), dp(kfjn), dp(resfjn), dp(par),
+                                          gidx.ctypes.data_as(C.POINTER(C.c_int)), C.byref(n))
+
+        r.put("yconduc", c.yconduc)
+        r.set_callback("userfsrc", userfsrc)
+        r.L.b200_copy_all_in_()
+        r.L.b200_update_device_()
+        assert len(calls) == 1 and np.array_equal(fjn, f0)
+        h = int(r.get("b200_handle"))
+        fo, ko = np.zeros(18 * lf), np.zeros(18 * lf)
+        assert L.nekcem_b200_get_graphene(h, dp(fo), dp(ko)) == 0
+        for m in range(18):
+            assert np.array_equal(fo[m * lf + u.graphindex], u.fjn[m * nf + u.graphindex])
+        assert np.abs(fo).max() > 1e-3
+        L.nekcem_b200_destroy(h)
+        r.close()
+    finally:
+        del os.environ["NEKCEM_B200_HOST_ONLY"]
