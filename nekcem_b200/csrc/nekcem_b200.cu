@@ -173,6 +173,7 @@ struct Ctx {
     unsigned char *ade_mask = nullptr;
     unsigned char *elflag_d = nullptr; // per element: bit 0 PML, bit 1 ADE, bit 2 constant metrics
     std::vector<char> ade_el; // per element: contains ADE nodes
+    std::vector<double> ade_host_j, ade_host_k; // host-only contexts: what set_drude/lorentz received
     // graphene sheets (userfsrc hook): compact per-face-point state, index q = position in the
     // user's graphindex list.  Host staging until setup, then device-resident.
     std::vector<int32_t> g_fp;              // 0-based face points
@@ -1489,10 +1490,11 @@ static int set_ade(int handle, int kind, const double *jn, const double *kjn, co
 {
     Ctx *c = get(handle);
     if (!c) return 1;
-    if (c->host_only) return fail("host-only planning context");
     if (n < 0 || (n > 0 && (!index || !params))) return fail("bad ADE arguments");
-    CUDA_OK(cudaSetDevice(c->d.device));
-    CUDA_OK(cudaStreamSynchronize(c->s_compute));
+    if (!c->host_only) {
+        CUDA_OK(cudaSetDevice(c->d.device));
+        CUDA_OK(cudaStreamSynchronize(c->s_compute));
+    }
     cudaFree(c->ade_j); cudaFree(c->ade_k); cudaFree(c->ade_par); cudaFree(c->ade_mask);
     c->ade_j = c->ade_k = c->ade_par = nullptr;
     c->ade_mask = nullptr;
@@ -1509,22 +1511,34 @@ static int set_ade(int handle, int kind, const double *jn, const double *kjn, co
         c->ade_el[(index[q] - 1) / c->nxyz] = 1;
     }
     const size_t bj = sizeof(double) * nj * c->npts, bp = sizeof(double) * np * c->npts;
+    const int64_t lp = c->ld_pts ? c->ld_pts : c->npts; // the user's (lpts,k) arrays
+    // compact (npts,k) view of a user array: the array itself when lpts == npts, else packed here
+    std::vector<double> packed;
+    auto compact = [&](const double *src, int ncomp) -> const double * {
+        if (lp == c->npts) return src;
+        packed.resize((size_t)ncomp * c->npts);
+        for (int q = 0; q < ncomp; q++)
+            memcpy(packed.data() + (size_t)q * c->npts, src + (size_t)q * lp, sizeof(double) * c->npts);
+        return packed.data();
+    };
+    if (c->host_only) {
+        // planning context: keep what would be uploaded (inspected through get_ade)
+        c->ade_host_j.assign((size_t)nj * c->npts, 0.0);
+        c->ade_host_k.assign((size_t)nj * c->npts, 0.0);
+        if (jn) { const double *p = compact(jn, nj); c->ade_host_j.assign(p, p + (size_t)nj * c->npts); }
+        if (kjn) { const double *p = compact(kjn, nj); c->ade_host_k.assign(p, p + (size_t)nj * c->npts); }
+        c->ade_kind = kind;
+        return 0;
+    }
     CUDA_OK(cudaMalloc(&c->ade_j, bj));
     CUDA_OK(cudaMalloc(&c->ade_k, bj));
     CUDA_OK(cudaMalloc(&c->ade_par, bp));
     CUDA_OK(cudaMalloc(&c->ade_mask, c->npts));
-    const int64_t lp = c->ld_pts ? c->ld_pts : c->npts; // the user's (lpts,k) arrays
-    auto h2d = [&](double *dst, const double *src, int ncomp) -> cudaError_t {
-        if (lp == c->npts)
-            return cudaMemcpy(dst, src, sizeof(double) * ncomp * c->npts, cudaMemcpyHostToDevice);
-        return cudaMemcpy2D(dst, sizeof(double) * c->npts, src, sizeof(double) * lp,
-                            sizeof(double) * c->npts, ncomp, cudaMemcpyHostToDevice);
-    };
-    if (jn) CUDA_OK(h2d(c->ade_j, jn, nj));
+    if (jn) CUDA_OK(cudaMemcpy(c->ade_j, compact(jn, nj), bj, cudaMemcpyHostToDevice));
     else CUDA_OK(cudaMemset(c->ade_j, 0, bj));
-    if (kjn) CUDA_OK(h2d(c->ade_k, kjn, nj));
+    if (kjn) CUDA_OK(cudaMemcpy(c->ade_k, compact(kjn, nj), bj, cudaMemcpyHostToDevice));
     else CUDA_OK(cudaMemset(c->ade_k, 0, bj));
-    CUDA_OK(h2d(c->ade_par, params, np));
+    CUDA_OK(cudaMemcpy(c->ade_par, compact(params, np), bp, cudaMemcpyHostToDevice));
     CUDA_OK(cudaMemcpy(c->ade_mask, mask.data(), c->npts, cudaMemcpyHostToDevice));
     c->ade_kind = kind;
     return 0;
@@ -1547,18 +1561,32 @@ int nekcem_b200_get_ade(int handle, double *jn, double *kjn)
     Ctx *c = get(handle);
     if (!c) return 1;
     if (!c->ade_kind) return fail("no Drude/Lorentz state has been set");
-    CUDA_OK(cudaSetDevice(c->d.device));
-    CUDA_OK(cudaStreamSynchronize(c->s_compute));
     const int nj = c->ade_kind == 1 ? 3 : 6;
     const int64_t lp = c->ld_pts ? c->ld_pts : c->npts;
-    auto d2h = [&](double *dst, const double *src) -> cudaError_t {
-        if (lp == c->npts)
-            return cudaMemcpy(dst, src, sizeof(double) * nj * c->npts, cudaMemcpyDeviceToHost);
-        return cudaMemcpy2D(dst, sizeof(double) * lp, src, sizeof(double) * c->npts,
-                            sizeof(double) * c->npts, nj, cudaMemcpyDeviceToHost);
+    const size_t cnt = (size_t)nj * c->npts;
+    if (!c->host_only) {
+        CUDA_OK(cudaSetDevice(c->d.device));
+        CUDA_OK(cudaStreamSynchronize(c->s_compute));
+    }
+    // compact (npts,k) state -> the user's (lpts,k) array
+    std::vector<double> tmp;
+    auto fetch = [&](double *dst, const double *dev, const std::vector<double> &host) -> int {
+        if (lp == c->npts && !c->host_only) {
+            CUDA_OK(cudaMemcpy(dst, dev, sizeof(double) * cnt, cudaMemcpyDeviceToHost));
+            return 0;
+        }
+        const double *src = host.data();
+        if (!c->host_only) {
+            tmp.resize(cnt);
+            CUDA_OK(cudaMemcpy(tmp.data(), dev, sizeof(double) * cnt, cudaMemcpyDeviceToHost));
+            src = tmp.data();
+        }
+        for (int q = 0; q < nj; q++)
+            memcpy(dst + (size_t)q * lp, src + (size_t)q * c->npts, sizeof(double) * c->npts);
+        return 0;
     };
-    if (jn) CUDA_OK(d2h(jn, c->ade_j));
-    if (kjn) CUDA_OK(d2h(kjn, c->ade_k));
+    if (jn && fetch(jn, c->ade_j, c->ade_host_j)) return 1;
+    if (kjn && fetch(kjn, c->ade_k, c->ade_host_k)) return 1;
     return 0;
 }
 

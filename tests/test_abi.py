@@ -358,3 +358,45 @@ def test_shim_registers_graphene_through_the_users_userfsrc_on_the_host():
         r.close()
     finally:
         del os.environ["NEKCEM_B200_HOST_ONLY"]
+
+
+def test_shim_registers_drude_arrays_of_a_padded_size_on_the_host():
+    """tests/drude with jn(lpts,3), params(lpts,2) dimensioned by a padded SIZE: the .usr's
+    usersrc -> cem_maxwell_drude call (made once by b200_update_device) registers them through
+    the library twin with the declared leading dimension; get_ade writes them back in the same
+    layout (host-only context)."""
+    from oracle import cases, refrun
+    if not refrun.available("dropin"):
+        pytest.skip("oracle/_ref/libnekcem_ref_dropin.so is not built")
+    c = cases.case_drude()
+    u = c.user
+    os.environ["NEKCEM_B200_HOST_ONLY"] = "1"
+    try:
+        r = refrun.ReferenceRun(c, kind="dropin", pad_elems=3)
+        drop, L = refrun.lib("dropin"), lib()
+        n, lp = c.npts, r.lpts1
+        pad = lambda a, m: np.concatenate([np.concatenate([a[k * n:(k + 1) * n], np.full(lp - n, np.nan)])
+                                           for k in range(m)])
+        jn, kjn, resjn, par = pad(u.jn, 3), pad(u.kjn, 3), pad(u.resjn, 3), pad(u.params, 2)
+        idx1 = (u.index + 1).astype(np.int32)
+        nn = C.c_int(idx1.size)
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+
+        def usersrc(tt, *res):
+            drop.cem_maxwell_drude_(dp(jn), dp(kjn), dp(resjn), dp(par),
+                                    idx1.ctypes.data_as(C.POINTER(C.c_int)), C.byref(nn))
+
+        r.set_callback("usersrc", usersrc)
+        r.L.b200_copy_all_in_()
+        r.L.b200_update_device_()
+        h = int(r.get("b200_handle"))
+        jo, ko = np.full(3 * lp, -7.0), np.full(3 * lp, -7.0)
+        assert L.nekcem_b200_get_ade(h, dp(jo), dp(ko)) == 0
+        for k in range(3):
+            assert np.array_equal(jo[k * lp:k * lp + n], u.jn[k * n:(k + 1) * n])
+            assert np.all(jo[k * lp + n:(k + 1) * lp] == -7.0)      # padding neither read nor written
+        assert np.abs(u.jn).max() > 1e-3
+        L.nekcem_b200_destroy(h)
+        r.close()
+    finally:
+        del os.environ["NEKCEM_B200_HOST_ONLY"]
