@@ -72,7 +72,12 @@ typedef struct nekcem_b200_desc {
     int32_t ifupwind;    /* param(19)=0 -> 1 (C0=1); central flux -> 0 (C0=0)        */
     int32_t ifpec;       /* any 'PEC' face (setlog, src/nek5_bdry.F:68-92)           */
     int32_t ifpml;       /* any 'PML' face                                           */
-    int32_t device;      /* CUDA device ordinal; -1 = host-only planning context     */
+    int32_t device;      /* CUDA device ordinal; -1 = host-only planning context:
+                            face pairing, exchange plan and registrations work, uploaded
+                            arrays are kept on the host for inspection, every compute call
+                            fails.  NEKCEM_B200_HOST_ONLY in the environment forces this
+                            mode (test aid for driving the Fortran shim without a GPU); it
+                            is not a CPU fallback -- nothing is ever computed on the host  */
     int32_t strict;      /* 1: no-FMA kernels, bit-faithful to the CPU arithmetic    */
     int32_t rank;        /* MPI rank (nid) and size (np): one rank <-> one GPU       */
     int32_t nranks;
