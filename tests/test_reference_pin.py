@@ -1080,3 +1080,21 @@ def test_pin_padded_size_layout():
         assert np.array_equal(r.field(name), getattr(c, name)), name
     assert np.abs(c.hn).max() > 1e-3
     r.close()
+
+
+@pytest.mark.parametrize("imode", [1, 2])
+def test_pin_central_flux_2d(imode):
+    """param(19) = 1 (central flux, C0 = 0) through cem_maxwell_flux2d, TE and TM"""
+    from oracle import oracle as O
+    import math
+    mesh = O.box_mesh((3, 3), ((0.0, 1.0),) * 2, ("P  ",) * 4)
+    c = O.RefCase(mesh, 6, imode=imode, upwind=False,
+                  usrdat2=lambda case: cases._rescale(case, (0.0, 0.0), (2 * math.pi, 2 * math.pi)))
+    c.set_dt(-2e-3)
+    shn, sen = cases.usersol_2dboxper(c, 0.0)
+    c.hn[:] = shn; c.en[:] = sen
+    r = refrun.ReferenceRun(c)
+    assert r.get("ifcentral") == 1 and r.get("ifupwind") == 0
+    c.step(5); r.step(5)
+    _assert_same(c, r)
+    r.close()
