@@ -1098,3 +1098,41 @@ def test_pin_central_flux_2d(imode):
     c.step(5); r.step(5)
     _assert_same(c, r)
     r.close()
+
+
+@pytest.mark.parametrize("kind", ["drude", "lorentz"])
+def test_pin_ade_in_3d(kind):
+    """cem_maxwell_drude / cem_maxwell_lorentz on a 3D mesh (the shipped tests use them in 2D):
+    a periodic box whose lower half is dispersive, random initial currents; the reference's
+    routine is called from a test-side usersrc on its own copies of the arrays"""
+    from oracle import oracle as O
+    c = cases.case_boxper((3, 4, 3), 5, dt=-2e-3)
+    n = c.npts
+    low = np.repeat((c.ym1 < np.pi).reshape(c.nelt, -1).all(axis=1), c.nxyz)
+    index = np.nonzero(low)[0].astype(np.int32)
+    npar, nj = (2, 3) if kind == "drude" else (3, 6)
+    params = np.zeros(npar * n)
+    params[0:n][low] = 0.3
+    params[n:2 * n][low] = 4.0
+    if npar == 3:
+        params[2 * n:][low] = 2.5
+    rng = np.random.default_rng(11)
+    jn = np.zeros(nj * n)
+    for k in range(nj):
+        jn[k * n:(k + 1) * n][low] = 0.1 * rng.standard_normal(int(low.sum()))
+    kjn, resjn = np.zeros(nj * n), np.zeros(nj * n)
+    jr, kr, rr, pr = jn.copy(), kjn.copy(), resjn.copy(), params.copy()
+    fn_o = c.L.ora_cem_maxwell_drude if kind == "drude" else c.L.ora_cem_maxwell_lorentz
+    c.set_callback("usersrc", lambda tt, *res: fn_o(C.byref(c.s), O.dp(jn), O.dp(kjn), O.dp(resjn),
+                                                      O.dp(params), O.ip(index), int(index.size)))
+    r = refrun.ReferenceRun(c)
+    fn_r = r.L.cem_maxwell_drude_ if kind == "drude" else r.L.cem_maxwell_lorentz_
+    idx1 = (index + 1).astype(np.int32)
+    nn = C.c_int(idx1.size)
+    r.set_callback("usersrc", lambda tt, *res: fn_r(_dp(jr), _dp(kr), _dp(rr), _dp(pr),
+                                                      idx1.ctypes.data_as(C.POINTER(C.c_int)),
+                                                      C.byref(nn)))
+    c.step(6); r.step(6)
+    _assert_same(c, r)
+    assert np.array_equal(jn, jr) and np.array_equal(kjn, kr) and np.abs(jn).max() > 1e-2
+    r.close()
