@@ -1136,3 +1136,42 @@ def test_pin_ade_in_3d(kind):
     _assert_same(c, r)
     assert np.array_equal(jn, jr) and np.array_equal(kjn, kr) and np.abs(jn).max() > 1e-2
     r.close()
+
+
+@pytest.mark.parametrize("imode", [1, 2])
+@pytest.mark.parametrize("upwind", [True, False])
+def test_pin_deformed_2d_mesh_with_pec_walls(imode, upwind):
+    """a sheared, non-affine 2D mesh (all four metric terms, oblique face normals) with PEC walls,
+    upwind and central flux, TE and TM: geometry from the oracle, time stepping bit for bit"""
+    from oracle import oracle as O
+    mesh = O.box_mesh((4, 4), ((-1.0, 1.0),) * 2, ("PEC",) * 4)
+
+    def warp(case):
+        x, y = case.xm1.copy(), case.ym1.copy()
+        case.xm1[:] = x + 0.07 * np.sin(np.pi * y)
+        case.ym1[:] = y + 0.05 * np.sin(np.pi * x) * np.cos(0.5 * np.pi * y)
+
+    c = O.RefCase(mesh, 7, imode=imode, upwind=upwind, usrdat2=warp)
+    c.set_dt(-2e-3)
+    c.hn[:], c.en[:] = cases.usersol_2dboxpec(c, 0.0)
+    r = refrun.ReferenceRun(c)
+    c.step(6); r.step(6)
+    _assert_same(c, r)
+    r.close()
+
+
+def test_pin_warped_3d_mesh_time_stepping():
+    """sheared, non-affine 3D elements (all nine cofactors vary inside an element), periodic:
+    10 steps bit for bit"""
+    c = _geometry_case("warped")
+    c.set_dt(-5e-4)
+    # periodic in the unwarped coordinates: a smooth field of the reference box
+    n = c.npts
+    x, y, z = c.xm1, c.ym1, c.zm1
+    c.hn[0:n] = np.sin(2 * np.pi * y) * np.cos(2 * np.pi * z)
+    c.hn[n:2 * n] = np.cos(2 * np.pi * x)
+    c.en[2 * n:] = np.sin(2 * np.pi * x) * np.sin(2 * np.pi * y)
+    r = refrun.ReferenceRun(c)
+    c.step(10); r.step(10)
+    _assert_same(c, r)
+    r.close()
