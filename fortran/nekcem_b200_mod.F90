@@ -220,6 +220,89 @@ module nekcem_b200
        import :: c_int
        integer(c_int), value :: handle, rkstep
      end function
+     !> leading dimensions of the reference's storage (SIZE pads lelt): (lpts1,3) fields, a .usr's
+     !> (lpts,k) ADE and (lxzfl,3,6) graphene arrays
+     integer(c_int) function nekcem_b200_set_leading_dims(handle, lpts, lxzfl) &
+          bind(C, name='nekcem_b200_set_leading_dims')
+       import :: c_int, c_int64_t
+       integer(c_int), value :: handle
+       integer(c_int64_t), value :: lpts, lxzfl
+     end function
+     integer(c_int) function nekcem_b200_set_array_ld(handle, which, host, ld) &
+          bind(C, name='nekcem_b200_set_array_ld')
+       import :: c_int, c_int64_t, c_double
+       integer(c_int), value :: handle, which
+       real(c_double), intent(in) :: host(*)
+       integer(c_int64_t), value :: ld
+     end function
+     integer(c_int) function nekcem_b200_get_array_ld(handle, which, host, ld) &
+          bind(C, name='nekcem_b200_get_array_ld')
+       import :: c_int, c_int64_t, c_double
+       integer(c_int), value :: handle, which
+       real(c_double), intent(inout) :: host(*)
+       integer(c_int64_t), value :: ld
+     end function
+     !> cem_maxwell_op alone (amult of the exponential / eigenvalue drivers): result in KHN / KEN
+     integer(c_int) function nekcem_b200_apply_rhs(handle, rktime) &
+          bind(C, name='nekcem_b200_apply_rhs')
+       import :: c_int, c_double
+       integer(c_int), value :: handle
+       real(c_double), value :: rktime
+     end function
+     integer(c_int) function nekcem_b200_apply_filter(handle) &
+          bind(C, name='nekcem_b200_apply_filter')
+       import :: c_int
+       integer(c_int), value :: handle
+     end function
+     integer(c_int) function nekcem_b200_get_rk_coefficients(handle, a, b, c) &
+          bind(C, name='nekcem_b200_get_rk_coefficients')
+       import :: c_int, c_double
+       integer(c_int), value :: handle
+       real(c_double), intent(out) :: a(5), b(5), c(6)
+     end function
+     !> device slices of peer ipeer (0-based) for an exchange done by the host's CUDA-aware MPI
+     integer(c_int) function nekcem_b200_halo_buffers(handle, ipeer, send, recv, count) &
+          bind(C, name='nekcem_b200_halo_buffers')
+       import :: c_int, c_int32_t, c_int64_t, c_ptr
+       integer(c_int), value :: handle
+       integer(c_int32_t), value :: ipeer
+       type(c_ptr), intent(out) :: send, recv
+       integer(c_int64_t), intent(out) :: count
+     end function
+     integer(c_int) function nekcem_b200_plan_npeers(handle, npeers, nhalo) &
+          bind(C, name='nekcem_b200_plan_npeers')
+       import :: c_int, c_int32_t, c_int64_t
+       integer(c_int), value :: handle
+       integer(c_int32_t), intent(out) :: npeers
+       integer(c_int64_t), intent(out) :: nhalo
+     end function
+     integer(c_int) function nekcem_b200_plan_peer(handle, ipeer, peer_rank, count, send_facepts) &
+          bind(C, name='nekcem_b200_plan_peer')
+       import :: c_int, c_int32_t, c_int64_t, c_ptr
+       integer(c_int), value :: handle
+       integer(c_int32_t), value :: ipeer
+       integer(c_int32_t), intent(out) :: peer_rank
+       integer(c_int64_t), intent(out) :: count
+       type(c_ptr), value :: send_facepts          ! c_null_ptr: only rank and count
+     end function
+     !> usersol of the layered-media tests on the device; wave: the 40 reals of
+     !> nekcem_b200_planewave in declaration order (see include/nekcem_b200.h)
+     integer(c_int) function nekcem_b200_error_sums_planewave(handle, wave, region, inpml, time, &
+          sumsq, linf) bind(C, name='nekcem_b200_error_sums_planewave')
+       import :: c_int, c_double, c_signed_char
+       integer(c_int), value :: handle
+       real(c_double), intent(in) :: wave(40)
+       integer(c_signed_char), intent(in) :: region(*), inpml(*)
+       real(c_double), value :: time
+       real(c_double), intent(out) :: sumsq(6), linf(6)
+     end function
+     integer(c_int) function nekcem_b200_geometry_info(handle, n_const, masses_shared) &
+          bind(C, name='nekcem_b200_geometry_info')
+       import :: c_int, c_int32_t, c_int64_t
+       integer(c_int), value :: handle
+       integer(c_int64_t), intent(out) :: n_const
+       integer(c_int32_t), intent(out) :: masses_shared
+     end function
      integer(c_int) function nekcem_b200_algorithmic_bytes(handle, bytes_per_stage) &
           bind(C, name='nekcem_b200_algorithmic_bytes')
        import :: c_int, c_double
