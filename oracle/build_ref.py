@@ -118,6 +118,21 @@ def available() -> bool:
     return os.path.isdir(os.path.join(REF, "src"))
 
 
+def _f2c_lite():
+    """the translator module, loaded by file path: oracle/ itself must never be put on sys.path
+    (`import oracle` would then resolve to oracle/oracle.py instead of the package, also in
+    processes spawned later)"""
+    import importlib.util
+    name = "oracle_f2c_lite"
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, os.path.join(HERE, "f2c_lite.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def build(force: bool = False, verbose: bool = False) -> str | None:
     """returns the library path, or None when the reference tree is absent and no prebuilt
     library exists"""
@@ -130,8 +145,7 @@ def build(force: bool = False, verbose: bool = False) -> str | None:
         t = os.path.getmtime(LIB)
         if all(os.path.getmtime(s) < t for s in srcs + mine):
             return LIB
-    sys.path.insert(0, HERE)
-    import f2c_lite
+    f2c_lite = _f2c_lite()
     os.makedirs(OUT, exist_ok=True)
     inc = [os.path.join(REF, "tests/3dboxper"), os.path.join(REF, "src")]
     ctext, em = f2c_lite.translate([(os.path.join(REF, u[0]),) + tuple(u[1:]) for u in UNITS], inc,
@@ -154,7 +168,7 @@ def build(force: bool = False, verbose: bool = False) -> str | None:
 
 def build_dropin(inc, verbose=False):
     """libnekcem_ref_dropin.so (needs nekcem_b200/lib/libnekcem_b200.so; skipped without it)"""
-    import f2c_lite
+    f2c_lite = _f2c_lite()
     if not os.path.exists(os.path.join(PRODUCT_LIB_DIR, "libnekcem_b200.so")):
         return None
     units = []

@@ -19,8 +19,8 @@ ROOT = os.path.dirname(HERE)
 
 @pytest.fixture(scope="module")
 def lib(tmp_path_factory):
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import f2c_lite
+    from oracle import f2c_lite     # (package import: never put oracle/ itself on sys.path --
+    #                                 `import oracle` would then find oracle/oracle.py)
     d = tmp_path_factory.mktemp("f2c")
     text, _ = f2c_lite.translate([(os.path.join(HERE, "f2c_semantics.F"),
                                    ["t_arith", "t_loops", "t_count", "t_implicit"])], [HERE], ())
