@@ -303,7 +303,9 @@ int nekcem_b200_vtk_payload(int handle, int which, int as_double, void *out);
 int nekcem_b200_last_step_ms(int handle, float *ms, int64_t *launches);
 
 /* Options.  "external_exchange": see nekcem_b200_stage_pack.  Performance tunables (no effect on
- * results): "pf_dist": reserved (accepted, ignored).
+ * results): "pipeline" (default 1): 1 = the persistent bulk-copy stage kernel (stage_pipe.cu) for
+ * the orders it covers, 0 = the slab kernel (stage_slab.cu) for every order; "pipeline_ctas"
+ * (default 0 = fill the device): upper bound on the persistent kernel's grid.
  * "const_metrics" (default 1): exploit exact, bitwise redundancy found in the geometry at setup
  * -- elements whose nine cofactors rxmn..tzmn (src/GEOM:30-45) hold one value each over the
  * whole element read them once per element instead of once per node, and bitwise identical

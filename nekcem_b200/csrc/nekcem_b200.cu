@@ -29,6 +29,7 @@
 
 namespace nkb {
 int launch_stage_slab(const StageArgs &a, const double *Dhost, int nx1, bool aux, bool cm, void *stream);
+int launch_stage_pipe(const StageArgs &a, const double *Dhost, int nx1, bool aux, bool cm, void *stream);
 int launch_stage2d(const StageArgs &a, const double *Dhost, int nx1, bool aux, void *stream);
 }
 
@@ -195,6 +196,15 @@ struct Ctx {
     // redundancy found in the geometry at setup (exact, bitwise): elements whose nine cofactors
     // do not vary over the element read them once per element; identical hbm1/ebm1 share one array
     bool opt_const_metrics = true;
+    // 1 (default): the persistent bulk-copy kernel (stage_pipe.cu) for the orders it covers;
+    // 0: the slab kernel (stage_slab.cu) everywhere
+    bool opt_pipeline = true;
+    // 3D: mirror of the fields on the x faces (StageArgs::xtr_in); 0 = gather from the volume
+    bool opt_xtrace = true;
+    double *xtr[2] = {nullptr, nullptr};
+    int64_t ldx = 0;
+    bool xtr_valid = false; // xtr[cur] holds the traces of u[cur]
+    int opt_pipeline_ctas = 0; // > 0: cap the persistent grid (tests: many items per CTA on small meshes)
     bool masses_same = false;
     bool geom_scanned = false;
     int64_t n_const_metric_el = 0;
@@ -270,6 +280,19 @@ void rk_storage(Ctx *c)
 // ---------------------------------------------------------------------------------------
 // small device kernels
 // ---------------------------------------------------------------------------------------
+// x-face mirror of the fields (StageArgs::xtr_in): entry t = (2e + side)*n^2 + (j + n*k)
+__global__ void xtrace_fill_kernel(const double *u, long long ld, double *xtr, long long ldx, int n,
+                                   long long nent)
+{
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= nent) return;
+    const int n2 = n * n;
+    const long long es = t / n2;
+    const int jk = (int)(t - es * n2);
+    const long long node = (es >> 1) * (long long)n2 * n + ((es & 1) ? n - 1 : 0) + (long long)n * jk;
+    for (int c = 0; c < 6; c++) xtr[c * ldx + t] = u[c * ld + node];
+}
+
 __global__ void half_inverse_kernel(const double *x, double *y, long long n)
 {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -845,6 +868,19 @@ int run_stage(Ctx *c, int rkstep /*1..5*/, int phase = 0)
     a.hY = c->hY; a.Y1 = c->dev[NKB_Y_1]; a.hZ = c->hZ; a.Z1 = c->dev[NKB_Z_1];
     a.vmapP = c->vmapP_d;
     a.halo = c->halo;
+    if (c->xtr[0]) {
+        if (!c->xtr_valid) {
+            const long long nent = 2ll * c->n * c->n * c->d.nelt;
+            xtrace_fill_kernel<<<(unsigned)((nent + 255) / 256), 256, 0, c->s_compute>>>(
+                c->u[c->cur], c->ld, c->xtr[c->cur], c->ldx, c->n, nent);
+            CUDA_OK(cudaGetLastError());
+            c->xtr_valid = true;
+        }
+        a.xtr_in = c->xtr[c->cur];
+        a.xtr_out = c->xtr[c->cur ^ 1];
+        a.ldx = c->ldx;
+    }
+    a.grid_cap = c->opt_pipeline_ctas;
     a.ca = c->rk4a[rkstep - 1];
     a.cb = c->rk4b[rkstep - 1];
     a.dt = c->dt;
@@ -893,10 +929,17 @@ int run_stage(Ctx *c, int rkstep /*1..5*/, int phase = 0)
         nkb::StageArgs b = a;
         b.elist = c->elist_d + c->list_off[q];
         b.nel = c->list_n[q];
-        int rc = c->d.ldim == 3
-                     ? nkb::launch_stage_slab(b, c->D_host.data(), c->n, (q & 1) != 0, (q & 2) != 0,
-                                              c->s_compute)
-                     : nkb::launch_stage2d(b, c->D_host.data(), c->n, (q & 1) != 0, c->s_compute);
+        int rc = -1;
+        if (c->d.ldim == 3) {
+            if (c->opt_pipeline)
+                rc = nkb::launch_stage_pipe(b, c->D_host.data(), c->n, (q & 1) != 0, (q & 2) != 0,
+                                            c->s_compute);
+            if (rc < 0)
+                rc = nkb::launch_stage_slab(b, c->D_host.data(), c->n, (q & 1) != 0, (q & 2) != 0,
+                                            c->s_compute);
+        } else {
+            rc = nkb::launch_stage2d(b, c->D_host.data(), c->n, (q & 1) != 0, c->s_compute);
+        }
         if (rc < 0) return fail("nx1=%d is not supported by the stage kernels (2..16)", c->n);
         if (rc > 0) return fail("stage kernel launch failed: %s",
                                 cudaGetErrorString(cudaGetLastError()));
@@ -1041,6 +1084,7 @@ int apply_filter(Ctx *c)
         c->u[c->cur], c->ld, c->filter_d, n, nz, c->nxyz);
     CUDA_OK(cudaGetLastError());
     c->last_launches++;
+    c->xtr_valid = false;
     if (c->d.ldim == 2) {
         // the 2D stage kernels never write the three inactive components, so both ping-pong
         // buffers must hold the same (now filtered) values of them
@@ -1139,6 +1183,7 @@ int nekcem_b200_destroy(int handle)
         if (c->has_comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
         for (auto &p : c->dev) cudaFree(p);
         cudaFree(c->u[0]); cudaFree(c->u[1]); cudaFree(c->kf);
+        cudaFree(c->xtr[0]); cudaFree(c->xtr[1]);
         cudaFree(c->hY); cudaFree(c->hZ); cudaFree(c->vmapP_d); cudaFree(c->elist_d);
         cudaFree(c->sendbuf); cudaFree(c->halo); cudaFree(c->send_node);
         cudaFree(c->src_prof); cudaFree(c->red_d);
@@ -1178,6 +1223,7 @@ int nekcem_b200_set_array(int handle, int which, const double *host, int64_t cou
     if (which == NKB_HN || which == NKB_EN || which == NKB_KHN || which == NKB_KEN) {
         double *base = (which == NKB_HN || which == NKB_EN) ? c->u[c->cur] : c->kf;
         const int c0 = (which == NKB_HN || which == NKB_KHN) ? 0 : 3;
+        c->xtr_valid = false;
         CUDA_OK(cudaMemcpy2D(base + c0 * c->ld, sizeof(double) * c->ld, host,
                              sizeof(double) * c->npts, sizeof(double) * c->npts, 3,
                              cudaMemcpyHostToDevice));
@@ -1377,7 +1423,33 @@ int nekcem_b200_setup(int handle)
     cudaFree(c->send_node);
     c->vmapP_d = nullptr; c->sendbuf = c->halo = nullptr; c->send_node = nullptr;
     CUDA_OK(cudaMalloc(&c->vmapP_d, sizeof(int) * c->nxzfl));
-    CUDA_OK(cudaMemcpy(c->vmapP_d, c->vmapP.data(), sizeof(int) * c->nxzfl, cudaMemcpyHostToDevice));
+    cudaFree(c->xtr[0]); cudaFree(c->xtr[1]);
+    c->xtr[0] = c->xtr[1] = nullptr;
+    c->xtr_valid = false;
+    const long long n_xtr = 2ll * c->n * c->n * c->d.nelt;
+    if (c->d.ldim == 3 && c->opt_xtrace && n_xtr < nkb::XTR_BIAS - 4) {
+        // neighbour traces across an x face come from the compact mirror: own face slot +x/-x
+        // (1, 3) and the neighbour node on an x face of its own element (i = 0 or n-1)
+        std::vector<int32_t> pm(c->vmapP);
+        const int n = c->n, n2 = n * n, nfp = 6 * n2;
+        for (int64_t fp = 0; fp < c->nxzfl; fp++) {
+            const int slot = (int)(fp % nfp) / n2;
+            const int32_t v = c->vmapP[fp];
+            if (v < 0 || (slot != 1 && slot != 3)) continue;
+            const int node = v % c->nxyz, i = node % n;
+            if (i != 0 && i != n - 1) continue;
+            const int64_t t = ((int64_t)(v / c->nxyz) * 2 + (i ? 1 : 0)) * n2 + node / n;
+            pm[fp] = (int32_t)(-(3 + (int64_t)nkb::XTR_BIAS + t));
+        }
+        CUDA_OK(cudaMemcpy(c->vmapP_d, pm.data(), sizeof(int) * c->nxzfl, cudaMemcpyHostToDevice));
+        c->ldx = (n_xtr + 31) / 32 * 32;
+        for (int q = 0; q < 2; q++) {
+            CUDA_OK(cudaMalloc(&c->xtr[q], sizeof(double) * 6 * c->ldx));
+            CUDA_OK(cudaMemset(c->xtr[q], 0, sizeof(double) * 6 * c->ldx));
+        }
+    } else {
+        CUDA_OK(cudaMemcpy(c->vmapP_d, c->vmapP.data(), sizeof(int) * c->nxzfl, cudaMemcpyHostToDevice));
+    }
     {
         std::vector<unsigned char> ef(c->d.nelt, 0);
         for (int32_t e : c->pml_el) ef[e] |= 1;
@@ -1750,9 +1822,19 @@ int nekcem_b200_set_option(int handle, const char *name, int value)
     Ctx *c = get(handle);
     if (!c) return 1;
     if (!name) return fail("null option name");
-    if (strcmp(name, "pf_dist") == 0) {
-        if (value < 0) return fail("pf_dist must be >= 0");
-        return 0; // reserved
+    if (strcmp(name, "pipeline") == 0) {
+        c->opt_pipeline = value != 0;
+        return 0;
+    }
+    if (strcmp(name, "xtrace") == 0) {
+        // takes effect at the next nekcem_b200_setup
+        c->opt_xtrace = value != 0;
+        return 0;
+    }
+    if (strcmp(name, "pipeline_ctas") == 0) {
+        if (value < 0) return fail("pipeline_ctas must be >= 0");
+        c->opt_pipeline_ctas = value;
+        return 0;
     }
     if (strcmp(name, "const_metrics") == 0) {
         // 1 (default): exploit exact redundancy of the geometry (constant cofactors per element,

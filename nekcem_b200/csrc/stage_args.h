@@ -4,6 +4,8 @@
 
 namespace nkb {
 
+constexpr int XTR_BIAS = 1 << 30;
+
 struct StageArgs {
     // fields: ping-pong H,E (6 components, leading dimension ld) and the RK register k
     const double *u_in;
@@ -19,10 +21,19 @@ struct StageArgs {
     // the reference evaluates 0.5/Y0 first in every product, src/cem_maxwell.F:976-979)
     const double *unx, *uny, *unz, *area, *hY, *Y1, *hZ, *Z1;
     const int *vmapP;   // >=0: local volume node of the neighbour trace; -1: PEC mirror;
-                        // -2: unpaired non-PEC face; <=-3: halo slot -(v+3)
+                        // -2: unpaired non-PEC face; <=-3: s = -(v+3): halo slot s, or, for
+                        // s >= XTR_BIAS (3D), entry s - XTR_BIAS of the x-face mirror
     const double *halo; // [nhalo][6] traces received from peer ranks
+    // 3D: compact mirror of the fields on the -x/+x faces of every element, (6, ldx), entry
+    // (2e + side)*n^2 + j + n*k.  A neighbour trace across an x face is a stride-n gather in the
+    // volume array (one 32-byte sector and one L1 tag per value); from the mirror it is a
+    // contiguous read.  Written by the epilogue next to the fields (ping-pong like them).
+    const double *xtr_in;
+    double *xtr_out;
+    long long ldx;
     const int *elist;   // element ids handled by this launch
     int nel;
+    int grid_cap;       // persistent kernels: at most this many CTAs (0: fill the device)
     double ca, cb, dt, C0;
     // PML auxiliary fields (PML launches only) -- src/PML
     const double *sig, *eps, *mu;

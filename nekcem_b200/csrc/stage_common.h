@@ -24,6 +24,23 @@ __device__ __forceinline__ void prefetch_chunk(const void *base, int bytes, int 
     if (lane == 0) prefetch_l2(b + bytes - 8);
 }
 
+// neighbour trace of a 3D face point from its vmapP code: base pointer of component 0 and the
+// stride between components.  vp >= 0 volume node; vp <= -3: halo slot or x-face mirror entry;
+// otherwise (PEC / unpaired: value unused) the node `dflt`.
+__device__ __forceinline__ const double *nbr_trace(const StageArgs &a, int vp, long long dflt,
+                                                   long long &stride)
+{
+    if (vp >= 0) { stride = a.ld; return a.u_in + vp; }
+    if (vp <= -3) {
+        const int s = -(vp + 3);
+        if (s >= XTR_BIAS) { stride = a.ldx; return a.xtr_in + (s - XTR_BIAS); }
+        stride = 1;
+        return a.halo + 6ll * (long long)s;
+    }
+    stride = a.ld;
+    return a.u_in + dflt;
+}
+
 // ---- shared-memory layout of one field component of an element (or of a k-slab of it) --------
 __host__ __device__ constexpr int pad_j(int n) { return (n == 6 || n == 14) ? 3 : (n == 12 ? 1 : 0); }
 __host__ __device__ constexpr int pad_k(int n)

@@ -502,9 +502,11 @@ __global__ void __launch_bounds__(Slab<N, KS>::NT, CM ? Slab<N, KS>::MINB_CM : S
     // (c) neighbour traces of those face points -> L2
 #pragma unroll
     for (int f = 0; f < FPT; f++)
-        if (fvp[f] >= 0) {
+        if (fvp[f] >= 0 || -(fvp[f] + 3) >= XTR_BIAS) {
+            long long st;
+            const double *nb = nbr_trace(a, fvp[f], sbase, st);
 #pragma unroll
-            for (int c = 0; c < 6; c++) prefetch_l2(a.u_in + c * a.ld + fvp[f]);
+            for (int c = 0; c < 6; c++) prefetch_l2(nb + c * st);
         }
     __syncthreads();
 
@@ -550,10 +552,8 @@ __global__ void __launch_bounds__(Slab<N, KS>::NT, CM ? Slab<N, KS>::MINB_CM : S
             const double hY = ldg(a.hY + jf), Y1 = ldg(a.Y1 + jf);
             const double hZ = ldg(a.hZ + jf), Z1 = ldg(a.Z1 + jf);
             // neighbour trace: volume node, halo slot, or (unused) the first node of the slab
-            const double *nb = vp >= 0 ? a.u_in + vp
-                                       : (vp <= -3 ? a.halo + 6ll * (long long)(-(vp + 3))
-                                                   : a.u_in + sbase);
-            const long long st = vp <= -3 ? 1 : a.ld;
+            long long st;
+            const double *nb = nbr_trace(a, vp, sbase, st);
             double pv[6];
 #pragma unroll
             for (int c = 0; c < 6; c++) pv[c] = ldg(nb + c * st);
@@ -716,13 +716,18 @@ __global__ void __launch_bounds__(Slab<N, KS>::NT, CM ? Slab<N, KS>::MINB_CM : S
 #pragma unroll
                     for (int c = 0; c < 3; c++) {
                         const double t = a.ca * kk[x][c] + a.dt * (r[c] * mb[x]);
+                        const double un = o[c] + a.cb * t;
                         if (SLAB_ST_CS) {
                             __stcs(a.kf + (cb0 + c) * a.ld + gi, t);
-                            __stcs(a.u_out + (cb0 + c) * a.ld + gi, o[c] + a.cb * t);
+                            __stcs(a.u_out + (cb0 + c) * a.ld + gi, un);
                         } else {
                             a.kf[(cb0 + c) * a.ld + gi] = t;
-                            a.u_out[(cb0 + c) * a.ld + gi] = o[c] + a.cb * t;
+                            a.u_out[(cb0 + c) * a.ld + gi] = un;
                         }
+                        // x-face mirror of the new fields (stage_args.h)
+                        if (a.xtr_out != nullptr && (pi == 0 || pi == N - 1))
+                            a.xtr_out[(cb0 + c) * a.ldx + (2ll * e + (pi ? 1 : 0)) * N2 + pj +
+                                      N * (k0 + kl)] = un;
                     }
                 }
             }

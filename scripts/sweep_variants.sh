@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: scripts/sweep_variants.sh "N:E" name1 name2 ...   (variants built by build_variants.sh)
+# usage: scripts/sweep_variants.sh "N:E [opts]" name1 name2 ...   (variants built by build_variants.sh)
 cfg=$1; shift
 for v in "$@"; do
   echo "== $v"
