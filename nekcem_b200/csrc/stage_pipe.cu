@@ -46,6 +46,9 @@ namespace {
 #ifndef PIPE_NBR_PREFETCH
 #define PIPE_NBR_PREFETCH 1 // 1: L2 prefetch of the neighbour traces at P0
 #endif
+#ifndef PIPE_L2_AHEAD
+#define PIPE_L2_AHEAD 0 // 1: L2 prefetch of the next item's fields and rx..sz one item ahead
+#endif
 #ifndef PIPE_SKIP
 #define PIPE_SKIP 0 // timing experiments only (wrong results): 1 P1, 2 P2, 4 flux, 8 P4, 16 relayout
 #endif
@@ -66,13 +69,24 @@ __host__ __device__ constexpr int p_nt_for(int items)
     int passes = (items + 255) / 256;
     return p_round32((items + passes - 1) / passes);
 }
-// slabs per element: the thickest slab whose five regions leave room for two CTAs per SM
+// slabs per element.  Whole elements (KS = 1) wherever the regions fit one SM: two CTAs per SM up
+// to nx1 = 8, one CTA of 512 threads for nx1 = 9, 10 (measured: 0.69 / 0.67 of the HBM roofline
+// against 0.52 / 0.42 with two half-element slabs per element, whose t-lines through the other
+// slab come from L2).  Above that only thin slabs fit next to the staging regions.
 __host__ __device__ constexpr int pipe_ks_for(int n)
 {
 #ifdef PIPE_KS_OVERRIDE_N
     if (n == PIPE_KS_OVERRIDE_N) return PIPE_KS_OVERRIDE;
 #endif
-    return n <= 8 ? 1 : (n <= 10 ? 2 : (n <= 11 ? 3 : (n <= 12 ? 4 : (n <= 13 ? 5 : 8))));
+    return n <= 10 ? 1 : (n <= 11 ? 3 : (n <= 12 ? 4 : (n <= 13 ? 5 : 8)));
+}
+
+// skew of the E components in U and R for the group-interleaved s-pencil lanes
+// (scripts/smem_banks_pipe.py, for the slab thickness pipe_ks_for gives)
+__host__ __device__ constexpr int pipe_he_for(int n)
+{
+    return n == 6 ? 14 : n == 7 ? 3 : n == 8 ? 8 : n == 9 ? 10 : n == 10 ? 5 : n == 11 ? 15
+         : n == 13 ? 12 : n == 14 ? 10 : n == 15 ? 9 : 0;
 }
 
 template <int N, int KS>
@@ -88,7 +102,7 @@ struct PT {
 #ifdef PIPE_NT
     static constexpr int NT = PIPE_NT;
 #else
-    static constexpr int NT = p_max(p_nt_for(RS_ITEMS), p_round32(N2));
+    static constexpr int NT = (KS == 1 && N >= 9) ? 512 : p_max(p_nt_for(RS_ITEMS), p_round32(N2));
 #endif
     static constexpr int SC = Lay<N>::SK * KB; // component stride in U and R
     static constexpr int XL = p_even(N2 * KB + 2); // linear slab of one array + alignment slack
@@ -102,13 +116,15 @@ struct PT {
     static constexpr int F_ITEMS = FXY + FZ;
     static constexpr int FPT = (F_ITEMS + NT - 1) / NT;
     static constexpr int NBAR = 5;
+    // w3mn of one element in shared memory (small elements), else read through L1
+    static constexpr bool W3S = N3 <= 512;
     // the E components of U and R start HE doubles later than a multiple of the component stride
     // (PIPE_IG: the s-pencil lanes interleave the H and E groups, so that both read one cofactor
     // address; the skew puts their field and residual accesses on different banks)
-    static constexpr int HE = PIPE_IG ? 8 : 0;
+    static constexpr int HE = PIPE_IG ? pipe_he_for(N) : 0;
     static constexpr int OFF_U = 0, OFF_R = 6 * SC + HE, OFF_X = 12 * SC + 2 * HE,
                          OFF_Y = OFF_X + 6 * XL, OFF_Z = OFF_Y + YL, OFF_W = OFF_Z + 3 * XL,
-                         OFF_BAR = OFF_W + p_even(N3);
+                         OFF_BAR = OFF_W + (W3S ? p_even(N3) : 0);
     static constexpr size_t SMEM = sizeof(double) * (OFF_BAR + NBAR + 1);
     // work item w of an r/s pencil phase -> output share h, group g (0: curl H, 1: -curl E),
     // pencil (pa, pb).  h is warp-uniform (it selects code).
@@ -179,6 +195,14 @@ __device__ __forceinline__ uint32_t bulk_load(double *dst, const double *src, in
         "l"(s - head), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
     return bytes;
+}
+// L2 prefetch of the same aligned range (no shared-memory destination, no completion)
+__device__ __forceinline__ void bulk_prefetch(const double *src, int cnt)
+{
+    const uintptr_t s = (uintptr_t)src;
+    const uint32_t head = (uint32_t)(s & 15);
+    const uint32_t bytes = (head + (uint32_t)cnt * 8u + 15u) & ~15u;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(s - head), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ uint32_t bulk_bytes(const double *src, int cnt)
 {
@@ -377,7 +401,7 @@ __global__ void __launch_bounds__(PT<N, KS>::NT, PT<N, KS>::MINB)
     double *X = smem + C::OFF_X; // [6][XL] rx..sz, then kH,kE
     double *Y = smem + C::OFF_Y; // fields landing zone [6][XL], then face arrays [8][FL]
     double *Z = smem + C::OFF_Z; // [3][XL] tx..tz
-    double *W3 = smem + C::OFF_W; // w3mn of one element (the same for every item)
+    const double *W3 = C::W3S ? smem + C::OFF_W : a.w3; // w3mn of one element
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
     uint64_t *b_fld = bar, *b_face = bar + 1, *b_cof = bar + 2, *b_k = bar + 3, *b_cot = bar + 4;
 
@@ -392,7 +416,8 @@ __global__ void __launch_bounds__(PT<N, KS>::NT, PT<N, KS>::MINB)
         for (int b = 0; b < C::NBAR; b++) mbar_init(bar + b, 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < N3; i += NT) W3[i] = ldg(a.w3 + i);
+    if constexpr (C::W3S)
+        for (int i = tid; i < N3; i += NT) smem[C::OFF_W + i] = ldg(a.w3 + i);
     __syncthreads();
 
     // ---- producers: every lane of warp 0 arrives on the barrier with the bytes of its own copies
@@ -514,6 +539,7 @@ __global__ void __launch_bounds__(PT<N, KS>::NT, PT<N, KS>::MINB)
 
     int q = blockIdx.x;
     int e = q < nitems ? a.elist[q / KS] : 0;
+    int en = q + G < nitems ? a.elist[(q + G) / KS] : 0; // element of the next item
     int fvp[FPT];
     if (q < nitems) {
 #pragma unroll
@@ -544,8 +570,8 @@ __global__ void __launch_bounds__(PT<N, KS>::NT, PT<N, KS>::MINB)
         const long long sbase = ebase + k0 * N2; // first node of the slab
         const int qn = q + G, sn_ = qn % KS;
         const bool more = qn < nitems;
-        // element of the next item: needed by the producers from the flux phase on
-        const int en = more ? ldg(a.elist + qn / KS) : 0;
+        // element of the item after the next (the producers need the next one's early)
+        const int enn = qn + G < nitems ? ldg(a.elist + (qn + G) / KS) : 0;
 
         int fsn[FPT], fjs[FPT], fyi[FPT];
 #pragma unroll
@@ -576,7 +602,17 @@ __global__ void __launch_bounds__(PT<N, KS>::NT, PT<N, KS>::MINB)
                 for (int c = 0; c < 6; c++) prefetch_l2(nb + c * st);
             }
         __syncthreads();
-        if (w0) issue_face(e, s);
+        if (w0) {
+            issue_face(e, s);
+            // the two streams whose shared-memory region frees late (fields: after the flux phase,
+            // rx..sz: after the epilogue) start their trip from HBM now, into L2
+            if (PIPE_L2_AHEAD && more) {
+                const int cnt = N2 * C::kb(sn_);
+                const long long nb = slab_base(en, sn_);
+                if (lane < 6) bulk_prefetch(a.u_in + (long long)lane * a.ld + nb, cnt);
+                else if (lane < 12 && !CM) bulk_prefetch(a.met[lane - 6] + nb, cnt);
+            }
+        }
 
         // constant-metric elements: the nine cofactors of the element (first node)
         double cmrs[6] = {0, 0, 0, 0, 0, 0}, cmt[6] = {0, 0, 0, 0, 0, 0};
@@ -851,6 +887,7 @@ __global__ void __launch_bounds__(PT<N, KS>::NT, PT<N, KS>::MINB)
         __syncthreads();
         if (w0 && more && !CM) issue_cof(en, sn_);
         e = en;
+        en = enn;
 #pragma unroll
         for (int f = 0; f < FPT; f++) fvp[f] = fvn[f];
     }
@@ -899,10 +936,20 @@ bool aligned16(const void *p) { return ((uintptr_t)p & 15) == 0; }
 
 } // namespace
 
-// returns 0 ok, -1 order not covered by this kernel (the caller uses launch_stage_slab), >0 CUDA
-// failure.  Dhost = dxm1 (n*n, column-major).
-int launch_stage_pipe(const StageArgs &a, const double *Dhost, int nx1, bool pml, bool cm,
-                      void *stream)
+// One translation unit per order: the Makefile compiles this file once per nx1 with
+// -DPIPE_ONLY_N=<nx1> (entry point launch_stage_pipe_n<nx1>); stage_pipe_dispatch.cu selects.
+// -DPIPE_SINGLE (developer variants, scripts/build_variants.sh): this unit is the only order and
+// also provides launch_stage_pipe itself.
+#ifndef PIPE_ONLY_N
+#error "compile with -DPIPE_ONLY_N=<nx1>"
+#endif
+#define PIPE_CAT2(a, b) a##b
+#define PIPE_CAT(a, b) PIPE_CAT2(a, b)
+
+// returns 0 ok, -1 the arrays do not meet the alignment the bulk copies need (the caller uses
+// launch_stage_slab), >0 CUDA failure.  Dhost = dxm1 (n*n, column-major).
+int PIPE_CAT(launch_stage_pipe_n, PIPE_ONLY_N)(const StageArgs &a, const double *Dhost, bool pml,
+                                               bool cm, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
     // the bulk copies assume 16-byte aligned arrays and an even leading dimension
@@ -911,14 +958,16 @@ int launch_stage_pipe(const StageArgs &a, const double *Dhost, int nx1, bool pml
               aligned16(a.Y1) && aligned16(a.hZ) && aligned16(a.Z1);
     for (int q = 0; q < 9; q++) ok = ok && aligned16(a.met[q]);
     if (!ok) return -1;
-    switch (nx1) {
-#ifdef PIPE_ONLY_N
-    case PIPE_ONLY_N: return pipe_launch_n<PIPE_ONLY_N>(a, Dhost, pml, cm, st);
-#else
-    case 8: return pipe_launch_n<8>(a, Dhost, pml, cm, st);
-#endif
-    default: return -1;
-    }
+    return pipe_launch_n<PIPE_ONLY_N>(a, Dhost, pml, cm, st);
 }
+
+#ifdef PIPE_SINGLE
+int launch_stage_pipe(const StageArgs &a, const double *Dhost, int nx1, bool pml, bool cm,
+                      void *stream)
+{
+    if (nx1 != PIPE_ONLY_N) return -1;
+    return PIPE_CAT(launch_stage_pipe_n, PIPE_ONLY_N)(a, Dhost, pml, cm, stream);
+}
+#endif
 
 } // namespace nkb

@@ -10,13 +10,16 @@ other=$([ $which = pipe ] && echo slab || echo pipe)
 NVCC=/usr/local/cuda/bin/nvcc
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 FLAGS="$ARCH -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -fvisibility=hidden -ccbin /usr/bin/g++"
-make -s _obj/nekcem_b200.o _obj/stage2d.o _obj/fortran_abi.o _obj/stage_$other.o
+extra=""; [ $which = pipe ] && extra="-DPIPE_SINGLE"
+make -s _obj/nekcem_b200.o _obj/stage2d.o _obj/fortran_abi.o _obj/stage_slab.o
+[ $which = slab ] && make -s _obj/stage_pipe_dispatch.o $(ls _obj/stage_pipe_n*.o 2>/dev/null)
+pipeobjs=$([ $which = slab ] && ls _obj/stage_pipe_dispatch.o _obj/stage_pipe_n*.o || echo _obj/stage_slab.o)
 mkdir -p ../lib/variants _obj/variants
 for spec in "$@"; do
   name="${spec%%=*}"; defs="${spec#*=}"
   (
-    $NVCC $FLAGS $defs -Xptxas -v -c stage_$which.cu -o _obj/variants/$name.o 2> _obj/variants/$name.log
-    $NVCC $ARCH -shared -o ../lib/variants/$name.so _obj/nekcem_b200.o _obj/stage2d.o _obj/variants/$name.o _obj/stage_$other.o _obj/fortran_abi.o -lcudart -ldl
+    $NVCC $FLAGS $extra $defs -Xptxas -v -c stage_$which.cu -o _obj/variants/$name.o 2> _obj/variants/$name.log
+    $NVCC $ARCH -shared -o ../lib/variants/$name.so _obj/nekcem_b200.o _obj/stage2d.o _obj/variants/$name.o $pipeobjs _obj/fortran_abi.o -lcudart -ldl
     grep -E "Used|spill" _obj/variants/$name.log | paste - - | awk -v n=$name '{print n": "$0}' | sed 's/ptxas info    ://g' | head -4
   ) &
 done

@@ -11,7 +11,7 @@ from helpers import incident_3ddielectric, rel_l2, solver_from_refcase
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
 # orders (nx1) the pipelined kernel covers; the others fall through to the slab kernel
-PIPE_ORDERS = [8]
+PIPE_ORDERS = [8, 9, 10]
 
 
 def _fields(s):
@@ -34,8 +34,11 @@ def test_pipe_periodic_box_vs_oracle(nx1, ctas):
     s.set_option("pipeline_ctas", ctas)
     c.step(3); s.step(3)
     assert rel_l2(_fields(s), _fields(c)) <= TOL
+    # the RK register is dt*res: res is a difference of O(N^2) larger terms (FMA contraction on the
+    # device, none in the oracle), so its relative error grows with the order -- 2e-12 at nx1 = 12,
+    # 1e-11 at nx1 = 16, identical for the slab kernel -- while the fields stay at 1e-14
     kg = np.concatenate([s.get_array("khn"), s.get_array("ken")])
-    assert rel_l2(kg, np.concatenate([c.khn, c.ken])) <= TOL
+    assert rel_l2(kg, np.concatenate([c.khn, c.ken])) <= (TOL if nx1 <= 10 else 1e-10)
     s.close()
 
 
