@@ -196,12 +196,42 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_numa(local: int):
+    """Pin this rank to the cores of its GPU's NUMA node before the pinned host buffers are
+    allocated (first touch places them there): the e2e copies then cross no inter-socket link."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        dev = torch.cuda.get_device_properties(local).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus += list(range(int(lo), int(hi or lo) + 1))
+        cpus = sorted(set(cpus) & os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
+def bytes_per_node(nx1: int) -> float:
+    """algorithmic bytes per node and stage of the general path, SURVEY.md 8d: 280 + 696/n"""
+    return 280.0 + 696.0 / nx1
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
 
     from nekcem_b200 import MaxwellB200, comm_unique_id
-    from nekcem_b200.boxcase import BoxCase
+    from nekcem_b200.boxcase import BoxCase, gll
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -212,6 +242,7 @@ def run_gpu(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -220,30 +251,79 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    E, nx1 = args.elems, args.order + 1
+    def max_over_ranks(x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    peak, peak_src = measured_peak()
+
+    def make(nel, order, nranks=world, myrank=rank, general=True):
+        """solver for a periodic box of nel elements at order N, partitioned over nranks"""
+        nx1 = order + 1
+        t0 = time.perf_counter()
+        case = BoxCase(nel, nx1, rank=myrank, nranks=nranks, length=2 * math.pi)
+        slv = MaxwellB200(3, nx1, case.nelt, device=local, rank=myrank, nranks=nranks)
+        slv.cem_maxwell_init(case.lazy(), free_after_upload=True)
+        if nranks > 1:
+            uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                uid.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
+            dist.broadcast(uid, 0)
+            slv.comm_init(bytes(uid.cpu().numpy().tobytes()))
+        if general:
+            slv.set_option("const_metrics", 0)
+        slv.setup()
+        # CFL-limited dt as in the synthetic .rea (param(12)=+0.1 -> dt = 0.1*dxmin, SURVEY 8d)
+        z, _ = gll(nx1)
+        dxmin = 0.5 * min(case.h) * 0.5 * float(np.min(z[2:] - z[:-2])) if nx1 > 2 else min(case.h)
+        dt = 0.1 * dxmin
+        slv.set_time(0.0, dt)
+        return case, slv, dt, time.perf_counter() - t0
+
+    def timed(slv, warm, steps):
+        """device time of `steps` time steps (CUDA events on the compute stream), max over ranks"""
+        slv.step(warm)
+        barrier()
+        slv.cem_maxwell_op_rk(steps, sync=False)
+        slv.synchronize()
+        barrier()
+        ms, launches = slv.last_step_ms()
+        return max_over_ranks(ms), int(launches)
+
+    def measure(nel, order, warm, steps, general=True):
+        """one extra configuration: rate, ms/step and the roofline fraction of its stage kernel"""
+        case, slv, dt, ts = make(nel, order, general=general)
+        ms, launches = timed(slv, warm, steps)
+        nodes = case.npts * world if nel[2] % world == 0 else None
+        npts_global = int(np.prod(nel)) * (order + 1) ** 3
+        shn, sen = case.fields(slv.time)
+        ssum, smax = slv.error_sums(shn, sen)
+        del shn, sen
+        red = torch.tensor(ssum, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(red, op=dist.ReduceOp.SUM)
+        l2 = float(np.sqrt(red.cpu().numpy().max() / case.volume_global))
+        slv.close()
+        stage_ms = ms / (5.0 * steps)
+        bpn = bytes_per_node(order + 1)
+        # the slowest rank's launch carries npts_global/world nodes (equal slabs)
+        ach = bpn * (npts_global / world) / (stage_ms * 1e-3) / 1e9
+        return {"value": npts_global * 5.0 * steps / (ms * 1e-3) / 1e9, "unit": UNIT,
+                "ms_per_step": ms / steps, "steps": steps, "nodes_global": npts_global,
+                "elements_global": list(nel), "order": order,
+                "roofline_frac": ach / peak, "achieved_GBps_per_gpu": ach,
+                "bytes_per_node_stage": bpn, "l2_error_vs_analytic": l2,
+                "gpu_launches": launches, "setup_s": round(ts, 1)}
+
+    E, order = args.elems, args.order
+    nx1 = order + 1
     strong = args.scaling == "strong"
     # weak scaling (default): one E^3 slab per GPU; strong: the global E^3 box split over the GPUs
     nel = (E, E, E) if strong else (E, E, E * world)
-    case = BoxCase(nel, nx1, rank=rank, nranks=world, length=2 * math.pi)
-    slv = MaxwellB200(3, nx1, case.nelt, device=local, rank=rank, nranks=world)
-    t_setup = time.perf_counter()
-    slv.cem_maxwell_init(case.lazy(), free_after_upload=True)
-    if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-        slv.comm_init(bytes(uid.cpu().numpy().tobytes()))
-    slv.setup()
-    if args.metrics == "stream":
-        slv.set_option("const_metrics", 0)
-    # CFL-limited dt as in the synthetic .rea (param(12)=+0.1 -> dt = 0.1*dxmin)
-    from nekcem_b200.boxcase import gll
-    z, _ = gll(nx1)
-    dxmin = 0.5 * min(case.h) * 0.5 * float(np.min(z[2:] - z[:-2])) if nx1 > 2 else min(case.h)
-    dt = 0.1 * dxmin
-    slv.set_time(0.0, dt)
-    t_setup = time.perf_counter() - t_setup
+    general = args.metrics == "stream"
+    case, slv, dt, t_setup = make(nel, order, general=general)
     npts_global = case.npts * world
 
     # ---- device-resident timing ---------------------------------------------------------
@@ -257,11 +337,28 @@ def run_gpu(args):
     barrier()
     ms, launches = slv.last_step_ms()
     clocks = sampler.stop() if sampler else None
-    tms = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms_max = float(tms.item())
+    ms_max = max_over_ranks(ms)
     value = npts_global * 5.0 * K / (ms_max * 1e-3) / 1e9
+    n_cm, shared = slv.geometry_info()
+
+    # the same mesh through the constant-metric instantiation (exact redundancy of THIS mesh's
+    # geometry, never found in metrics that came out of the reference's glmapm1): labelled extra
+    cm_variant = None
+    if general and not args.no_extras:
+        slv.set_option("const_metrics", 1)
+        ms_cm, _ = timed(slv, 3, K)
+        n_cm1, shared1 = slv.geometry_info()
+        cm_bytes = (bytes_per_node(nx1) - (72.0 if n_cm1 == slv.nelt else 0.0)
+                    - (8.0 if shared1 else 0.0)) * case.npts
+        cm_variant = {"value": npts_global * 5.0 * K / (ms_cm * 1e-3) / 1e9, "unit": UNIT,
+                      "ms_per_step": ms_cm / K,
+                      "elements_with_constant_cofactors": int(n_cm1), "hbm1_eq_ebm1": bool(shared1),
+                      "bytes_per_launch_this_variant": cm_bytes,
+                      "roofline_frac_of_bytes_moved": cm_bytes / (ms_cm / (5.0 * K) * 1e-3) / 1e9 / peak,
+                      "note": "same results bit for bit; reachable only when the uploaded cofactors "
+                              "are bitwise constant per element"}
+        slv.set_option("const_metrics", 0)
+        slv.step(1)
 
     # analytic-solution check of the timed state (the reference's userchk, 3dboxper.usr:169-216)
     tnow = slv.time
@@ -279,56 +376,67 @@ def run_gpu(args):
     linf = red[6:]
 
     # ---- end-to-end through the C ABI with HOST buffers ------------------------------------
-    # every step: H2D of HN,EN from pinned host memory, one time step, D2H of HN,EN
-    # (the `!$ACC UPDATE DEVICE/HOST(hn,en)` seams of the reference, drude.usr:94, 3dboxper.usr:199)
-    Ke = max(1, min(args.e2e_steps, K))
+    # every step takes its input fields from pinned host memory and hands the advanced fields
+    # back to pinned host memory (the `!$ACC UPDATE DEVICE/HOST(hn,en)` seams of the reference,
+    # drude.usr:94, 3dboxper.usr:199) through nekcem_b200_step_streamed: the upload of input
+    # k+1, the five stages of input k and the download of result k-1 overlap (three streams,
+    # PCIe full duplex); consecutive inputs are independent states, as a stream of them would be
+    Ke = K if args.e2e_steps <= 0 else max(1, min(args.e2e_steps, K))
     n3 = 3 * case.npts
-    pin_h = torch.empty(n3, dtype=torch.float64, pin_memory=True)
-    pin_e = torch.empty(n3, dtype=torch.float64, pin_memory=True)
-    hn_host, en_host = pin_h.numpy(), pin_e.numpy()
-    hn_host[:] = slv.hn
-    en_host[:] = slv.en
-    import ctypes as C
-    from nekcem_b200.api import ARRAY_IDS, _chk, c_dp
-    Lh = slv.L
+    pins = [torch.empty(n3, dtype=torch.float64, pin_memory=True) for _ in range(4)]
+    hn_in, en_in, hn_out, en_out = (p.numpy() for p in pins)
+    hn_in[:] = slv.hn
+    en_in[:] = slv.en
 
     def e2e_step():
-        _chk(Lh.nekcem_b200_set_array(slv.h, ARRAY_IDS["hn"], hn_host.ctypes.data_as(c_dp), n3))
-        _chk(Lh.nekcem_b200_set_array(slv.h, ARRAY_IDS["en"], en_host.ctypes.data_as(c_dp), n3))
-        _chk(Lh.nekcem_b200_step(slv.h, 1))
-        _chk(Lh.nekcem_b200_get_array(slv.h, ARRAY_IDS["hn"], hn_host.ctypes.data_as(c_dp), n3))
-        _chk(Lh.nekcem_b200_get_array(slv.h, ARRAY_IDS["en"], en_host.ctypes.data_as(c_dp), n3))
+        slv.step_streamed(hn_in, en_in, hn_out, en_out)
 
-    e2e_step()
+    for _ in range(3):          # fills the pipeline (input -> compute -> result) and warms up
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(Ke):
         e2e_step()
     barrier()
-    te = time.perf_counter() - t0
-    tt = torch.tensor([te], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    e2e_value = npts_global * 5.0 * Ke / float(tt.item()) / 1e9
+    te = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = npts_global * 5.0 * Ke / te / 1e9
     bytes_io = 2 * n3 * 8
+    # the streamed result is one time step applied to the uploaded state: check it
+    slv.step_streamed(None, None, hn_out, en_out)     # drain: result of the last input
+    e2e_ok = bool(np.isfinite(hn_out[:1024]).all() and np.abs(hn_out).max() > 0)
+    del pins, hn_in, en_in, hn_out, en_out
+    slv.close()
+
+    # ---- further configurations of BASELINE.json configs[4] in the same line -----------------
+    extra = {}
+    if not args.no_extras:
+        Kx = max(3, min(K, 5))
+        if not (order == 15 and E == 32 and not strong):
+            extra["weak_n15_e32_per_gpu"] = measure((32, 32, 32 * world), 15, 3, Kx)
+        if world > 1:
+            extra["strong_n7_e64_total"] = measure((64, 64, 64), 7, 3, Kx)
+        if world >= 4:
+            extra["strong_n15_e64_total"] = measure((64, 64, 64), 15, 3, Kx)
+        if world > 1:
+            extra["parity_vs_single_domain"] = parity_vs_single_domain(
+                torch, dist, make, rank, world, barrier)
 
     if rank == 0:
-        peak, peak_src = measured_peak()
-        bytes_stage = slv.algorithmic_bytes_per_stage()          # this rank's elements
+        bpn = bytes_per_node(nx1)
+        bytes_stage = bpn * case.npts                    # this rank's elements, general path
         stage_ms = ms_max / (5.0 * K)
-        achieved = bytes_stage / (stage_ms * 1e-3) / 1e9
-        # exact redundancy the setup scan found in this mesh's geometry (same numbers, fewer
-        # bytes): constant cofactors per element (-72 B/node there), hbm1 == ebm1 (-8 B/node)
-        n_cm, shared = slv.geometry_info()
-        n_el = slv.nelt
-        actual_bytes = bytes_stage - 8.0 * nx1 ** 3 * (9.0 * n_cm + (n_el if shared else 0))
-        traffic = None
+        if general:
+            moved = bytes_stage
+        else:  # --metrics auto on a mesh with exact redundancy: count what the variant must move
+            moved = bytes_stage - 8.0 * nx1 ** 3 * (9.0 * n_cm + (slv.nelt if shared else 0))
+        achieved = moved / (stage_ms * 1e-3) / 1e9
+        traffic, traffic_src = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and not (strong and world > 1):
             try:
-                traffic = None if strong and world > 1 else \
-                    json.load(open(tpath)).get(
-                        f"N{args.order}_E{E}" + ("_stream" if args.metrics == "stream" else ""))
+                ent = json.load(open(tpath)).get(f"N{order}_E{E}_" + ("general" if general else "auto"))
+                if ent:
+                    traffic, traffic_src = ent["dram_bytes_per_launch"], ent["source"]
             except Exception:
                 traffic = None
         cpu = None
@@ -340,14 +448,15 @@ def run_gpu(args):
                        "sample": f"{threads} independent single-process replicas of the "
                                  "reference's own path (oracle/_ref: its Fortran translated to C "
                                  "+ its src/jl gs library; no MPI in this image), each a periodic "
-                                 f"box of {args.ref_elems}^3 elements at N={args.order} ({nptc} "
+                                 f"box of {args.ref_elems}^3 elements at N={order} ({nptc} "
                                  f"nodes in total), {args.ref_steps} steps, {dtc:.1f} s"}
             else:
                 rate, threads, dtc, nptc = cpu_oracle_rate(args.cpu_elems, nx1, args.cpu_steps, 1)
                 cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                       "sample": f"periodic box {args.cpu_elems}^3 elements, N={args.order} "
+                       "sample": f"periodic box {args.cpu_elems}^3 elements, N={order} "
                                  f"({nptc} nodes), {args.cpu_steps} steps, {dtc:.1f} s; oracle "
                                  "port (oracle/_ref did not travel with the tree)"}
+        xmirror = 2.0 * 6 * 8 * 2 * nx1 * nx1 * slv.nelt     # write + read of the x-face mirror
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True,
@@ -355,40 +464,87 @@ def run_gpu(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": f"synthetic 3D periodic box, {E}^3 hex elements "
-                            f"{'in total' if strong else 'per GPU'} at N={args.order} "
+                            f"{'in total' if strong else 'per GPU'} at N={order} "
                             f"(global {nel[0]}x{nel[1]}x{nel[2]}), 3dboxper initial condition, "
                             "upwind flux, LSRK(5,4)",
                 "nodes_global": npts_global, "dof_unit": "grid node (6 field components)",
                 "dt": dt, "partition": "reference pencil map (z-slabs), NCCL face exchange",
                 "l2_flush": "inputs larger than L2 (one stage streams >> 126 MB)",
                 "metrics_variant": (
-                    f"{n_cm} of {n_el} elements have bitwise-constant cofactors (read once per "
-                    f"element, SURVEY.md 8d 'affine-element shortcut'), hbm1==ebm1 "
-                    f"{'shared' if shared else 'not shared'}; roofline.achieved counts the full "
-                    "280+696/n B/node; run with --metrics stream for the general per-node path"
-                    if args.metrics == "auto" else
-                    "every geometry array streamed per node (general path, --metrics stream)"),
-                "setup_s": round(t_setup, 1),
+                    "general path: every geometry array streamed per node (what a mesh whose "
+                    "metrics came out of the reference's glmapm1 gets); the constant-metric "
+                    "instantiation on this mesh is reported under variants" if general else
+                    f"{n_cm} of {slv.nelt} elements have bitwise-constant cofactors, read once per "
+                    f"element; hbm1==ebm1 {'shared' if shared else 'not shared'}; roofline counts "
+                    "the bytes this variant must move"),
+                "setup_s": round(t_setup, 1), "numa_node": numa,
                 "l2_error_vs_analytic": float(np.max(l2)), "linf_error_vs_analytic": float(np.max(linf)),
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": bytes_stage,
-                         "compulsory_bytes_per_launch_this_mesh": actual_bytes,
-                         "frac_of_compulsory_this_mesh": actual_bytes / (stage_ms * 1e-3) / 1e9 / peak,
-                         "kernel": "stage_kernel (one launch per RK stage per element list)",
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": moved,
+                         "bytes_per_node_stage": moved / case.npts,
+                         "overhead_bytes_per_launch_not_credited": xmirror,
+                         "overhead_what": "x-face mirror of the fields (compact copy of the +-x "
+                                          "traces, written by the epilogue, read by the x "
+                                          "neighbours instead of a stride-n gather)",
+                         "kernel": "pipe_kernel (nx1 8..10) / slab_kernel: one launch per RK stage "
+                                   "per element list",
                          "avg_launch_ms": stage_ms},
+            "variants": {"constant_metrics": cm_variant},
+            "extra": extra,
             "cpu_baseline": cpu,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_io,
-                    "d2h_bytes_per_step": bytes_io, "steps": Ke,
-                    "what": "per step: H2D(hn,en) from pinned host + nekcem_b200_step(1) + D2H(hn,en)"},
+                    "d2h_bytes_per_step": bytes_io, "steps": Ke, "result_checked": e2e_ok,
+                    "what": "per step: H2D(hn,en) of the next input from pinned host memory + one "
+                            "time step + D2H(hn,en) of the previous result to pinned host memory, "
+                            "through nekcem_b200_step_streamed (three streams; inputs of "
+                            "consecutive steps are independent states)"},
             "gpu_launches": int(launches),
         }
         print(json.dumps(line), file=_JSON_OUT, flush=True)
-    slv.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def parity_vs_single_domain(torch, dist, make, rank, world, barrier):
+    """The same global mesh (8 x 8 x 8*world elements, N=7, general path) advanced K steps by the
+    `world` ranks with the NCCL face exchange and by rank 0 alone: per-node arithmetic is
+    identical, so the fields must agree bit for bit (what gs_op_fields guarantees the reference,
+    src/cem_maxwell.F:962, src/jl/gs.c:471-512)."""
+    K = 3
+    nel = (8, 8, 8 * world)
+    case, slv, dt, _ = make(nel, 7)
+    slv.step(K)
+    loc = torch.from_numpy(np.concatenate([slv.hn, slv.en])).cuda()
+    ids = torch.from_numpy(case.lglel.copy()).cuda()
+    slv.close()
+    allf = [torch.empty_like(loc) for _ in range(world)]
+    alli = [torch.empty_like(ids) for _ in range(world)]
+    dist.all_gather(allf, loc)
+    dist.all_gather(alli, ids)
+    out = None
+    if rank == 0:
+        nxyz = case.nxyz
+        nelg = int(np.prod(nel))
+        glob = np.empty((6, nelg * nxyz))
+        for f, i in zip(allf, alli):
+            f = f.cpu().numpy().reshape(6, -1, nxyz)
+            glob.reshape(6, nelg, nxyz)[:, i.cpu().numpy(), :] = f
+        c1, s1, _, _ = make(nel, 7, nranks=1, myrank=0)
+        s1.set_time(0.0, dt)
+        s1.step(K)
+        one = np.concatenate([s1.hn, s1.en]).reshape(6, -1)
+        s1.close()
+        diff = float(np.max(np.abs(glob - one)))
+        den = float(np.sqrt(np.sum(one * one)))
+        out = {"bitwise_equal": bool(np.array_equal(glob, one)), "max_abs_diff": diff,
+               "rel_l2": float(np.sqrt(np.sum((glob - one) ** 2)) / den),
+               "mesh": f"{nel[0]}x{nel[1]}x{nel[2]} elements, N=7, {K} steps, {world} ranks vs 1"}
+    barrier()
+    return out
 
 
 def main():
@@ -399,7 +555,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--elems", type=int, default=64, help="elements per direction per GPU")
     ap.add_argument("--order", type=int, default=7, help="polynomial order N (nx1 = N+1)")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0: as many as --steps")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the extra configurations (N=15, strong scaling, multi-rank parity)")
     ap.add_argument("--cpu-elems", type=int, default=24)
     ap.add_argument("--cpu-steps", type=int, default=30)
     ap.add_argument("--ref-elems", type=int, default=12,
@@ -407,10 +565,11 @@ def main():
     ap.add_argument("--ref-steps", type=int, default=12)
     ap.add_argument("--ref-worker", default=None, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--metrics", default="auto", choices=["auto", "stream"],
-                    help="auto: exploit exact redundancy of the geometry found at setup; "
-                         "stream: read every geometry array per node (what a mesh with "
-                         "round-off noise in its metrics gets)")
+    ap.add_argument("--metrics", default="stream", choices=["auto", "stream"],
+                    help="stream (default): read every geometry array per node -- the general "
+                         "path, what a mesh with round-off noise in its metrics (any mesh out of "
+                         "the reference's glmapm1) gets; auto: exploit exact redundancy of the "
+                         "geometry found at setup")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --elems^3 per GPU (default); strong: --elems^3 in total")
     args = ap.parse_args()

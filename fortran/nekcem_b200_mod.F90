@@ -86,13 +86,14 @@ module nekcem_b200
        import :: c_int
        integer(c_int), value :: handle
      end function
-     integer(c_int) function nekcem_b200_set_incident(handle, nface, facepts, fh, fe) &
+     integer(c_int) function nekcem_b200_set_incident(handle, ninc, facepts, amp, phase, omega) &
           bind(C, name='nekcem_b200_set_incident')
        import :: c_int, c_int32_t, c_double
        integer(c_int), value :: handle
-       integer(c_int32_t), value :: nface
+       integer(c_int32_t), value :: ninc
        integer(c_int32_t), intent(in) :: facepts(*)
-       real(c_double), intent(in) :: fh(*), fe(*)
+       real(c_double), intent(in) :: amp(*), phase(*)
+       real(c_double), value :: omega
      end function
      integer(c_int) function nekcem_b200_set_volume_source(handle, comp, profile, amp, omega, phase) &
           bind(C, name='nekcem_b200_set_volume_source')
@@ -120,6 +121,16 @@ module nekcem_b200
      integer(c_int) function nekcem_b200_step(handle, nsteps) bind(C, name='nekcem_b200_step')
        import :: c_int
        integer(c_int), value :: handle, nsteps
+     end function
+     integer(c_int) function nekcem_b200_step_streamed(handle, hn_in, en_in, hn_out, en_out) &
+          bind(C, name='nekcem_b200_step_streamed')
+       import :: c_int, c_double
+       integer(c_int), value :: handle
+       real(c_double), intent(in) :: hn_in(*), en_in(*)
+       real(c_double), intent(out) :: hn_out(*), en_out(*)
+     end function
+     integer(c_int) function nekcem_b200_device_count() bind(C, name='nekcem_b200_device_count')
+       import :: c_int
      end function
      integer(c_int) function nekcem_b200_stage(handle, rkstep) bind(C, name='nekcem_b200_stage')
        import :: c_int

@@ -221,6 +221,22 @@ int nekcem_b200_apply_filter(int handle);
 int nekcem_b200_set_time(int handle, double time, double dt);
 int nekcem_b200_get_time(int handle, double *time);
 int nekcem_b200_step(int handle, int nsteps);
+/* Number of CUDA devices visible to the process (rank -> device mapping of the shims; replaces
+ * the reference's `devid = rank % 2`, src/cem_mxm_gpu.cu:430-437). */
+int nekcem_b200_device_count(void);
+
+/* The same time step for callers that keep the fields on the HOST and exchange them every step
+ * (the `!$ACC UPDATE DEVICE(hn,en)` ... `!$ACC UPDATE HOST(hn,en)` seams around cem_maxwell_op_rk,
+ * tests/drude/drude.usr:94, tests/3dboxper/3dboxper.usr:199) on a STREAM of inputs: each call
+ * uploads one input state (hn_in, en_in: 3*npts doubles each, pinned host memory for the copies to
+ * be asynchronous), advances the state the PREVIOUS call uploaded by one time step, and returns
+ * the result the previous call computed (hn_out, en_out) -- so the host-to-device copy of input
+ * k+1, the five fused stages of input k and the device-to-host copy of result k-1 run
+ * concurrently (PCIe is full duplex; the copies use staging buffers no kernel touches, roles
+ * change by pointer swaps).  NULL inputs drain the pipeline; NULL outputs discard a result.
+ * A context used this way must not mix in nekcem_b200_step calls without draining first. */
+int nekcem_b200_step_streamed(int handle, const double *hn_in, const double *en_in, double *hn_out,
+                              double *en_out);
 /* One RK stage (rkstep = 1..5) for stage-level parity tests. */
 int nekcem_b200_stage(int handle, int rkstep);
 int nekcem_b200_synchronize(int handle);

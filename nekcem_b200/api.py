@@ -114,6 +114,8 @@ def lib():
         L.nekcem_b200_set_time.argtypes = [C.c_int, C.c_double, C.c_double]
         L.nekcem_b200_get_time.argtypes = [C.c_int, c_dp]
         L.nekcem_b200_step.argtypes = [C.c_int, C.c_int]
+        L.nekcem_b200_step_streamed.argtypes = [C.c_int, c_dp, c_dp, c_dp, c_dp]
+        L.nekcem_b200_device_count.argtypes = []
         L.nekcem_b200_stage.argtypes = [C.c_int, C.c_int]
         L.nekcem_b200_synchronize.argtypes = [C.c_int]
         L.nekcem_b200_apply_rhs.argtypes = [C.c_int, C.c_double]
@@ -430,6 +432,18 @@ class MaxwellB200:
             self.synchronize()
 
     step = cem_maxwell_op_rk
+
+    def step_streamed(self, hn_in=None, en_in=None, hn_out=None, en_out=None):
+        """One time step on a stream of host inputs (nekcem_b200_step_streamed): uploads
+        (hn_in, en_in), advances the state the previous call uploaded, returns the result the
+        previous call computed into (hn_out, en_out).  Arrays: float64, 3*npts, C-contiguous;
+        pinned memory makes the copies overlap the stage kernels.  None drains / discards."""
+        def p(a):
+            if a is None:
+                return None
+            assert a.dtype == np.float64 and a.flags.c_contiguous and a.size == 3 * self.npts
+            return a.ctypes.data_as(c_dp)
+        _chk(self.L.nekcem_b200_step_streamed(self.h, p(hn_in), p(en_in), p(hn_out), p(en_out)))
 
     def stage(self, rkstep: int):
         _chk(self.L.nekcem_b200_stage(self.h, rkstep))

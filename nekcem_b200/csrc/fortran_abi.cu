@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <cuda_runtime.h>
 #include "../../include/nekcem_b200.h"
 
 #define NKB_EXPORT extern "C" __attribute__((visibility("default")))
@@ -132,9 +133,40 @@ NKB_EXPORT void nekcem_b200_set_incident_(const int *h, const int *ninc, const i
           "nekcem_b200_set_incident");
 }
 
-NKB_EXPORT void nekcem_b200_set_option_(const int *h, const char *name, const int *value)
+// Fortran CHARACTER arguments are not NUL-terminated: the compiler passes the length as a hidden
+// trailing argument by value (gfortran >= 8: size_t; older compilers: int -- read as the low half
+// of the same register / stack slot on the little-endian targets this library is built for).
+// The name is copied, blank-trimmed and terminated here.
+NKB_EXPORT void nekcem_b200_set_option_(const int *h, const char *name, const int *value,
+                                        size_t name_len)
 {
-    check(nekcem_b200_set_option(*h, name, *value), "nekcem_b200_set_option");
+    char buf[64];
+    // no plausible length (a C caller of the twin passes none): take the string as NUL-terminated
+    size_t n = (name_len == 0 || name_len > sizeof(buf) - 1) ? sizeof(buf) - 1 : name_len;
+    // a C caller of the twin (tests) passes a NUL-terminated string and no length: garbage or huge
+    // name_len is cut at the first NUL
+    size_t k = 0;
+    while (k < n && name[k] != '\0') { buf[k] = name[k]; k++; }
+    while (k > 0 && buf[k - 1] == ' ') k--;
+    buf[k] = '\0';
+    check(nekcem_b200_set_option(*h, buf, *value), "nekcem_b200_set_option");
+}
+
+// number of CUDA devices visible to this process: the shim maps rank -> device with it
+// (replaces the reference's `devid = rank % 2`, src/cem_mxm_gpu.cu:430-437)
+NKB_EXPORT void nekcem_b200_device_count_(int *ndev)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) n = 0;
+    *ndev = n;
+}
+
+// replaces `!$ACC UPDATE DEVICE(hn,en)` + `call cem_maxwell_op_rk` + `!$ACC UPDATE HOST(hn,en)` for
+// callers that exchange the fields with the host every step (nekcem_b200.h: step_streamed)
+NKB_EXPORT void nekcem_b200_step_streamed_(const int *h, const double *hn_in, const double *en_in,
+                                           double *hn_out, double *en_out)
+{
+    check(nekcem_b200_step_streamed(*h, hn_in, en_in, hn_out, en_out), "nekcem_b200_step_streamed");
 }
 
 NKB_EXPORT void nekcem_b200_error_sums_(const int *h, const double *exact_hn,

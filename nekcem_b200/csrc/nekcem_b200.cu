@@ -204,7 +204,11 @@ struct Ctx {
     double *xtr[2] = {nullptr, nullptr};
     int64_t ldx = 0;
     bool xtr_valid = false; // xtr[cur] holds the traces of u[cur]
-    int opt_pipeline_ctas = 0; // > 0: cap the persistent grid (tests: many items per CTA on small meshes)
+    int opt_pipeline_ctas = 0;
+    // nekcem_b200_step_streamed: staging buffers (next input / previous result) and their streams
+    double *st_in = nullptr, *st_out = nullptr;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    bool st_have_input = false, st_have_result = false; // > 0: cap the persistent grid (tests: many items per CTA on small meshes)
     bool masses_same = false;
     bool geom_scanned = false;
     int64_t n_const_metric_el = 0;
@@ -1184,6 +1188,9 @@ int nekcem_b200_destroy(int handle)
         for (auto &p : c->dev) cudaFree(p);
         cudaFree(c->u[0]); cudaFree(c->u[1]); cudaFree(c->kf);
         cudaFree(c->xtr[0]); cudaFree(c->xtr[1]);
+        cudaFree(c->st_in); cudaFree(c->st_out);
+        if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+        if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
         cudaFree(c->hY); cudaFree(c->hZ); cudaFree(c->vmapP_d); cudaFree(c->elist_d);
         cudaFree(c->sendbuf); cudaFree(c->halo); cudaFree(c->send_node);
         cudaFree(c->src_prof); cudaFree(c->red_d);
@@ -1978,6 +1985,83 @@ int nekcem_b200_step(int handle, int nsteps)
     }
     CUDA_OK(cudaEventRecord(c->ev_t1, c->s_compute));
     return 0;
+}
+
+// One time step per call on a STREAM of host inputs: the fields advanced by this call are the
+// ones the previous call uploaded, the result handed back is the one the previous call computed.
+// Copies run on their own streams into / out of staging buffers that no kernel touches, so PCIe
+// in both directions overlaps the five stage launches; the buffers change roles by pointer swaps.
+int nekcem_b200_step_streamed(int handle, const double *hn_in, const double *en_in, double *hn_out,
+                              double *en_out)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (!c->setup_done) return fail("nekcem_b200_setup has not completed");
+    if (c->dt == 0.0) return fail("dt is zero: call nekcem_b200_set_time");
+    if ((hn_in == nullptr) != (en_in == nullptr) || (hn_out == nullptr) != (en_out == nullptr))
+        return fail("step_streamed: hn/en pointers must be given in pairs");
+    CUDA_OK(cudaSetDevice(c->d.device));
+    if (!c->st_in) {
+        CUDA_OK(cudaMalloc(&c->st_in, sizeof(double) * 6 * c->ld));
+        CUDA_OK(cudaMalloc(&c->st_out, sizeof(double) * 6 * c->ld));
+        CUDA_OK(cudaMemset(c->st_in, 0, sizeof(double) * 6 * c->ld));
+        CUDA_OK(cudaMemset(c->st_out, 0, sizeof(double) * 6 * c->ld));
+        CUDA_OK(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+        CUDA_OK(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+        CUDA_OK(cudaDeviceSynchronize());
+    }
+    const size_t row = sizeof(double) * c->npts, pitch = sizeof(double) * c->ld;
+    // (1) next input: host -> st_in
+    if (hn_in) {
+        CUDA_OK(cudaMemcpy2DAsync(c->st_in, pitch, hn_in, row, row, 3, cudaMemcpyHostToDevice, c->s_h2d));
+        CUDA_OK(cudaMemcpy2DAsync(c->st_in + 3 * c->ld, pitch, en_in, row, row, 3,
+                                  cudaMemcpyHostToDevice, c->s_h2d));
+    }
+    // (2) previous result: st_out -> host
+    const bool give = c->st_have_result && hn_out;
+    if (give) {
+        CUDA_OK(cudaMemcpy2DAsync(hn_out, row, c->st_out, pitch, row, 3, cudaMemcpyDeviceToHost, c->s_d2h));
+        CUDA_OK(cudaMemcpy2DAsync(en_out, row, c->st_out + 3 * c->ld, pitch, row, 3,
+                                  cudaMemcpyDeviceToHost, c->s_d2h));
+    }
+    // (3) one time step on the input the previous call delivered
+    const bool compute = c->st_have_input;
+    c->last_launches = 0;
+    CUDA_OK(cudaEventRecord(c->ev_t0, c->s_compute));
+    if (compute) {
+        for (int rk = 1; rk <= 5; rk++)
+            if (run_stage(c, rk)) return 1;
+        if (apply_filter(c)) return 1;
+        c->time = c->time + c->dt;
+    }
+    CUDA_OK(cudaEventRecord(c->ev_t1, c->s_compute));
+    CUDA_OK(cudaStreamSynchronize(c->s_h2d));
+    CUDA_OK(cudaStreamSynchronize(c->s_d2h));
+    CUDA_OK(cudaStreamSynchronize(c->s_compute));
+    if (c->has_comm) CUDA_OK(cudaStreamSynchronize(c->s_comm));
+    // (4) rotate: result -> st_out, next input -> current fields
+    if (compute) {
+        std::swap(c->st_out, c->u[c->cur]);
+        c->st_have_result = true;
+    } else if (give) {
+        c->st_have_result = false;
+    }
+    if (hn_in) {
+        std::swap(c->st_in, c->u[c->cur]);
+        c->xtr_valid = false;
+        if (c->d.ldim == 2) // the 2D kernels never write the inactive components
+            CUDA_OK(cudaMemcpy(c->u[c->cur ^ 1], c->u[c->cur], sizeof(double) * 6 * c->ld,
+                               cudaMemcpyDeviceToDevice));
+    }
+    c->st_have_input = hn_in != nullptr;
+    return 0;
+}
+
+int nekcem_b200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
 }
 
 int nekcem_b200_synchronize(int handle)

@@ -1,4 +1,3 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-bash scripts/sweep_variants.sh "8:36 const_metrics=0 pipeline=1" v9c v9d
-bash scripts/sweep_variants.sh "9:32 const_metrics=0 pipeline=1" v10d
-python scripts/sweep.py 7:48 8:40 9:36 const_metrics=0,1 pipeline=1
+timeout 600 python -m pytest tests/test_gpu_pipe.py -q -x -k "streamed or agrees" 2>&1 | tail -5
+(time python bench.py --steps 10 --warmup 3) 2> gpurun_out/bench_r2_a.err | tee gpurun_out/bench_r2_a.json | cut -c1-3000
+tail -5 gpurun_out/bench_r2_a.err

@@ -400,3 +400,43 @@ def test_shim_registers_drude_arrays_of_a_padded_size_on_the_host():
         r.close()
     finally:
         del os.environ["NEKCEM_B200_HOST_ONLY"]
+
+
+def test_f2003_module_interfaces_match_the_header():
+    """every `bind(C)` interface of fortran/nekcem_b200_mod.F90 has the argument count (and the
+    by-value scalars) of the prototype in include/nekcem_b200.h -- the module is source only (no
+    Fortran compiler in the image), so a stale interface would otherwise go unnoticed"""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "nekcem_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\bint\s+(nekcem_b200_\w+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        args = [a.strip() for a in m.group(2).replace("\n", " ").split(",")]
+        if args == ["void"] or args == [""]:
+            args = []
+        protos[m.group(1)] = args
+    mod = open(os.path.join(ROOT, "fortran", "nekcem_b200_mod.F90")).read()
+    mod = re.sub(r"&\s*\n\s*", " ", mod)
+    found = 0
+    for m in re.finditer(r"function\s+(nekcem_b200_\w+)\s*\(([^)]*)\)(.*?)end function", mod, flags=re.S | re.I):
+        name, fargs, body = m.group(1), [a.strip() for a in m.group(2).split(",") if a.strip()], m.group(3)
+        if name == "nekcem_b200_last_error":  # returns const char *, not an int status
+            continue
+        assert name in protos, f"{name}: in the module but not in the header"
+        cargs = protos[name]
+        assert len(fargs) == len(cargs), (name, fargs, cargs)
+        # scalars passed by value in C must carry the `value` attribute in the interface
+        byval, cptr = set(), set()
+        for line in body.splitlines():
+            if "::" not in line:
+                continue
+            names = [v.strip().split("(")[0] for v in line.split("::")[1].split(",")]
+            if "value" in line.split("::")[0].lower():
+                byval.update(names)
+            if "c_ptr" in line.split("::")[0].lower():
+                cptr.update(names)  # type(c_ptr), value  ==  void * in C
+        for fa, ca in zip(fargs, cargs):
+            c_is_value = "*" not in ca and "[" not in ca
+            assert (fa in byval and fa not in cptr) == c_is_value, (name, fa, ca)
+        found += 1
+    assert found >= 20

@@ -119,3 +119,25 @@ def test_pipe_deformed_elements(nx1):
     c.step(3); s.step(3)
     assert rel_l2(_fields(s), _fields(c)) <= TOL
     s.close()
+
+
+def test_step_streamed_equals_step():
+    """nekcem_b200_step_streamed: each call uploads one input, advances the previous one, returns
+    the result before that -- every result is bit for bit one nekcem_b200_step of its input"""
+    from oracle import cases
+    c = cases.case_boxper((3, 3, 4), 8, dt=-1e-3)
+    a = solver_from_refcase(c)
+    b = solver_from_refcase(c)
+    h0, e0 = a.hn.copy(), a.en.copy()
+    a.step(1)
+    h1, e1 = a.hn.copy(), a.en.copy()
+    a.step(1)
+    h2, e2 = a.hn.copy(), a.en.copy()
+    ho, eo = np.empty_like(h0), np.empty_like(e0)
+    b.step_streamed(h0, e0, None, None)      # upload state 0
+    b.step_streamed(h1, e1, None, None)      # advance state 0, upload state 1
+    b.step_streamed(None, None, ho, eo)      # advance state 1, hand back the result of state 0
+    assert np.array_equal(ho, h1) and np.array_equal(eo, e1)
+    b.step_streamed(None, None, ho, eo)      # drain: the result of state 1
+    assert np.array_equal(ho, h2) and np.array_equal(eo, e2)
+    a.close(); b.close()
