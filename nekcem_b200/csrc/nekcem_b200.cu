@@ -797,7 +797,7 @@ int ensure_dev(Ctx *c, int which)
     if (c->dev[which]) return 0;
     const int64_t cnt = array_count(c, which);
     CUDA_OK(cudaMalloc(&c->dev[which], sizeof(double) * cnt));
-    CUDA_OK(cudaMemset(c->dev[which], 0, sizeof(double) * cnt));
+    CUDA_OK(cudaMemsetAsync(c->dev[which], 0, sizeof(double) * cnt, c->s_compute));
     return 0;
 }
 
@@ -1077,11 +1077,13 @@ int apply_filter(Ctx *c)
     if (!c->filter_d) return 0;
     const int n = c->n, nz = c->d.ldim == 3 ? n : 1;
     const size_t smem = sizeof(double) * (2 * (size_t)c->nxyz + (size_t)n * n);
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {}; // per device
+    const int dev = c->d.device;
+    if (dev < 0 || dev >= 64) return fail("device index %d out of range", dev);
+    if (!configured[dev]) {
         CUDA_OK(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)(sizeof(double) * (2 * 4096 + 256))));
-        configured = true;
+        configured[dev] = true;
     }
     const int nt = c->nxyz >= 256 ? 256 : ((c->nxyz + 31) / 32) * 32;
     filter_kernel<<<dim3((unsigned)c->d.nelt, 6), nt, smem, c->s_compute>>>(
@@ -1231,17 +1233,22 @@ int nekcem_b200_set_array(int handle, int which, const double *host, int64_t cou
         double *base = (which == NKB_HN || which == NKB_EN) ? c->u[c->cur] : c->kf;
         const int c0 = (which == NKB_HN || which == NKB_KHN) ? 0 : 3;
         c->xtr_valid = false;
-        CUDA_OK(cudaMemcpy2D(base + c0 * c->ld, sizeof(double) * c->ld, host,
-                             sizeof(double) * c->npts, sizeof(double) * c->npts, 3,
-                             cudaMemcpyHostToDevice));
+        // on the compute stream (the kernels' streams are non-blocking: a copy on the legacy
+        // stream would not be ordered against them), completed before returning
+        CUDA_OK(cudaMemcpy2DAsync(base + c0 * c->ld, sizeof(double) * c->ld, host,
+                                  sizeof(double) * c->npts, sizeof(double) * c->npts, 3,
+                                  cudaMemcpyHostToDevice, c->s_compute));
         // 2D modes never write the inactive components: keep both ping-pong buffers alike
         if (c->d.ldim == 2 && (which == NKB_HN || which == NKB_EN))
-            CUDA_OK(cudaMemcpy2D(c->u[c->cur ^ 1] + c0 * c->ld, sizeof(double) * c->ld, host,
-                                 sizeof(double) * c->npts, sizeof(double) * c->npts, 3,
-                                 cudaMemcpyHostToDevice));
+            CUDA_OK(cudaMemcpy2DAsync(c->u[c->cur ^ 1] + c0 * c->ld, sizeof(double) * c->ld, host,
+                                      sizeof(double) * c->npts, sizeof(double) * c->npts, 3,
+                                      cudaMemcpyHostToDevice, c->s_compute));
+        CUDA_OK(cudaStreamSynchronize(c->s_compute));
     } else {
         if (ensure_dev(c, which)) return 1;
-        CUDA_OK(cudaMemcpy(c->dev[which], host, sizeof(double) * count, cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMemcpyAsync(c->dev[which], host, sizeof(double) * count, cudaMemcpyHostToDevice,
+                                c->s_compute));
+        CUDA_OK(cudaStreamSynchronize(c->s_compute));
         if (which == NKB_DXM1) c->D_host.assign(host, host + count);
         if ((which >= NKB_RXMN && which <= NKB_TZMN) || which == NKB_HBM1 || which == NKB_EBM1)
             c->geom_scanned = false;

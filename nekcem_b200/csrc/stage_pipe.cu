@@ -49,6 +49,9 @@ namespace {
 #ifndef PIPE_L2_AHEAD
 #define PIPE_L2_AHEAD 0 // 1: L2 prefetch of the next item's fields and rx..sz one item ahead
 #endif
+#ifndef PIPE_XOUT
+#define PIPE_XOUT 1 // 1: the x-face mirror is written coalesced from shared memory
+#endif
 #ifndef PIPE_SKIP
 #define PIPE_SKIP 0 // timing experiments only (wrong results): 1 P1, 2 P2, 4 flux, 8 P4, 16 relayout
 #endif
@@ -102,7 +105,8 @@ struct PT {
 #ifdef PIPE_NT
     static constexpr int NT = PIPE_NT;
 #else
-    static constexpr int NT = (KS == 1 && N >= 9) ? 512 : p_max(p_nt_for(RS_ITEMS), p_round32(N2));
+    static constexpr int NT = (KS == 1 && N == 10) ? 640 : (KS == 1 && N == 9) ? 512
+                              : p_max(p_nt_for(RS_ITEMS), p_round32(N2));
 #endif
     static constexpr int SC = Lay<N>::SK * KB; // component stride in U and R
     static constexpr int XL = p_even(N2 * KB + 2); // linear slab of one array + alignment slack
@@ -149,7 +153,8 @@ struct PT {
     __host__ __device__ static constexpr int kb(int s) { return (s + 1) * N / KS - s * N / KS; }
     static constexpr int MINB_SMEM = (227 * 1024) / ((int)SMEM + 1024);
     static constexpr int MINB_THR = 2048 / NT;
-    static constexpr int MINB_REG = 65536 / (NT * PIPE_REGS);
+    static constexpr int REGS = NT > 512 ? 96 : PIPE_REGS;
+    static constexpr int MINB_REG = 65536 / (NT * REGS);
     static constexpr int MINB0 = p_min(p_min(MINB_SMEM, MINB_THR), MINB_REG);
     static constexpr int MINB = MINB0 < 1 ? 1 : (MINB0 > 4 ? 4 : MINB0);
 };
@@ -561,6 +566,21 @@ __global__ void __launch_bounds__(PT<N, KS>::NT, PT<N, KS>::MINB)
     const int pi = pnd % N, pj = pnd / N;
     const bool pok = ps < NPL;
 
+    // x-face mirror of an item's new fields: R (parked by its epilogue) -> global, 2*N*kb
+    // consecutive entries per component and side.  Runs after the item's last barrier and before
+    // the next item's P1 touches R.
+    auto xout = [&](int pe, int psl) {
+        const int pk0 = C::k0(psl), cnt = N * C::kb(psl);
+        for (int v = tid; v < 12 * cnt; v += NT) {
+            const int cs = v / cnt, p = v - cs * cnt;   // (component, side), point j + N*kl
+            const int c = cs >> 1, side = cs & 1;
+            const int j = p % N, kl = p / N;
+            a.xtr_out[c * a.ldx + (2ll * pe + side) * N2 + N * pk0 + p] =
+                R[c * SC + (c >= 3 ? HE : 0) + Lay<N>::at(side ? N - 1 : 0, j, kl)];
+        }
+    };
+    int xo_e = -1, xo_s = 0; // item whose mirror entries still sit in R
+
     uint32_t par = 0;
 #pragma unroll 1
     for (; q < nitems; q += G, par ^= 1) {
@@ -579,6 +599,8 @@ __global__ void __launch_bounds__(PT<N, KS>::NT, PT<N, KS>::MINB)
             face_point(f, s, fjs[f], fsn[f], fyi[f]);
             if (KS > 1) fyi[f] += (int)(((long long)e * NF) & 1);
         }
+
+        if (PIPE_XOUT && xo_e >= 0) xout(xo_e, xo_s);
 
         // ---- P0: fields of the slab: landing zone -> U (bank-conflict-free layout) -------------
         mbar_wait(b_fld, par);
@@ -876,21 +898,27 @@ __global__ void __launch_bounds__(PT<N, KS>::NT, PT<N, KS>::MINB)
                         const double un = o[c] + a.cb * t;
                         __stcs(a.kf + (cb0 + c) * a.ld + gi, t);
                         __stcs(a.u_out + (cb0 + c) * a.ld + gi, un);
-                        // x-face mirror of the new fields (stage_args.h)
-                        if (!(PIPE_SKIP & 128) && a.xtr_out != nullptr && (pi == 0 || pi == N - 1))
-                            a.xtr_out[(cb0 + c) * a.ldx + (2ll * e + (pi ? 1 : 0)) * N2 + pj +
-                                      N * (k0 + kl)] = un;
+                        // x-face mirror of the new fields (stage_args.h): parked in this node's
+                        // (now dead) residual slot, written out coalesced by xout() below
+                        if (!(PIPE_SKIP & 128) && a.xtr_out != nullptr && (pi == 0 || pi == N - 1)) {
+                            if (PIPE_XOUT) R[(cb0 + c) * SC + sn] = un;
+                            else
+                                a.xtr_out[(cb0 + c) * a.ldx + (2ll * e + (pi ? 1 : 0)) * N2 + pj +
+                                          N * (k0 + kl)] = un;
+                        }
                     }
                 }
             }
         }
         __syncthreads();
         if (w0 && more && !CM) issue_cof(en, sn_);
+        if (PIPE_XOUT && !(PIPE_SKIP & 128) && a.xtr_out != nullptr) { xo_e = e; xo_s = s; }
         e = en;
         en = enn;
 #pragma unroll
         for (int f = 0; f < FPT; f++) fvp[f] = fvn[f];
     }
+    if (PIPE_XOUT && xo_e >= 0) xout(xo_e, xo_s);
 }
 
 template <int N, bool PML, bool CM>

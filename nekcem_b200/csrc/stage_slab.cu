@@ -740,13 +740,16 @@ int launch_inst(const StageParams<N> &prm, cudaStream_t st)
 {
     constexpr int KS = ks_for(N);
     using C = Slab<N, KS>;
-    static bool configured = false;
-    if (!configured) {
+    // the opt-in to > 48 KB of dynamic shared memory is a per-device attribute
+    static bool configured[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 1;
+    if (!configured[dev]) {
         if (cudaFuncSetAttribute(slab_kernel<N, KS, PML, CM>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)C::SMEM) != cudaSuccess)
             return 1;
-        configured = true;
+        configured[dev] = true;
     }
     slab_kernel<N, KS, PML, CM><<<KS * prm.a.nel, C::NT, C::SMEM, st>>>(prm);
     return cudaGetLastError() == cudaSuccess ? 0 : 2;
