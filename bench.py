@@ -258,6 +258,7 @@ def run_gpu(args):
         return float(t.item())
 
     peak, peak_src = measured_peak()
+    transports = set()
 
     def make(nel, order, nranks=world, myrank=rank, general=True):
         """solver for a periodic box of nel elements at order N, partitioned over nranks"""
@@ -274,7 +275,10 @@ def run_gpu(args):
             slv.comm_init(bytes(uid.cpu().numpy().tobytes()))
         if general:
             slv.set_option("const_metrics", 0)
+        if args.transport == "nccl":
+            slv.set_option("p2p", 0)
         slv.setup()
+        transports.add(slv.transport())
         # CFL-limited dt as in the synthetic .rea (param(12)=+0.1 -> dt = 0.1*dxmin)
         z, _ = gll(nx1)
         dxmin = 0.5 * min(case.h) * 0.5 * float(np.min(z[2:] - z[:-2])) if nx1 > 2 else min(case.h)
@@ -468,7 +472,8 @@ def run_gpu(args):
                             f"(global {nel[0]}x{nel[1]}x{nel[2]}), 3dboxper initial condition, "
                             "upwind flux, LSRK(5,4)",
                 "nodes_global": npts_global, "dof_unit": "grid node (6 field components)",
-                "dt": dt, "partition": "reference pencil map (z-slabs), NCCL face exchange",
+                "dt": dt, "partition": "reference pencil map (z-slabs)",
+                "face_exchange": sorted(transports),
                 "l2_flush": "inputs larger than L2 (one stage streams >> 126 MB)",
                 "metrics_variant": (
                     "general path: every geometry array streamed per node (what a mesh whose "
@@ -570,6 +575,9 @@ def main():
                          "path, what a mesh with round-off noise in its metrics (any mesh out of "
                          "the reference's glmapm1) gets; auto: exploit exact redundancy of the "
                          "geometry found at setup")
+    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"],
+                    help="inter-GPU face exchange: stores into the peers' halo buffers over NVLink "
+                         "(default) or grouped ncclSend/ncclRecv")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: --elems^3 per GPU (default); strong: --elems^3 in total")
     args = ap.parse_args()

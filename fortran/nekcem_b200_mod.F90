@@ -129,6 +129,17 @@ module nekcem_b200
        real(c_double), intent(in) :: hn_in(*), en_in(*)
        real(c_double), intent(out) :: hn_out(*), en_out(*)
      end function
+     integer(c_int) function nekcem_b200_restart_ingest(handle, which, as_double, payload) &
+          bind(C, name='nekcem_b200_restart_ingest')
+       import :: c_int, c_ptr
+       integer(c_int), value :: handle, which, as_double
+       type(c_ptr), value :: payload
+     end function
+     integer(c_int) function nekcem_b200_transport(handle, kind) bind(C, name='nekcem_b200_transport')
+       import :: c_int, c_int32_t
+       integer(c_int), value :: handle
+       integer(c_int32_t), intent(out) :: kind
+     end function
      integer(c_int) function nekcem_b200_device_count() bind(C, name='nekcem_b200_device_count')
        import :: c_int
      end function

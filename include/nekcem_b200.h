@@ -221,6 +221,11 @@ int nekcem_b200_apply_filter(int handle);
 int nekcem_b200_set_time(int handle, double time, double dt);
 int nekcem_b200_get_time(int handle, double *time);
 int nekcem_b200_step(int handle, int nsteps);
+/* Transport of the inter-rank face exchange chosen at setup: 0 = no inter-rank faces, 1 = grouped
+ * ncclSend/ncclRecv on a side stream, 2 = stores into the peers' halo buffers over NVLink (CUDA
+ * IPC), fused with the pack kernel. */
+int nekcem_b200_transport(int handle, int32_t *kind);
+
 /* Number of CUDA devices visible to the process (rank -> device mapping of the shims; replaces
  * the reference's `devid = rank % 2`, src/cem_mxm_gpu.cu:430-437). */
 int nekcem_b200_device_count(void);
@@ -314,6 +319,19 @@ int nekcem_b200_error_sums_planewave(int handle, const nekcem_b200_planewave *wa
  * 12 B/node over PCIe instead of 48 and the host touches no node. */
 int nekcem_b200_vtk_payload(int handle, int which, int as_double, void *out);
 
+/* Restart hand-off, read side.  Replaces the field part of `restart_swap` (src/io.F:637-781; called
+ * from cem_maxwell_init_fields when ifrestart, src/cem_maxwell.F:200-202): payload = the bytes
+ * readfield4 / readfield4_double deliver for one "VECTORS" section of a restart file written by
+ * cem_restart_out / cem_out (src/io.F:411-491) -- three values per node, big-endian, float32 (as_double
+ * = 0, param(87) != 0) or float64 --, in this rank's element order (i.e. after the reference's
+ * swap_real_backward, which stays with the file I/O on the host).  Byte swap, cast and
+ * de-interleave (save2vectors, src/io.F:790-810) run on the device: which = 0 fills EN, 1 fills HN.
+ * The exact inverse of nekcem_b200_vtk_payload.  The reference's restart files hold EN and HN only;
+ * the rest of the state (RK registers, PML fields, ADE and sheet currents) travels through
+ * nekcem_b200_get_array / set_array / get_ade / get_graphene, see tests
+ * test_checkpoint_resume_full_state_bitwise. */
+int nekcem_b200_restart_ingest(int handle, int which, int as_double, const void *payload);
+
 /* Device-time of the last nekcem_b200_step call in milliseconds (CUDA events on the
  * compute stream) and the number of kernels it launched. */
 int nekcem_b200_last_step_ms(int handle, float *ms, int64_t *launches);
@@ -321,7 +339,10 @@ int nekcem_b200_last_step_ms(int handle, float *ms, int64_t *launches);
 /* Options.  "external_exchange": see nekcem_b200_stage_pack.  Performance tunables (no effect on
  * results): "pipeline" (default 1): 1 = the persistent bulk-copy stage kernel (stage_pipe.cu) for
  * the orders it covers, 0 = the slab kernel (stage_slab.cu) for every order; "pipeline_ctas"
- * (default 0 = fill the device): upper bound on the persistent kernel's grid.
+ * (default 0 = fill the device): upper bound on the persistent kernel's grid; "p2p" (default 1, read
+ * at setup, the same on every rank): inter-GPU face exchange by stores into the peers' halo
+ * buffers over NVLink (CUDA IPC) instead of ncclSend/ncclRecv; "xtrace" (default 1, read at
+ * setup): neighbour traces across x faces from a compact mirror of the fields.
  * "const_metrics" (default 1): exploit exact, bitwise redundancy found in the geometry at setup
  * -- elements whose nine cofactors rxmn..tzmn (src/GEOM:30-45) hold one value each over the
  * whole element read them once per element instead of once per node, and bitwise identical

@@ -110,12 +110,14 @@ def lib():
         L.nekcem_b200_set_filter.argtypes = [C.c_int, c_dp]
         L.nekcem_b200_apply_filter.argtypes = [C.c_int]
         L.nekcem_b200_vtk_payload.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.nekcem_b200_restart_ingest.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.nekcem_b200_geometry_info.argtypes = [C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]
         L.nekcem_b200_set_time.argtypes = [C.c_int, C.c_double, C.c_double]
         L.nekcem_b200_get_time.argtypes = [C.c_int, c_dp]
         L.nekcem_b200_step.argtypes = [C.c_int, C.c_int]
         L.nekcem_b200_step_streamed.argtypes = [C.c_int, c_dp, c_dp, c_dp, c_dp]
         L.nekcem_b200_device_count.argtypes = []
+        L.nekcem_b200_transport.argtypes = [C.c_int, C.POINTER(C.c_int32)]
         L.nekcem_b200_stage.argtypes = [C.c_int, C.c_int]
         L.nekcem_b200_synchronize.argtypes = [C.c_int]
         L.nekcem_b200_apply_rhs.argtypes = [C.c_int, C.c_double]
@@ -412,6 +414,16 @@ class MaxwellB200:
         _chk(self.L.nekcem_b200_vtk_payload(self.h, w, int(as_double), buf.ctypes.data_as(C.c_void_p)))
         return buf.tobytes()
 
+    def restart_ingest(self, which: str, payload: bytes, as_double: bool = True):
+        """The field part of ``restart_swap`` (src/io.F:637-781): fill EN ('en') or HN ('hn') from
+        the big-endian "VECTORS" section of a restart file (float32 unless as_double), this rank's
+        element order; byte swap, cast and de-interleave run on the device."""
+        w = {"en": 0, "hn": 1}[which]
+        buf = np.frombuffer(payload, dtype=np.uint8)
+        assert buf.size == 3 * self.npts * (8 if as_double else 4)
+        _chk(self.L.nekcem_b200_restart_ingest(self.h, w, int(as_double),
+                                               buf.ctypes.data_as(C.c_void_p)))
+
     def set_option(self, name: str, value: int):
         _chk(self.L.nekcem_b200_set_option(self.h, name.encode(), int(value)))
 
@@ -432,6 +444,12 @@ class MaxwellB200:
             self.synchronize()
 
     step = cem_maxwell_op_rk
+
+    def transport(self) -> str:
+        """transport of the inter-rank face exchange chosen at setup"""
+        k = C.c_int32(0)
+        _chk(self.L.nekcem_b200_transport(self.h, C.byref(k)))
+        return {0: "none", 1: "nccl-sendrecv", 2: "peer-memory-push"}[int(k.value)]
 
     def step_streamed(self, hn_in=None, en_in=None, hn_out=None, en_out=None):
         """One time step on a stream of host inputs (nekcem_b200_step_streamed): uploads

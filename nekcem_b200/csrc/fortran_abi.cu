@@ -152,6 +152,14 @@ NKB_EXPORT void nekcem_b200_set_option_(const int *h, const char *name, const in
     check(nekcem_b200_set_option(*h, buf, *value), "nekcem_b200_set_option");
 }
 
+// replaces the field part of `restart_swap` (src/io.F:764-775): payload = what readfield4[_double]
+// delivered, after swap_real_backward
+NKB_EXPORT void nekcem_b200_restart_ingest_(const int *h, const int *which, const int *as_double,
+                                            const void *payload)
+{
+    check(nekcem_b200_restart_ingest(*h, *which, *as_double, payload), "nekcem_b200_restart_ingest");
+}
+
 // number of CUDA devices visible to this process: the shim maps rank -> device with it
 // (replaces the reference's `devid = rank % 2`, src/cem_mxm_gpu.cu:430-437)
 NKB_EXPORT void nekcem_b200_device_count_(int *ndev)

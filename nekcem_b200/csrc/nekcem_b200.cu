@@ -62,6 +62,13 @@ int fail(const char *fmt, ...)
             return fail("NCCL error at %s:%d: %s", __FILE__, __LINE__, (g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?")); \
     } while (0)
 
+// one destination of pack_push_kernel (device table)
+struct PushPeer {
+    double *dst[2];            // the peer's halo slice for this rank, even / odd stages
+    unsigned long long *flag;  // the peer's flag for this rank
+    long long src_off, count;  // this rank's send slice: face points [src_off, src_off + count)
+};
+
 struct Peer {
     int rank = -1;
     std::vector<int64_t> send_fp; // local face points, sorted by shared id
@@ -205,6 +212,17 @@ struct Ctx {
     int64_t ldx = 0;
     bool xtr_valid = false; // xtr[cur] holds the traces of u[cur]
     int opt_pipeline_ctas = 0;
+    // Inter-GPU face exchange over peer memory (default when every peer's buffers can be opened
+    // through CUDA IPC): pack_push_kernel stores the packed traces straight into the peer's halo
+    // buffer over NVLink and raises the peer's flag; no NCCL call in the time loop.
+    bool opt_p2p = true, p2p_ok = false;
+    double *halo2 = nullptr;                 // [2][6*nhalo]: halo of even / odd stages
+    unsigned long long *flags_d = nullptr;   // [nranks]: last stage whose traces rank r delivered
+    unsigned int *done_d = nullptr;          // [npeers] block counters of pack_push_kernel
+    struct PushPeer *push_d = nullptr;       // [npeers]
+    int *peer_rank_d = nullptr;              // [npeers]
+    std::vector<void *> ipc_opened;
+    unsigned long long stage_no = 0;
     // nekcem_b200_step_streamed: staging buffers (next input / previous result) and their streams
     double *st_in = nullptr, *st_out = nullptr;
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
@@ -340,16 +358,16 @@ __global__ void arrays_differ_kernel(const double *a, const double *b, long long
 // pack the traces of the send face points: sendbuf[q][c] = u[c][send_node[q]]
 // (+ the incident field of tagged send face points, so that the peer sees the same trace the
 // reference's gs_op_fields sum would give it)
-__global__ void pack_kernel(const double *u, long long ld, const int *send_node, double *sendbuf,
-                            long long nsend, const int *inc_send, const double *inc_amp,
-                            const double *inc_phase, int inc_n, double inc_wt,
-                            const int *g_send, const int *send_fp, const double *fs_val, int fs_n,
-                            const double *unx, const double *uny, const double *unz)
+// packed trace value t = 6*q + c of the send list (what the peer's face sum needs from this side)
+__device__ __forceinline__ double packed_trace(long long t, const double *u, long long ld,
+                                               const int *send_node, const int *inc_send,
+                                               const double *inc_amp, const double *inc_phase,
+                                               int inc_n, double inc_wt, const int *g_send,
+                                               const int *send_fp, const double *fs_val, int fs_n,
+                                               const double *unx, const double *uny, const double *unz)
 {
-    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (t >= nsend * 6) return;
-    long long q = t / 6;
-    int c = (int)(t - q * 6);
+    const long long q = t / 6;
+    const int c = (int)(t - q * 6);
     double v = u[c * ld + send_node[q]];
     if (inc_send != nullptr) {
         const int qi = inc_send[q];
@@ -369,7 +387,63 @@ __global__ void pack_kernel(const double *u, long long ld, const int *send_node,
             v -= d;
         }
     }
-    sendbuf[t] = v;
+    return v;
+}
+
+__global__ void pack_kernel(const double *u, long long ld, const int *send_node, double *sendbuf,
+                            long long nsend, const int *inc_send, const double *inc_amp,
+                            const double *inc_phase, int inc_n, double inc_wt,
+                            const int *g_send, const int *send_fp, const double *fs_val, int fs_n,
+                            const double *unx, const double *uny, const double *unz)
+{
+    long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= nsend * 6) return;
+    sendbuf[t] = packed_trace(t, u, ld, send_node, inc_send, inc_amp, inc_phase, inc_n, inc_wt,
+                              g_send, send_fp, fs_val, fs_n, unx, uny, unz);
+}
+
+// The exchange that replaces gs_op_fields between ranks (src/cem_maxwell.F:962), fused with the
+// pack: blockIdx.y = peer; every value goes straight into the peer GPU's halo buffer (a store over
+// NVLink into memory opened through CUDA IPC), and the last block of a peer's slice publishes the
+// stage number in the peer's flag after a system-scope fence.  The peer's boundary-element launch
+// is ordered behind wait_flags_kernel, which spins on those flags.
+__global__ void pack_push_kernel(const double *u, long long ld, const int *send_node,
+                                 const PushPeer *tab, int parity, unsigned long long stage_no,
+                                 int me, unsigned int *done, const int *inc_send,
+                                 const double *inc_amp, const double *inc_phase, int inc_n,
+                                 double inc_wt, const int *g_send, const int *send_fp,
+                                 const double *fs_val, int fs_n, const double *unx,
+                                 const double *uny, const double *unz)
+{
+    const PushPeer pp = tab[blockIdx.y];
+    const long long tot = 6 * pp.count;
+    const unsigned int nb = (unsigned int)((tot + blockDim.x - 1) / blockDim.x);
+    if (blockIdx.x >= nb) return;
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t < tot)
+        pp.dst[parity][t] = packed_trace(6 * pp.src_off + t, u, ld, send_node, inc_send, inc_amp,
+                                         inc_phase, inc_n, inc_wt, g_send, send_fp, fs_val, fs_n,
+                                         unx, uny, unz);
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(done + blockIdx.y, 1u);
+        if (prev == nb - 1) {
+            done[blockIdx.y] = 0;
+            __threadfence_system();
+            *(volatile unsigned long long *)(pp.flag + me) = stage_no;
+        }
+    }
+}
+
+__global__ void wait_flags_kernel(const unsigned long long *flags, const int *peer_rank, int npeers,
+                                  unsigned long long stage_no)
+{
+    if ((int)threadIdx.x < npeers) {
+        const volatile unsigned long long *f = flags + peer_rank[threadIdx.x];
+        while (*f < stage_no) { }
+    }
+    __threadfence_system();
 }
 
 // Graphene sheets: one thread per face point of the user's graphindex list advances the surface
@@ -569,6 +643,28 @@ __global__ void vtk_payload_kernel(const double *u, long long ld, long long npts
         const unsigned int lo = (unsigned int)b, hi = (unsigned int)(b >> 32);
         out[t] = ((unsigned long long)__byte_perm(lo, 0, 0x0123) << 32) | __byte_perm(hi, 0, 0x0123);
     }
+}
+
+// The inverse of vtk_payload_kernel: big-endian float32 / float64 triples of a restart file's field
+// section -> the three components of EN or HN (readfield4[_double] + save2vectors,
+// src/io.F:764-775, 790-810).  A float32 restart recovers 7-8 digits, as the reference notes (:664).
+template <typename IN>
+__global__ void restart_ingest_kernel(const IN *in, double *u, long long ld, long long npts)
+{
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= 3 * npts) return;
+    const long long i = t / 3;
+    const int c = (int)(t - 3 * i);
+    double v;
+    if constexpr (sizeof(IN) == 4) {
+        v = (double)__uint_as_float(__byte_perm(in[t], 0, 0x0123));
+    } else {
+        const unsigned long long b = in[t];
+        const unsigned int lo = (unsigned int)b, hi = (unsigned int)(b >> 32);
+        v = __longlong_as_double((long long)(((unsigned long long)__byte_perm(lo, 0, 0x0123) << 32) |
+                                             __byte_perm(hi, 0, 0x0123)));
+    }
+    u[c * ld + i] = v;
 }
 
 // cem_error against a plane wave in two half spaces with a graded PML decay (device-side usersol
@@ -780,6 +876,110 @@ int exchange_singletons_nccl(Ctx *c)
     return plan_remote(c, counts.data(), all.data());
 }
 
+// Peer-memory transport of the face exchange: every rank publishes CUDA IPC handles of its halo
+// and flag buffers plus the offsets at which it expects each peer's traces (one NCCL all-gather at
+// setup); afterwards the time loop needs no NCCL call.  All ranks agree on the outcome: if any
+// rank cannot open a peer's buffers, everybody keeps the NCCL send/recv path.
+void release_p2p(Ctx *c)
+{
+    for (void *q : c->ipc_opened) cudaIpcCloseMemHandle(q);
+    c->ipc_opened.clear();
+    cudaFree(c->halo2); cudaFree(c->flags_d); cudaFree(c->done_d); cudaFree(c->push_d);
+    cudaFree(c->peer_rank_d);
+    c->halo2 = nullptr; c->flags_d = nullptr; c->done_d = nullptr; c->push_d = nullptr;
+    c->peer_rank_d = nullptr;
+    c->p2p_ok = false;
+}
+
+int setup_p2p(Ctx *c)
+{
+    release_p2p(c);
+    if (!c->has_comm || c->d.nranks < 2 || c->opt_external_exchange) return 0;
+    const int R = c->d.nranks, me = c->d.rank;
+    const size_t nh = (size_t)std::max<int64_t>(c->nhalo, 1);
+    int64_t ok = c->opt_p2p ? 1 : 0;
+    CUDA_OK(cudaMalloc(&c->halo2, sizeof(double) * 2 * 6 * nh));
+    CUDA_OK(cudaMemset(c->halo2, 0, sizeof(double) * 2 * 6 * nh));
+    CUDA_OK(cudaMalloc(&c->flags_d, sizeof(unsigned long long) * R));
+    CUDA_OK(cudaMemset(c->flags_d, 0, sizeof(unsigned long long) * R));
+    cudaIpcMemHandle_t hh{}, hf{};
+    if (cudaIpcGetMemHandle(&hh, c->halo2) != cudaSuccess ||
+        cudaIpcGetMemHandle(&hf, c->flags_d) != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0;
+    }
+    // blob: ok, nhalo, halo handle, flag handle, offsets of every rank's traces in my halo (-1: none)
+    const size_t B = 16 + 2 * sizeof(cudaIpcMemHandle_t) + 8 * (size_t)R;
+    std::vector<char> mine(B, 0), all(B * R);
+    int64_t nhalo64 = c->nhalo;
+    memcpy(mine.data(), &ok, 8);
+    memcpy(mine.data() + 8, &nhalo64, 8);
+    memcpy(mine.data() + 16, &hh, sizeof(hh));
+    memcpy(mine.data() + 16 + sizeof(hh), &hf, sizeof(hf));
+    std::vector<int64_t> offs(R, -1);
+    for (auto &p : c->peers) offs[p.rank] = p.off;
+    memcpy(mine.data() + 16 + 2 * sizeof(hh), offs.data(), 8 * (size_t)R);
+    char *d_all = nullptr;
+    CUDA_OK(cudaMalloc(&d_all, B * (R + 1)));
+    CUDA_OK(cudaMemcpy(d_all + B * R, mine.data(), B, cudaMemcpyHostToDevice));
+    NCCL_OK(g_nccl.AllGather(d_all + B * R, d_all, B, ncclInt8, c->comm, c->s_comm));
+    CUDA_OK(cudaStreamSynchronize(c->s_comm));
+    CUDA_OK(cudaMemcpy(all.data(), d_all, B * R, cudaMemcpyDeviceToHost));
+    std::vector<PushPeer> tab;
+    std::vector<int> pranks;
+    for (auto &p : c->peers) {
+        const char *rb = all.data() + B * (size_t)p.rank;
+        int64_t rok = 0, rnh = 0, roff = -1;
+        memcpy(&rok, rb, 8);
+        memcpy(&rnh, rb + 8, 8);
+        memcpy(&roff, rb + 16 + 2 * sizeof(hh) + 8 * (size_t)me, 8);
+        if (!ok || !rok || roff < 0) { ok = 0; break; }
+        cudaIpcMemHandle_t rhh, rhf;
+        memcpy(&rhh, rb + 16, sizeof(rhh));
+        memcpy(&rhf, rb + 16 + sizeof(rhh), sizeof(rhf));
+        void *ph = nullptr, *pf = nullptr;
+        if (cudaIpcOpenMemHandle(&ph, rhh, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError(); ok = 0; break;
+        }
+        c->ipc_opened.push_back(ph);
+        if (cudaIpcOpenMemHandle(&pf, rhf, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError(); ok = 0; break;
+        }
+        c->ipc_opened.push_back(pf);
+        PushPeer pp;
+        pp.dst[0] = (double *)ph + 6 * roff;
+        pp.dst[1] = (double *)ph + 6 * (size_t)std::max<int64_t>(rnh, 1) + 6 * roff;
+        pp.flag = (unsigned long long *)pf;
+        pp.src_off = p.off;
+        pp.count = (long long)p.send_fp.size();
+        tab.push_back(pp);
+        pranks.push_back(p.rank);
+    }
+    // everybody must take the same path: all-gather the outcome
+    CUDA_OK(cudaMemcpy(d_all + 8 * R, &ok, 8, cudaMemcpyHostToDevice));
+    NCCL_OK(g_nccl.AllGather(d_all + 8 * R, d_all, 1, ncclInt64, c->comm, c->s_comm));
+    CUDA_OK(cudaStreamSynchronize(c->s_comm));
+    std::vector<int64_t> oks(R);
+    CUDA_OK(cudaMemcpy(oks.data(), d_all, 8 * (size_t)R, cudaMemcpyDeviceToHost));
+    CUDA_OK(cudaFree(d_all));
+    for (auto v : oks) if (!v) ok = 0;
+    if (!ok) {
+        release_p2p(c);
+        return 0;
+    }
+    if (!tab.empty()) {
+        CUDA_OK(cudaMalloc(&c->push_d, sizeof(PushPeer) * tab.size()));
+        CUDA_OK(cudaMemcpy(c->push_d, tab.data(), sizeof(PushPeer) * tab.size(), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMalloc(&c->peer_rank_d, sizeof(int) * pranks.size()));
+        CUDA_OK(cudaMemcpy(c->peer_rank_d, pranks.data(), sizeof(int) * pranks.size(), cudaMemcpyHostToDevice));
+        CUDA_OK(cudaMalloc(&c->done_d, sizeof(unsigned int) * tab.size()));
+        CUDA_OK(cudaMemset(c->done_d, 0, sizeof(unsigned int) * tab.size()));
+    }
+    c->stage_no = 0;
+    c->p2p_ok = true;
+    return 0;
+}
+
 int require(Ctx *c, std::initializer_list<int> ids)
 {
     static const char *names[NKB_ARRAY_COUNT] = {
@@ -955,7 +1155,26 @@ int run_stage(Ctx *c, int rkstep /*1..5*/, int phase = 0)
     if (exchange && phase == 0 && c->opt_external_exchange)
         return fail("external_exchange is set: drive the stages with nekcem_b200_stage_pack / "
                     "nekcem_b200_stage_compute");
-    if (exchange && phase != 2) {
+    const bool p2p = exchange && phase == 0 && c->p2p_ok;
+    if (p2p) {
+        // peer-memory transport: traces go straight into the peers' halo buffers
+        c->stage_no++;
+        const int parity = (int)(c->stage_no & 1);
+        a.halo = c->halo2 + (size_t)parity * 6 * c->nhalo;
+        CUDA_OK(cudaStreamWaitEvent(c->s_comm, c->ev_stage, 0));
+        if (c->g_send_d) CUDA_OK(cudaStreamWaitEvent(c->s_comm, c->ev_sheet, 0));
+        long long mx = 0;
+        for (auto &p : c->peers) mx = std::max<long long>(mx, 6 * (long long)p.send_fp.size());
+        pack_push_kernel<<<dim3((unsigned)((mx + 255) / 256), (unsigned)c->peers.size()), 256, 0,
+                           c->s_comm>>>(
+            a.u_in, c->ld, c->send_node, c->push_d, parity, c->stage_no, c->d.rank, c->done_d,
+            c->inc_send_d, c->inc_amp_d, c->inc_phase_d, (int)c->inc_fp.size(), a.inc_wt,
+            c->g_send_d, c->send_fp_d, c->g_fj, a.fs_n, a.unx, a.uny,
+            c->d.ldim == 3 ? a.unz : nullptr);
+        CUDA_OK(cudaGetLastError());
+        c->last_launches++;
+    }
+    if (exchange && phase != 2 && !p2p) {
         // side stream: pack stage-start traces, grouped send/recv (replaces gs_op_fields
         // between ranks, src/cem_maxwell.F:962); overlaps the interior-element launches
         CUDA_OK(cudaStreamWaitEvent(c->s_comm, c->ev_stage, 0));
@@ -972,7 +1191,7 @@ int run_stage(Ctx *c, int rkstep /*1..5*/, int phase = 0)
         CUDA_OK(cudaStreamSynchronize(c->s_comm));
         return 0;
     }
-    if (exchange && phase == 0) {
+    if (exchange && phase == 0 && !p2p) {
         NCCL_OK(g_nccl.GroupStart());
         for (auto &p : c->peers) {
             const size_t cnt = p.send_fp.size() * 6;
@@ -984,7 +1203,15 @@ int run_stage(Ctx *c, int rkstep /*1..5*/, int phase = 0)
     }
     for (int q = 0; q < 4; q++)
         if (launch_list(q)) return 1;
-    if (exchange && phase == 0) CUDA_OK(cudaStreamWaitEvent(c->s_compute, c->ev_halo, 0));
+    if (p2p) {
+        // boundary elements start once every peer has published this stage's traces
+        wait_flags_kernel<<<1, 32, 0, c->s_compute>>>(c->flags_d, c->peer_rank_d,
+                                                      (int)c->peers.size(), c->stage_no);
+        CUDA_OK(cudaGetLastError());
+        c->last_launches++;
+    } else if (exchange && phase == 0) {
+        CUDA_OK(cudaStreamWaitEvent(c->s_compute, c->ev_halo, 0));
+    }
     for (int q = 4; q < 8; q++)
         if (launch_list(q)) return 1;
     CUDA_OK(cudaEventRecord(c->ev_stage, c->s_compute));
@@ -1160,7 +1387,12 @@ int nekcem_b200_create(const nekcem_b200_desc *desc, int *handle)
             return fail("device %d is sm_%d%d; this library is built for sm_100a (B200) only",
                         desc->device, prop.major, prop.minor);
         CUDA_OK(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
-        CUDA_OK(cudaStreamCreateWithFlags(&c->s_comm, cudaStreamNonBlocking));
+        {   // the exchange kernels are tiny and on the critical path of the boundary elements:
+            // their stream outranks the persistent stage kernels
+            int lo = 0, hi = 0;
+            CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CUDA_OK(cudaStreamCreateWithPriority(&c->s_comm, cudaStreamNonBlocking, hi));
+        }
         CUDA_OK(cudaEventCreateWithFlags(&c->ev_stage, cudaEventDisableTiming));
         CUDA_OK(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
         CUDA_OK(cudaEventCreateWithFlags(&c->ev_sheet, cudaEventDisableTiming));
@@ -1190,6 +1422,7 @@ int nekcem_b200_destroy(int handle)
         for (auto &p : c->dev) cudaFree(p);
         cudaFree(c->u[0]); cudaFree(c->u[1]); cudaFree(c->kf);
         cudaFree(c->xtr[0]); cudaFree(c->xtr[1]);
+        release_p2p(c);
         cudaFree(c->st_in); cudaFree(c->st_out);
         if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
         if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
@@ -1493,6 +1726,7 @@ int nekcem_b200_setup(int handle)
         CUDA_OK(cudaMalloc(&c->halo, sizeof(double) * 6 * c->nhalo));
         CUDA_OK(cudaMemset(c->halo, 0, sizeof(double) * 6 * c->nhalo));
     }
+    if (setup_p2p(c)) return 1;
     cudaFree(c->inc_own_d); cudaFree(c->inc_nbr_d); cudaFree(c->inc_send_d);
     cudaFree(c->inc_amp_d); cudaFree(c->inc_phase_d);
     c->inc_own_d = c->inc_nbr_d = c->inc_send_d = nullptr;
@@ -1840,6 +2074,11 @@ int nekcem_b200_set_option(int handle, const char *name, int value)
         c->opt_pipeline = value != 0;
         return 0;
     }
+    if (strcmp(name, "p2p") == 0) {
+        // takes effect at the next nekcem_b200_setup (every rank must set the same value)
+        c->opt_p2p = value != 0;
+        return 0;
+    }
     if (strcmp(name, "xtrace") == 0) {
         // takes effect at the next nekcem_b200_setup
         c->opt_xtrace = value != 0;
@@ -2064,6 +2303,14 @@ int nekcem_b200_step_streamed(int handle, const double *hn_in, const double *en_
     return 0;
 }
 
+int nekcem_b200_transport(int handle, int32_t *kind)
+{
+    Ctx *c = get(handle);
+    if (!c || !kind) return 1;
+    *kind = c->peers.empty() ? 0 : (c->p2p_ok ? 2 : 1);
+    return 0;
+}
+
 int nekcem_b200_device_count(void)
 {
     int n = 0;
@@ -2222,6 +2469,40 @@ int nekcem_b200_vtk_payload(int handle, int which, int as_double, void *out)
     if (e1 == cudaSuccess) e1 = cudaMemcpy(out, buf, bytes, cudaMemcpyDeviceToHost);
     cudaFree(buf);
     CUDA_OK(e1);
+    return 0;
+}
+
+int nekcem_b200_restart_ingest(int handle, int which, int as_double, const void *payload)
+{
+    Ctx *c = get(handle);
+    if (!c) return 1;
+    if (c->host_only) return fail("host-only planning context: no device arrays");
+    if (which != 0 && which != 1) return fail("restart_ingest: which must be 0 (EN) or 1 (HN)");
+    if (!payload) return fail("null payload pointer");
+    CUDA_OK(cudaSetDevice(c->d.device));
+    const size_t esz = as_double ? 8 : 4, bytes = esz * 3 * (size_t)c->npts;
+    void *buf = nullptr;
+    CUDA_OK(cudaMalloc(&buf, bytes));
+    cudaError_t e1 = cudaMemcpyAsync(buf, payload, bytes, cudaMemcpyHostToDevice, c->s_compute);
+    const long long tot = 3 * (long long)c->npts;
+    const unsigned grid = (unsigned)((tot + 255) / 256);
+    const int c0 = which == 0 ? 3 : 0;
+    for (int b = 0; b < (c->d.ldim == 2 ? 2 : 1) && e1 == cudaSuccess; b++) {
+        // 2D modes never write the inactive components: both ping-pong buffers take the state
+        double *base = c->u[c->cur ^ b] + c0 * c->ld;
+        if (as_double)
+            restart_ingest_kernel<unsigned long long><<<grid, 256, 0, c->s_compute>>>(
+                (const unsigned long long *)buf, base, c->ld, c->npts);
+        else
+            restart_ingest_kernel<unsigned int><<<grid, 256, 0, c->s_compute>>>(
+                (const unsigned int *)buf, base, c->ld, c->npts);
+        e1 = cudaGetLastError();
+    }
+    if (e1 == cudaSuccess) e1 = cudaStreamSynchronize(c->s_compute);
+    cudaFree(buf);
+    CUDA_OK(e1);
+    c->xtr_valid = false;
+    c->have[which == 0 ? NKB_EN : NKB_HN] = true;
     return 0;
 }
 

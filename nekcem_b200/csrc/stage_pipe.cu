@@ -84,11 +84,22 @@ __host__ __device__ constexpr int pipe_ks_for(int n)
     return n <= 10 ? 1 : (n <= 11 ? 3 : (n <= 12 ? 4 : (n <= 13 ? 5 : 8)));
 }
 
+// Layout of one component of U / R.  As Lay<N> (stage_common.h) except where the group-interleaved
+// s-pencil lanes of this kernel prefer another padding (scripts/smem_banks_pipe.py: weighted
+// wavefronts per access over all phases): nx1 = 10 without the k padding.
+template <int N>
+struct PLay : Lay<N> {};
+template <>
+struct PLay<10> {
+    static constexpr int SJ = 10, SK = 100, SC = 1000;
+    __device__ __forceinline__ static int at(int i, int j, int k) { return i + 10 * j + 100 * k; }
+};
+
 // skew of the E components in U and R for the group-interleaved s-pencil lanes
 // (scripts/smem_banks_pipe.py, for the slab thickness pipe_ks_for gives)
 __host__ __device__ constexpr int pipe_he_for(int n)
 {
-    return n == 6 ? 14 : n == 7 ? 3 : n == 8 ? 8 : n == 9 ? 10 : n == 10 ? 5 : n == 11 ? 15
+    return n == 6 ? 14 : n == 7 ? 3 : n == 8 ? 8 : n == 9 ? 14 : n == 10 ? 2 : n == 11 ? 15
          : n == 13 ? 12 : n == 14 ? 10 : n == 15 ? 9 : 0;
 }
 
@@ -108,7 +119,7 @@ struct PT {
     static constexpr int NT = (KS == 1 && N == 10) ? 640 : (KS == 1 && N == 9) ? 512
                               : p_max(p_nt_for(RS_ITEMS), p_round32(N2));
 #endif
-    static constexpr int SC = Lay<N>::SK * KB; // component stride in U and R
+    static constexpr int SC = PLay<N>::SK * KB; // component stride in U and R
     static constexpr int XL = p_even(N2 * KB + 2); // linear slab of one array + alignment slack
     // face staging: KS == 1: the 6*N2 points of the element are contiguous per array;
     // KS > 1: the slab's strips of the four x/y faces and one z face
@@ -220,8 +231,8 @@ __device__ __forceinline__ int par_of(const double *p) { return (int)(((uintptr_
 template <int N, int DIR, int KOFF>
 __device__ __forceinline__ int ps_at(int m, int pa, int pb)
 {
-    return DIR == 0 ? Lay<N>::at(m, pa, pb)
-                    : (DIR == 1 ? Lay<N>::at(pa, m, pb) : Lay<N>::at(pa, pb, m - KOFF));
+    return DIR == 0 ? PLay<N>::at(m, pa, pb)
+                    : (DIR == 1 ? PLay<N>::at(pa, m, pb) : PLay<N>::at(pa, pb, m - KOFF));
 }
 // slab-local linear node of position m along the pencil (DIR 2: m counts from the slab's k0)
 template <int N, int DIR>
@@ -381,7 +392,7 @@ __device__ __forceinline__ void pipe_t_phase(const double (&D)[N * N], const Sta
                     double cc[3];
                     if constexpr (CM) curl_part(d, cm[0], cm[1], cm[2], cc);
                     else curl_part(d, cofs[nl], cofs[C::XL + nl], cofs[2 * C::XL + nl], cc);
-                    double *Ro = Rd + Lay<N>::at(pa, pb, o);
+                    double *Ro = Rd + PLay<N>::at(pa, pb, o);
                     Ro[0] = Ro[0] + wv * cc[0];
                     Ro[C::SC] = Ro[C::SC] + wv * cc[1];
                     Ro[2 * C::SC] = Ro[2 * C::SC] + wv * cc[2];
@@ -533,7 +544,7 @@ __global__ void __launch_bounds__(PT<N, KS>::NT, PT<N, KS>::MINB)
             yi = 4 * C::SEGXY + fp0;
         }
         fjs = slot < 0 ? -1 : slot * N2 + fp0;
-        fsn = Lay<N>::at(ci, cj, kl);
+        fsn = PLay<N>::at(ci, cj, kl);
         if (KS == 1) fyi = slot < 0 ? 0 : fjs; // the element's 6*N2 points are staged contiguously
         else {
             // + parity of the strip's first point (the arrays themselves are 16-byte aligned)
@@ -576,7 +587,7 @@ __global__ void __launch_bounds__(PT<N, KS>::NT, PT<N, KS>::MINB)
             const int c = cs >> 1, side = cs & 1;
             const int j = p % N, kl = p / N;
             a.xtr_out[c * a.ldx + (2ll * pe + side) * N2 + N * pk0 + p] =
-                R[c * SC + (c >= 3 ? HE : 0) + Lay<N>::at(side ? N - 1 : 0, j, kl)];
+                R[c * SC + (c >= 3 ? HE : 0) + PLay<N>::at(side ? N - 1 : 0, j, kl)];
         }
     };
     int xo_e = -1, xo_s = 0; // item whose mirror entries still sit in R
@@ -611,7 +622,7 @@ __global__ void __launch_bounds__(PT<N, KS>::NT, PT<N, KS>::MINB)
             for (int x = 0; x < SPER; x++) {
                 const int pl = ps + NPL * x, c = pl / KB, kl = pl - c * KB;
                 if (pok && pl < 6 * KB && kl < kb && !(PIPE_SKIP & 16))
-                    U[c * SC + (c >= 3 ? HE : 0) + Lay<N>::at(pi, pj, kl)] = Y[c * XL + off + kl * N2 + pnd];
+                    U[c * SC + (c >= 3 ? HE : 0) + PLay<N>::at(pi, pj, kl)] = Y[c * XL + off + kl * N2 + pnd];
             }
         }
         // neighbour traces of this thread's face points -> L2
@@ -866,7 +877,7 @@ __global__ void __launch_bounds__(PT<N, KS>::NT, PT<N, KS>::MINB)
                 const int kl = pl - g * KB;
                 if (pok && pl < 2 * KB && kl < kb) {
                     const int nl = pnd + kl * N2;
-                    const int sn = Lay<N>::at(pi, pj, kl) + (g == 0 ? HE : 0);
+                    const int sn = PLay<N>::at(pi, pj, kl) + (g == 0 ? HE : 0);
                     const long long gi = sbase + nl;
                     const int cb0 = g == 0 ? 3 : 0; // components being updated
                     double r[3] = {R[cb0 * SC + sn], R[(cb0 + 1) * SC + sn], R[(cb0 + 2) * SC + sn]};

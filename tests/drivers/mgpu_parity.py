@@ -60,7 +60,11 @@ if rank == 0:
     uid.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
 dist.broadcast(uid, 0)
 s.comm_init(uid.cpu().numpy().tobytes())
+if os.environ.get("NEKCEM_B200_P2P", "1") == "0":
+    s.set_option("p2p", 0)   # grouped ncclSend/ncclRecv instead of stores into peer memory
 s.setup()
+want_transport = "nccl-sendrecv" if os.environ.get("NEKCEM_B200_P2P", "1") == "0" else "peer-memory-push"
+assert s.transport() == want_transport, s.transport()
 s.set_time(0.0, ref.dt)
 s.step(nsteps)
 ref.step(nsteps)
@@ -73,7 +77,7 @@ if ade is not None and ade[2].size:
     ncomp = ref.user.jn.size // ref.npts
     err = max(err, rel_l2(jg, ref.user.jn.reshape(ncomp, -1)[:, vol].ravel()))
 vm, peers, nhalo, ni, nb = s.plan()
-print(f"rank {rank}/{world}: rel-L2 vs oracle {err:.3e}; peers {[p for p, _ in peers]} nhalo {nhalo} "
+print(f"rank {rank}/{world}: {s.transport()} rel-L2 vs oracle {err:.3e}; peers {[p for p, _ in peers]} nhalo {nhalo} "
       f"interior {ni} boundary {nb}", flush=True)
 ok = torch.tensor([1 if err <= 1e-12 else 0], device="cuda")
 dist.all_reduce(ok, op=dist.ReduceOp.MIN)

@@ -33,7 +33,9 @@ def test_library_exports_every_declared_symbol():
               "nekcem_b200_set_filter_", "nekcem_b200_set_rk_coefficients_",
               "nekcem_b200_vtk_payload_", "nekcem_b200_sync_host_", "nekcem_b200_sync_device_",
               "cem_3d_graphene_current_", "cem_te_graphene_current_",
-              "cem_tm_graphene_current_"):
+              "cem_tm_graphene_current_", "nekcem_b200_step_streamed_",
+              "nekcem_b200_restart_ingest_", "nekcem_b200_device_count_",
+              "nekcem_b200_set_option_"):
         assert hasattr(L, n), f"Fortran twin {n} missing"
 
 
