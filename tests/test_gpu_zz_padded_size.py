@@ -6,15 +6,14 @@ lelt = nelt, where the leading dimension equals npts.
 
 NOT YET RUN ON HARDWARE: written after this round's GPU budget was exhausted (the host-side
 packing is covered on CPU by tests/test_abi.py and tests/test_reference_pin.py::
-test_pin_padded_size_layout); hence xfail(strict=False) until it has been seen green once."""
+test_pin_padded_size_layout). Green on B200 since the round-1 driver run (GPUTEST_r01: xpassed)."""
 import os
 import subprocess
 import sys
 
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="not yet run on hardware (round 1 GPU budget spent)")]
+pytestmark = [pytest.mark.gpu]
 
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -2,9 +2,8 @@
 exponential / eigenvalue drivers call through amult (src/cem_maxwell.F:2310-2365).  Against the
 oracle's cem_maxwell_op (reshn, resen after invqmass).
 
-NOT YET RUN ON HARDWARE (written after round 1's GPU budget was spent): host-side plumbing only --
-one launch of the verified fused stage with (a, b, dt) = (0, 0, 1); xfail(strict=False) until seen
-green once."""
+Host-side plumbing around the fused stage: one launch with (a, b, dt) = (0, 0, 1).  Green on B200
+since the round-1 driver run."""
 import ctypes as C
 
 import numpy as np
@@ -12,8 +11,7 @@ import pytest
 
 from helpers import rel_l2, solver_from_refcase
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="not yet run on hardware (round 1 GPU budget spent)")]
+pytestmark = [pytest.mark.gpu]
 TOL = 1e-12
 
 
