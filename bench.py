@@ -260,12 +260,13 @@ def run_gpu(args):
     peak, peak_src = measured_peak()
     transports = set()
 
-    def make(nel, order, nranks=world, myrank=rank, general=True):
+    def make(nel, order, nranks=world, myrank=rank, general=True, **variant):
         """solver for a periodic box of nel elements at order N, partitioned over nranks"""
         nx1 = order + 1
         t0 = time.perf_counter()
-        case = BoxCase(nel, nx1, rank=myrank, nranks=nranks, length=2 * math.pi)
-        slv = MaxwellB200(3, nx1, case.nelt, device=local, rank=myrank, nranks=nranks)
+        case = BoxCase(nel, nx1, rank=myrank, nranks=nranks, length=2 * math.pi, **variant)
+        slv = MaxwellB200(3, nx1, case.nelt, device=local, rank=myrank, nranks=nranks,
+                          ifpml=bool(variant.get("pml")))
         slv.cem_maxwell_init(case.lazy(), free_after_upload=True)
         if nranks > 1:
             uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -296,29 +297,37 @@ def run_gpu(args):
         ms, launches = slv.last_step_ms()
         return max_over_ranks(ms), int(launches)
 
-    def measure(nel, order, warm, steps, general=True):
+    def measure(nel, order, warm, steps, general=True, **variant):
         """one extra configuration: rate, ms/step and the roofline fraction of its stage kernel"""
-        case, slv, dt, ts = make(nel, order, general=general)
+        case, slv, dt, ts = make(nel, order, general=general, **variant)
         ms, launches = timed(slv, warm, steps)
-        nodes = case.npts * world if nel[2] % world == 0 else None
         npts_global = int(np.prod(nel)) * (order + 1) ** 3
-        shn, sen = case.fields(slv.time)
-        ssum, smax = slv.error_sums(shn, sen)
-        del shn, sen
+        if variant:   # no closed-form solution: the fields must stay finite and bounded
+            zero = np.zeros(3 * case.npts)
+            ssum, smax = slv.error_sums(zero, zero)
+            del zero
+        else:
+            shn, sen = case.fields(slv.time)
+            ssum, smax = slv.error_sums(shn, sen)
+            del shn, sen
         red = torch.tensor(ssum, dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(red, op=dist.ReduceOp.SUM)
         l2 = float(np.sqrt(red.cpu().numpy().max() / case.volume_global))
+        npml = int(case.array("pmlptr").size)
         slv.close()
         stage_ms = ms / (5.0 * steps)
-        bpn = bytes_per_node(order + 1)
+        # SURVEY.md 8d: + 240 B per node of a PML element
+        bpn = bytes_per_node(order + 1) + 240.0 * npml / max(case.nelt, 1)
         # the slowest rank's launch carries npts_global/world nodes (equal slabs)
         ach = bpn * (npts_global / world) / (stage_ms * 1e-3) / 1e9
         return {"value": npts_global * 5.0 * steps / (ms * 1e-3) / 1e9, "unit": UNIT,
                 "ms_per_step": ms / steps, "steps": steps, "nodes_global": npts_global,
                 "elements_global": list(nel), "order": order,
                 "roofline_frac": ach / peak, "achieved_GBps_per_gpu": ach,
-                "bytes_per_node_stage": bpn, "l2_error_vs_analytic": l2,
+                "bytes_per_node_stage": bpn,
+                ("l2_norm_of_fields" if variant else "l2_error_vs_analytic"): l2,
+                "pml_elements_per_rank": npml, "variant": {k: str(v) for k, v in variant.items()},
                 "gpu_launches": launches, "setup_s": round(ts, 1)}
 
     E, order = args.elems, args.order
@@ -417,6 +426,12 @@ def run_gpu(args):
         Kx = max(3, min(K, 5))
         if not (order == 15 and E == 32 and not strong):
             extra["weak_n15_e32_per_gpu"] = measure((32, 32, 32 * world), 15, 3, Kx)
+        if world == 1:
+            # the auxiliary paths at benchmark size (BASELINE.json configs[2], [3]): every element a
+            # PML element (tests/3dboxpml), two materials + PML layers (tests/3ddielectric)
+            extra["aux_all_pml_n7_e40"] = measure((40, 40, 40), 7, 3, Kx, pml="all")
+            extra["aux_two_materials_pml_layers_n7_e40"] = measure(
+                (40, 40, 40), 7, 3, Kx, pml="layers", eps_upper=4.0)
         if world > 1:
             extra["strong_n7_e64_total"] = measure((64, 64, 64), 7, 3, Kx)
         if world >= 4:

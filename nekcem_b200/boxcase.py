@@ -133,7 +133,17 @@ class BoxCase:
     ``rank``/``nranks`` select the local elements by the reference's pencil map; local order is
     ascending global element id (lglel)."""
 
-    def __init__(self, nel, nx1, rank=0, nranks=1, length=2 * math.pi, bc="P"):
+    def __init__(self, nel, nx1, rank=0, nranks=1, length=2 * math.pi, bc="P", eps_upper=1.0,
+                 pml=False):
+        """``eps_upper`` != 1: permittivity eps_upper in the upper half of the box (element rows
+        ey >= EY/2), 1 below -- the two-material layout of tests/3ddielectric at benchmark size:
+        masses, impedances Y_0..Z_1 as cem_maxwell_materials builds them (src/cem_maxwell.F:262-325).
+        ``pml``: True / "all": every element is a PML element with a smooth synthetic sigma profile
+        (the tests/3dboxpml layout at benchmark size; the numbers only have to keep the run
+        bounded); "layers": the two bottom and two top element rows in y (the PML thickness of
+        tests/3ddielectric)."""
+        self.eps_upper = float(eps_upper)
+        self.pml = "all" if pml is True else (pml or False)
         self.nel = tuple(int(v) for v in nel)
         self.nx1 = int(nx1)
         self.rank, self.nranks = rank, nranks
@@ -228,7 +238,13 @@ class BoxCase:
     ARRAY_NAMES = ("dxm1", "w3mn", "rxmn", "rymn", "rzmn", "sxmn", "symn", "szmn", "txmn",
                    "tymn", "tzmn", "bmn", "hbm1", "ebm1", "unxm", "unym", "unzm", "aream",
                    "Y_0", "Y_1", "Z_0", "Z_1", "glo_num", "cempec", "pmlptr", "volvm1", "hn",
-                   "en")
+                   "en", "permittivity", "permeability", "pmlsigma", "pmlbn", "pmldn")
+
+    def _eps_el(self):
+        """permittivity of the local elements"""
+        EX, EY, EZ = self.nel
+        _, ey, _ = self._exyz()
+        return np.where(ey >= EY // 2, self.eps_upper, 1.0)
 
     def array(self, name: str, t: float = 0.0):
         """One COMMON array by its reference name (generated on demand so that a 64^3 case
@@ -250,8 +266,29 @@ class BoxCase:
             return np.zeros(npts)
         if name == "bmn":
             return np.tile((hx * hy * hz / 8.0) * w3, nelt)
-        if name in ("hbm1", "ebm1"):  # eps = mu = 1
+        if name == "permeability":
+            return np.ones(npts)
+        if name == "permittivity":
+            return np.repeat(self._eps_el(), self.nxyz)
+        if name == "hbm1":  # 1/(mu*bm), mu = 1
             return np.tile(1.0 / ((hx * hy * hz / 8.0) * w3), nelt)
+        if name == "ebm1":  # 1/(eps*bm)  (src/cem_maxwell.F:183-186)
+            if self.eps_upper == 1.0:
+                return np.tile(1.0 / ((hx * hy * hz / 8.0) * w3), nelt)
+            bm = (hx * hy * hz / 8.0) * w3
+            return (1.0 / (self._eps_el()[:, None] * bm[None, :])).reshape(-1)
+        if name == "pmlsigma":
+            # (npts,3): smooth, positive, below the stability bound of the synthetic dt
+            x, y, zc = self.coords()
+            L = self.length
+            return np.concatenate([0.3 * np.sin(np.pi * x / L) ** 2, 0.3 * np.sin(np.pi * y / L) ** 2,
+                                   0.3 * np.sin(np.pi * zc / L) ** 2])
+        if name in ("pmlbn", "pmldn"):
+            # B = mu H, D = eps E at t = 0 (userini of tests/3ddielectric, :67-78)
+            hn, en = self.fields(t)
+            if name == "pmlbn":
+                return hn
+            return (en.reshape(3, -1) * np.repeat(self._eps_el(), self.nxyz)[None, :]).reshape(-1)
         if name in ("unxm", "unym", "unzm", "aream"):
             f = np.zeros((6, self.nxzf))
             if name == "unxm":
@@ -269,7 +306,18 @@ class BoxCase:
         if name in ("Y_0", "Y_1", "Z_0", "Z_1"):
             # eps = mu = 1: Z = Y = 1 on both sides; on PEC faces the materials quirk also
             # ends with Z_0 = Z_1 = Z^- (src/cem_maxwell.F:297-320)
-            return np.ones(nxzfl)
+            if self.eps_upper == 1.0:
+                return np.ones(nxzfl)
+            # two materials: own-side value + the neighbour's across each face;
+            # X_0 = (X^- + X^+)/2, X_1 = X^+  (src/cem_maxwell.F:283-320)
+            own = np.sqrt(self._eps_el()) if name[0] == "Y" else 1.0 / np.sqrt(self._eps_el())
+            EX, EY, EZ = self.nel
+            ex, ey, ez = self._exyz()
+            up = lambda eyy: np.where(eyy % EY >= EY // 2, self.eps_upper, 1.0)
+            nb_eps = np.stack([up(ey - 1), up(ey), up(ey + 1), up(ey), up(ey), up(ey)], axis=1)
+            nbr = np.sqrt(nb_eps) if name[0] == "Y" else 1.0 / np.sqrt(nb_eps)
+            val = 0.5 * (own[:, None] + nbr) if name[2] == "0" else nbr
+            return np.repeat(val.reshape(-1), self.nxzf)
         if name == "glo_num":
             return self.face_ids()
         if name == "cempec":
@@ -277,7 +325,10 @@ class BoxCase:
                 return np.zeros(0, dtype=np.int64)
             return np.nonzero(self.face_ids() == 0)[0]
         if name == "pmlptr":
-            return np.zeros(0, dtype=np.int64)
+            if self.pml == "layers":
+                _, ey, _ = self._exyz()
+                return np.nonzero((ey < 2) | (ey >= self.nel[1] - 2))[0].astype(np.int64)
+            return np.arange(nelt, dtype=np.int64) if self.pml else np.zeros(0, dtype=np.int64)
         if name == "volvm1":
             return self.volume_global
         if name in ("hn", "en"):
@@ -291,6 +342,8 @@ class BoxCase:
 
         class _Lazy(dict):
             def __contains__(self, k):
+                if k in ("permittivity", "permeability", "pmlsigma", "pmlbn", "pmldn") and not case.pml:
+                    return False
                 return k in case.ARRAY_NAMES and (with_fields or k not in ("hn", "en"))
 
             def __getitem__(self, k):
@@ -314,5 +367,6 @@ class BoxCase:
 
     def arrays(self, with_fields=True, t=0.0) -> dict:
         """All COMMON arrays for MaxwellB200.cem_maxwell_init as a plain dict."""
+        aux = ("permittivity", "permeability", "pmlsigma", "pmlbn", "pmldn")
         return {k: self.array(k, t) for k in self.ARRAY_NAMES
-                if with_fields or k not in ("hn", "en")}
+                if (with_fields or k not in ("hn", "en")) and (self.pml or k not in aux)}

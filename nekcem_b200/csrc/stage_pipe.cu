@@ -49,6 +49,9 @@ namespace {
 #ifndef PIPE_L2_AHEAD
 #define PIPE_L2_AHEAD 0 // 1: L2 prefetch of the next item's fields and rx..sz one item ahead
 #endif
+#ifndef PIPE_PML_L2
+#define PIPE_PML_L2 1 // 1: L2 prefetch of a PML element's auxiliary arrays at the start of the item
+#endif
 #ifndef PIPE_XOUT
 #define PIPE_XOUT 1 // 1: the x-face mirror is written coalesced from shared memory
 #endif
@@ -637,6 +640,21 @@ __global__ void __launch_bounds__(PT<N, KS>::NT, PT<N, KS>::MINB)
         __syncthreads();
         if (w0) {
             issue_face(e, s);
+            if (PML && PIPE_PML_L2 && (a.elflag[e] & 1)) {
+                // PML elements: the epilogue reads 18 more arrays per node through the LSU (sigma,
+                // eps, mu, bm, B, D and their RK registers); start them towards L2 now
+                const int cnt = N2 * kb;
+                const double *src = nullptr;
+                if (lane < 3) src = a.sig + (long long)lane * a.npts;
+                else if (lane < 6) src = a.pB + (long long)(lane - 3) * a.npts;
+                else if (lane < 9) src = a.pD + (long long)(lane - 6) * a.npts;
+                else if (lane < 12) src = a.kB + (long long)(lane - 9) * a.npts;
+                else if (lane < 15) src = a.kD + (long long)(lane - 12) * a.npts;
+                else if (lane == 15) src = a.eps;
+                else if (lane == 16) src = a.mu;
+                else if (lane == 17) src = a.bmn;
+                if (src != nullptr) bulk_prefetch(src + sbase, cnt);
+            }
             // the two streams whose shared-memory region frees late (fields: after the flux phase,
             // rx..sz: after the epilogue) start their trip from HBM now, into L2
             if (PIPE_L2_AHEAD && more) {
@@ -885,10 +903,7 @@ __global__ void __launch_bounds__(PT<N, KS>::NT, PT<N, KS>::MINB)
                     if (PML) { // auxiliary ODEs of this node, in the reference's order:
                         // pml_step (+ PML half of rk_maxwell_ab), then the usersrc ADEs
                         const int ef = a.elflag[e];
-                        if (ef & 1) {
-#pragma unroll
-                            for (int c = 0; c < 3; c++) r[c] = pml_component(a, gi, c, g == 0, r[c], o[c]);
-                        }
+                        if (ef & 1) pml_node3(a, gi, g == 0, r, o);
                         if ((ef & 2) && g == 0 && a.ade_mask[gi]) {
 #pragma unroll
                             for (int c = 0; c < 3; c++) r[c] = ade_component(a, gi, c, r[c], o[c]);

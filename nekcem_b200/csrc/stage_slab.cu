@@ -695,10 +695,7 @@ __global__ void __launch_bounds__(Slab<N, KS>::NT, CM ? Slab<N, KS>::MINB_CM : S
                     if (PML) { // auxiliary ODEs of this node, in the reference's order:
                         // pml_step (+ PML half of rk_maxwell_ab), then the usersrc ADEs
                         const int ef = a.elflag[e];
-                        if (ef & 1) {
-#pragma unroll
-                            for (int c = 0; c < 3; c++) r[c] = pml_component(a, gi, c, g == 0, r[c], o[c]);
-                        }
+                        if (ef & 1) pml_node3(a, gi, g == 0, r, o);
                         if ((ef & 2) && g == 0 && a.ade_mask[gi]) {
 #pragma unroll
                             for (int c = 0; c < 3; c++) r[c] = ade_component(a, gi, c, r[c], o[c]);

@@ -1,1 +1,2 @@
-timeout 900 python -m pytest tests/test_gpu_pipe.py -q -x -k "3dboxpml or restart" 2>&1 | tail -4
+timeout 600 python -m pytest tests/test_gpu_pipe.py tests/test_gpu_parity.py -q -x -k "pml or dielectric" 2>&1 | tail -3
+python scripts/_aux.py

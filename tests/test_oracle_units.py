@@ -140,3 +140,29 @@ def test_planewave_parameters_reproduce_usersol(which):
         ph, pe = planewave_numpy(c, a, tt)
         assert np.abs(sh).max() > 0.5
         assert np.abs(sh - ph).max() <= 1e-15 and np.abs(se - pe).max() <= 1e-15
+
+
+def test_boxcase_two_material_arrays_match_the_oracles_setup():
+    """nekcem_b200/boxcase.py generates the benchmark meshes analytically; its two-material variant
+    (masses, impedances) must equal what the oracle's restatement of cem_maxwell_materials and the
+    inverse-mass setup (src/cem_maxwell.F:183-186, 262-325) builds for the same box"""
+    import numpy as np
+    from nekcem_b200.boxcase import BoxCase
+    from oracle import oracle as O
+    nel, nx1 = (3, 4, 3), 5
+    mesh = O.box_mesh(nel, ((0.0, 2 * np.pi),) * 3, ("P  ",) * 6)
+
+    def uservp(case):
+        e = np.arange(case.nelt)
+        ey = (e // nel[0]) % nel[1]
+        case.permittivity[:] = np.repeat(np.where(ey >= nel[1] // 2, 4.0, 1.0), case.nxyz)
+        case.permeability[:] = 1.0
+
+    c = O.RefCase(mesh, nx1, upwind=True, uservp=uservp)
+    b = BoxCase(nel, nx1, eps_upper=4.0)
+    for k in ("Y_0", "Y_1", "Z_0", "Z_1"):
+        assert np.array_equal(getattr(c, k), b.array(k)), k
+    for k in ("hbm1", "ebm1", "bmn", "permittivity", "permeability"):
+        assert np.allclose(getattr(c, k), b.array(k), rtol=1e-12, atol=0), k
+    assert BoxCase(nel, nx1, pml="layers").array("pmlptr").size == 2 * 2 * 3 * 3
+    assert BoxCase(nel, nx1, pml=True).array("pmlsigma").size == 3 * b.npts
