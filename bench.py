@@ -231,7 +231,7 @@ def run_gpu(args):
     import torch.distributed as dist
 
     from nekcem_b200 import MaxwellB200, comm_unique_id
-    from nekcem_b200.boxcase import BoxCase, gll
+    from nekcem_b200.boxcase import BoxCase, BoxCase2D, gll
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -329,6 +329,33 @@ def run_gpu(args):
                 ("l2_norm_of_fields" if variant else "l2_error_vs_analytic"): l2,
                 "pml_elements_per_rank": npml, "variant": {k: str(v) for k, v in variant.items()},
                 "gpu_launches": launches, "setup_s": round(ts, 1)}
+
+    def measure_2d(E2, order, warm, steps):
+        """the 2D TE path (stage2d_kernel; tests/drude, tests/2dboxper are 2D) on a periodic box of
+        E2 x E2 elements.  Algorithmic bytes: 144 B/node + 84 B/face point = 144 + 336/n."""
+        nx1 = order + 1
+        t0 = time.perf_counter()
+        case = BoxCase2D((E2, E2), nx1, imode=1)
+        slv = MaxwellB200(2, nx1, case.nelt, imode=1, device=local)
+        slv.cem_maxwell_init(case.arrays())
+        slv.setup()
+        z, _ = gll(nx1)
+        slv.set_time(0.0, 0.1 * 0.5 * min(case.h) * 0.5 * float(np.min(z[2:] - z[:-2])))
+        ts = time.perf_counter() - t0
+        ms, launches = timed(slv, warm, steps)
+        shn, sen = case.fields(slv.time)
+        ssum, _ = slv.error_sums(shn, sen)
+        l2 = float(np.sqrt(ssum.max() / case.volume_global))
+        slv.close()
+        stage_ms = ms / (5.0 * steps)
+        bpn = 144.0 + 336.0 / nx1
+        ach = bpn * case.npts / (stage_ms * 1e-3) / 1e9
+        return {"value": case.npts * 5.0 * steps / (ms * 1e-3) / 1e9, "unit": UNIT,
+                "ms_per_step": ms / steps, "steps": steps, "nodes_global": case.npts,
+                "elements_global": [E2, E2], "order": order, "roofline_frac": ach / peak,
+                "achieved_GBps_per_gpu": ach, "bytes_per_node_stage": bpn,
+                "l2_error_vs_analytic": l2, "gpu_launches": launches, "setup_s": round(ts, 1),
+                "kernel": "stage2d_kernel (TE)"}
 
     E, order = args.elems, args.order
     nx1 = order + 1
@@ -432,6 +459,7 @@ def run_gpu(args):
             extra["aux_all_pml_n7_e40"] = measure((40, 40, 40), 7, 3, Kx, pml="all")
             extra["aux_two_materials_pml_layers_n7_e40"] = measure(
                 (40, 40, 40), 7, 3, Kx, pml="layers", eps_upper=4.0)
+            extra["aux_2d_te_n7_e512"] = measure_2d(512, 7, 3, Kx)
         if world > 1:
             extra["strong_n7_e64_total"] = measure((64, 64, 64), 7, 3, Kx)
         if world >= 4:

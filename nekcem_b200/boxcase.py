@@ -370,3 +370,118 @@ class BoxCase:
         aux = ("permittivity", "permeability", "pmlsigma", "pmlbn", "pmldn")
         return {k: self.array(k, t) for k in self.ARRAY_NAMES
                 if (with_fields or k not in ("hn", "en")) and (self.pml or k not in aux)}
+
+
+class BoxCase2D:
+    """Uniform periodic box [0,L]^2 of nel=(EX,EY) elements, order N = nx1-1, eps=mu=1, for the 2D
+    TE (imode 1: Ex,Ey,Hz) / TM (imode 2: Hx,Hy,Ez) path: the arrays of tests/2dboxper at any size,
+    generated analytically (conventions as the reference's 2D setup: rxm1 = hy/2, sym1 = hx/2,
+    tzm1 = 1, faces -y,+x,+y,-x).  Single rank."""
+
+    ARRAY_NAMES = BoxCase.ARRAY_NAMES[:28]
+
+    def __init__(self, nel, nx1, imode=1, length=2 * math.pi):
+        self.nel = tuple(int(v) for v in nel)
+        self.nx1, self.imode, self.length = int(nx1), int(imode), float(length)
+        EX, EY = self.nel
+        if min(self.nel) < 3:
+            raise ValueError("periodic directions need >= 3 elements")
+        n = self.nx1
+        self.nelt = EX * EY
+        self.nxyz, self.nxzf, self.nfaces = n * n, n, 4
+        self.npts = self.nxyz * self.nelt
+        self.nxzfl = self.nxzf * 4 * self.nelt
+        self.z, self.w = gll(n)
+        self.D = dgll(self.z)
+        self.h = (self.length / EX, self.length / EY)
+        self.volume_global = self.length ** 2
+        self.lglel = np.arange(self.nelt, dtype=np.int64)
+
+    def coords(self):
+        n = self.nx1
+        EX, EY = self.nel
+        g = np.arange(self.nelt)
+        ex, ey = g % EX, g // EX
+        xi = (self.z + 1.0) * 0.5
+        X = (ex[:, None] + xi[None, :]) * self.h[0]
+        Y = (ey[:, None] + xi[None, :]) * self.h[1]
+        shape = (self.nelt, n, n)
+        return (np.broadcast_to(X[:, None, :], shape).reshape(-1),
+                np.broadcast_to(Y[:, :, None], shape).reshape(-1))
+
+    def fields(self, t=0.0):
+        """(hn, en) of tests/2dboxper/2dboxper.usr:33-105 (omega = sqrt(2))"""
+        x, y = self.coords()
+        n = self.npts
+        om = math.sqrt(2.0)
+        hn = np.zeros(3 * n); en = np.zeros(3 * n)
+        if self.imode == 2:
+            th, te = math.sin(om * t) / om, math.cos(om * t)
+            hn[0:n] = np.cos(x) * np.sin(y) * th
+            hn[n:2 * n] = -np.sin(x) * np.cos(y) * th
+            en[2 * n:] = np.cos(x) * np.cos(y) * te
+        else:
+            th, te = math.cos(om * t), math.sin(om * t) / om
+            hn[2 * n:] = np.sin(x) * np.sin(y) * th
+            en[0:n] = np.sin(x) * np.cos(y) * te
+            en[n:2 * n] = -np.cos(x) * np.sin(y) * te
+        return hn, en
+
+    def face_ids(self):
+        EX, EY = self.nel
+        NE = EX * EY
+        n = self.nx1
+        g = np.arange(NE)
+        ex, ey = g % EX, g // EX
+        nbr = lambda dx, dy: ((ex + dx) % EX) + EX * ((ey + dy) % EY)
+        p = np.arange(n, dtype=np.int64)[None, :]
+        out = np.zeros((NE, 4, n), dtype=np.int64)
+        for slot, d, owner in ((0, 1, nbr(0, -1)), (1, 0, g), (2, 1, g), (3, 0, nbr(-1, 0))):
+            out[:, slot, :] = (d * NE + owner.astype(np.int64))[:, None] * n + p + 1
+        return out.reshape(-1)
+
+    def array(self, name, t=0.0):
+        n, nelt, npts, nxzfl = self.nx1, self.nelt, self.npts, self.nxzfl
+        hx, hy = self.h
+        if name == "dxm1":
+            return np.ascontiguousarray(self.D.T).reshape(-1)
+        w3 = (self.w[None, :] * self.w[:, None]).reshape(-1)
+        if name == "w3mn":
+            return w3
+        if name == "rxmn":
+            return np.full(npts, hy / 2.0)
+        if name == "symn":
+            return np.full(npts, hx / 2.0)
+        if name == "tzmn":
+            return np.ones(npts)
+        if name in ("rymn", "rzmn", "sxmn", "szmn", "txmn", "tymn"):
+            return np.zeros(npts)
+        if name == "bmn":
+            return np.tile((hx * hy / 4.0) * w3, nelt)
+        if name in ("hbm1", "ebm1"):
+            return np.tile(1.0 / ((hx * hy / 4.0) * w3), nelt)
+        if name in ("unxm", "unym", "unzm", "aream"):
+            f = np.zeros((4, n))
+            if name == "unxm":
+                f[1], f[3] = 1.0, -1.0
+            elif name == "unym":
+                f[0], f[2] = -1.0, 1.0
+            elif name == "aream":
+                f[0] = f[2] = (hx / 2.0) * self.w
+                f[1] = f[3] = (hy / 2.0) * self.w
+            return np.tile(f.reshape(-1), nelt)
+        if name in ("Y_0", "Y_1", "Z_0", "Z_1"):
+            return np.ones(nxzfl)
+        if name == "glo_num":
+            return self.face_ids()
+        if name in ("cempec", "pmlptr"):
+            return np.zeros(0, dtype=np.int64)
+        if name == "volvm1":
+            return self.volume_global
+        if name in ("hn", "en"):
+            hn, en = self.fields(t)
+            return hn if name == "hn" else en
+        raise KeyError(name)
+
+    def arrays(self, t=0.0):
+        return {k: self.array(k, t) for k in self.ARRAY_NAMES}

@@ -166,3 +166,25 @@ def test_boxcase_two_material_arrays_match_the_oracles_setup():
         assert np.allclose(getattr(c, k), b.array(k), rtol=1e-12, atol=0), k
     assert BoxCase(nel, nx1, pml="layers").array("pmlptr").size == 2 * 2 * 3 * 3
     assert BoxCase(nel, nx1, pml=True).array("pmlsigma").size == 3 * b.npts
+
+
+def test_boxcase2d_arrays_match_the_oracles_setup():
+    """the analytic 2D periodic box of nekcem_b200/boxcase.py (benchmark meshes for the TE / TM
+    path) against the oracle's setup of tests/2dboxper on the same 3 x 4 box"""
+    import numpy as np
+    from nekcem_b200.boxcase import BoxCase2D
+    from oracle import cases
+    for imode in (1, 2):
+        c = cases.case_2dboxper(imode, nx1=5, nel=(3, 4))
+        b = BoxCase2D((3, 4), 5, imode=imode)
+        for k in ("dxm1", "w3mn", "rxmn", "rymn", "sxmn", "symn", "tzmn", "bmn", "unxm", "unym",
+                  "aream", "Y_0", "Y_1", "Z_0", "Z_1", "hn", "en"):
+            assert np.allclose(getattr(c, k), b.array(k), rtol=0, atol=1e-13), (imode, k)
+        assert np.allclose(c.hbm1, b.array("hbm1"), rtol=1e-12)
+
+        def pairs(g):
+            d = {}
+            for i, v in enumerate(g):
+                d.setdefault(int(v), []).append(i)
+            return sorted(tuple(v) for v in d.values())
+        assert pairs(c.glo_num) == pairs(b.array("glo_num"))
