@@ -1,3 +1,2 @@
-timeout 600 bash scripts/ncu_capture.sh 7:40 r2_pipe_n8_allpml const_metrics=0 case:pml=all
-timeout 600 bash scripts/ncu_capture.sh 7:512 r2_stage2d_te_n8 case:dim=2
-tail -3 gpurun_out/prof_r2_stage2d_te_n8.log
+bash scripts/sweep_variants.sh "15:24 const_metrics=0" c16 a16 b16
+bash scripts/sweep_variants.sh "12:26 const_metrics=0" c13 a13
