@@ -78,7 +78,8 @@ typedef struct nekcem_b200_desc {
                             fails.  NEKCEM_B200_HOST_ONLY in the environment forces this
                             mode (test aid for driving the Fortran shim without a GPU); it
                             is not a CPU fallback -- nothing is ever computed on the host  */
-    int32_t strict;      /* 1: no-FMA kernels, bit-faithful to the CPU arithmetic    */
+    int32_t strict;      /* 1: kernels compiled without FMA contraction (-fmad=false);
+                            built for the 2D path (ldim = 2), refused for ldim = 3      */
     int32_t rank;        /* MPI rank (nid) and size (np): one rank <-> one GPU       */
     int32_t nranks;
 } nekcem_b200_desc;

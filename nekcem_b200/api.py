@@ -154,10 +154,12 @@ class MaxwellB200:
 
     def __init__(self, ldim: int, nx1: int, nelt: int, imode: int = 3, upwind: bool = True,
                  ifpec: bool = False, ifpml: bool = False, device: int = 0, rank: int = 0,
-                 nranks: int = 1):
+                 nranks: int = 1, strict: bool = False):
+        """strict: the no-FMA instantiations (2D contexts only): the arithmetic of the reference's
+        x86-64 build operation for operation"""
         self.L = lib()
         d = Desc(ABI_VERSION, ldim, nx1, nelt, imode, int(upwind), int(ifpec), int(ifpml),
-                 device, 0, rank, nranks)
+                 device, int(strict), rank, nranks)
         h = C.c_int(-1)
         _chk(self.L.nekcem_b200_create(C.byref(d), C.byref(h)))
         self.h = h.value

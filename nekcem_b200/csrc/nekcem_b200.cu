@@ -25,12 +25,17 @@
 
 #include "../../include/nekcem_b200.h"
 #include "stage_args.h"
+#include "graphene_args.h"
 #include "stage_graphene.h"
 
 namespace nkb {
 int launch_stage_slab(const StageArgs &a, const double *Dhost, int nx1, bool aux, bool cm, void *stream);
 int launch_stage_pipe(const StageArgs &a, const double *Dhost, int nx1, bool aux, bool cm, void *stream);
 int launch_stage2d(const StageArgs &a, const double *Dhost, int nx1, bool aux, void *stream);
+// the same two kernels compiled with -fmad=false (desc.strict, 2D contexts)
+int launch_stage2d_strict(const StageArgs &a, const double *Dhost, int nx1, bool aux, void *stream);
+int launch_graphene(const GrapheneArgs &g, void *stream);
+int launch_graphene_strict(const GrapheneArgs &g, void *stream);
 }
 
 namespace {
@@ -446,62 +451,7 @@ __global__ void wait_flags_kernel(const unsigned long long *flags, const int *pe
     __threadfence_system();
 }
 
-// Graphene sheets: one thread per face point of the user's graphindex list advances the surface
-// current ADEs of that point by one RK stage (stage_graphene.h) from the stage-start fields,
-// exactly where the reference's userfsrc runs (own-side face values after userinc, before the
-// face sum).  Slot m = 0 of fj then holds fjn(j,:,1), which the stage kernels subtract from
-// -(n x H) on both sides of the face.
-struct GrapheneArgs {
-    const double *u;
-    long long ld;
-    int ng, imode;
-    const int *fp, *node;
-    const double *unx, *uny, *unz, *hY, *yc, *par;
-    double *fj, *kj;
-    const int *inc_own;
-    const double *inc_amp, *inc_phase;
-    int inc_n;
-    double inc_wt, ca, cb, dt;
-};
-__global__ void graphene_kernel(GrapheneArgs g)
-{
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= g.ng) return;
-    const int j = g.fp[q];
-    const long long nd = g.node[q];
-    double H[3], E[3];
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-        H[c] = g.u[c * g.ld + nd];
-        E[c] = g.u[(3 + c) * g.ld + nd];
-    }
-    if (g.inc_own != nullptr) { // userinc precedes the flux (src/cem_maxwell.F:498)
-        const int qi = g.inc_own[j];
-        if (qi >= 0) {
-            const double ui = cos(g.inc_phase[qi] - g.inc_wt);
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                H[c] += g.inc_amp[c * g.inc_n + qi] * ui;
-                E[c] += g.inc_amp[(3 + c) * g.inc_n + qi] * ui;
-            }
-        }
-    }
-    const double n[3] = {g.unx[j], g.uny[j], g.unz ? g.unz[j] : 0.0};
-    double par[12], fj[18], kj[18];
-#pragma unroll
-    for (int m = 0; m < 12; m++) par[m] = g.par[(long long)m * g.ng + q];
-#pragma unroll
-    for (int m = 0; m < 18; m++) {
-        fj[m] = g.fj[(long long)m * g.ng + q];
-        kj[m] = g.kj[(long long)m * g.ng + q];
-    }
-    nkb::graphene_point(g.imode, H, E, n, g.hY[j], g.yc[q], par, fj, kj, g.ca, g.cb, g.dt);
-#pragma unroll
-    for (int m = 0; m < 18; m++) {
-        g.fj[(long long)m * g.ng + q] = fj[m];
-        g.kj[(long long)m * g.ng + q] = kj[m];
-    }
-}
+// (graphene_kernel: graphene.cu)
 
 // cem_error partial sums (src/cem_common.F:1335-1355): per block, per component
 __global__ void error_kernel(const double *u, long long ld, const double *exact, long long npts,
@@ -1112,7 +1062,7 @@ int run_stage(Ctx *c, int rkstep /*1..5*/, int phase = 0)
     if (!c->g_fp.empty() && phase != 2) {
         // userfsrc -> cem_*_graphene_current: needs only stage-start data, so it runs first on
         // the compute stream; every stage launch of this stage is ordered after it
-        GrapheneArgs g{};
+        nkb::GrapheneArgs g{};
         g.u = a.u_in; g.ld = c->ld;
         g.ng = a.fs_n; g.imode = c->d.imode;
         g.fp = c->g_fp_d; g.node = c->g_node_d;
@@ -1122,8 +1072,9 @@ int run_stage(Ctx *c, int rkstep /*1..5*/, int phase = 0)
         g.inc_own = c->inc_own_d; g.inc_amp = c->inc_amp_d; g.inc_phase = c->inc_phase_d;
         g.inc_n = a.inc_n; g.inc_wt = a.inc_wt;
         g.ca = a.ca; g.cb = a.cb; g.dt = a.dt;
-        graphene_kernel<<<(unsigned)((g.ng + 127) / 128), 128, 0, c->s_compute>>>(g);
-        CUDA_OK(cudaGetLastError());
+        if ((c->d.strict ? nkb::launch_graphene_strict(g, c->s_compute)
+                         : nkb::launch_graphene(g, c->s_compute)) != 0)
+            return fail("graphene kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         c->last_launches++;
         if (c->g_send_d) CUDA_OK(cudaEventRecord(c->ev_sheet, c->s_compute));
     }
@@ -1142,7 +1093,9 @@ int run_stage(Ctx *c, int rkstep /*1..5*/, int phase = 0)
                 rc = nkb::launch_stage_slab(b, c->D_host.data(), c->n, (q & 1) != 0, (q & 2) != 0,
                                             c->s_compute);
         } else {
-            rc = nkb::launch_stage2d(b, c->D_host.data(), c->n, (q & 1) != 0, c->s_compute);
+            rc = c->d.strict
+                     ? nkb::launch_stage2d_strict(b, c->D_host.data(), c->n, (q & 1) != 0, c->s_compute)
+                     : nkb::launch_stage2d(b, c->D_host.data(), c->n, (q & 1) != 0, c->s_compute);
         }
         if (rc < 0) return fail("nx1=%d is not supported by the stage kernels (2..16)", c->n);
         if (rc > 0) return fail("stage kernel launch failed: %s",
@@ -1354,7 +1307,8 @@ int nekcem_b200_create(const nekcem_b200_desc *desc, int *handle)
     if (desc->nx1 < 2 || desc->nx1 > 16)
         return fail("nx1=%d outside the supported range 2..16", desc->nx1);
     if (desc->nelt < 1) return fail("nelt must be >= 1");
-    if (desc->strict != 0) return fail("strict (no-FMA) kernels are not built in this version");
+    if (desc->strict != 0 && desc->ldim != 2)
+        return fail("strict (no-FMA) kernels exist for the 2D path only (ldim = 2)");
     if (desc->nranks < 1 || desc->rank < 0 || desc->rank >= desc->nranks)
         return fail("bad rank/nranks %d/%d", desc->rank, desc->nranks);
     auto c = std::make_unique<Ctx>();

@@ -225,7 +225,12 @@ int launch_n(const StageArgs &a, const double *Dhost, bool aux, cudaStream_t st)
 } // namespace
 
 // returns 0 ok, -1 unsupported order, >0 CUDA failure.  Dhost = dxm1 (n*n, column-major).
+// compiled twice (Makefile): as is, and with -fmad=false -DNKB_STRICT (desc.strict)
+#ifdef NKB_STRICT
+int launch_stage2d_strict(const StageArgs &a, const double *Dhost, int nx1, bool aux, void *stream)
+#else
 int launch_stage2d(const StageArgs &a, const double *Dhost, int nx1, bool aux, void *stream)
+#endif
 {
     cudaStream_t st = (cudaStream_t)stream;
     switch (nx1) {

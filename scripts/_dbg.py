@@ -1,15 +1,16 @@
 import sys, numpy as np
 sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
-from helpers import rel_l2, solver_from_refcase
+from helpers import rel_l2
+import test_gpu_zgraphene as T
 from oracle import cases
-for nx1 in (11, 12, 13, 16):
-    for pipeline in (0, 1):
-        c = cases.case_boxper((3, 3, 4), nx1, dt=-1e-3)
-        s = solver_from_refcase(c)
-        s.set_option("pipeline", pipeline)
-        c.step(3); s.step(3)
-        f = rel_l2(np.concatenate([s.get_array("hn"), s.get_array("en")]), np.concatenate([c.hn, c.en]))
-        kg = np.concatenate([s.get_array("khn"), s.get_array("ken")]); ko = np.concatenate([c.khn, c.ken])
-        per = [rel_l2(kg[i*c.npts:(i+1)*c.npts], ko[i*c.npts:(i+1)*c.npts]) for i in range(6)]
-        print(nx1, pipeline, "fields", f, "k", rel_l2(kg, ko), "percomp", ["%.1e" % p for p in per], "absmax k", np.abs(ko).max(), flush=True)
+for inc in (True, False):
+    for strict in (False, True):
+        c = cases.case_2dgraphene(1)
+        if not inc:
+            c.s.userinc = type(c.s.userinc)()
+        s = T._solver(c, incident=inc, strict=strict)
+        s.step(200); c.step(200)
+        (fg, fo), (kg, ko) = T._sheet_state(c, s)
+        print("incident", inc, "strict", strict, "fields %.2e fj %.2e kj %.2e" % (rel_l2(T._fields(s), T._fields(c)), rel_l2(fg, fo), rel_l2(kg, ko)),
+              "bitwise fields", np.array_equal(T._fields(s), T._fields(c)), "max|f|", np.abs(T._fields(c)).max(), flush=True)
         s.close()

@@ -1,2 +1,1 @@
-bash scripts/sweep_variants.sh "15:24 const_metrics=0" c16 a16 b16
-bash scripts/sweep_variants.sh "12:26 const_metrics=0" c13 a13
+timeout 900 python -m pytest tests/test_gpu_zgraphene.py tests/test_gpu_zz_tworank_local.py -q -x 2>&1 | tail -4

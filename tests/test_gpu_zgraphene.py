@@ -16,22 +16,25 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-12
 # RK registers of the sheet ODEs: kfjn = ca*kfjn + dt*res, where the critical-point residuals
 # res = -a_21*j - a_22*j' + b_2*f (a_21 ~ 4.6e5) are differences of terms 1e3..1e4 times larger
-# than the result.  The device contracts a*b+c to FMA, the oracle does not, so the last-bit
-# differences of those terms show up magnified in k (measured 4e-12 on B200) while the currents
-# fjn -- what enters the flux -- and the fields agree to ~3e-15.
-KTOL = 1e-10
+# than the result: they are ill-conditioned.  The ORACLE ITSELF moves its kfjn by 3e-12 (and its
+# fields by 1e-15) when the last bit of the initial fields is flipped
+# (tests/test_oracle_units.py::test_sheet_rk_registers_are_ill_conditioned), so no implementation
+# that differs from it by round-off can agree better; measured on B200: 3.7e-12 (2dgraphene as
+# shipped, 200 steps), the same with the no-FMA build (desc.strict), while the currents fjn -- what
+# enters the flux -- and the fields agree to ~3e-15 / 3e-14.
+KTOL = 2e-11
 
 
 def _fields(obj):
     return np.concatenate([obj.hn, obj.en])
 
 
-def _solver(c, gindex=None, incident=True):
+def _solver(c, gindex=None, incident=True, strict=False):
     u = c.user
     from nekcem_b200 import MaxwellB200
     from helpers import arrays_from_refcase
     s = MaxwellB200(c.ldim, c.nx1, c.nelt, imode=c.imode, upwind=True, ifpec=c.ifpec,
-                    ifpml=c.ifpml, device=0)
+                    ifpml=c.ifpml, device=0, strict=strict)
     s.cem_maxwell_init(arrays_from_refcase(c))
     if incident:
         s.set_incident(*u.incident(c))
@@ -75,6 +78,30 @@ def test_kat_2dgraphene_on_gpu(imode):
     assert rel_l2(s.get_array("pmlbn"), c.pmlbn) <= TOL
     assert rel_l2(s.get_array("pmldn"), c.pmldn) <= TOL
     s.close()
+
+
+@pytest.mark.parametrize("imode", [1, 2])
+def test_2dgraphene_strict_mode_demonstrates_the_fma_argument(imode):
+    """desc.strict = 1 (2D contexts): the 2D stage kernel and the graphene kernel compiled with
+    -fmad=false.  Round 1 blamed FMA contraction for the 4e-12 of the sheet RK registers; the strict
+    build shows that FMA is not it -- both builds sit at the same 3.6e-12 / 3.7e-12, which is the
+    conditioning of those registers (KTOL above: the oracle moves by 3e-12 under a last-bit
+    perturbation of its own input).  Everything else meets 1e-12 in both builds."""
+    from oracle import cases
+    out = {}
+    for strict in (False, True):
+        c = cases.case_2dgraphene(imode)
+        s = _solver(c, strict=strict)
+        s.step(200); c.step(200)
+        (fg, fo), (kg, ko) = _sheet_state(c, s)
+        out[strict] = (rel_l2(_fields(s), _fields(c)), rel_l2(fg, fo), rel_l2(kg, ko),
+                       rel_l2(s.get_array("pmldn"), c.pmldn))
+        s.close()
+    print("2dgraphene imode", imode, "rel-L2 (fields, fj, kj, pmldn): default", out[False],
+          "strict", out[True])
+    for o in out.values():
+        assert o[0] <= TOL and o[1] <= TOL and o[3] <= TOL and o[2] <= KTOL, out
+    assert abs(out[True][2] - out[False][2]) <= 0.5 * out[False][2], out  # FMA is not the cause
 
 
 def test_3dgraphene_parity_and_tolerances():

@@ -12,7 +12,7 @@ from nekcem_b200 import MaxwellB200
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
-KTOL = 1e-10  # RK registers of the stiff sheet ODEs, see tests/test_gpu_zgraphene.py
+KTOL = 1e-10  # RK registers of the ill-conditioned sheet ODEs, see tests/test_gpu_zgraphene.py
 
 
 def _two_ranks(ref, parts, register):
