@@ -53,7 +53,10 @@ namespace {
 #define PIPE_PML_L2 1 // 1: L2 prefetch of a PML element's auxiliary arrays at the start of the item
 #endif
 #ifndef PIPE_XOUT
-#define PIPE_XOUT 1 // 1: the x-face mirror is written coalesced from shared memory
+// 1: the x-face mirror is written coalesced from shared memory at the top of the next item;
+// 0: straight from the epilogue.  With one CTA per SM (nx1 = 9, 10) the extra pass is serial time
+// (measured 0.68 -> 0.695), with two it is free.
+#define PIPE_XOUT (PIPE_ONLY_N <= 8)
 #endif
 #ifndef PIPE_SKIP
 #define PIPE_SKIP 0 // timing experiments only (wrong results): 1 P1, 2 P2, 4 flux, 8 P4, 16 relayout
