@@ -43,6 +43,9 @@ namespace {
 #ifndef PIPE_FLUX_LAST
 #define PIPE_FLUX_LAST 1 // 1: t-pencils before the flux phase (gathers in flight meanwhile)
 #endif
+#ifndef PIPE_IG_T
+#define PIPE_IG_T 0 // 1: the t-pencil lanes interleave the two groups as well
+#endif
 #ifndef PIPE_NBR_PREFETCH
 #define PIPE_NBR_PREFETCH 1 // 1: L2 prefetch of the neighbour traces at P0
 #endif
@@ -342,9 +345,18 @@ __device__ __forceinline__ void pipe_t_phase(const double (&D)[N * N], const Sta
 #pragma unroll 1
         for (int w = tid; w < C::T_ITEMS; w += C::NT) {
             const int h = w / C::T_BLK, r = w - h * C::T_BLK;
-            const int g = r / C::N2, p = r - g * C::N2;
+            int g, pa, pb;
+            if (PIPE_IG_T) { // lanes: i (N) x group (2) x j: both groups read one cofactor address
+                const int q = r / N;
+                pa = r - q * N;
+                g = r >= 2 * C::N2 ? 2 : (q & 1);
+                pb = q >> 1;
+            } else {
+                g = r / C::N2;
+                const int p = r - g * C::N2;
+                pa = p % N; pb = p / N;
+            }
             if (g > 1) continue;
-            const int pa = p % N, pb = p / N;
             pipe_split<N, 2, K0, K0, K1, C::TSPLIT, C::SC, C::XL, CM>(
                 D, U + (g ? 3 * C::SC + HE : 0), R + (g ? 0 : 3 * C::SC + HE), cofs, cm,
                 W3 + K0 * C::N2, pa, pb, g ? -1.0 : 1.0, h);
