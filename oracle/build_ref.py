@@ -110,7 +110,7 @@ LIB_DROPIN = os.path.join(OUT, "libnekcem_ref_dropin.so")
 REPO = os.path.dirname(HERE)
 SHIM = (os.path.join(REPO, "fortran", "cem_maxwell_b200_f77.F"),
         ["b200_copy_all_in", "b200_update_device", "b200_op_rk", "b200_update_host",
-         "b200_copy_all_out"])
+         "b200_restart_out", "b200_restart_swap", "b200_copy_all_out"])
 PRODUCT_LIB_DIR = os.path.join(REPO, "nekcem_b200", "lib")
 
 

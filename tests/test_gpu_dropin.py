@@ -198,3 +198,39 @@ def test_dropin_volume_source_registered_like_a_usr_would():
     r.close()
     assert np.abs(want).max() > 1e-6
     assert rel_l2(got, want) <= TOL
+
+
+def test_dropin_restart_handoff_through_the_shim():
+    """The reference's `maxwell-restart` test (tests/restart/restart.usr:70-165) through the
+    Fortran shim and the COMMON blocks: HN, EN = 1.0 go to the device, b200_restart_out delivers the
+    payloads cem_out / cem_restart_out would write, the fields are overwritten with 2.0 on host and
+    device, b200_restart_swap (the field part of restart_swap) reads the payloads back, and after
+    b200_update_host the COMMON arrays must hold 1.0 again -- the .usr demands cem_error <= 1e-15;
+    here every bit."""
+    from oracle import cases
+    refrun = _refrun()
+    case = cases.case_boxper((3, 3, 3), 8, dt=-1e-3)
+    n3 = 3 * case.npts
+    r = refrun.ReferenceRun(case, kind="dropin")
+    if not hasattr(r.L, "b200_restart_swap_"):
+        pytest.skip("oracle/_ref was built before the shim had the restart routines")
+    for k in ("hn", "en"):
+        r.view(k)[:n3] = 1.0
+    r.L.b200_copy_all_in_()
+    r.L.b200_update_device_()
+    buf_e = np.zeros(n3); buf_h = np.zeros(n3)
+    dbl = C.c_int(1)
+    dp = C.POINTER(C.c_double)
+    r.L.b200_restart_out_(buf_e.ctypes.data_as(dp), buf_h.ctypes.data_as(dp), C.byref(dbl))
+    assert buf_e.tobytes() == np.ones(n3).astype(">f8").tobytes()      # big-endian 1.0
+    for k in ("hn", "en"):
+        r.view(k)[:n3] = 2.0
+    r.L.b200_update_device_()                                            # the device holds 2.0
+    r.L.b200_restart_swap_(buf_e.ctypes.data_as(dp), buf_h.ctypes.data_as(dp), C.byref(dbl))
+    for k in ("hn", "en"):
+        r.view(k)[:n3] = -7.0
+    r.L.b200_update_host_()
+    for k in ("hn", "en"):
+        assert np.array_equal(r.view(k)[:n3], np.ones(n3)), k
+    r.L.b200_copy_all_out_()
+    r.close()
