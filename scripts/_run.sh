@@ -1,1 +1,4 @@
-timeout 900 python -m pytest tests/test_gpu_dropin.py -q -x 2>&1 | tail -4
+bash scripts/sweep_variants.sh "15:24 const_metrics=0 pipeline=1" w16
+bash scripts/sweep_variants.sh "12:26 const_metrics=0 pipeline=1" w13
+bash scripts/sweep_variants.sh "11:28 const_metrics=0 pipeline=1" w12
+bash scripts/sweep_variants.sh "10:32 const_metrics=0 pipeline=1" w11
