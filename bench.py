@@ -423,7 +423,16 @@ def run_gpu(args):
     # PCIe full duplex); consecutive inputs are independent states, as a stream of them would be
     Ke = K if args.e2e_steps <= 0 else max(1, min(args.e2e_steps, K))
     n3 = 3 * case.npts
-    pins = [torch.empty(n3, dtype=torch.float64, pin_memory=True) for _ in range(4)]
+    e2e_buffers = "separate pinned input and output buffers"
+    try:
+        pins = [torch.empty(n3, dtype=torch.float64, pin_memory=True) for _ in range(4)]
+    except RuntimeError:
+        # not enough pinnable host memory for 4 x 3*npts doubles per rank: results come back into
+        # the input buffers (the upload of input k+1 then reads what the download of result k-1
+        # is writing; same bytes over PCIe, the values of later inputs are undefined)
+        pins = [torch.empty(n3, dtype=torch.float64, pin_memory=True) for _ in range(2)]
+        pins = pins + pins
+        e2e_buffers = "outputs written into the input buffers (host memory limit)"
     hn_in, en_in, hn_out, en_out = (p.numpy() for p in pins)
     hn_in[:] = slv.hn
     en_in[:] = slv.en
@@ -546,6 +555,7 @@ def run_gpu(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_io,
                     "d2h_bytes_per_step": bytes_io, "steps": Ke, "result_checked": e2e_ok,
+                    "host_buffers": e2e_buffers,
                     "what": "per step: H2D(hn,en) of the next input from pinned host memory + one "
                             "time step + D2H(hn,en) of the previous result to pinned host memory, "
                             "through nekcem_b200_step_streamed (three streams; inputs of "
