@@ -31,6 +31,7 @@
 namespace nkb {
 int launch_stage_slab(const StageArgs &a, const double *Dhost, int nx1, bool aux, bool cm, void *stream);
 int launch_stage_pipe(const StageArgs &a, const double *Dhost, int nx1, bool aux, bool cm, void *stream);
+int launch_stage_sweep(const StageArgs &a, const double *Dhost, int nx1, bool aux, bool cm, void *stream);
 int launch_stage2d(const StageArgs &a, const double *Dhost, int nx1, bool aux, void *stream);
 // the same two kernels compiled with -fmad=false (desc.strict, 2D contexts)
 int launch_stage2d_strict(const StageArgs &a, const double *Dhost, int nx1, bool aux, void *stream);
@@ -211,6 +212,7 @@ struct Ctx {
     // 1 (default): the persistent bulk-copy kernel (stage_pipe.cu) for the orders it covers;
     // 0: the slab kernel (stage_slab.cu) everywhere
     bool opt_pipeline = true;
+    bool opt_sweep = false; // plane-sweep kernel for nx1 = 11..16 (stage_sweep.cu)
     // 3D: mirror of the fields on the x faces (StageArgs::xtr_in); 0 = gather from the volume
     bool opt_xtrace = true;
     double *xtr[2] = {nullptr, nullptr};
@@ -1086,7 +1088,10 @@ int run_stage(Ctx *c, int rkstep /*1..5*/, int phase = 0)
         b.nel = c->list_n[q];
         int rc = -1;
         if (c->d.ldim == 3) {
-            if (c->opt_pipeline)
+            if (c->opt_pipeline && c->opt_sweep)
+                rc = nkb::launch_stage_sweep(b, c->D_host.data(), c->n, (q & 1) != 0, (q & 2) != 0,
+                                             c->s_compute);
+            if (rc < 0 && c->opt_pipeline)
                 rc = nkb::launch_stage_pipe(b, c->D_host.data(), c->n, (q & 1) != 0, (q & 2) != 0,
                                             c->s_compute);
             if (rc < 0)
@@ -2026,6 +2031,10 @@ int nekcem_b200_set_option(int handle, const char *name, int value)
     if (!name) return fail("null option name");
     if (strcmp(name, "pipeline") == 0) {
         c->opt_pipeline = value != 0;
+        return 0;
+    }
+    if (strcmp(name, "sweep") == 0) {
+        c->opt_sweep = value != 0;
         return 0;
     }
     if (strcmp(name, "p2p") == 0) {
