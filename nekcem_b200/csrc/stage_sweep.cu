@@ -52,29 +52,31 @@ __host__ __device__ constexpr int s_min(int a, int b) { return a < b ? a : b; }
 template <int N>
 struct SW {
     static constexpr int N2 = N * N, N3 = N2 * N, NF = 6 * N2;
-    static constexpr int H = 4;                      // output shares of a pencil
-    static constexpr int NO = (N + H - 1) / H;       // outputs per share
-    static constexpr int RS_BLK = s_round32(6 * N);  // (direction, component, line) pencils of a share
+    static constexpr int NO = 2;                     // outputs per pencil share
+    static constexpr int H = (N + NO - 1) / NO;      // output shares of a pencil
+    static constexpr int RS_BLK = s_round32(2 * N);  // (direction, line) pencils of a share
     static constexpr int RS_ITEMS = H * RS_BLK;
-    static constexpr int NTN = 3 * N2;               // node threads (i, j, c)
-    static constexpr int NT = s_max(s_round32(NTN), RS_ITEMS);
-    static constexpr int NARR = 19;                  // rows of a ring stage
+    static constexpr int NT = s_max(s_round32(N2), RS_ITEMS);
+    static constexpr int NARR = 16;                  // rows of a ring stage
     static constexpr int PL = s_even(N2 + 2);        // one row (+ alignment slack of the bulk copy)
     static constexpr int STG = NARR * PL;
-    static constexpr int RW = N + 1;                 // row stride of a derivative plane
+    static constexpr int RW = N | 1;                 // row stride of a source / derivative plane (odd)
     static constexpr int DPL = s_even(RW * N);
     static constexpr int LF = s_even(NF);
     static constexpr int FPT = (NF + NT - 1) / NT;   // face points per thread
-    static constexpr int FIXED = 18 * DPL + 3 * LF + s_even(N2) + 16;
+    static constexpr int FIXED = 12 * DPL + 6 * DPL + 3 * LF + 16;
     static constexpr int CAP = (227 * 1024 - 1024) / 8;
-    // CTAs per SM: two when registers (>= 80 per thread) and the ring (>= 3 stages) allow
-    static constexpr bool TWO = 65536 / (2 * NT) >= 80 && (CAP / 2 - FIXED) / STG >= 3;
-    static constexpr int MINB = TWO ? 2 : 1;
-    static constexpr int NSTG0 = ((TWO ? CAP / 2 : CAP) - FIXED) / STG;
+#ifdef SWEEP_MINB
+    static constexpr int MINB = SWEEP_MINB;
+#else
+    // CTAs per SM: two when the ring keeps >= 3 stages and the k-lines fit the registers
+    static constexpr int MINB = ((CAP / 2 - FIXED) / STG >= 3 && 65536 / (2 * NT) >= 160) ? 2 : 1;
+#endif
+    static constexpr int NSTG0 = (CAP / MINB - FIXED) / STG;
     static constexpr int NSTG = s_min(s_min(NSTG0, SWEEP_NSTG_MAX), N);
     static_assert(NSTG >= 2, "ring too small");
-    static constexpr int OFF_RING = 0, OFF_DD = NSTG * STG, OFF_L = OFF_DD + 18 * DPL,
-                         OFF_DT = OFF_L + 3 * LF, OFF_BAR = OFF_DT + s_even(N2);
+    static constexpr int OFF_RING = 0, OFF_DD = NSTG * STG, OFF_PP = OFF_DD + 12 * DPL,
+                         OFF_L = OFF_PP + 6 * DPL, OFF_BAR = OFF_L + 3 * LF;
     static constexpr size_t SMEM = sizeof(double) * (OFF_BAR + NSTG + 2);
 };
 
@@ -132,27 +134,47 @@ __device__ __forceinline__ void bulk_prefetch(const double *src, int cnt)
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(s - head), "r"(bytes) : "memory");
 }
 
-// One thread, outputs O0..O1-1 of one line of one component:
-//   out(o) = sum_m D(o,m) in(m)      (mxfK order, left to right)
-template <int N, int O0, int O1>
+// One thread, outputs O0..O1-1 of one line of the three source components:
+//   out_c(o) = sum_m D(o,m) in_c(m)      (mxfK order, left to right)
+template <int N, int O0, int O1, int CS>
 __device__ __forceinline__ void sweep_pencil(const double (&D)[N * N], const double *in, int sm,
                                              double *out, int so)
 {
     constexpr int NO = O1 - O0;
     if constexpr (NO > 0) {
-        double acc[NO];
+        double acc[3][NO];
 #pragma unroll
         for (int m = 0; m < N; m++) {
-            const double u = in[m * sm];
+            const double u0 = in[m * sm], u1 = in[CS + m * sm], u2 = in[2 * CS + m * sm];
 #pragma unroll
             for (int o = 0; o < NO; o++) {
                 const double dv = D[(O0 + o) + N * m];
-                if (m == 0) acc[o] = dv * u;
-                else acc[o] = acc[o] + dv * u;
+                if (m == 0) {
+                    acc[0][o] = dv * u0; acc[1][o] = dv * u1; acc[2][o] = dv * u2;
+                } else {
+                    acc[0][o] = acc[0][o] + dv * u0;
+                    acc[1][o] = acc[1][o] + dv * u1;
+                    acc[2][o] = acc[2][o] + dv * u2;
+                }
             }
         }
 #pragma unroll
-        for (int o = 0; o < NO; o++) out[(O0 + o) * so] = acc[o];
+        for (int o = 0; o < NO; o++) {
+            out[(O0 + o) * so] = acc[0][o];
+            out[CS + (O0 + o) * so] = acc[1][o];
+            out[2 * CS + (O0 + o) * so] = acc[2][o];
+        }
+    }
+}
+
+// dispatch on the (warp-uniform) output share h: outputs [2h, 2h+2) of 0..N-1
+template <int N, int CS, int HH = 0>
+__device__ __forceinline__ void sweep_share(const double (&D)[N * N], const double *in, int sm,
+                                            double *out, int so, int h)
+{
+    if constexpr (2 * HH < N) {
+        if (h == HH) sweep_pencil<N, 2 * HH, s_min(2 * HH + 2, N), CS>(D, in, sm, out, so);
+        else sweep_share<N, CS, HH + 1>(D, in, sm, out, so, h);
     }
 }
 
@@ -162,13 +184,13 @@ __global__ void __launch_bounds__(SW<N>::NT, SW<N>::MINB)
 {
     using C = SW<N>;
     constexpr int N2 = C::N2, N3 = C::N3, NF = C::NF, NT = C::NT, PL = C::PL, STG = C::STG;
-    constexpr int RW = C::RW, DPL = C::DPL, LF = C::LF, NSTG = C::NSTG, FPT = C::FPT, NO = C::NO;
+    constexpr int RW = C::RW, DPL = C::DPL, LF = C::LF, NSTG = C::NSTG, FPT = C::FPT;
     const StageArgs &a = prm.a;
     extern __shared__ __align__(16) double smem[];
-    double *ring = smem + C::OFF_RING; // [NSTG][19][PL]
-    double *DD = smem + C::OFF_DD;     // [2][3 directions][3 components][DPL]
+    double *ring = smem + C::OFF_RING; // [NSTG][16][PL]: 9 cofactors, 3 RK registers, 3 old fields, mass
+    double *DD = smem + C::OFF_DD;     // [2][r,s][3 components][DPL] derivatives of a plane
+    double *PP = smem + C::OFF_PP;     // [2][3 components][DPL] source components of a plane
     double *L = smem + C::OFF_L;       // [3][LF] lifts of the item's output components
-    double *Dt = smem + C::OFF_DT;     // Dt[k*N + m] = D(k, m)
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
 
     const int tid = threadIdx.x;
@@ -186,25 +208,27 @@ __global__ void __launch_bounds__(SW<N>::NT, SW<N>::MINB)
         for (int b = 0; b < NSTG; b++) mbar_init(full + b, 32);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int x = tid; x < N2; x += NT) Dt[x] = prm.D[(x / N) + N * (x % N)];
     __syncthreads();
 
-    // node thread (i, j, c)
-    const bool node = tid < C::NTN;
-    const int nc = node ? tid / N2 : 0;
-    const int pnd = node ? tid - nc * N2 : 0;
+    // node thread (i, j): all three components of the nodes (i, j, .)
+    const bool node = tid < N2;
+    const int pnd = node ? tid : 0;
     const int pi = pnd % N, pj = pnd / N;
-    const int ca_ = (nc + 1) % 3, cb_ = (nc + 2) % 3; // the two components the curl of c needs
+    const int pp = pi + RW * pj; // its place in a source / derivative plane
+    // pencil of this thread: share h of the outputs (warp-uniform), direction d (0: r, 1: s), line
+    const int ph = tid / C::RS_BLK, pr = tid - ph * C::RS_BLK;
+    const bool pen = tid < C::RS_ITEMS && pr < 2 * N;
+    const int pd = pr / N, pline = pr - pd * N;
+    const int p_in = pd ? pline : pline * RW, p_sm = pd ? RW : 1; // r: along i, s: along j
 
     // producer: every lane of warp 0 arrives with the bytes of its own copy (one row each)
     auto issue_plane = [&](int e, int k, int stg) {
         const long long off = (long long)e * N3 + (long long)k * N2;
         const double *src = nullptr;
-        if (lane < 3) src = a.u_in + (long long)(srcc + lane) * a.ld;
-        else if (lane < 12) src = a.met[lane - 3];
-        else if (lane < 15) src = a.kf + (long long)(outc + lane - 12) * a.ld;
-        else if (lane < 18) src = a.u_in + (long long)(outc + lane - 15) * a.ld;
-        else if (lane == 18) src = mass;
+        if (lane < 9) src = a.met[lane];
+        else if (lane < 12) src = a.kf + (long long)(outc + lane - 9) * a.ld;
+        else if (lane < 15) src = a.u_in + (long long)(outc + lane - 12) * a.ld;
+        else if (lane == 15) src = mass;
         uint32_t bytes = 0;
         if (src != nullptr) bytes = bulk_bytes(src + off, N2);
         mbar_arrive_tx(full + stg, bytes);
@@ -241,13 +265,13 @@ __global__ void __launch_bounds__(SW<N>::NT, SW<N>::MINB)
 
     // ring bookkeeping: planes are numbered through the items of this CTA; plane t lives in stage
     // t % NSTG and completes phase (t / NSTG) & 1 of that stage's barrier
-    int istg = 0, ik = 0;   // next plane to issue: stage, plane index (>= N: of the next item)
+    int ik = 0;             // next plane to issue (>= N: of the next item)
     int cstg = 0;           // stage of the plane being consumed
     uint32_t parbits = 0;   // per stage: parity of the phase its next consumer waits for
     if (q < nitems && w0) {
         for (int x = 0; x < NSTG; x++) issue_plane(e, x, x);
     }
-    if (q < nitems) { ik = NSTG; istg = 0; } // NSTG <= N
+    if (q < nitems) ik = NSTG; // NSTG <= N
 
 #pragma unroll 1
     for (; q < nitems; q += G) {
@@ -255,12 +279,14 @@ __global__ void __launch_bounds__(SW<N>::NT, SW<N>::MINB)
         const bool more = q + G < nitems;
         const int enn = q + 2 * G < nitems ? ldg(a.elist + ((q + 2 * G) >> 1)) : 0;
 
-        // ---- k-line of this thread's source component -> registers --------------------------------
-        double col[N];
+        // ---- k-lines of the three source components through node (i, j) -> registers --------------
+        double col[3][N];
         {
-            const double *gp = a.u_in + (long long)(srcc + nc) * a.ld + ebase + pnd;
+            const double *gp = a.u_in + (long long)srcc * a.ld + ebase + pnd;
 #pragma unroll
-            for (int m = 0; m < N; m++) col[m] = node ? ldg(gp + N2 * m) : 0.0;
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int m = 0; m < N; m++) col[c][m] = node ? ldg(gp + c * a.ld + N2 * m) : 0.0;
         }
 
         // ---- surface flux of the item's output components -> L (flux3d, src/cem_maxwell.F:922-1002)
@@ -280,6 +306,7 @@ __global__ void __launch_bounds__(SW<N>::NT, SW<N>::MINB)
                 for (int c = 0; c < 6; c++) ov[c] = ldg(a.u_in + (long long)c * a.ld + ebase + nd);
                 const double unx = ldg(a.unx + jf), uny = ldg(a.uny + jf), unz = ldg(a.unz + jf);
                 const double ar = ldg(a.area + jf);
+                const double h0 = ldg((g ? a.hY : a.hZ) + jf), i1 = ldg((g ? a.Y1 : a.Z1) + jf);
                 double Hx = ov[0], Hy = ov[1], Hz = ov[2], Ex = ov[3], Ey = ov[4], Ez = ov[5];
                 double pHx = pv[0], pHy = pv[1], pHz = pv[2], pEx = pv[3], pEy = pv[4], pEz = pv[5];
                 if (a.inc_own != nullptr) { // userinc hook (src/cem_maxwell.F:498)
@@ -321,7 +348,7 @@ __global__ void __launch_bounds__(SW<N>::NT, SW<N>::MINB)
                     s3 = 0.0; s4 = 0.0; s5 = 0.0;
                 }
                 if (g) { // flux into resH (:976-986)
-                    const double hY = ldg(a.hY + jf), Y1 = ldg(a.Y1 + jf);
+                    const double hY = h0, Y1 = i1;
                     const double Y02 = -(hY * Y1), C02Y = hY * a.C0;
                     const double fu1 = uny * s5 - unz * s4;
                     const double fu2 = unz * s3 - unx * s5;
@@ -330,7 +357,7 @@ __global__ void __launch_bounds__(SW<N>::NT, SW<N>::MINB)
                     L[LF + fj] = ar * (Y02 * s1 - C02Y * fu2);
                     L[2 * LF + fj] = ar * (Y02 * s2 - C02Y * fu3);
                 } else { // flux into resE (:987-997)
-                    const double hZ = ldg(a.hZ + jf), Z1 = ldg(a.Z1 + jf);
+                    const double hZ = h0, Z1 = i1;
                     const double Z02 = hZ * Z1, C02Z = hZ * a.C0;
                     const double fw1 = uny * s2 - unz * s1;
                     const double fw2 = unz * s0 - unx * s2;
@@ -350,75 +377,101 @@ __global__ void __launch_bounds__(SW<N>::NT, SW<N>::MINB)
             fvn[f] = (fj < 0 || !more) ? -2 : ldg(a.vmapP + (long long)en * NF + fj);
         }
 
-        // derivatives of plane kk -> DD[kk & 1]: r/s pencils from the plane's source rows in the
-        // ring, t-derivative from the registers
-        auto derivs = [&](int kk, int stg, uint32_t par) {
-            mbar_wait(full + stg, par);
-            double *dd = DD + (kk & 1) * 9 * DPL;
-            const int poff = (int)((ebase + (long long)kk * N2) & 1);
-            const double *P = ring + stg * STG + poff;
-#pragma unroll 1
-            for (int w = tid; w < C::RS_ITEMS; w += NT) {
-                const int h = w / C::RS_BLK, r = w - h * C::RS_BLK;
-                if (r < 6 * N) {
-                    const int d = r / (3 * N), r2 = r - d * 3 * N;
-                    const int c = r2 / N, line = r2 - c * N;
-                    const double *in = P + c * PL + (d ? line : line * N);
-                    double *out = dd + (d * 3 + c) * DPL + (d ? line : line * RW);
-                    const int sm = d ? N : 1, so = d ? RW : 1;
-                    if (h == 0) sweep_pencil<N, 0, s_min(NO, N)>(prm.D, in, sm, out, so);
-                    else if (h == 1) sweep_pencil<N, s_min(NO, N), s_min(2 * NO, N)>(prm.D, in, sm, out, so);
-                    else if (h == 2) sweep_pencil<N, s_min(2 * NO, N), s_min(3 * NO, N)>(prm.D, in, sm, out, so);
-                    else sweep_pencil<N, s_min(3 * NO, N), N>(prm.D, in, sm, out, so);
-                }
-            }
-            if (node) {
-                const double *dr = Dt + kk * N;
-                double acc = dr[0] * col[0];
+        // source planes 0 and 1 -> PP (from the registers)
+        if (node) {
 #pragma unroll
-                for (int m = 1; m < N; m++) acc = acc + dr[m] * col[m];
-                dd[(6 + nc) * DPL + pi + RW * pj] = acc;
+            for (int c = 0; c < 3; c++) {
+                PP[c * DPL + pp] = col[c][0];
+                PP[(3 + c) * DPL + pp] = col[c][1];
             }
+        }
+        __syncthreads();
+        // r/s pencils of plane kk: PP[kk & 1] -> DD[kk & 1]
+        auto pencils = [&](int kk) {
+            if (pen)
+                sweep_share<N, DPL>(prm.D, PP + (kk & 1) * 3 * DPL + p_in, p_sm,
+                                    DD + (kk & 1) * 6 * DPL + pd * 3 * DPL + p_in, p_sm, ph);
         };
-
-        derivs(0, cstg, (parbits >> cstg) & 1u);
+        pencils(0);
         __syncthreads(); // L and the derivatives of plane 0 are complete
 
 #pragma unroll 1
         for (int k = 0; k < N; k++) {
             const int nstg = cstg + 1 == NSTG ? 0 : cstg + 1;
-            if (k + 1 < N) derivs(k + 1, nstg, (parbits >> nstg) & 1u);
+            if (k + 1 < N) pencils(k + 1);
 
             // ---- plane k: weighted curl, lifts, inverse mass, low-storage RK update ---------------
-            mbar_wait(full + cstg, (parbits >> cstg) & 1u);
             if (node) {
                 const long long pbase = ebase + (long long)k * N2;
-                const int poff = (int)(pbase & 1);
-                const double *S = ring + cstg * STG + poff + pnd;
-                const double *dd = DD + (k & 1) * 9 * DPL + pi + RW * pj;
                 const long long gi = pbase + pnd;
+                // source components of plane k+2 (for its pencils, next step but one)
+                double pn[3] = {0.0, 0.0, 0.0};
+                if (k + 2 < N) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) pn[c] = ldg(a.u_in + (long long)(srcc + c) * a.ld + gi + 2 * N2);
+                }
                 const double wv = sg * ldg(a.w3 + pnd + k * N2);
-                // direction d: d_b * M_a - d_a * M_b  (curl_part, stage_common.h)
-                const double p0 = dd[(0 + cb_) * DPL] * S[(3 + ca_) * PL] - dd[(0 + ca_) * DPL] * S[(3 + cb_) * PL];
-                const double p1 = dd[(3 + cb_) * DPL] * S[(6 + ca_) * PL] - dd[(3 + ca_) * DPL] * S[(6 + cb_) * PL];
-                const double p2 = dd[(6 + cb_) * DPL] * S[(9 + ca_) * PL] - dd[(6 + ca_) * DPL] * S[(9 + cb_) * PL];
-                double r = (p0 + p1) * wv;
-                r = r + wv * p2;
-                const double *Lc = L + nc * LF;
-                if (pi == 0) r += Lc[3 * N2 + pj + N * k];
-                if (pi == N - 1) r += Lc[1 * N2 + pj + N * k];
-                if (pj == 0) r += Lc[0 * N2 + pi + N * k];
-                if (pj == N - 1) r += Lc[2 * N2 + pi + N * k];
-                if (k == 0) r += Lc[4 * N2 + pnd];
-                if (k == N - 1) r += Lc[5 * N2 + pnd];
-                if (a.src_prof != nullptr && a.src_comp - outc == nc) // usersrc hook
-                    r -= ldg(a.src_prof + gi) * (a.src_tfac * ldg(a.bmn + gi));
-                const double t = a.ca * S[(12 + nc) * PL] + a.dt * (r * S[18 * PL]);
-                const double un = S[(15 + nc) * PL] + a.cb * t;
-                __stcs(a.kf + (long long)(outc + nc) * a.ld + gi, t);
-                __stcs(a.u_out + (long long)(outc + nc) * a.ld + gi, un);
-                if (a.xtr_out != nullptr && (pi == 0 || pi == N - 1))
-                    a.xtr_out[(long long)(outc + nc) * a.ldx + (2ll * e + (pi ? 1 : 0)) * N2 + pj + N * k] = un;
+                // t-derivatives from the registers: row k of D, left to right
+                double dt[3];
+                {
+                    const double d0 = prm.D[k];
+                    dt[0] = d0 * col[0][0]; dt[1] = d0 * col[1][0]; dt[2] = d0 * col[2][0];
+#pragma unroll
+                    for (int m = 1; m < N; m++) {
+                        const double dm = prm.D[k + N * m];
+                        dt[0] = dt[0] + dm * col[0][m];
+                        dt[1] = dt[1] + dm * col[1][m];
+                        dt[2] = dt[2] + dm * col[2][m];
+                    }
+                }
+                const double *dd = DD + (k & 1) * 6 * DPL + pp;
+                const double dr[3] = {dd[0], dd[DPL], dd[2 * DPL]};
+                const double ds[3] = {dd[3 * DPL], dd[4 * DPL], dd[5 * DPL]};
+                mbar_wait(full + cstg, (parbits >> cstg) & 1u);
+                const double *S = ring + cstg * STG + (int)(pbase & 1) + pnd;
+                double cr[3], cs[3], ct[3], r[3];
+                curl_part(dr, S[0], S[PL], S[2 * PL], cr);
+                curl_part(ds, S[3 * PL], S[4 * PL], S[5 * PL], cs);
+                curl_part(dt, S[6 * PL], S[7 * PL], S[8 * PL], ct);
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    r[c] = (cr[c] + cs[c]) * wv;
+                    r[c] = r[c] + wv * ct[c];
+                }
+                // lifts: x-, y-, z-faces in turn
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const double *Lc = L + c * LF;
+                    if (pi == 0) r[c] += Lc[3 * N2 + pj + N * k];
+                    if (pi == N - 1) r[c] += Lc[1 * N2 + pj + N * k];
+                    if (pj == 0) r[c] += Lc[0 * N2 + pi + N * k];
+                    if (pj == N - 1) r[c] += Lc[2 * N2 + pi + N * k];
+                    if (k == 0) r[c] += Lc[4 * N2 + pnd];
+                    if (k == N - 1) r[c] += Lc[5 * N2 + pnd];
+                }
+                if (a.src_prof != nullptr) { // usersrc hook: res(comp) -= profile*(tfac*bm)
+                    const int cs2 = a.src_comp - outc;
+                    if (cs2 >= 0 && cs2 < 3) {
+                        const double sv2 = ldg(a.src_prof + gi) * (a.src_tfac * ldg(a.bmn + gi));
+                        if (cs2 == 0) r[0] -= sv2;
+                        else if (cs2 == 1) r[1] -= sv2;
+                        else r[2] -= sv2;
+                    }
+                }
+                const double mb = S[15 * PL];
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const double t = a.ca * S[(9 + c) * PL] + a.dt * (r[c] * mb);
+                    const double un = S[(12 + c) * PL] + a.cb * t;
+                    __stcs(a.kf + (long long)(outc + c) * a.ld + gi, t);
+                    __stcs(a.u_out + (long long)(outc + c) * a.ld + gi, un);
+                    if (a.xtr_out != nullptr && (pi == 0 || pi == N - 1))
+                        a.xtr_out[(long long)(outc + c) * a.ldx + (2ll * e + (pi ? 1 : 0)) * N2 + pj + N * k] = un;
+                }
+                if (k + 2 < N) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) PP[(k & 1) * 3 * DPL + c * DPL + pp] = pn[c];
+                }
             }
             __syncthreads();
             // the stage of plane k is free: it takes the plane NSTG ahead (of this or the next item)
@@ -429,10 +482,10 @@ __global__ void __launch_bounds__(SW<N>::NT, SW<N>::MINB)
                 if (more && k == N / 2) {
                     // next item: k-lines of the source components and the face data towards L2
                     if (lane < 3) bulk_prefetch(a.u_in + (long long)(srcc + lane) * a.ld + (long long)en * N3, N3);
-                    else if (lane < 11) {
+                    else if (lane < 9) {
                         const double *fa = lane == 3 ? a.unx : lane == 4 ? a.uny : lane == 5 ? a.unz
-                                         : lane == 6 ? a.area : lane == 7 ? a.hY : lane == 8 ? a.Y1
-                                         : lane == 9 ? a.hZ : a.Z1;
+                                         : lane == 6 ? a.area : lane == 7 ? (g ? a.hY : a.hZ)
+                                         : (g ? a.Y1 : a.Z1);
                         bulk_prefetch(fa + (long long)en * NF, NF);
                     }
                 }
