@@ -78,8 +78,10 @@ typedef struct nekcem_b200_desc {
                             fails.  NEKCEM_B200_HOST_ONLY in the environment forces this
                             mode (test aid for driving the Fortran shim without a GPU); it
                             is not a CPU fallback -- nothing is ever computed on the host  */
-    int32_t strict;      /* 1: kernels compiled without FMA contraction (-fmad=false);
-                            built for the 2D path (ldim = 2), refused for ldim = 3      */
+    int32_t strict;      /* 1: the stage kernels and the graphene kernel compiled without FMA
+                            contraction (-fmad=false): every product and sum is rounded
+                            separately, as in the reference's x86-64 build.  3D contexts
+                            then run the slab formulation at every order (slower)        */
     int32_t rank;        /* MPI rank (nid) and size (np): one rank <-> one GPU       */
     int32_t nranks;
 } nekcem_b200_desc;

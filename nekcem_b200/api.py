@@ -155,8 +155,9 @@ class MaxwellB200:
     def __init__(self, ldim: int, nx1: int, nelt: int, imode: int = 3, upwind: bool = True,
                  ifpec: bool = False, ifpml: bool = False, device: int = 0, rank: int = 0,
                  nranks: int = 1, strict: bool = False):
-        """strict: the no-FMA instantiations (2D contexts only): the arithmetic of the reference's
-        x86-64 build operation for operation"""
+        """strict: the no-FMA instantiations of the stage kernels (3D: the slab formulation at every
+        order; 2D) and of the graphene kernel: every product and sum rounded separately, as in the
+        reference's x86-64 build"""
         self.L = lib()
         d = Desc(ABI_VERSION, ldim, nx1, nelt, imode, int(upwind), int(ifpec), int(ifpml),
                  device, int(strict), rank, nranks)

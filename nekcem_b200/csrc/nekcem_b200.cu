@@ -33,7 +33,9 @@ int launch_stage_slab(const StageArgs &a, const double *Dhost, int nx1, bool aux
 int launch_stage_pipe(const StageArgs &a, const double *Dhost, int nx1, bool aux, bool cm, void *stream);
 int launch_stage_sweep(const StageArgs &a, const double *Dhost, int nx1, bool aux, bool cm, void *stream);
 int launch_stage2d(const StageArgs &a, const double *Dhost, int nx1, bool aux, void *stream);
-// the same two kernels compiled with -fmad=false (desc.strict, 2D contexts)
+// the same kernels compiled with -fmad=false (desc.strict; 3D contexts then use the slab
+// formulation at every order)
+int launch_stage_slab_strict(const StageArgs &a, const double *Dhost, int nx1, bool aux, bool cm, void *stream);
 int launch_stage2d_strict(const StageArgs &a, const double *Dhost, int nx1, bool aux, void *stream);
 int launch_graphene(const GrapheneArgs &g, void *stream);
 int launch_graphene_strict(const GrapheneArgs &g, void *stream);
@@ -1088,13 +1090,16 @@ int run_stage(Ctx *c, int rkstep /*1..5*/, int phase = 0)
         b.nel = c->list_n[q];
         int rc = -1;
         if (c->d.ldim == 3) {
-            if (c->opt_pipeline && c->opt_sweep)
+            if (c->d.strict)
+                rc = nkb::launch_stage_slab_strict(b, c->D_host.data(), c->n, (q & 1) != 0,
+                                                   (q & 2) != 0, c->s_compute);
+            else if (c->opt_pipeline && c->opt_sweep)
                 rc = nkb::launch_stage_sweep(b, c->D_host.data(), c->n, (q & 1) != 0, (q & 2) != 0,
                                              c->s_compute);
-            if (rc < 0 && c->opt_pipeline)
+            if (rc < 0 && c->opt_pipeline && !c->d.strict)
                 rc = nkb::launch_stage_pipe(b, c->D_host.data(), c->n, (q & 1) != 0, (q & 2) != 0,
                                             c->s_compute);
-            if (rc < 0)
+            if (rc < 0 && !c->d.strict)
                 rc = nkb::launch_stage_slab(b, c->D_host.data(), c->n, (q & 1) != 0, (q & 2) != 0,
                                             c->s_compute);
         } else {
@@ -1312,8 +1317,6 @@ int nekcem_b200_create(const nekcem_b200_desc *desc, int *handle)
     if (desc->nx1 < 2 || desc->nx1 > 16)
         return fail("nx1=%d outside the supported range 2..16", desc->nx1);
     if (desc->nelt < 1) return fail("nelt must be >= 1");
-    if (desc->strict != 0 && desc->ldim != 2)
-        return fail("strict (no-FMA) kernels exist for the 2D path only (ldim = 2)");
     if (desc->nranks < 1 || desc->rank < 0 || desc->rank >= desc->nranks)
         return fail("bad rank/nranks %d/%d", desc->rank, desc->nranks);
     auto c = std::make_unique<Ctx>();

@@ -67,6 +67,9 @@ namespace {
 #ifndef PIPE_REGS
 #define PIPE_REGS 128
 #endif
+#ifndef PIPE_W3S_MAX
+#define PIPE_W3S_MAX 1000 // w3mn of one element in shared memory up to this many nodes
+#endif
 #ifndef PIPE_IG
 #define PIPE_IG 1 // 1: r/s-pencil lanes interleave the H and E groups (cofactor reads broadcast)
 #endif
@@ -140,8 +143,10 @@ struct PT {
     static constexpr int F_ITEMS = FXY + FZ;
     static constexpr int FPT = (F_ITEMS + NT - 1) / NT;
     static constexpr int NBAR = 5;
-    // w3mn of one element in shared memory (small elements), else read through L1
-    static constexpr bool W3S = N3 <= 512;
+    // w3mn of one element in shared memory wherever it fits next to the regions (whole elements:
+    // nx1 <= 10), else read through L1.  nx1 = 9: 0.691 -> 0.704 of the roofline against L1 reads
+    // (the streaming gathers keep evicting the table)
+    static constexpr bool W3S = N3 <= PIPE_W3S_MAX;
     // the E components of U and R start HE doubles later than a multiple of the component stride
     // (PIPE_IG: the s-pencil lanes interleave the H and E groups, so that both read one cofactor
     // address; the skew puts their field and residual accesses on different banks)

@@ -49,6 +49,9 @@ namespace {
 #ifndef SLAB_T_PIPE
 #define SLAB_T_PIPE 1 // 1: software-pipelined t-lines from global memory (KS > 1)
 #endif
+#ifndef SLAB_W3S
+#define SLAB_W3S 1 // 1: the slab's share of w3mn in shared memory; 0: read through L1
+#endif
 #ifndef SLAB_COF_SLOTS
 #define SLAB_COF_SLOTS 1
 #endif
@@ -85,14 +88,20 @@ struct Slab {
 #ifdef SLAB_NT
     static constexpr int NT = SLAB_NT;
 #else
-    static constexpr int NT = nt_for(RS_ITEMS);
+    // nx1 = 13: two i-j planes (338 nodes) per pass of the plane-mapped staging and epilogue loops
+    // instead of one plane on 256 threads (measured 0.485 -> 0.520 of the roofline; the same move at
+    // nx1 = 14, 416 threads at 72 registers, loses: 0.539 -> 0.501)
+    static constexpr int NT = N == 13 ? 352 : nt_for(RS_ITEMS);
 #endif
     static constexpr int SC = Lay<N>::SK * KB; // component stride in smem
     static constexpr int FXY = 4 * N * KB;     // face points on the x/y faces of a slab
     static constexpr int FZ = KS == 1 ? 2 * N2 : N2;
     static constexpr int F_ITEMS = FXY + FZ;
     static constexpr int FPT = (F_ITEMS + NT - 1) / NT;
-    static constexpr size_t SMEM = sizeof(double) * 12 * SC;
+    // U[6][SC], R[6][SC] and the slab's share of w3mn (linear, KB*N2: every node reads its weight
+    // four times -- s- and t-part of both curl groups -- and the streaming loads keep evicting the
+    // table from L1: nx1 = 10 in the pipelined kernel gained 5 % from the same move)
+    static constexpr size_t SMEM = sizeof(double) * (12 * SC + (SLAB_W3S ? KB * N2 : 0));
     __host__ __device__ static constexpr int k0(int s) { return s * N / KS; }
     __host__ __device__ static constexpr int kb(int s) { return (s + 1) * N / KS - s * N / KS; }
     // cofactor batches: outputs whose cofactors are loaded together
@@ -104,7 +113,7 @@ struct Slab {
 #ifdef SLAB_REG_CAP
     static constexpr int REG_CAP = SLAB_REG_CAP;
 #else
-    static constexpr int REG_CAP = NO >= 7 ? 128 : 96;
+    static constexpr int REG_CAP = N == 13 ? 88 : (NO >= 7 ? 128 : 96);
 #endif
     static constexpr int MINB_SMEM = (227 * 1024) / ((int)SMEM + 1024);
     static constexpr int MINB_THR = 2048 / NT;
@@ -149,8 +158,8 @@ __device__ __forceinline__ int n_at(int m, int pa, int pb)
 template <int N, int DIR, int KOFF, int O0, int O1, int PB, int SC, bool GSRC, bool CM>
 __device__ __forceinline__ void pencil_phase(const double (&D)[N * N], const StageArgs &a,
                                              const double *U, const double *gsrc, double *R,
-                                             int pa, int pb, long long gbase, int wbase, double sg,
-                                             long long mbase)
+                                             const double *w3s, int pa, int pb, long long gbase,
+                                             int wbase, double sg, long long mbase)
 {
     // cofactor of node nd: a.met[q][mbase + nd] in general (mbase = gbase).  CM = elements
     // with constant metrics (found bitwise at setup): mbase = first node of the element and
@@ -174,7 +183,7 @@ __device__ __forceinline__ void pencil_phase(const double (&D)[N * N], const Sta
 #pragma unroll
                     for (int q = 0; q < 3; q++) cof[sl][x][q] = ldg(a.met[6 + q] + gi);
                 }
-                if constexpr (DIR != 0) wv[sl][x] = sg * ldg(a.w3 + wbase + nd);
+                if constexpr (DIR != 0) wv[sl][x] = sg * w3s[wbase + nd];
             }
         };
         // cofactors of the first batch(es): in flight during the contraction
@@ -259,25 +268,25 @@ __device__ __forceinline__ void pencil_phase(const double (&D)[N * N], const Sta
 template <int N, int DIR, int KOFF, int LO, int HI, int SPLIT, int PB, int SC, bool GSRC, bool CM>
 __device__ __forceinline__ void pencil_split(const double (&D)[N * N], const StageArgs &a,
                                              const double *U, const double *gsrc, double *R,
-                                             int pa, int pb, long long gbase, int wbase,
-                                             double sg, int h, long long mbase)
+                                             const double *w3s, int pa, int pb, long long gbase,
+                                             int wbase, double sg, int h, long long mbase)
 {
     constexpr int L = HI - LO, HN = (L + SPLIT - 1) / SPLIT;
     constexpr int E1 = LO + (HN < L ? HN : L), E2 = LO + (2 * HN < L ? 2 * HN : L),
                   E3 = LO + (3 * HN < L ? 3 * HN : L);
-    if (h == 0) pencil_phase<N, DIR, KOFF, LO, E1, PB, SC, GSRC, CM>(D, a, U, gsrc, R, pa, pb, gbase, wbase, sg, mbase);
+    if (h == 0) pencil_phase<N, DIR, KOFF, LO, E1, PB, SC, GSRC, CM>(D, a, U, gsrc, R, w3s, pa, pb, gbase, wbase, sg, mbase);
     if (SPLIT > 1 && h == 1)
-        pencil_phase<N, DIR, KOFF, E1, E2, PB, SC, GSRC, CM>(D, a, U, gsrc, R, pa, pb, gbase, wbase, sg, mbase);
+        pencil_phase<N, DIR, KOFF, E1, E2, PB, SC, GSRC, CM>(D, a, U, gsrc, R, w3s, pa, pb, gbase, wbase, sg, mbase);
     if (SPLIT > 2 && h == 2)
-        pencil_phase<N, DIR, KOFF, E2, E3, PB, SC, GSRC, CM>(D, a, U, gsrc, R, pa, pb, gbase, wbase, sg, mbase);
+        pencil_phase<N, DIR, KOFF, E2, E3, PB, SC, GSRC, CM>(D, a, U, gsrc, R, w3s, pa, pb, gbase, wbase, sg, mbase);
     if (SPLIT > 3 && h == 3)
-        pencil_phase<N, DIR, KOFF, E3, HI, PB, SC, GSRC, CM>(D, a, U, gsrc, R, pa, pb, gbase, wbase, sg, mbase);
+        pencil_phase<N, DIR, KOFF, E3, HI, PB, SC, GSRC, CM>(D, a, U, gsrc, R, w3s, pa, pb, gbase, wbase, sg, mbase);
 }
 
 // t-pencils of slab S (compile-time k range)
 template <int N, int KS, int S, bool CM>
 __device__ __forceinline__ void t_phase(const double (&D)[N * N], const StageArgs &a, const double *U,
-                                        double *R, long long ebase, int tid)
+                                        double *R, const double *w3s, long long ebase, int tid)
 {
     using C = Slab<N, KS>;
     constexpr int K0 = C::k0(S), K1 = K0 + C::kb(S);
@@ -294,7 +303,7 @@ __device__ __forceinline__ void t_phase(const double (&D)[N * N], const StageArg
             double *Rd = R + (g ? 0 : 3) * C::SC;
             const double *gs = a.u_in + (g ? 3 : 0) * a.ld + ebase;
             pencil_split<N, 2, K0, K0, K1, C::TSPLIT, PB_T, C::SC, (KS > 1), CM>(
-                D, a, Us, gs, Rd, pa, pb, ebase, 0, g ? -1.0 : 1.0, h, ebase);
+                D, a, Us, gs, Rd, w3s, pa, pb, ebase, -K0 * C::N2, g ? -1.0 : 1.0, h, ebase);
         }
     } else {
         // KS > 1: the lines come from global memory (L2).  Software pipeline over the flat
@@ -332,7 +341,7 @@ __device__ __forceinline__ void t_phase(const double (&D)[N * N], const StageArg
                     const long long gi = CM ? ebase : ebase + nd + C::N2 * (K0 + o);
 #pragma unroll
                     for (int q = 0; q < 3; q++) cof[o][q] = ldg(a.met[6 + q] + gi);
-                    wv[o] = (g ? -1.0 : 1.0) * ldg(a.w3 + nd + C::N2 * (K0 + o));
+                    wv[o] = (g ? -1.0 : 1.0) * w3s[nd + C::N2 * o];
                 }
             }
 #pragma unroll
@@ -372,6 +381,7 @@ __global__ void __launch_bounds__(Slab<N, KS>::NT, CM ? Slab<N, KS>::MINB_CM : S
     extern __shared__ double smem[];
     double *U = smem;          // [6][SC] H,E of the slab at stage start
     double *R = smem + 6 * SC; // [6][SC] residuals resH,resE
+    double *W3sm = smem + 12 * SC; // [kb*N2] w3mn of the slab's nodes
 
     const int tid = threadIdx.x;
     const int e = a.elist[blockIdx.x / KS];
@@ -453,6 +463,9 @@ __global__ void __launch_bounds__(Slab<N, KS>::NT, CM ? Slab<N, KS>::MINB_CM : S
             }
         }
     }
+    if (SLAB_W3S)
+        for (int i = tid; i < nslab; i += NT) W3sm[i] = ldg(a.w3 + k0 * N2 + i);
+    const double *W3s = SLAB_W3S ? W3sm : a.w3 + k0 * N2;
     // (b) this thread's face points: slot, smem node, round; neighbour ids
     //     face slots in the reference's order (cemface, cem_common.F:234-260): -y,+x,+y,-x,-z,+z
     int fvp[FPT], fsn[FPT], fjs[FPT];
@@ -518,8 +531,8 @@ __global__ void __launch_bounds__(Slab<N, KS>::NT, CM ? Slab<N, KS>::MINB_CM : S
         const int pa = p % N, pb = p / N;
         if (g < 2 && pb < kb)
             pencil_split<N, 0, 0, 0, N, C::SPLIT, C::NO, SC, false, CM>(
-                prm.D, a, U + (g ? 3 : 0) * SC, nullptr, R + (g ? 0 : 3) * SC, pa, pb, sbase,
-                k0 * N2, g ? -1.0 : 1.0, h, sbase);
+                prm.D, a, U + (g ? 3 : 0) * SC, nullptr, R + (g ? 0 : 3) * SC, W3s, pa, pb, sbase,
+                0, g ? -1.0 : 1.0, h, sbase);
     }
     __syncthreads();
     if (SLAB_PF_MODE == 1 && !CM) pf_vol(6, 9);
@@ -531,8 +544,8 @@ __global__ void __launch_bounds__(Slab<N, KS>::NT, CM ? Slab<N, KS>::MINB_CM : S
         const int pa = p % N, pb = p / N;
         if (g < 2 && pb < kb)
             pencil_split<N, 1, 0, 0, N, C::SPLIT, C::PB_S, SC, false, CM>(
-                prm.D, a, U + (g ? 3 : 0) * SC, nullptr, R + (g ? 0 : 3) * SC, pa, pb, sbase,
-                k0 * N2, g ? -1.0 : 1.0, h, CM ? ebase : sbase);
+                prm.D, a, U + (g ? 3 : 0) * SC, nullptr, R + (g ? 0 : 3) * SC, W3s, pa, pb, sbase,
+                0, g ? -1.0 : 1.0, h, CM ? ebase : sbase);
     }
     __syncthreads();
     if (SLAB_PF_MODE == 1) pf_vol(9, 17);
@@ -654,12 +667,12 @@ __global__ void __launch_bounds__(Slab<N, KS>::NT, CM ? Slab<N, KS>::MINB_CM : S
     }
 
     // ---- P4: t-pencils, thread (g,h,i,j) ---------------------------------------------------------
-    if constexpr (KS == 1) t_phase<N, KS, 0, CM>(prm.D, a, U, R, ebase, tid);
+    if constexpr (KS == 1) t_phase<N, KS, 0, CM>(prm.D, a, U, R, W3s, ebase, tid);
     else {
-        if (s == 0) t_phase<N, KS, 0, CM>(prm.D, a, U, R, ebase, tid);
-        if (KS > 1 && s == 1) t_phase<N, KS, (KS > 1 ? 1 : 0), CM>(prm.D, a, U, R, ebase, tid);
-        if (KS > 2 && s == 2) t_phase<N, KS, (KS > 2 ? 2 : 0), CM>(prm.D, a, U, R, ebase, tid);
-        if (KS > 3 && s == 3) t_phase<N, KS, (KS > 3 ? 3 : 0), CM>(prm.D, a, U, R, ebase, tid);
+        if (s == 0) t_phase<N, KS, 0, CM>(prm.D, a, U, R, W3s, ebase, tid);
+        if (KS > 1 && s == 1) t_phase<N, KS, (KS > 1 ? 1 : 0), CM>(prm.D, a, U, R, W3s, ebase, tid);
+        if (KS > 2 && s == 2) t_phase<N, KS, (KS > 2 ? 2 : 0), CM>(prm.D, a, U, R, W3s, ebase, tid);
+        if (KS > 3 && s == 3) t_phase<N, KS, (KS > 3 ? 3 : 0), CM>(prm.D, a, U, R, W3s, ebase, tid);
     }
     __syncthreads();
 
@@ -767,8 +780,15 @@ int launch_n(const StageArgs &a, const double *Dhost, bool pml, bool cm, cudaStr
 
 // returns 0 ok, -1 unsupported order, >0 CUDA failure.  Dhost = dxm1 (n*n, column-major).
 // cm: every element of the list has constant metrics (elflag bit 2).
+// Compiled twice (Makefile): as is, and with -fmad=false -DNKB_STRICT (desc.strict: every product
+// and sum rounded separately, as the reference's x86-64 build does).
+#ifdef NKB_STRICT
+int launch_stage_slab_strict(const StageArgs &a, const double *Dhost, int nx1, bool pml, bool cm,
+                             void *stream)
+#else
 int launch_stage_slab(const StageArgs &a, const double *Dhost, int nx1, bool pml, bool cm,
                       void *stream)
+#endif
 {
     cudaStream_t st = (cudaStream_t)stream;
 #ifdef SLAB_ONLY_N

@@ -69,10 +69,11 @@ def incident_3ddielectric(c, elems=None):
     return j, amp, phase, u.omega
 
 
-def solver_from_refcase(c, device=0, incident=None, ade=None):
-    """ade = (kind, jn, kjn, params, index0) registers a Drude/Lorentz ADE."""
+def solver_from_refcase(c, device=0, incident=None, ade=None, strict=False):
+    """ade = (kind, jn, kjn, params, index0) registers a Drude/Lorentz ADE; strict = the no-FMA
+    instantiations (desc.strict)."""
     s = MaxwellB200(c.ldim, c.nx1, c.nelt, imode=c.imode, upwind=bool(c.s.ifupwind),
-                    ifpec=c.ifpec, ifpml=c.ifpml, device=device)
+                    ifpec=c.ifpec, ifpml=c.ifpml, device=device, strict=strict)
     s.cem_maxwell_init(arrays_from_refcase(c))
     if incident is not None:
         s.set_incident(*incident)
