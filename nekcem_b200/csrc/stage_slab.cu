@@ -50,7 +50,7 @@ namespace {
 #define SLAB_T_PIPE 1 // 1: software-pipelined t-lines from global memory (KS > 1)
 #endif
 #ifndef SLAB_W3S
-#define SLAB_W3S 1 // 1: the slab's share of w3mn in shared memory; 0: read through L1
+#define SLAB_W3S 1 // 1: the slab's share of w3mn in shared memory where that pays; 0: always through L1
 #endif
 #ifndef SLAB_COF_SLOTS
 #define SLAB_COF_SLOTS 1
@@ -60,7 +60,11 @@ __host__ __device__ constexpr int ks_for(int n)
 #ifdef KS_OVERRIDE_N
     if (n == KS_OVERRIDE_N) return KS_OVERRIDE;
 #endif
-    return n <= 8 ? 1 : (n <= 12 ? 2 : 4);
+    // nx1 = 13: three slabs (4, 4, 5 planes) on 352 threads (two i-j planes per pass of the
+    // plane-mapped loops; measured, same box: 0.485 with four slabs on 256 threads, 0.53 with four
+    // on 352, 0.56 with three on 352, 0.45-0.53 with five on 192).  Thinner slabs lose at nx1 = 14, 15
+    // as well (five slabs: 0.54 -> 0.51, 0.565 -> 0.53): the t-lines are re-read once per slab.
+    return n <= 8 ? 1 : (n <= 12 ? 2 : (n == 13 ? 3 : 4));
 }
 __host__ __device__ constexpr int rsplit_for(int n) { return n <= 5 ? 4 : 2; }
 __host__ __device__ constexpr int round32(int x) { return ((x + 31) / 32) * 32; }
@@ -89,8 +93,8 @@ struct Slab {
     static constexpr int NT = SLAB_NT;
 #else
     // nx1 = 13: two i-j planes (338 nodes) per pass of the plane-mapped staging and epilogue loops
-    // instead of one plane on 256 threads (measured 0.485 -> 0.520 of the roofline; the same move at
-    // nx1 = 14, 416 threads at 72 registers, loses: 0.539 -> 0.501)
+    // instead of one plane on 256 threads (see ks_for; the same move at nx1 = 14, 416 threads at 72
+    // registers, loses: 0.539 -> 0.501, and at nx1 = 11, 384 threads at 80 registers: 0.580 -> 0.576)
     static constexpr int NT = N == 13 ? 352 : nt_for(RS_ITEMS);
 #endif
     static constexpr int SC = Lay<N>::SK * KB; // component stride in smem
@@ -98,10 +102,13 @@ struct Slab {
     static constexpr int FZ = KS == 1 ? 2 * N2 : N2;
     static constexpr int F_ITEMS = FXY + FZ;
     static constexpr int FPT = (F_ITEMS + NT - 1) / NT;
-    // U[6][SC], R[6][SC] and the slab's share of w3mn (linear, KB*N2: every node reads its weight
-    // four times -- s- and t-part of both curl groups -- and the streaming loads keep evicting the
-    // table from L1: nx1 = 10 in the pipelined kernel gained 5 % from the same move)
-    static constexpr size_t SMEM = sizeof(double) * (12 * SC + (SLAB_W3S ? KB * N2 : 0));
+    // U[6][SC], R[6][SC] and, for nx1 = 12, 13, the slab's share of w3mn (linear, KB*N2).  Every
+    // node reads its weight four times (s- and t-part of both curl groups) and the streaming loads
+    // keep evicting the table from L1: the pipelined kernel gained 2-5 % at nx1 = 9, 10 from the
+    // move.  Here, same box, general path: nx1 = 12, 13 +2 %; nx1 = 11, 14, 15 +-0; nx1 = 16 -11 %
+    // (two CTAs then need the 228 KB carve-out and the kernel's other loads lose half their L1).
+    static constexpr bool W3S = SLAB_W3S && (N == 12 || N == 13);
+    static constexpr size_t SMEM = sizeof(double) * (12 * SC + (W3S ? KB * N2 : 0));
     __host__ __device__ static constexpr int k0(int s) { return s * N / KS; }
     __host__ __device__ static constexpr int kb(int s) { return (s + 1) * N / KS - s * N / KS; }
     // cofactor batches: outputs whose cofactors are loaded together
@@ -463,9 +470,9 @@ __global__ void __launch_bounds__(Slab<N, KS>::NT, CM ? Slab<N, KS>::MINB_CM : S
             }
         }
     }
-    if (SLAB_W3S)
+    if (C::W3S)
         for (int i = tid; i < nslab; i += NT) W3sm[i] = ldg(a.w3 + k0 * N2 + i);
-    const double *W3s = SLAB_W3S ? W3sm : a.w3 + k0 * N2;
+    const double *W3s = C::W3S ? W3sm : a.w3 + k0 * N2;
     // (b) this thread's face points: slot, smem node, round; neighbour ids
     //     face slots in the reference's order (cemface, cem_common.F:234-260): -y,+x,+y,-x,-z,+z
     int fvp[FPT], fsn[FPT], fjs[FPT];
@@ -673,6 +680,7 @@ __global__ void __launch_bounds__(Slab<N, KS>::NT, CM ? Slab<N, KS>::MINB_CM : S
         if (KS > 1 && s == 1) t_phase<N, KS, (KS > 1 ? 1 : 0), CM>(prm.D, a, U, R, W3s, ebase, tid);
         if (KS > 2 && s == 2) t_phase<N, KS, (KS > 2 ? 2 : 0), CM>(prm.D, a, U, R, W3s, ebase, tid);
         if (KS > 3 && s == 3) t_phase<N, KS, (KS > 3 ? 3 : 0), CM>(prm.D, a, U, R, W3s, ebase, tid);
+        if (KS > 4 && s == 4) t_phase<N, KS, (KS > 4 ? 4 : 0), CM>(prm.D, a, U, R, W3s, ebase, tid);
     }
     __syncthreads();
 
