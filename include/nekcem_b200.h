@@ -66,7 +66,8 @@ enum nekcem_b200_array {
 typedef struct nekcem_b200_desc {
     int32_t abi_version; /* NEKCEM_B200_ABI_VERSION */
     int32_t ldim;        /* 3, or 2 for the TE/TM modes (cem_maxwell_flux2d path)     */
-    int32_t nx1;         /* points per direction, N+1 (SIZE: lx1)                    */
+    int32_t nx1;         /* points per direction, N+1 (SIZE: lx1): 2..24, the range of the
+                            reference's mxm (mxf1..mxf24, src/nek5_mxm_std.F)          */
     int32_t nelt;        /* local element count (SIZE/DIMN)                          */
     int32_t imode;       /* 3 = 3D, 2 = TM, 1 = TE (src/INPUT:18-47, cem_param.F)    */
     int32_t ifupwind;    /* param(19)=0 -> 1 (C0=1); central flux -> 0 (C0=0)        */

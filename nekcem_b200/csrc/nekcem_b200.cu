@@ -1107,7 +1107,7 @@ int run_stage(Ctx *c, int rkstep /*1..5*/, int phase = 0)
                      ? nkb::launch_stage2d_strict(b, c->D_host.data(), c->n, (q & 1) != 0, c->s_compute)
                      : nkb::launch_stage2d(b, c->D_host.data(), c->n, (q & 1) != 0, c->s_compute);
         }
-        if (rc < 0) return fail("nx1=%d is not supported by the stage kernels (2..16)", c->n);
+        if (rc < 0) return fail("nx1=%d is not supported by the stage kernels (2..24)", c->n);
         if (rc > 0) return fail("stage kernel launch failed: %s",
                                 cudaGetErrorString(cudaGetLastError()));
         c->last_launches++;
@@ -1271,8 +1271,9 @@ int apply_filter(Ctx *c)
     const int dev = c->d.device;
     if (dev < 0 || dev >= 64) return fail("device index %d out of range", dev);
     if (!configured[dev]) {
+        // two copies of the largest element (nx1 = 24) and the filter matrix: 225.8 KB
         CUDA_OK(cudaFuncSetAttribute(filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)(sizeof(double) * (2 * 4096 + 256))));
+                                     (int)(sizeof(double) * (2 * 13824 + 576))));
         configured[dev] = true;
     }
     const int nt = c->nxyz >= 256 ? 256 : ((c->nxyz + 31) / 32) * 32;
@@ -1314,8 +1315,9 @@ int nekcem_b200_create(const nekcem_b200_desc *desc, int *handle)
           (desc->ldim == 2 && (desc->imode == 1 || desc->imode == 2))))
         return fail("need ldim=3 with imode=3, or ldim=2 with imode=1 (TE) / 2 (TM); got ldim=%d "
                     "imode=%d", desc->ldim, desc->imode);
-    if (desc->nx1 < 2 || desc->nx1 > 16)
-        return fail("nx1=%d outside the supported range 2..16", desc->nx1);
+    // the reference's own range: mxf1..mxf24 (src/nek5_mxm_std.F)
+    if (desc->nx1 < 2 || desc->nx1 > 24)
+        return fail("nx1=%d outside the supported range 2..24", desc->nx1);
     if (desc->nelt < 1) return fail("nelt must be >= 1");
     if (desc->nranks < 1 || desc->rank < 0 || desc->rank >= desc->nranks)
         return fail("bad rank/nranks %d/%d", desc->rank, desc->nranks);

@@ -1,4 +1,4 @@
-// Fused 2D (TE / TM) Maxwell RK-stage kernel for sm_100a, 2 <= nx1 <= 16.
+// Fused 2D (TE / TM) Maxwell RK-stage kernel for sm_100a, 2 <= nx1 <= 24.
 //
 // The 2D modes evolve three components: TM (imode 2) Hx, Hy, Ez; TE (imode 1) Ex, Ey, Hz
 // [cem_maxwell, src/cem_maxwell.F:584-596].  One thread owns one node of one element for the whole
@@ -249,6 +249,14 @@ int launch_stage2d(const StageArgs &a, const double *Dhost, int nx1, bool aux, v
     case 14: return launch_n<14>(a, Dhost, aux, st);
     case 15: return launch_n<15>(a, Dhost, aux, st);
     case 16: return launch_n<16>(a, Dhost, aux, st);
+    case 17: return launch_n<17>(a, Dhost, aux, st);
+    case 18: return launch_n<18>(a, Dhost, aux, st);
+    case 19: return launch_n<19>(a, Dhost, aux, st);
+    case 20: return launch_n<20>(a, Dhost, aux, st);
+    case 21: return launch_n<21>(a, Dhost, aux, st);
+    case 22: return launch_n<22>(a, Dhost, aux, st);
+    case 23: return launch_n<23>(a, Dhost, aux, st);
+    case 24: return launch_n<24>(a, Dhost, aux, st);
     default: return -1;
     }
 }

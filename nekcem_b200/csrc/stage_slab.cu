@@ -1,4 +1,6 @@
-// Fused Maxwell RK-stage kernel for sm_100a, "element-slab" formulation, 2 <= nx1 <= 16.
+// Fused Maxwell RK-stage kernel for sm_100a, "element-slab" formulation, 2 <= nx1 <= 24
+// (the reference ships mxf1..mxf24, src/nek5_mxm_std.F; orders above 16 are covered for
+// completeness with slabs of three planes and are not tuned).
 //
 // One launch = one RK stage over a list of elements.  One CTA = one k-SLAB of one element
 // (slab = all nodes with k0 <= k < k0+kb; KS slabs per element, KS = 1 for nx1 <= 8), and it
@@ -64,9 +66,10 @@ __host__ __device__ constexpr int ks_for(int n)
     // plane-mapped loops; measured, same box: 0.485 with four slabs on 256 threads, 0.53 with four
     // on 352, 0.56 with three on 352, 0.45-0.53 with five on 192).  Thinner slabs lose at nx1 = 14, 15
     // as well (five slabs: 0.54 -> 0.51, 0.565 -> 0.53): the t-lines are re-read once per slab.
+    if (n > 16) return (n + 2) / 3; // nx1 = 17..24: three planes per slab (83-166 KB of shared memory)
     return n <= 8 ? 1 : (n <= 12 ? 2 : (n == 13 ? 3 : 4));
 }
-__host__ __device__ constexpr int rsplit_for(int n) { return n <= 5 ? 4 : 2; }
+__host__ __device__ constexpr int rsplit_for(int n) { return (n <= 5 || n > 16) ? 4 : 2; }
 __host__ __device__ constexpr int round32(int x) { return ((x + 31) / 32) * 32; }
 __host__ __device__ constexpr int nt_for(int items)
 {
@@ -95,7 +98,9 @@ struct Slab {
     // nx1 = 13: two i-j planes (338 nodes) per pass of the plane-mapped staging and epilogue loops
     // instead of one plane on 256 threads (see ks_for; the same move at nx1 = 14, 416 threads at 72
     // registers, loses: 0.539 -> 0.501, and at nx1 = 11, 384 threads at 80 registers: 0.580 -> 0.576)
-    static constexpr int NT = N == 13 ? 352 : nt_for(RS_ITEMS);
+    // at least one i-j plane of threads (the plane-mapped staging and epilogue loops; only nx1 > 16
+    // has fewer pencil items than plane nodes)
+    static constexpr int NT = N == 13 ? 352 : (nt_for(RS_ITEMS) > round32(N2) ? nt_for(RS_ITEMS) : round32(N2));
 #endif
     static constexpr int SC = Lay<N>::SK * KB; // component stride in smem
     static constexpr int FXY = 4 * N * KB;     // face points on the x/y faces of a slab
@@ -297,7 +302,8 @@ __device__ __forceinline__ void t_phase(const double (&D)[N * N], const StageArg
 {
     using C = Slab<N, KS>;
     constexpr int K0 = C::k0(S), K1 = K0 + C::kb(S);
-    if constexpr (KS == 1 || !SLAB_T_PIPE) {
+    // nx1 > 16: no software pipeline (two t-lines of 17..24 values would not fit the registers)
+    if constexpr (KS == 1 || !SLAB_T_PIPE || (N > 16)) {
         constexpr int NOT = (K1 - K0 + C::TSPLIT - 1) / C::TSPLIT;
         constexpr int PB_T = NOT <= 8 ? NOT : (NOT + 1) / 2;
 #pragma unroll 1
@@ -681,6 +687,9 @@ __global__ void __launch_bounds__(Slab<N, KS>::NT, CM ? Slab<N, KS>::MINB_CM : S
         if (KS > 2 && s == 2) t_phase<N, KS, (KS > 2 ? 2 : 0), CM>(prm.D, a, U, R, W3s, ebase, tid);
         if (KS > 3 && s == 3) t_phase<N, KS, (KS > 3 ? 3 : 0), CM>(prm.D, a, U, R, W3s, ebase, tid);
         if (KS > 4 && s == 4) t_phase<N, KS, (KS > 4 ? 4 : 0), CM>(prm.D, a, U, R, W3s, ebase, tid);
+        if (KS > 5 && s == 5) t_phase<N, KS, (KS > 5 ? 5 : 0), CM>(prm.D, a, U, R, W3s, ebase, tid);
+        if (KS > 6 && s == 6) t_phase<N, KS, (KS > 6 ? 6 : 0), CM>(prm.D, a, U, R, W3s, ebase, tid);
+        if (KS > 7 && s == 7) t_phase<N, KS, (KS > 7 ? 7 : 0), CM>(prm.D, a, U, R, W3s, ebase, tid);
     }
     __syncthreads();
 
@@ -788,15 +797,36 @@ int launch_n(const StageArgs &a, const double *Dhost, bool pml, bool cm, cudaStr
 
 // returns 0 ok, -1 unsupported order, >0 CUDA failure.  Dhost = dxm1 (n*n, column-major).
 // cm: every element of the list has constant metrics (elflag bit 2).
-// Compiled twice (Makefile): as is, and with -fmad=false -DNKB_STRICT (desc.strict: every product
-// and sum rounded separately, as the reference's x86-64 build does).
+// Compiled four times (Makefile): nx1 = 2..16 and (-DSLAB_HI) nx1 = 17..24, each as is and with
+// -fmad=false -DNKB_STRICT (desc.strict: every product and sum rounded separately, as the
+// reference's x86-64 build does).
 #ifdef NKB_STRICT
-int launch_stage_slab_strict(const StageArgs &a, const double *Dhost, int nx1, bool pml, bool cm,
-                             void *stream)
+#define SLAB_LAUNCH launch_stage_slab_strict
+#define SLAB_LAUNCH_HI launch_stage_slab_hi_strict
 #else
-int launch_stage_slab(const StageArgs &a, const double *Dhost, int nx1, bool pml, bool cm,
-                      void *stream)
+#define SLAB_LAUNCH launch_stage_slab
+#define SLAB_LAUNCH_HI launch_stage_slab_hi
 #endif
+int SLAB_LAUNCH_HI(const StageArgs &a, const double *Dhost, int nx1, bool pml, bool cm, void *stream);
+
+#ifdef SLAB_HI
+int SLAB_LAUNCH_HI(const StageArgs &a, const double *Dhost, int nx1, bool pml, bool cm, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (nx1) {
+    case 17: return launch_n<17>(a, Dhost, pml, cm, st);
+    case 18: return launch_n<18>(a, Dhost, pml, cm, st);
+    case 19: return launch_n<19>(a, Dhost, pml, cm, st);
+    case 20: return launch_n<20>(a, Dhost, pml, cm, st);
+    case 21: return launch_n<21>(a, Dhost, pml, cm, st);
+    case 22: return launch_n<22>(a, Dhost, pml, cm, st);
+    case 23: return launch_n<23>(a, Dhost, pml, cm, st);
+    case 24: return launch_n<24>(a, Dhost, pml, cm, st);
+    default: return -1;
+    }
+}
+#else
+int SLAB_LAUNCH(const StageArgs &a, const double *Dhost, int nx1, bool pml, bool cm, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
 #ifdef SLAB_ONLY_N
@@ -819,9 +849,10 @@ int launch_stage_slab(const StageArgs &a, const double *Dhost, int nx1, bool pml
     case 14: return launch_n<14>(a, Dhost, pml, cm, st);
     case 15: return launch_n<15>(a, Dhost, pml, cm, st);
     case 16: return launch_n<16>(a, Dhost, pml, cm, st);
-    default: return -1;
+    default: return SLAB_LAUNCH_HI(a, Dhost, nx1, pml, cm, stream);
     }
 #endif
 }
+#endif
 
 } // namespace nkb

@@ -21,7 +21,7 @@ def _fields(c):
     return np.concatenate([c.hn, c.en])
 
 
-@pytest.mark.parametrize("nx1", [5, 8, 9, 12, 16])
+@pytest.mark.parametrize("nx1", [5, 8, 9, 12, 16, 20])
 def test_strict_3d_periodic_box_vs_oracle(nx1):
     from oracle import cases
     c = cases.case_boxper((3, 3, 3), nx1, dt=-1e-3)

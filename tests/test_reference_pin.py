@@ -76,7 +76,7 @@ def test_pin_stage_by_stage():
     r.close()
 
 
-@pytest.mark.parametrize("nx1", [2, 3, 5, 8, 12, 16, 17])
+@pytest.mark.parametrize("nx1", [2, 3, 5, 8, 12, 16, 17, 20, 24])
 def test_pin_orders(nx1):
     """mxm dispatches to a different unrolled mxfK for every order (src/nek5_mxm_std.F)"""
     c, r = _pair(cases.case_boxper((2, 2, 2), nx1))
@@ -196,7 +196,7 @@ def test_pin_cemface_numbering():
 # setup routines whose output the path consumes: also translated from the
 # reference, so the oracle's restated setup is pinned too
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n", list(range(2, 18)))
+@pytest.mark.parametrize("n", list(range(2, 25)))
 def test_pin_gll_nodes_weights_and_dgll(n):
     """ZWGLL (-> ZWGLJ -> ZWGLJD -> JACG/JACOBF, ENDW1/2, GAMMAF, PNORMJ) and DGLL (PNLEG),
     src/nek5_speclib.F:107-122, 240-283, 423-521, 807-912"""
