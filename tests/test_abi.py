@@ -51,6 +51,13 @@ def test_array_enum_matches_header():
 def test_bad_arguments_fail_loudly():
     with pytest.raises(NekcemB200Error, match="nx1"):
         MaxwellB200(3, 40, 8, device=-1)
+    # the reference's own range of orders: mxf1..mxf24 (src/nek5_mxm_std.F)
+    with pytest.raises(NekcemB200Error, match="nx1"):
+        MaxwellB200(3, 25, 8, device=-1)
+    with pytest.raises(NekcemB200Error, match="nx1"):
+        MaxwellB200(2, 1, 8, imode=1, device=-1)
+    for ldim, imode in ((3, 3), (2, 1)):
+        MaxwellB200(ldim, 24, 2, imode=imode, device=-1, strict=True).close()
     with pytest.raises(NekcemB200Error, match="imode"):
         MaxwellB200(2, 8, 8, imode=3, device=-1)
     with pytest.raises(NekcemB200Error, match="imode"):
