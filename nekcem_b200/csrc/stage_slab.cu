@@ -97,9 +97,9 @@ struct Slab {
 #else
     // nx1 = 13: two i-j planes (338 nodes) per pass of the plane-mapped staging and epilogue loops
     // instead of one plane on 256 threads (see ks_for; the same move at nx1 = 14, 416 threads at 72
-    // registers, loses: 0.539 -> 0.501, and at nx1 = 11, 384 threads at 80 registers: 0.580 -> 0.576)
-    // at least one i-j plane of threads (the plane-mapped staging and epilogue loops; only nx1 > 16
-    // has fewer pencil items than plane nodes)
+    // registers, loses: 0.539 -> 0.501, and at nx1 = 11, 384 threads at 80 registers: 0.580 -> 0.576).
+    // Every order: at least one i-j plane of threads (only nx1 > 16 has fewer pencil items than
+    // nodes in a plane).
     static constexpr int NT = N == 13 ? 352 : (nt_for(RS_ITEMS) > round32(N2) ? nt_for(RS_ITEMS) : round32(N2));
 #endif
     static constexpr int SC = Lay<N>::SK * KB; // component stride in smem
