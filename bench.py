@@ -546,7 +546,7 @@ def run_gpu(args):
                          "overhead_what": "x-face mirror of the fields (compact copy of the +-x "
                                           "traces, written by the epilogue, read by the x "
                                           "neighbours instead of a stride-n gather)",
-                         "kernel": "pipe_kernel (nx1 8..10) / slab_kernel: one launch per RK stage "
+                         "kernel": "pipe_kernel (nx1 5, 7..10) / slab_kernel: one launch per RK stage "
                                    "per element list",
                          "avg_launch_ms": stage_ms},
             "variants": {"constant_metrics": cm_variant},

@@ -16,6 +16,9 @@ PIPE_ORDER_LIST(PIPE_DECL)
 int launch_stage_pipe(const StageArgs &a, const double *Dhost, int nx1, bool pml, bool cm,
                       void *stream)
 {
+    // nx1 = 5, 7: general lists only (measured against the slab kernel, same box: nx1 = 7 general
+    // 0.58 -> 0.615, constant-metric 0.715 -> 0.67; nx1 = 5: 0.45 -> 0.53 / +-0; nx1 = 6 loses both)
+    if (nx1 < 8 && cm) return -1;
     switch (nx1) {
         PIPE_ORDER_LIST(PIPE_CASE)
     default: return -1;

@@ -11,7 +11,7 @@ from helpers import incident_3ddielectric, rel_l2, solver_from_refcase
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
 # orders (nx1) the pipelined kernel covers; the others fall through to the slab kernel
-PIPE_ORDERS = [8, 9, 10]
+PIPE_ORDERS = [5, 7, 8, 9, 10]
 
 
 def _fields(s):
