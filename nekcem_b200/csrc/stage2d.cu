@@ -25,10 +25,18 @@ struct Cfg2 {
     static constexpr int EB = 256 / N2 > 0 ? (256 / N2 > 8 ? 8 : 256 / N2) : 1; // elements per CTA
     static constexpr int NT = ((EB * N2 + 31) / 32) * 32;
     static constexpr int NF = 4 * N;
+#ifndef S2D_MINB
+#define S2D_MINB 4
+#endif
+    // resident CTAs per SM asked of the compiler for the plain instantiation: the kernel is bound
+    // by load latency (long_scoreboard 6.8 stall cycles per issue at three CTAs of 80 registers);
+    // four CTAs at 64 registers, a few spills included: 0.70 -> 0.79 of the roofline at N=7 (512^2
+    // elements, TE); five or six CTAs spill too much (0.66 / 0.65)
+    static constexpr int MINB = NT <= 256 ? S2D_MINB : 1;
 };
 
 template <int N, bool AUX>
-__global__ void __launch_bounds__(Cfg2<N>::NT)
+__global__ void __launch_bounds__(Cfg2<N>::NT, AUX ? 1 : Cfg2<N>::MINB)
     stage2d_kernel(const __grid_constant__ StageParams<N> prm)
 {
     using C = Cfg2<N>;
